@@ -1,0 +1,177 @@
+/* gsmcal.h - C ABI of the B200-native GSM sync/calibration hot path.
+ *
+ * Each entry point replaces one MATLAB function (or inline call site) of
+ * JiaoXianjun/multi-rtl-sdr-calibration; the reference has no FFI of its own, its boundary is the
+ * MATLAB function call, so a same-named MEX gateway (multi-rtl-sdr-calibration_b200/mex/) binds
+ * these symbols and shadows the .m file.  Citations are file:line into the reference.
+ *
+ * Conventions (all entry points)
+ *   - plain pointers + sizes; HOST memory unless a parameter says otherwise; caller allocates outputs.
+ *   - matrices are column-major as MATLAB holds them; one stream (dongle / scanned frequency) per column.
+ *   - complex128 is interleaved (re,im) pairs of doubles ("double[2]").
+ *   - positions / indices are 1-based doubles exactly as the reference returns them.
+ *   - return value: GSMCAL_OK or a negative error code; gsmcal_last_error() gives the text.
+ *     The reference's own failure *sentinels* (-1 / [-1,-1] / inf) are NOT errors: they are reported
+ *     through the count/length outputs (-1 means "the scalar -1") so a gateway can rebuild them.
+ *   - every compute call runs hand-written sm_100a kernels; there is no CPU fallback: without a CUDA
+ *     device the call fails with GSMCAL_ERR_CUDA.
+ */
+#ifndef GSMCAL_H
+#define GSMCAL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSMCAL_OK            0
+#define GSMCAL_ERR_ARG      -1   /* malformed argument */
+#define GSMCAL_ERR_CUDA     -2   /* CUDA runtime failure / no device */
+#define GSMCAL_ERR_CAPACITY -3   /* caller-provided output too small */
+#define GSMCAL_ERR_RANGE    -4   /* the reference would raise an index-out-of-bounds error here */
+
+#define GSMCAL_ABI_VERSION 1
+
+int         gsmcal_abi_version(void);
+const char *gsmcal_last_error(void);
+int         gsmcal_device_count(void);          /* 0 when no CUDA device is usable */
+int         gsmcal_set_device(int device);      /* device used by the calling thread's later calls */
+void        gsmcal_release(void);               /* frees cached device workspaces (mexAtExit) */
+
+/* ---- K1  b = raw2iq(a)                                             raw2iq.m:5-8 ------------------
+ * a: (2*n_iq) x n_col, I at odd rows; b: n_iq x n_col complex128.  uint8 (what rtl_tcp delivers,
+ * multi_rtl_sdr_split_scanner.m:70) or double holding 0..255 (fread, gsm_sync_demod.m:96). */
+int gsmcal_raw2iq_u8 (const uint8_t *a, int64_t n_iq, int64_t n_col, double *b);
+int gsmcal_raw2iq_f64(const double  *a, int64_t n_iq, int64_t n_col, double *b);
+
+/* ---- K2  r = filter(coef,1,s); r = r(1:decim:end,:)   gsm_sync_demod.m:34,110,117;
+ *          multi_rtl_sdr_gsm_FCCH_scanner.m:53,133,135; multi_rtl_sdr_split_scanner.m:54,155-156 ----
+ * s: n x n_col complex128, coef: n_taps real (<=128), r: ceil(n/decim) x n_col complex128. */
+int gsmcal_fir1(int order, double wn, double *coef /* order+1 */);      /* MATLAB fir1(order, wn) */
+int gsmcal_fir_filter(const double *coef, int n_taps, const double *s, int64_t n, int64_t n_col,
+                      int decim, double *r);
+/* fused raw2iq -> filter -> decimate straight from the uint8 wire format (same result as the two calls) */
+int gsmcal_raw2iq_fir_u8(const uint8_t *a, int64_t n_iq, int64_t n_col, const double *coef, int n_taps,
+                         int decim, double *r);
+/* r = chn_filter_8x_4x(s)  chn_filter_8x_4x.m:5-15 (60-tap Num, keep rows 1:2:end);
+ * r = chn_filter_4x(s)     chn_filter_4x.m:5-13   (30-tap Num).  Num recovered from the .fda sessions. */
+int gsmcal_chn_filter_8x_4x(const double *s, int64_t n, int64_t n_col, double *r /* ceil(n/2) x n_col */);
+int gsmcal_chn_filter_4x   (const double *s, int64_t n, int64_t n_col, double *r /* n x n_col */);
+int gsmcal_chn_filter_taps (int which /* 8 or 4 */, double *coef /* >=60 */, int *n_taps);
+
+/* ---- scanners: mean(abs(r(1:decim:end,:)).^2,1) after raw2iq [+ filter]
+ *      scan_band_power_spectrum.m:80-85 (coef NULL, decim 1); multi_rtl_sdr_split_scanner.m:154-156 ---- */
+int gsmcal_band_power_u8(const uint8_t *a, int64_t n_iq, int64_t n_col, const double *coef, int n_taps,
+                         int decim, double *power /* n_col, linear */);
+
+/* ---- K3  [hit_flag,hit_idx,hit_avg_snr,hit_snr] = move_fft_snr_runtime_avg(s,mv_len,fft_len,th)
+ *          move_fft_snr_runtime_avg.m:5-50.   No hit: 0, -1, inf, inf.  fft_len <= 128. ---- */
+int gsmcal_move_fft_snr_runtime_avg(const double *s, int64_t len, int mv_len, int fft_len, double th,
+                                    int *hit_flag, double *hit_idx, double *hit_avg_snr, double *hit_snr);
+/* the per-window SNR trace the reference computes and discards (move_fft_snr_runtime_avg.m:15,28), all
+ * len-fft_len+1 windows, no early exit: the "moving-FFT SNR scan" of BASELINE config 4 */
+int gsmcal_move_fft_snr_trace(const double *s, int64_t len, int fft_len, double *snr);
+/* [hit_flag,hit_idx,hit_snr] = specific_fft_snr_fix_avg(s,target_set,fft_len,th,avg_snr)
+ * specific_fft_snr_fix_avg.m:5-34 */
+int gsmcal_specific_fft_snr_fix_avg(const double *s, int64_t len, int64_t target_first, int64_t target_last,
+                                    int fft_len, double th, double avg_snr,
+                                    int *hit_flag, double *hit_idx, double *hit_snr);
+
+/* ---- K4  [position,snr] = FCCH_coarse_position(s,decimation_ratio)   FCCH_coarse_position.m:5-94 ----
+ * *n_out = -1 -> position = snr = -1 (scalars); else 1 x n_out rows.  cap >= gsmcal_max_bursts(). */
+int gsmcal_FCCH_coarse_position(const double *s, int64_t len, int decimation_ratio,
+                                double *position, double *snr, int64_t cap, int64_t *n_out);
+int64_t gsmcal_max_bursts(int64_t len_decimated, int decimation_ratio);   /* FCCH_coarse_position.m:38 */
+
+/* ---- K5-K8  [FCCH_pos,r,sampling_ppm,carrier_ppm] = FCCH_fine_correction(s,base_position,osr,carrier_freq)
+ *             FCCH_fine_correction.m:5-197 ----
+ * *n_pos = -1 -> FCCH_pos is the scalar -1, else 1 x n_pos.  *r_len = -1 -> r is the scalar -1, else r holds
+ * r_len complex128 (r_cap >= n).  ppm = +inf on the sentinel paths. */
+int gsmcal_FCCH_fine_correction(const double *s, int64_t n, const double *base_position, int64_t n_base,
+                                int oversampling_ratio, double carrier_freq,
+                                double *FCCH_pos, int64_t pos_cap, int64_t *n_pos,
+                                double *r, int64_t r_cap, int64_t *r_len,
+                                double *sampling_ppm, double *carrier_ppm);
+
+/* ---- T1  s = gsm_SCH_training_sequence_gen(osr)   gsm_SCH_training_sequence_gen.m:5-45 ----
+ * 64*osr complex128.  GMSK per GSM 05.04 (BT 0.3, L 4, h 0.5); not a bit match of comm.GMSKModulator. */
+int gsmcal_SCH_training_sequence_gen(int oversampling_ratio, double *s);
+
+/* ---- K9-K10  [pos_info,r,sampling_ppm] = SCH_corr_rate_correction(s,FCCH_pos,sch_training_sequence,osr)
+ *              SCH_corr_rate_correction.m:5-182 ----
+ * *n_rows = -1 -> pos_info = [-1,-1] (1x2); else n_rows x 2 (column-major: n_rows positions then n_rows
+ * types), possibly all -1 (the 3H x 2 sentinel).  rows_cap >= 6*n_fcch. */
+int gsmcal_SCH_corr_rate_correction(const double *s, int64_t n, const double *FCCH_pos, int64_t n_fcch,
+                                    const double *sch_training_sequence, int oversampling_ratio,
+                                    double *pos_info, int64_t rows_cap, int64_t *n_rows,
+                                    double *r, int64_t r_cap, int64_t *r_len, double *sampling_ppm);
+
+/* ---- K8/K7  [r,carrier_ppm] = carrier_correct_post_SCH(s,pos_info,osr,carrier_freq)
+ *             carrier_correct_post_SCH.m:5-83 ---- */
+int gsmcal_carrier_correct_post_SCH(const double *s, int64_t n, const double *pos_info, int64_t n_rows,
+                                    int oversampling_ratio, double carrier_freq,
+                                    double *r, int64_t r_cap, int64_t *r_len, double *carrier_ppm);
+
+/* ---- K11  ppm_out = total_ppm_calculation(ppm_in)   total_ppm_calculation.m:5-21 ---- */
+int gsmcal_total_ppm_calculation(const double *ppm_in, int64_t n, double *ppm_out);
+
+/* ---- batched pipeline: gsm_sync_demod.m:107-124 for many dongle streams in one call ------------------
+ * raw: n_streams rows of 2*n_iq uint8 (row d == column d of the reference's 2N x D matrix `s`).
+ * Returns exactly what the function-by-function chain returns per stream (positions, pos_info, ppm),
+ * but never materialises the intermediate N-sample complex streams: every stage evaluates the samples
+ * it needs from the uint8 input on the fly. */
+typedef struct gsmcal_stream_result {
+    int32_t n_coarse;            /* FCCH_coarse_position: -1 -> position = -1 */
+    int32_t n_fcch;              /* FCCH_fine_correction: -1 -> FCCH_pos = -1 */
+    int32_t n_pos_info;          /* SCH_corr_rate_correction: -1 -> pos_info = [-1,-1] */
+    int32_t flags;               /* GSMCAL_FLAG_* */
+    int64_t r_len[3];            /* length of r after fine / SCH / post-SCH; -1 -> scalar -1 */
+    double  sampling_ppm[2];     /* FCCH stage, SCH stage (inf on sentinel paths) */
+    double  carrier_ppm[2];      /* FCCH stage, post-SCH stage */
+    double  total_sampling_ppm;  /* total_ppm_calculation of the two */
+    double  total_carrier_ppm;
+} gsmcal_stream_result;
+
+#define GSMCAL_FLAG_FINE_SPACING   1   /* FCCH_fine_correction.m:95-102 */
+#define GSMCAL_FLAG_FINE_LOW_SNR   2   /* FCCH_fine_correction.m:192-196 */
+#define GSMCAL_FLAG_SCH_EDGE       4   /* SCH_corr_rate_correction.m:59-63 */
+#define GSMCAL_FLAG_SCH_SPACING    8   /* SCH_corr_rate_correction.m:106-112 */
+#define GSMCAL_FLAG_POST_FEW_BCCH 16   /* carrier_correct_post_SCH.m:15-19 */
+#define GSMCAL_FLAG_FINE_FALLBACK 32   /* informational: a burst needed the all-bin fine search */
+
+#define GSMCAL_MEM_HOST   0
+#define GSMCAL_MEM_DEVICE 1
+
+/* B = gsmcal_max_bursts(ceil(n_iq/(osr*coarse_dr)), coarse_dr).  Optional outputs may be NULL.
+ * coarse_pos/coarse_snr/fcch_pos: [n_streams][B]; pos_info: [n_streams][6*B][2] (row-major rows of
+ * {position,type}).  raw_mem says where `raw` lives; results are always written to HOST memory.
+ * cuda_stream: a cudaStream_t (NULL = default stream); the call returns after the stream has drained. */
+int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t n_streams,
+                           double carrier_freq, const double *sch_training_sequence,
+                           const double *coef, int n_taps, int oversampling_ratio, int coarse_decimation,
+                           gsmcal_stream_result *results,
+                           double *coarse_pos, double *coarse_snr, double *fcch_pos, double *pos_info,
+                           void *cuda_stream);
+
+/* FCCH scanner per-channel processing, multi_rtl_sdr_gsm_FCCH_scanner.m:132-135,163-186, for n_chan
+ * captures in one call: raw2iq -> filter(coef) -> r(1:osr*dr:end) -> FCCH_coarse_position -> spacing
+ * acceptance.  snr[c]/num_hit[c] as the script computes them (0 when rejected). */
+int gsmcal_fcch_scan(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t n_chan,
+                     const double *coef, int n_taps, int oversampling_ratio, int coarse_decimation,
+                     double *snr, double *num_hit, double *position /* [n_chan][B] or NULL */,
+                     int32_t *n_position /* [n_chan] or NULL */, void *cuda_stream);
+
+/* kernel-launch counter (all launches since the last reset, this process) - for bench.py's gpu_launches */
+int64_t gsmcal_launch_count(int reset);
+
+/* measurement helpers used by bench.py for per-stage rooflines on device-resident buffers.
+ * stage: 0 colsum_u8, 1 raw2iq, 2 fir c128->c128, 3 fused u8->fir c128, 4 resample, 5 derotate,
+ *        6 fused u8->fir->decimate(64).  Buffers are DEVICE pointers sized by the caller. */
+int gsmcal_stage_launch(int stage, const void *in, void *out, int64_t n_iq, int64_t n_col,
+                        const double *coef, int n_taps, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSMCAL_H */

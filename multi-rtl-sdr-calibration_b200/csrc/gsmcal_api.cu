@@ -1,0 +1,809 @@
+// gsmcal_api.cu - the C ABI declared in include/gsmcal.h: host-side sequencing of the sm_100a kernels.
+// No torch types, no CPU fallback: every compute entry point fails with GSMCAL_ERR_CUDA without a device.
+#include "../../include/gsmcal.h"
+#include "gsmcal_kernels.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "chn_filter_taps.inc"
+
+static_assert(sizeof(gsmcal_stream_result) == sizeof(StreamResultDev), "result record layout");
+
+namespace {
+
+std::mutex g_mu;
+thread_local std::string g_err;
+thread_local int g_device = 0;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (expr);                                                                          \
+        if (e_ != cudaSuccess) return fail(GSMCAL_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define TRY(expr) do { int rc_ = (expr); if (rc_ != GSMCAL_OK) return rc_; } while (0)
+#define LAUNCH(kern, grid, block, smem, st, ...)                                                          \
+    do { kern<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__); ++g_launches; CU(cudaGetLastError()); } while (0)
+
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    int get(size_t bytes, void **out) {
+        if (bytes > cap) {
+            if (p) cudaFree(p);
+            p = nullptr; cap = 0;
+            size_t want = bytes + bytes / 8 + 256;
+            cudaError_t e = cudaMalloc(&p, want);
+            if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+            if (e != cudaSuccess) return fail(GSMCAL_ERR_CUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+            cap = want;
+        }
+        *out = p;
+        return GSMCAL_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Ctx {
+    bool attrs = false;
+    DevBuf in, out, work, tplbuf;
+    std::map<int, double2 *> tw;     // N -> exp(-2*pi*i*j/N)
+};
+std::map<int, Ctx> g_ctx;
+
+int ensure_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(GSMCAL_ERR_CUDA, "no CUDA device (the sm_100a kernels are the only implementation; there is no CPU fallback)"); }
+    CU(cudaSetDevice(g_device));
+    return GSMCAL_OK;
+}
+
+constexpr int kFineThreads = 320;
+size_t fine_smem(int osr) { int N = 148 * osr, ns = 2 * 64 * osr + 1 + N - 1; return (size_t)(3 * ns + GSMCAL_MAX_TAPS + 16) * sizeof(double2); }
+size_t tone_smem(int osr) { int N = 148 * osr; return (size_t)(5 * N + GSMCAL_MAX_TAPS + 16) * sizeof(double2); }
+size_t sch_smem(int osr) { int L = 64 * osr, ns = 16 * osr - 5 * osr + 1 + L - 1; return (size_t)(3 * ns + L + GSMCAL_MAX_TAPS + 16) * sizeof(double2); }
+
+int get_ctx(Ctx **out) {
+    TRY(ensure_device());
+    Ctx &c = g_ctx[g_device];
+    if (!c.attrs) {
+        CU(cudaFuncSetAttribute(fine_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(cudaFuncSetAttribute(tone_est_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(cudaFuncSetAttribute(sch_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CU(cudaFuncSetAttribute(fir_decim_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CU(cudaFuncSetAttribute(fir_decim_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        c.attrs = true;
+    }
+    *out = &c;
+    return GSMCAL_OK;
+}
+
+int get_twiddle(Ctx &c, int N, cudaStream_t st, const double2 **out) {
+    auto it = c.tw.find(N);
+    if (it == c.tw.end()) {
+        double2 *p = nullptr;
+        CU(cudaMalloc(&p, sizeof(double2) * N));
+        LAUNCH(twiddle_init_kernel, (N + 127) / 128, 128, 0, st, p, N);
+        c.tw[N] = p;
+        *out = p;
+    } else *out = it->second;
+    return GSMCAL_OK;
+}
+
+int set_taps(const double *coef, int n_taps, cudaStream_t st) {
+    if (n_taps < 1 || n_taps > GSMCAL_MAX_TAPS) return fail(GSMCAL_ERR_ARG, "n_taps must be 1..%d", GSMCAL_MAX_TAPS);
+    double tmp[GSMCAL_MAX_TAPS];
+    memset(tmp, 0, sizeof tmp);                          // zero padding on the old side adds exact zeros
+    memcpy(tmp, coef, sizeof(double) * n_taps);
+    CU(cudaMemcpyToSymbolAsync(c_taps, tmp, sizeof tmp, 0, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));                       // tmp lives on this stack frame
+    return GSMCAL_OK;
+}
+
+// ---- workspace carve-up ----------------------------------------------------------------------------
+struct Work {
+    StreamCtl *ctl; StreamResultDev *res;
+    double *coarse_pos, *coarse_snr, *fine_raw, *fcch_pos, *fo, *gate, *sch_raw, *sch_pos, *post_pos, *pos_info, *snr_map, *power;
+    int *sch_edge; unsigned char *kind; double2 *tpl;
+    i64 snr_stride;
+};
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int make_work(Ctx &c, i64 D, int cap, i64 snr_len, int tpl_len, Work *w) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+    size_t o_ctl = take(sizeof(StreamCtl) * D), o_res = take(sizeof(StreamResultDev) * D);
+    size_t per = sizeof(double) * D * cap;
+    size_t o_cp = take(per), o_cs = take(per), o_fr = take(per), o_fp = take(per), o_fo = take(per), o_g = take(per), o_sr = take(per), o_sp = take(per), o_pp = take(per);
+    size_t o_pi = take(per * 12), o_snr = take(sizeof(double) * D * snr_len), o_pw = take(sizeof(double) * D);
+    size_t o_se = take(sizeof(int) * D * cap), o_k = take(D * cap), o_tpl = take(sizeof(double2) * (tpl_len > 0 ? tpl_len : 1));
+    void *base;
+    TRY(c.work.get(off, &base));
+    char *b = static_cast<char *>(base);
+    w->ctl = (StreamCtl *)(b + o_ctl); w->res = (StreamResultDev *)(b + o_res);
+    w->coarse_pos = (double *)(b + o_cp); w->coarse_snr = (double *)(b + o_cs); w->fine_raw = (double *)(b + o_fr); w->fcch_pos = (double *)(b + o_fp);
+    w->fo = (double *)(b + o_fo); w->gate = (double *)(b + o_g); w->sch_raw = (double *)(b + o_sr); w->sch_pos = (double *)(b + o_sp); w->post_pos = (double *)(b + o_pp);
+    w->pos_info = (double *)(b + o_pi); w->snr_map = (double *)(b + o_snr); w->power = (double *)(b + o_pw);
+    w->sch_edge = (int *)(b + o_se); w->kind = (unsigned char *)(b + o_k); w->tpl = (double2 *)(b + o_tpl);
+    w->snr_stride = snr_len;
+    return GSMCAL_OK;
+}
+
+WinSrc mat_src(const double2 *base, i64 len, i64 stride, int interp) {
+    WinSrc s; memset(&s, 0, sizeof s);
+    s.lazy = 0; s.base = base; s.base_len = len; s.base_stride = stride; s.mat_interp = interp; s.dec = 1;
+    return s;
+}
+WinSrc lazy_src(const uint8_t *raw, i64 n_iq, int n_taps, int level, int dec) {
+    WinSrc s; memset(&s, 0, sizeof s);
+    s.lazy = 1; s.raw = raw; s.n_iq = n_iq; s.n_taps = n_taps; s.level = level; s.dec = dec;
+    return s;
+}
+
+// ---- stage launchers (device buffers) -------------------------------------------------------------
+int run_colsum_u8(const uint8_t *raw, i64 n_iq, i64 D, StreamCtl *ctl, cudaStream_t st) {
+    if (((uintptr_t)raw & 1) != 0) return fail(GSMCAL_ERR_ARG, "uint8 capture must start on an even address");
+    const i64 chunk = 512 * 1024;
+    i64 chunks = (2 * n_iq + chunk - 1) / chunk; if (chunks < 1) chunks = 1;
+    if (D > 65535) return fail(GSMCAL_ERR_ARG, "more than 65535 streams per call");
+    LAUNCH(colsum_u8_kernel, dim3((unsigned)chunks, (unsigned)D), 256, 0, st, raw, n_iq, chunk, ctl);
+    return GSMCAL_OK;
+}
+
+struct CoarseParams { int fft_len, mv_len, step10, step11, dr; i64 n_first; double th; };
+double host_mround(double x) { return x >= 0 ? floor(x + 0.5) : -floor(-x + 0.5); }
+int coarse_params(int dr, CoarseParams *p) {
+    if (dr < 1 || dr > 148) return fail(GSMCAL_ERR_ARG, "decimation_ratio out of range");
+    const double num_sym_per_frame = (625.0 / 4.0) * 8.0;
+    p->fft_len = 1 << (int)floor(log2(148.0 / dr));            // FCCH_coarse_position.m:17
+    p->mv_len = 10 * p->fft_len;                                // :22
+    p->th = 10.0;                                               // :21
+    p->n_first = (i64)ceil(23.0 * num_sym_per_frame / dr);      // :25
+    p->step10 = (int)host_mround(10.0 * num_sym_per_frame / dr);   // :35
+    p->step11 = (int)host_mround(11.0 * num_sym_per_frame / dr);   // :36
+    p->dr = dr;
+    return GSMCAL_OK;
+}
+
+int run_coarse(WinSrc src, i64 len, const CoarseParams &p, i64 D, int cap, Work &w, cudaStream_t st) {
+    const i64 n_win = p.n_first - (p.fft_len - 1);
+    size_t smem = sizeof(double2) * (p.fft_len + SNR_THREADS + p.fft_len);
+    LAUNCH(snr_map_kernel, dim3((unsigned)((n_win + SNR_THREADS - 1) / SNR_THREADS), (unsigned)D), SNR_THREADS, smem, st,
+           src, w.ctl, (i64)0, n_win, p.fft_len, w.snr_map, w.snr_stride);
+    LAUNCH(first_hit_scan_kernel, (unsigned)((D + 3) / 4), 128, 0, st, w.snr_map, w.snr_stride, n_win, p.mv_len, p.th, w.ctl, (int)D);
+    LAUNCH(coarse_chain_kernel, (unsigned)D, 32, 0, st, src, w.ctl, len, p.fft_len, p.th, p.step10, p.step11, p.dr, cap, w.coarse_pos, w.coarse_snr);
+    return GSMCAL_OK;
+}
+
+int run_fine(Ctx &c, WinSrc src_peak, WinSrc src_tone, i64 n_iq, int osr, double carrier_freq, i64 D, int cap, Work &w, cudaStream_t st) {
+    const double2 *tw; TRY(get_twiddle(c, 148 * osr, st, &tw));
+    LAUNCH(fine_peak_kernel, dim3((unsigned)cap, (unsigned)D), kFineThreads, fine_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw);
+    LAUNCH(fine_ppm_kernel, (unsigned)((D + 63) / 64), 64, 0, st, w.ctl, (int)D, cap, osr, n_iq, w.fine_raw, w.fcch_pos, w.kind);
+    LAUNCH(tone_est_kernel, dim3((unsigned)cap, (unsigned)D), TONE_THREADS, tone_smem(osr), st, src_tone, w.ctl, 1, w.fcch_pos, cap, osr, tw, w.fo, w.gate);
+    LAUNCH(fine_carrier_kernel, (unsigned)((D + 63) / 64), 64, 0, st, w.ctl, (int)D, cap, osr, carrier_freq, w.fo, w.gate);
+    return GSMCAL_OK;
+}
+
+int run_sch(WinSrc src, int osr, i64 D, int cap, Work &w, cudaStream_t st) {
+    LAUNCH(sch_corr_kernel, dim3((unsigned)cap, (unsigned)D), SCH_THREADS, sch_smem(osr), st, src, w.ctl, w.fcch_pos, cap, osr, w.tpl, w.sch_raw, w.sch_edge);
+    LAUNCH(sch_ppm_kernel, (unsigned)((D + 63) / 64), 64, 0, st, w.ctl, (int)D, cap, osr, w.sch_raw, w.sch_edge, w.sch_pos, w.kind, w.pos_info, w.post_pos);
+    return GSMCAL_OK;
+}
+
+int run_post(Ctx &c, WinSrc src, int osr, double carrier_freq, i64 D, int cap, Work &w, bool want_res, cudaStream_t st) {
+    const double2 *tw; TRY(get_twiddle(c, 148 * osr, st, &tw));
+    LAUNCH(tone_est_kernel, dim3((unsigned)cap, (unsigned)D), TONE_THREADS, tone_smem(osr), st, src, w.ctl, 2, w.post_pos, cap, osr, tw, w.fo, w.gate);
+    LAUNCH(post_carrier_kernel, (unsigned)((D + 63) / 64), 64, 0, st, w.ctl, (int)D, cap, osr, carrier_freq, w.fo, want_res ? w.res : nullptr);
+    return GSMCAL_OK;
+}
+
+template <bool U8>
+int run_fir(const void *in, i64 n, i64 in_stride, const StreamCtl *ctl, int n_taps, int decim, i64 D, double2 *out, i64 n_out, double *power, cudaStream_t st) {
+    if (decim < 1) return fail(GSMCAL_ERR_ARG, "decim must be >= 1");
+    if (n <= 0) return GSMCAL_OK;
+    if (decim == 1 && !power) {
+        unsigned gx = (unsigned)((n + FIR_TILE - 1) / FIR_TILE);
+        auto smem = [](int NT) { int n_in = FIR_TILE + NT - 1; return sizeof(double2) * (size_t)(n_in + n_in / 8 + 2); };
+        if (n_taps <= 32)      LAUNCH((fir_full_kernel<32, U8>), dim3(gx, (unsigned)D), FIR_THREADS, smem(32), st, in, n, in_stride, ctl, out, n_out);
+        else if (n_taps <= 48) LAUNCH((fir_full_kernel<48, U8>), dim3(gx, (unsigned)D), FIR_THREADS, smem(48), st, in, n, in_stride, ctl, out, n_out);
+        else if (n_taps <= 64) LAUNCH((fir_full_kernel<64, U8>), dim3(gx, (unsigned)D), FIR_THREADS, smem(64), st, in, n, in_stride, ctl, out, n_out);
+        else                   LAUNCH((fir_full_kernel<128, U8>), dim3(gx, (unsigned)D), FIR_THREADS, smem(128), st, in, n, in_stride, ctl, out, n_out);
+        return GSMCAL_OK;
+    }
+    int opb = 2048 / decim; if (opb < 1) opb = 1; if (opb > 1024) opb = 1024;
+    int n_in = (opb - 1) * decim + n_taps;
+    size_t smem = sizeof(double2) * (size_t)(n_in + n_in / 8 + 2);
+    unsigned gx = (unsigned)((n_out + opb - 1) / opb);
+    LAUNCH(fir_decim_kernel<U8>, dim3(gx, (unsigned)D), FIRD_THREADS, smem, st, in, n, in_stride, ctl, n_taps, decim, opb, out, n_out, n_out, power);
+    return GSMCAL_OK;
+}
+
+int run_resample_derotate(const double2 *in, i64 len_in, double e, int do_interp, double dphi, int do_derot, double2 *out, i64 len_out, cudaStream_t st) {
+    if (len_out <= 0) return GSMCAL_OK;
+    unsigned g = (unsigned)((len_out + 256 * DEROT_K - 1) / (256 * DEROT_K));
+    LAUNCH(resample_derotate_kernel, g, 256, 0, st, in, len_in, e, do_interp, dphi, do_derot, out, len_out);
+    return GSMCAL_OK;
+}
+
+int check_fir_args(const double *coef, int n_taps, const void *s, i64 n, i64 n_col, const void *r) {
+    if (!coef || !s || !r || n < 0 || n_col < 1) return fail(GSMCAL_ERR_ARG, "null pointer or negative size");
+    if (n_taps < 1 || n_taps > GSMCAL_MAX_TAPS) return fail(GSMCAL_ERR_ARG, "n_taps must be 1..%d", GSMCAL_MAX_TAPS);
+    return GSMCAL_OK;
+}
+
+void gmsk_template(int osr, double *out);
+
+}  // namespace
+
+// ====================================================================================================
+extern "C" {
+
+int gsmcal_abi_version(void) { return GSMCAL_ABI_VERSION; }
+const char *gsmcal_last_error(void) { return g_err.c_str(); }
+int gsmcal_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int gsmcal_set_device(int device) {
+    int n = gsmcal_device_count();
+    if (device < 0 || device >= n) return fail(GSMCAL_ERR_CUDA, "device %d not available (%d devices)", device, n);
+    g_device = device;
+    return GSMCAL_OK;
+}
+void gsmcal_release(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto &kv : g_ctx) {
+        cudaSetDevice(kv.first);
+        kv.second.in.release(); kv.second.out.release(); kv.second.work.release(); kv.second.tplbuf.release();
+        for (auto &t : kv.second.tw) cudaFree(t.second);
+        kv.second.tw.clear();
+    }
+}
+int64_t gsmcal_launch_count(int reset) { long long v = g_launches.load(); if (reset) g_launches = 0; return v; }
+
+int64_t gsmcal_max_bursts(int64_t len_decimated, int decimation_ratio) {
+    const double num_sym_per_frame = (625.0 / 4.0) * 8.0;
+    return (int64_t)ceil((double)len_decimated / (10.0 * num_sym_per_frame / decimation_ratio)) + 2;
+}
+
+// ---------------------------------------------------------------------------------------------------
+int gsmcal_raw2iq_u8(const uint8_t *a, int64_t n_iq, int64_t n_col, double *b) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!a || !b || n_iq < 0 || n_col < 1) return fail(GSMCAL_ERR_ARG, "raw2iq: bad arguments");
+    if (n_iq == 0) return GSMCAL_OK;
+    Ctx *c; TRY(get_ctx(&c));
+    cudaStream_t st = 0;
+    void *din, *dout; Work w;
+    TRY(c->in.get((size_t)2 * n_iq * n_col, &din));
+    TRY(c->out.get(sizeof(double2) * (size_t)n_iq * n_col, &dout));
+    TRY(make_work(*c, n_col, 1, 1, 0, &w));
+    CU(cudaMemcpyAsync(din, a, (size_t)2 * n_iq * n_col, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * n_col, st));
+    TRY(run_colsum_u8((const uint8_t *)din, n_iq, n_col, w.ctl, st));
+    i64 gx = (n_iq + 256 * 8 - 1) / (256 * 8); if (gx > 148 * 16) gx = 148 * 16; if (gx < 1) gx = 1;
+    LAUNCH(raw2iq_store_kernel, dim3((unsigned)gx, (unsigned)n_col), 256, 0, st, (const uint8_t *)din, n_iq, w.ctl, (double2 *)dout);
+    CU(cudaMemcpyAsync(b, dout, sizeof(double2) * (size_t)n_iq * n_col, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return GSMCAL_OK;
+}
+
+int gsmcal_raw2iq_f64(const double *a, int64_t n_iq, int64_t n_col, double *b) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!a || !b || n_iq < 0 || n_col < 1) return fail(GSMCAL_ERR_ARG, "raw2iq: bad arguments");
+    if (n_iq == 0) return GSMCAL_OK;
+    for (int64_t i = 0; i < 2 * n_iq * n_col; ++i)
+        if (!(a[i] >= 0.0 && a[i] <= 255.0 && a[i] == floor(a[i])))
+            return fail(GSMCAL_ERR_ARG, "raw2iq: double input must hold integers 0..255 (what fread(...,'uint8') returns)");
+    Ctx *c; TRY(get_ctx(&c));
+    cudaStream_t st = 0;
+    void *din, *dout; Work w;
+    TRY(c->in.get(sizeof(double) * (size_t)2 * n_iq * n_col, &din));
+    TRY(c->out.get(sizeof(double2) * (size_t)n_iq * n_col, &dout));
+    TRY(make_work(*c, n_col, 1, 1, 0, &w));
+    CU(cudaMemcpyAsync(din, a, sizeof(double) * (size_t)2 * n_iq * n_col, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * n_col, st));
+    i64 gx = (n_iq + 256 * 8 - 1) / (256 * 8); if (gx > 148 * 16) gx = 148 * 16; if (gx < 1) gx = 1;
+    LAUNCH(colsum_f64_kernel, dim3((unsigned)gx, (unsigned)n_col), 256, 0, st, (const double *)din, n_iq, w.ctl);
+    LAUNCH(raw2iq_store_f64_kernel, dim3((unsigned)gx, (unsigned)n_col), 256, 0, st, (const double *)din, n_iq, w.ctl, (double2 *)dout);
+    CU(cudaMemcpyAsync(b, dout, sizeof(double2) * (size_t)n_iq * n_col, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return GSMCAL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+int gsmcal_fir1(int order, double wn, double *coef) {
+    // MATLAB fir1(n, Wn): low-pass, Hamming window, scaled so the DC gain is exactly 1 (gsm_sync_demod.m:34)
+    if (order < 1 || order + 1 > GSMCAL_MAX_TAPS || !(wn > 0.0 && wn < 1.0) || !coef) return fail(GSMCAL_ERR_ARG, "fir1: bad arguments");
+    const int n = order + 1;
+    const double alpha = 0.5 * order;
+    double sum = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double m = i - alpha;
+        const double x = wn * m;
+        const double sinc = (x == 0.0) ? 1.0 : sin(M_PI * x) / (M_PI * x);
+        const double win = 0.54 - 0.46 * cos(2.0 * M_PI * i / order);
+        coef[i] = wn * sinc * win;
+        sum += coef[i];
+    }
+    for (int i = 0; i < n; ++i) coef[i] /= sum;
+    return GSMCAL_OK;
+}
+
+int gsmcal_fir_filter(const double *coef, int n_taps, const double *s, int64_t n, int64_t n_col, int decim, double *r) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(check_fir_args(coef, n_taps, s, n, n_col, r));
+    if (n == 0) return GSMCAL_OK;
+    Ctx *c; TRY(get_ctx(&c));
+    cudaStream_t st = 0;
+    const i64 n_out = (n + decim - 1) / decim;
+    void *din, *dout;
+    TRY(c->in.get(sizeof(double2) * (size_t)n * n_col, &din));
+    TRY(c->out.get(sizeof(double2) * (size_t)n_out * n_col, &dout));
+    TRY(set_taps(coef, n_taps, st));
+    CU(cudaMemcpyAsync(din, s, sizeof(double2) * (size_t)n * n_col, cudaMemcpyHostToDevice, st));
+    TRY(run_fir<false>(din, n, n, nullptr, n_taps, decim, n_col, (double2 *)dout, n_out, nullptr, st));
+    CU(cudaMemcpyAsync(r, dout, sizeof(double2) * (size_t)n_out * n_col, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return GSMCAL_OK;
+}
+
+int gsmcal_raw2iq_fir_u8(const uint8_t *a, int64_t n_iq, int64_t n_col, const double *coef, int n_taps, int decim, double *r) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    TRY(check_fir_args(coef, n_taps, a, n_iq, n_col, r));
+    if (n_iq == 0) return GSMCAL_OK;
+    Ctx *c; TRY(get_ctx(&c));
+    cudaStream_t st = 0;
+    const i64 n_out = (n_iq + decim - 1) / decim;
+    void *din, *dout; Work w;
+    TRY(c->in.get((size_t)2 * n_iq * n_col, &din));
+    TRY(c->out.get(sizeof(double2) * (size_t)n_out * n_col, &dout));
+    TRY(make_work(*c, n_col, 1, 1, 0, &w));
+    TRY(set_taps(coef, n_taps, st));
+    CU(cudaMemcpyAsync(din, a, (size_t)2 * n_iq * n_col, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * n_col, st));
+    TRY(run_colsum_u8((const uint8_t *)din, n_iq, n_col, w.ctl, st));
+    TRY(run_fir<true>(din, n_iq, 2 * n_iq, w.ctl, n_taps, decim, n_col, (double2 *)dout, n_out, nullptr, st));
+    CU(cudaMemcpyAsync(r, dout, sizeof(double2) * (size_t)n_out * n_col, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return GSMCAL_OK;
+}
+
+int gsmcal_chn_filter_taps(int which, double *coef, int *n_taps) {
+    if (!coef || !n_taps) return fail(GSMCAL_ERR_ARG, "chn_filter_taps: null");
+    if (which == 8) { memcpy(coef, kNum8x, sizeof kNum8x); *n_taps = 60; return GSMCAL_OK; }
+    if (which == 4) { memcpy(coef, kNum4x, sizeof kNum4x); *n_taps = 30; return GSMCAL_OK; }
+    return fail(GSMCAL_ERR_ARG, "chn_filter_taps: which must be 8 or 4");
+}
+int gsmcal_chn_filter_8x_4x(const double *s, int64_t n, int64_t n_col, double *r) { return gsmcal_fir_filter(kNum8x, 60, s, n, n_col, 2, r); }
+int gsmcal_chn_filter_4x(const double *s, int64_t n, int64_t n_col, double *r) { return gsmcal_fir_filter(kNum4x, 30, s, n, n_col, 1, r); }
+
+int gsmcal_band_power_u8(const uint8_t *a, int64_t n_iq, int64_t n_col, const double *coef, int n_taps, int decim, double *power) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!a || !power || n_iq < 1 || n_col < 1 || decim < 1) return fail(GSMCAL_ERR_ARG, "band_power: bad arguments");
+    Ctx *c; TRY(get_ctx(&c));
+    cudaStream_t st = 0;
+    void *din; Work w;
+    TRY(c->in.get((size_t)2 * n_iq * n_col, &din));
+    TRY(make_work(*c, n_col, 1, 1, 0, &w));
+    if (coef) TRY(set_taps(coef, n_taps, st));
+    CU(cudaMemcpyAsync(din, a, (size_t)2 * n_iq * n_col, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * n_col, st));
+    CU(cudaMemsetAsync(w.power, 0, sizeof(double) * n_col, st));
+    TRY(run_colsum_u8((const uint8_t *)din, n_iq, n_col, w.ctl, st));
+    const i64 n_out = (n_iq + decim - 1) / decim;
+    if (coef) {
+        TRY(run_fir<true>(din, n_iq, 2 * n_iq, w.ctl, n_taps, decim, n_col, nullptr, n_out, w.power, st));
+    } else {
+        i64 gx = (n_out + 2047) / 2048; if (gx > 1024) gx = 1024;
+        LAUNCH(power_u8_kernel, dim3((unsigned)gx, (unsigned)n_col), 256, 0, st, (const uint8_t *)din, n_iq, w.ctl, decim, w.power);
+    }
+    CU(cudaMemcpyAsync(power, w.power, sizeof(double) * n_col, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < n_col; ++i) power[i] /= (double)n_out;
+    return GSMCAL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+static int snr_windows(const double *s, int64_t len, int fft_len, i64 w0, i64 n_win, Ctx **cout, Work *w, cudaStream_t st) {
+    if (!s || len < 1 || fft_len < 1 || fft_len > 128) return fail(GSMCAL_ERR_ARG, "moving fft: bad arguments (fft_len <= 128)");
+    Ctx *c; TRY(get_ctx(&c));
+    void *din;
+    TRY(c->in.get(sizeof(double2) * (size_t)len, &din));
+    TRY(make_work(*c, 1, 1, n_win > 0 ? n_win : 1, 0, w));
+    CU(cudaMemcpyAsync(din, s, sizeof(double2) * (size_t)len, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(w->ctl, 0, sizeof(StreamCtl), st));
+    if (n_win > 0) {
+        WinSrc src = mat_src((const double2 *)din, len, len, 0);
+        size_t smem = sizeof(double2) * (fft_len + SNR_THREADS + fft_len);
+        LAUNCH(snr_map_kernel, dim3((unsigned)((n_win + SNR_THREADS - 1) / SNR_THREADS), 1), SNR_THREADS, smem, st, src, w->ctl, w0, n_win, fft_len, w->snr_map, w->snr_stride);
+    }
+    *cout = c;
+    return GSMCAL_OK;
+}
+
+int gsmcal_move_fft_snr_runtime_avg(const double *s, int64_t len, int mv_len, int fft_len, double th,
+                                    int *hit_flag, double *hit_idx, double *hit_avg_snr, double *hit_snr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!hit_flag || !hit_idx || !hit_avg_snr || !hit_snr || mv_len < 1) return fail(GSMCAL_ERR_ARG, "move_fft_snr_runtime_avg: bad arguments");
+    cudaStream_t st = 0; Ctx *c; Work w;
+    const i64 n_win = len - (fft_len - 1);
+    TRY(snr_windows(s, len, fft_len, 0, n_win, &c, &w, st));
+    StreamCtl h; memset(&h, 0, sizeof h); h.first_hit = -1;
+    if (n_win > 0) {
+        LAUNCH(first_hit_scan_kernel, 1, 32, 0, st, w.snr_map, w.snr_stride, n_win, mv_len, th, w.ctl, 1);
+        CU(cudaMemcpyAsync(&h, w.ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    if (h.first_hit > 0) { *hit_flag = 1; *hit_idx = h.first_hit; *hit_avg_snr = h.hit_avg_snr; *hit_snr = h.hit_snr; }
+    else { *hit_flag = 0; *hit_idx = -1; *hit_avg_snr = INFINITY; *hit_snr = INFINITY; }
+    return GSMCAL_OK;
+}
+
+int gsmcal_move_fft_snr_trace(const double *s, int64_t len, int fft_len, double *snr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!snr) return fail(GSMCAL_ERR_ARG, "snr trace: null output");
+    cudaStream_t st = 0; Ctx *c; Work w;
+    const i64 n_win = len - (fft_len - 1);
+    if (n_win < 1) return fail(GSMCAL_ERR_ARG, "snr trace: stream shorter than fft_len");
+    TRY(snr_windows(s, len, fft_len, 0, n_win, &c, &w, st));
+    CU(cudaMemcpyAsync(snr, w.snr_map, sizeof(double) * n_win, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return GSMCAL_OK;
+}
+
+int gsmcal_specific_fft_snr_fix_avg(const double *s, int64_t len, int64_t t0, int64_t t1, int fft_len, double th, double avg_snr,
+                                    int *hit_flag, double *hit_idx, double *hit_snr) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!hit_flag || !hit_idx || !hit_snr) return fail(GSMCAL_ERR_ARG, "specific_fft_snr_fix_avg: null output");
+    *hit_flag = 0; *hit_idx = -1; *hit_snr = INFINITY;
+    if (t1 < t0) return GSMCAL_OK;
+    if (t0 < 1 || t1 + fft_len - 1 > len) return fail(GSMCAL_ERR_RANGE, "specific_fft_snr_fix_avg: window outside the stream (MATLAB would raise an index error)");
+    cudaStream_t st = 0; Ctx *c; Work w;
+    const i64 n_win = t1 - t0 + 1;
+    TRY(snr_windows(s, len, fft_len, t0 - 1, n_win, &c, &w, st));
+    LAUNCH(specific_hit_kernel, 1, 32, 0, st, w.snr_map, n_win, th, avg_snr, w.sch_edge, w.power);
+    int off; double v;
+    CU(cudaMemcpyAsync(&off, w.sch_edge, sizeof off, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&v, w.power, sizeof v, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (off >= 0) { *hit_flag = 1; *hit_idx = (double)(t0 + off); *hit_snr = v; }
+    return GSMCAL_OK;
+}
+
+int gsmcal_FCCH_coarse_position(const double *s, int64_t len, int decimation_ratio, double *position, double *snr, int64_t cap_out, int64_t *n_out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!s || !position || !snr || !n_out || len < 1) return fail(GSMCAL_ERR_ARG, "FCCH_coarse_position: bad arguments");
+    CoarseParams p; TRY(coarse_params(decimation_ratio, &p));
+    if (p.n_first > len) return fail(GSMCAL_ERR_RANGE, "FCCH_coarse_position: stream shorter than 23 frames (s(1:%lld) would raise an index error)", (long long)p.n_first);
+    const int cap = (int)gsmcal_max_bursts(len, decimation_ratio);
+    Ctx *c; TRY(get_ctx(&c));
+    cudaStream_t st = 0; void *din; Work w;
+    TRY(c->in.get(sizeof(double2) * (size_t)len, &din));
+    TRY(make_work(*c, 1, cap, p.n_first, 0, &w));
+    CU(cudaMemcpyAsync(din, s, sizeof(double2) * (size_t)len, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl), st));
+    TRY(run_coarse(mat_src((const double2 *)din, len, len, 0), len, p, 1, cap, w, st));
+    StreamCtl h;
+    CU(cudaMemcpyAsync(&h, w.ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (h.n_coarse < 0) { *n_out = -1; return GSMCAL_OK; }
+    if (h.n_coarse > cap_out) return fail(GSMCAL_ERR_CAPACITY, "FCCH_coarse_position: %d hits, capacity %lld", h.n_coarse, (long long)cap_out);
+    CU(cudaMemcpy(position, w.coarse_pos, sizeof(double) * h.n_coarse, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(snr, w.coarse_snr, sizeof(double) * h.n_coarse, cudaMemcpyDeviceToHost));
+    *n_out = h.n_coarse;
+    return GSMCAL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+int gsmcal_FCCH_fine_correction(const double *s, int64_t n, const double *base_position, int64_t n_base, int osr, double carrier_freq,
+                                double *FCCH_pos, int64_t pos_cap, int64_t *n_pos, double *r, int64_t r_cap, int64_t *r_len,
+                                double *sampling_ppm, double *carrier_ppm) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!s || !n_pos || !r_len || !sampling_ppm || !carrier_ppm || n < 1 || n_base < 0 || osr < 1 || osr > 8) return fail(GSMCAL_ERR_ARG, "FCCH_fine_correction: bad arguments (osr 1..8)");
+    *n_pos = -1; *r_len = -1; *sampling_ppm = INFINITY; *carrier_ppm = INFINITY;
+    if (n_base < 5) return GSMCAL_OK;                                   // FCCH_fine_correction.m:12-15
+    if (!base_position || !FCCH_pos) return fail(GSMCAL_ERR_ARG, "FCCH_fine_correction: null positions");
+    const i64 len_s = n / osr;
+    for (int64_t i = 0; i < n_base; ++i) {
+        const double p = base_position[i];
+        if (p + 64 > (double)(len_s - 148 + 1)) break;
+        if (p != floor(p) || p - 64 < 1) return fail(GSMCAL_ERR_RANGE, "FCCH_fine_correction: base_position(%lld)=%g puts the search window before the first sample", (long long)i + 1, p);
+    }
+    Ctx *c; TRY(get_ctx(&c));
+    cudaStream_t st = 0; void *din; Work w;
+    const int cap = (int)n_base;
+    TRY(c->in.get(sizeof(double2) * (size_t)n, &din));
+    TRY(make_work(*c, 1, cap, 1, 0, &w));
+    CU(cudaMemcpyAsync(din, s, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, st));
+    StreamCtl h; memset(&h, 0, sizeof h); h.n_coarse = cap;
+    CU(cudaMemcpyAsync(w.ctl, &h, sizeof h, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(w.coarse_pos, base_position, sizeof(double) * cap, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    TRY(run_fine(*c, mat_src((const double2 *)din, n, n, 0), mat_src((const double2 *)din, n, n, 1), n, osr, carrier_freq, 1, cap, w, st));
+    CU(cudaMemcpyAsync(&h, w.ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *sampling_ppm = h.sppm1; *carrier_ppm = h.cppm1; *n_pos = h.n_fcch;
+    if (h.n_fcch > 0) {
+        if (h.n_fcch > pos_cap) return fail(GSMCAL_ERR_CAPACITY, "FCCH_fine_correction: FCCH_pos capacity");
+        CU(cudaMemcpy(FCCH_pos, w.fcch_pos, sizeof(double) * h.n_fcch, cudaMemcpyDeviceToHost));
+    }
+    *r_len = h.len1;
+    if (h.len1 >= 0) {
+        if (!r || h.len1 > r_cap) return fail(GSMCAL_ERR_CAPACITY, "FCCH_fine_correction: r capacity %lld < %lld", (long long)r_cap, (long long)h.len1);
+        if (!h.interp1_on && !h.derot1_on) memcpy(r, s, sizeof(double2) * (size_t)h.len1);     // r = s (:72)
+        else {
+            void *dout; TRY(c->out.get(sizeof(double2) * (size_t)h.len1, &dout));
+            TRY(run_resample_derotate((const double2 *)din, n, h.e1, h.interp1_on, h.dphi1, h.derot1_on, (double2 *)dout, h.len1, st));
+            CU(cudaMemcpyAsync(r, dout, sizeof(double2) * (size_t)h.len1, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
+    }
+    return GSMCAL_OK;
+}
+
+int gsmcal_SCH_training_sequence_gen(int osr, double *s) {
+    if (!s || osr < 1 || osr > 64) return fail(GSMCAL_ERR_ARG, "gsm_SCH_training_sequence_gen: bad arguments");
+    gmsk_template(osr, s);
+    return GSMCAL_OK;
+}
+
+int gsmcal_SCH_corr_rate_correction(const double *s, int64_t n, const double *FCCH_pos, int64_t n_fcch, const double *tpl, int osr,
+                                    double *pos_info, int64_t rows_cap, int64_t *n_rows, double *r, int64_t r_cap, int64_t *r_len, double *sampling_ppm) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!n_rows || !r_len || !sampling_ppm || osr < 1 || osr > 8) return fail(GSMCAL_ERR_ARG, "SCH_corr_rate_correction: bad arguments (osr 1..8)");
+    *n_rows = -1; *r_len = -1; *sampling_ppm = INFINITY;
+    if (n_fcch < 5) return GSMCAL_OK;                                    // SCH_corr_rate_correction.m:11-14
+    if (!s || !FCCH_pos || !tpl || !pos_info || n < 1) return fail(GSMCAL_ERR_ARG, "SCH_corr_rate_correction: null input");
+    const int cap = (int)n_fcch;
+    const int L = 64 * osr;
+    for (int i = 0; i < cap; ++i) if (FCCH_pos[i] != floor(FCCH_pos[i]) || FCCH_pos[i] + (625 * osr / 4) * 8 + 42 * osr - 8 * osr < 1)
+        return fail(GSMCAL_ERR_RANGE, "SCH_corr_rate_correction: FCCH_pos(%d) puts the search window before the first sample", i + 1);
+    Ctx *c; TRY(get_ctx(&c));
+    cudaStream_t st = 0; void *din; Work w;
+    TRY(c->in.get(sizeof(double2) * (size_t)n, &din));
+    TRY(make_work(*c, 1, cap, 1, L, &w));
+    CU(cudaMemcpyAsync(din, s, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(w.tpl, tpl, sizeof(double2) * L, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(w.fcch_pos, FCCH_pos, sizeof(double) * cap, cudaMemcpyHostToDevice, st));
+    StreamCtl h; memset(&h, 0, sizeof h); h.n_fcch = cap; h.sch_enable = 1; h.len1 = n;
+    CU(cudaMemcpyAsync(w.ctl, &h, sizeof h, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    TRY(run_sch(mat_src((const double2 *)din, n, n, 0), osr, 1, cap, w, st));
+    CU(cudaMemcpyAsync(&h, w.ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *sampling_ppm = h.sppm2; *n_rows = h.n_pos_info;
+    if (h.n_pos_info > 0) {
+        if (h.n_pos_info > rows_cap) return fail(GSMCAL_ERR_CAPACITY, "SCH_corr_rate_correction: pos_info capacity %lld < %d", (long long)rows_cap, h.n_pos_info);
+        std::vector<double> tmp(2 * (size_t)h.n_pos_info);
+        CU(cudaMemcpy(tmp.data(), w.pos_info, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < h.n_pos_info; ++i) { pos_info[i] = tmp[2 * i]; pos_info[h.n_pos_info + i] = tmp[2 * i + 1]; }
+    }
+    *r_len = h.len2;
+    if (h.len2 >= 0) {
+        if (!r || h.len2 > r_cap) return fail(GSMCAL_ERR_CAPACITY, "SCH_corr_rate_correction: r capacity");
+        if (!h.interp2_on) memcpy(r, s, sizeof(double2) * (size_t)h.len2);                    // r = s (:87,:120)
+        else {
+            void *dout; TRY(c->out.get(sizeof(double2) * (size_t)h.len2, &dout));
+            TRY(run_resample_derotate((const double2 *)din, n, h.e2, 1, 0.0, 0, (double2 *)dout, h.len2, st));
+            CU(cudaMemcpyAsync(r, dout, sizeof(double2) * (size_t)h.len2, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
+    }
+    return GSMCAL_OK;
+}
+
+int gsmcal_carrier_correct_post_SCH(const double *s, int64_t n, const double *pos_info, int64_t n_rows, int osr, double carrier_freq,
+                                    double *r, int64_t r_cap, int64_t *r_len, double *carrier_ppm) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!r_len || !carrier_ppm || n_rows < 0 || osr < 1 || osr > 8) return fail(GSMCAL_ERR_ARG, "carrier_correct_post_SCH: bad arguments");
+    *r_len = -1; *carrier_ppm = INFINITY;
+    if (n_rows > 0 && !pos_info) return fail(GSMCAL_ERR_ARG, "carrier_correct_post_SCH: null pos_info");
+    bool all_m1 = n_rows > 0;                                            // `if pos_info==-1` is true only when ALL elements are -1 (:10)
+    for (int64_t i = 0; i < 2 * n_rows; ++i) if (pos_info[i] != -1.0) { all_m1 = false; break; }
+    if (all_m1) return GSMCAL_OK;
+    int n_b = 0; std::vector<double> fpos;
+    for (int64_t i = 0; i < n_rows; ++i) {
+        if (pos_info[n_rows + i] == 2.0) ++n_b;
+        if (pos_info[n_rows + i] == 0.0) fpos.push_back(pos_info[i]);
+    }
+    if (n_b < 4) return GSMCAL_OK;                                       // :15-19
+    if (!s || n < 1) return fail(GSMCAL_ERR_ARG, "carrier_correct_post_SCH: null stream");
+    const int N = 148 * osr;
+    for (double p : fpos) if (p != floor(p) || p < 1 || p + N - 1 > (double)n) return fail(GSMCAL_ERR_RANGE, "carrier_correct_post_SCH: FCCH window outside the stream");
+    if (fpos.empty()) return fail(GSMCAL_ERR_RANGE, "carrier_correct_post_SCH: no FCCH rows (mean of empty is NaN in the reference)");
+    if (!r || n > r_cap) return fail(GSMCAL_ERR_CAPACITY, "carrier_correct_post_SCH: r capacity");
+    Ctx *c; TRY(get_ctx(&c));
+    cudaStream_t st = 0; void *din, *dout; Work w;
+    const int cap = (int)fpos.size();
+    TRY(c->in.get(sizeof(double2) * (size_t)n, &din));
+    TRY(c->out.get(sizeof(double2) * (size_t)n, &dout));
+    TRY(make_work(*c, 1, cap, 1, 0, &w));
+    CU(cudaMemcpyAsync(din, s, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(w.post_pos, fpos.data(), sizeof(double) * cap, cudaMemcpyHostToDevice, st));
+    StreamCtl h; memset(&h, 0, sizeof h); h.post_enable = 1; h.n_post_fcch = cap; h.len2 = n;
+    h.sppm1 = h.sppm2 = h.cppm1 = INFINITY;
+    CU(cudaMemcpyAsync(w.ctl, &h, sizeof h, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    TRY(run_post(*c, mat_src((const double2 *)din, n, n, 0), osr, carrier_freq, 1, cap, w, false, st));
+    CU(cudaMemcpyAsync(&h, w.ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *carrier_ppm = h.cppm2;
+    TRY(run_resample_derotate((const double2 *)din, n, 0.0, 0, h.dphi2, 1, (double2 *)dout, n, st));
+    CU(cudaMemcpyAsync(r, dout, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *r_len = n;
+    return GSMCAL_OK;
+}
+
+int gsmcal_total_ppm_calculation(const double *ppm_in, int64_t n, double *ppm_out) {
+    // total_ppm_calculation.m:5-21 - pure scalar host arithmetic (there is nothing to put on a GPU)
+    if (!ppm_out || n < 0 || (n > 0 && !ppm_in)) return fail(GSMCAL_ERR_ARG, "total_ppm_calculation: bad arguments");
+    bool all_inf = n > 0;
+    for (int64_t i = 0; i < n; ++i) if (!(std::isinf(ppm_in[i]) && ppm_in[i] > 0)) { all_inf = false; break; }
+    if (all_inf) { *ppm_out = INFINITY; return GSMCAL_OK; }
+    double acc = 1.0;
+    for (int64_t i = 0; i < n; ++i) acc = acc * (1.0 + ppm_in[i] * 1e-6);
+    *ppm_out = (acc - 1.0) * 1e6;
+    return GSMCAL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t D, double carrier_freq, const double *tpl,
+                           const double *coef, int n_taps, int osr, int coarse_dr, gsmcal_stream_result *results,
+                           double *coarse_pos, double *coarse_snr, double *fcch_pos, double *pos_info, void *cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!raw || !tpl || !coef || !results || n_iq < 1 || D < 1 || osr < 1 || osr > 8) return fail(GSMCAL_ERR_ARG, "calibrate_batch: bad arguments (osr 1..8)");
+    CoarseParams p; TRY(coarse_params(coarse_dr, &p));
+    const int dec = osr * coarse_dr;
+    const i64 len_dec = (n_iq + dec - 1) / dec;
+    if (p.n_first > len_dec) return fail(GSMCAL_ERR_RANGE, "calibrate_batch: capture shorter than 23 frames");
+    const int cap = (int)gsmcal_max_bursts(len_dec, coarse_dr);
+    Ctx *c; TRY(get_ctx(&c));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    Work w;
+    TRY(make_work(*c, D, cap, p.n_first, 64 * osr, &w));
+    TRY(set_taps(coef, n_taps, st));
+    const uint8_t *draw = raw;
+    if (raw_mem == GSMCAL_MEM_HOST) {
+        void *din; TRY(c->in.get((size_t)2 * n_iq * D, &din));
+        draw = (const uint8_t *)din;
+    }
+    CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * D, st));
+    CU(cudaMemcpyAsync(w.tpl, tpl, sizeof(double2) * 64 * osr, cudaMemcpyHostToDevice, st));
+    if (raw_mem == GSMCAL_MEM_HOST) {
+        // copy and reduce in slices of streams so the column sums overlap the PCIe transfer of the next slice
+        const size_t per = (size_t)2 * n_iq;
+        i64 slice = (i64)((256u << 20) / per); if (slice < 1) slice = 1;
+        cudaStream_t cp; CU(cudaStreamCreateWithFlags(&cp, cudaStreamNonBlocking));
+        cudaEvent_t ev0; CU(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
+        CU(cudaEventRecord(ev0, st)); CU(cudaStreamWaitEvent(cp, ev0, 0));
+        for (i64 d0 = 0; d0 < D; d0 += slice) {
+            const i64 nd = (D - d0 < slice) ? D - d0 : slice;
+            CU(cudaMemcpyAsync((void *)(draw + d0 * per), raw + d0 * per, per * nd, cudaMemcpyHostToDevice, cp));
+            cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            CU(cudaEventRecord(ev, cp)); CU(cudaStreamWaitEvent(st, ev, 0)); CU(cudaEventDestroy(ev));
+            TRY(run_colsum_u8(draw + d0 * per, n_iq, nd, w.ctl + d0, st));
+        }
+        CU(cudaEventDestroy(ev0)); CU(cudaStreamDestroy(cp));
+    } else {
+        TRY(run_colsum_u8(draw, n_iq, D, w.ctl, st));
+    }
+    TRY(run_coarse(lazy_src(draw, n_iq, n_taps, 0, dec), len_dec, p, D, cap, w, st));
+    TRY(run_fine(*c, lazy_src(draw, n_iq, n_taps, 0, 1), lazy_src(draw, n_iq, n_taps, 1, 1), n_iq, osr, carrier_freq, D, cap, w, st));
+    TRY(run_sch(lazy_src(draw, n_iq, n_taps, 2, 1), osr, D, cap, w, st));
+    TRY(run_post(*c, lazy_src(draw, n_iq, n_taps, 3, 1), osr, carrier_freq, D, cap, w, true, st));
+    CU(cudaMemcpyAsync(results, w.res, sizeof(StreamResultDev) * D, cudaMemcpyDeviceToHost, st));
+    if (coarse_pos) CU(cudaMemcpyAsync(coarse_pos, w.coarse_pos, sizeof(double) * D * cap, cudaMemcpyDeviceToHost, st));
+    if (coarse_snr) CU(cudaMemcpyAsync(coarse_snr, w.coarse_snr, sizeof(double) * D * cap, cudaMemcpyDeviceToHost, st));
+    if (fcch_pos) CU(cudaMemcpyAsync(fcch_pos, w.fcch_pos, sizeof(double) * D * cap, cudaMemcpyDeviceToHost, st));
+    if (pos_info) CU(cudaMemcpyAsync(pos_info, w.pos_info, sizeof(double) * D * cap * 12, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return GSMCAL_OK;
+}
+
+int gsmcal_fcch_scan(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t n_chan, const double *coef, int n_taps, int osr, int coarse_dr,
+                     double *snr, double *num_hit, double *position, int32_t *n_position, void *cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!raw || !coef || !snr || !num_hit || n_iq < 1 || n_chan < 1 || osr < 1) return fail(GSMCAL_ERR_ARG, "fcch_scan: bad arguments");
+    CoarseParams p; TRY(coarse_params(coarse_dr, &p));
+    const int dec = osr * coarse_dr;
+    const i64 len_dec = (n_iq + dec - 1) / dec;
+    if (p.n_first > len_dec) return fail(GSMCAL_ERR_RANGE, "fcch_scan: capture shorter than 23 frames");
+    const int cap = (int)gsmcal_max_bursts(len_dec, coarse_dr);
+    Ctx *c; TRY(get_ctx(&c));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    Work w;
+    TRY(make_work(*c, n_chan, cap, p.n_first, 0, &w));
+    TRY(set_taps(coef, n_taps, st));
+    const uint8_t *draw = raw;
+    if (raw_mem == GSMCAL_MEM_HOST) {
+        void *din; TRY(c->in.get((size_t)2 * n_iq * n_chan, &din));
+        CU(cudaMemcpyAsync(din, raw, (size_t)2 * n_iq * n_chan, cudaMemcpyHostToDevice, st));
+        draw = (const uint8_t *)din;
+    }
+    CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * n_chan, st));
+    TRY(run_colsum_u8(draw, n_iq, n_chan, w.ctl, st));
+    TRY(run_coarse(lazy_src(draw, n_iq, n_taps, 0, dec), len_dec, p, n_chan, cap, w, st));
+    LAUNCH(scan_accept_kernel, (unsigned)((n_chan + 63) / 64), 64, 0, st, w.ctl, (int)n_chan, cap, w.coarse_pos, w.coarse_snr, w.fo, w.gate);
+    CU(cudaMemcpyAsync(snr, w.fo, sizeof(double) * n_chan, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(num_hit, w.gate, sizeof(double) * n_chan, cudaMemcpyDeviceToHost, st));
+    if (position) CU(cudaMemcpyAsync(position, w.coarse_pos, sizeof(double) * n_chan * cap, cudaMemcpyDeviceToHost, st));
+    std::vector<StreamCtl> h;
+    if (n_position) { h.resize(n_chan); CU(cudaMemcpyAsync(h.data(), w.ctl, sizeof(StreamCtl) * n_chan, cudaMemcpyDeviceToHost, st)); }
+    CU(cudaStreamSynchronize(st));
+    if (n_position) for (int64_t i = 0; i < n_chan; ++i) n_position[i] = h[i].n_coarse;
+    return GSMCAL_OK;
+}
+
+int gsmcal_stage_launch(int stage, const void *in, void *out, int64_t n_iq, int64_t n_col, const double *coef, int n_taps, void *cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    Ctx *c; TRY(get_ctx(&c));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    static Work w; static i64 w_cols = 0;
+    if (stage == 0 || w_cols != n_col) { TRY(make_work(*c, n_col, 1, 1, 0, &w)); w_cols = n_col; }
+    if (coef) TRY(set_taps(coef, n_taps, st));
+    switch (stage) {
+    case 0:
+        CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * n_col, st));
+        return run_colsum_u8((const uint8_t *)in, n_iq, n_col, w.ctl, st);
+    case 1: {
+        i64 gx = (n_iq + 256 * 8 - 1) / (256 * 8); if (gx > 148 * 16) gx = 148 * 16;
+        LAUNCH(raw2iq_store_kernel, dim3((unsigned)gx, (unsigned)n_col), 256, 0, st, (const uint8_t *)in, n_iq, w.ctl, (double2 *)out);
+        return GSMCAL_OK; }
+    case 2: return run_fir<false>(in, n_iq, n_iq, nullptr, n_taps, 1, n_col, (double2 *)out, n_iq, nullptr, st);
+    case 3: return run_fir<true>(in, n_iq, 2 * n_iq, w.ctl, n_taps, 1, n_col, (double2 *)out, n_iq, nullptr, st);
+    case 4: for (i64 d = 0; d < n_col; ++d) TRY(run_resample_derotate((const double2 *)in + d * n_iq, n_iq, -35e-6, 1, 0.0, 0, (double2 *)out + d * n_iq, n_iq, st)); return GSMCAL_OK;
+    case 5: for (i64 d = 0; d < n_col; ++d) TRY(run_resample_derotate((const double2 *)in + d * n_iq, n_iq, 0.0, 0, 0.0123, 1, (double2 *)out + d * n_iq, n_iq, st)); return GSMCAL_OK;
+    case 6: return run_fir<true>(in, n_iq, 2 * n_iq, w.ctl, n_taps, 64, n_col, (double2 *)out, (n_iq + 63) / 64, nullptr, st);
+    default: return fail(GSMCAL_ERR_ARG, "stage_launch: unknown stage %d", stage);
+    }
+}
+
+}  // extern "C"
+
+// ====================================================================================================
+// T1  gsm_SCH_training_sequence_gen.m:17-19,32,39 - GMSK per GSM 05.04 (host code: 512 samples, once per session)
+// ====================================================================================================
+namespace {
+double gq_big_f(double u) { return u * 0.5 * erfc(-u / sqrt(2.0)) + exp(-0.5 * u * u) / sqrt(2.0 * M_PI); }
+double gq_big_g(double t) {
+    const double sigma = sqrt(log(2.0)) / (2.0 * M_PI * 0.3);
+    return (sigma / 2.0) * (gq_big_f((t + 0.5) / sigma) - gq_big_f((t - 0.5) / sigma));
+}
+double gmsk_q(double tau) {
+    if (tau < 0.0) tau = 0.0;
+    if (tau > 4.0) tau = 4.0;
+    const double g0 = gq_big_g(-2.0), g1 = gq_big_g(2.0);
+    return (gq_big_g(tau - 2.0) - g0) / (g1 - g0);
+}
+void gmsk_template(int osr, double *out) {
+    static const int bits[64] = {1, 0, 1, 1, 1, 0, 0, 1, 0, 1, 1, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0,
+                                 0, 0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 1, 0, 1, 1, 0, 1, 0, 1, 0, 0, 0,
+                                 1, 0, 1, 0, 1, 1, 1, 0, 1, 1, 0, 0, 0, 0, 1, 1, 0, 1, 1};
+    double a[64];
+    int prev = 0;
+    for (int k = 0; k < 64; ++k) { a[k] = (bits[k] == prev) ? 1.0 : -1.0; prev = bits[k]; }   // ~abs(diff([0;data])), bit 1 -> +1
+    for (int n = 0; n < 64 * osr; ++n) {
+        double phase = 0.0;
+        for (int k = 0; k < 64; ++k) phase += a[k] * gmsk_q(((double)n - (double)k * osr) / osr);
+        out[2 * n] = cos((M_PI / 2.0) * phase);
+        out[2 * n + 1] = sin((M_PI / 2.0) * phase);
+    }
+}
+}  // namespace

@@ -1,0 +1,1152 @@
+// gsmcal_kernels.cuh - hand-written sm_100a kernels of the GSM sync/calibration hot path.
+//
+// Every kernel is new (the reference is MATLAB); comments cite the reference
+// arithmetic each one reproduces as file:line into JiaoXianjun/multi-rtl-sdr-calibration.
+// All decision paths are IEEE fp64.  No cuFFT, no tensor cores (nothing here is a dense contraction).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+typedef long long i64;
+typedef unsigned long long u64;
+
+#define GSMCAL_MAX_TAPS 128
+#define GSMCAL_PI 3.14159265358979323846
+
+__constant__ double c_taps[GSMCAL_MAX_TAPS];      // FIR numerator of the current call (the analogue of `persistent coef`)
+
+// ---------------------------------------------------------------------------------------------------
+// per-stream control block: everything the tiny sequential stages decide, kept on the device so the
+// batched pipeline never synchronises with the host between stages.
+// ---------------------------------------------------------------------------------------------------
+struct StreamCtl {
+    u64    sum_i, sum_q;          // exact integer column sums of raw2iq.m:8
+    // coarse
+    int    n_coarse;              // -1: no FCCH found (FCCH_coarse_position.m:27-30)
+    int    first_hit;             // 1-based window index of the first hit, -1 none
+    double hit_avg_snr, hit_snr;
+    // FCCH fine
+    int    n_fine;                // first-round positions kept (last_idx, FCCH_fine_correction.m:65)
+    int    n_fcch;                // returned FCCH_pos count, -1 = scalar -1
+    int    interp1_on;            // r was resampled by (1+e1)
+    int    tone1_enable;          // carrier estimate runs (num_fcch >= 5)
+    int    derot1_on;
+    double e1, dphi1, sppm1, cppm1;
+    i64    len1;                  // length of r after FCCH_fine_correction, -1 = scalar -1
+    // SCH
+    int    sch_enable, n_sch, n_pos_info, interp2_on;
+    double e2, sppm2;
+    i64    len2;
+    // post-SCH
+    int    post_enable, n_post_fcch;
+    double cppm2, dphi2;
+    i64    len3;
+    int    flags;
+    int    pad_;
+};
+
+struct WinSrc {
+    int            lazy;        // 0: read a materialised complex128 stream, 1: evaluate from the uint8 capture
+    int            level;       // lazy: 0 filtered, 1 resampled(e1), 2 resampled+derotated, 3 resampled again (e2)
+    const double2 *base;        // materialised stream(s)
+    i64            base_len;    // samples per stream
+    i64            base_stride; // distance between streams
+    int            mat_interp;  // materialised: evaluate interp1(base, j*(1+e1)) on the fly
+    const uint8_t *raw;         // lazy: [n_streams][2*n_iq]
+    i64            n_iq;
+    int            n_taps;
+    int            dec;         // decimation applied on top (coarse stage: osr*dr), else 1
+};
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) {   // a * conj(b)
+    return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__device__ __forceinline__ double abs2_ref(double2 a) {            // abs(z).^2: sqrt first, then square
+    double h = hypot(a.x, a.y);
+    return h * h;
+}
+__device__ __forceinline__ double2 lerp_ref(double2 v0, double2 v1, double frac) {
+    // interp1 'linear': v0 + frac*(v1-v0), product and sum rounded separately (matches the oracle bit for bit)
+    return make_double2(__dadd_rn(v0.x, __dmul_rn(frac, __dsub_rn(v1.x, v0.x))),
+                        __dadd_rn(v0.y, __dmul_rn(frac, __dsub_rn(v1.y, v0.y))));
+}
+__device__ __forceinline__ double stream_mean(u64 sum, i64 n) { return (double)sum / (double)n; }
+
+// filtered sample L0[i] of one stream straight from the uint8 capture (zero initial state, DC removed):
+//   filter(coef,1,raw2iq(a))(i)  - gsm_sync_demod.m:107,110; oldest tap first as direct-form-II-transposed nests them
+__device__ __forceinline__ double2 fir_from_raw(const uint8_t *__restrict__ raw, i64 i, int n_taps, double mur, double mui) {
+    double ar = 0.0, ai = 0.0;
+    int kmax = (i < (i64)(n_taps - 1)) ? (int)i : n_taps - 1;
+    const uint8_t *p = raw + 2 * (i - kmax);
+    for (int k = kmax; k >= 0; --k, p += 2) {
+        double h = c_taps[k];
+        ar = fma(h, (double)p[0] - mur, ar);
+        ai = fma(h, (double)p[1] - mui, ai);
+    }
+    return make_double2(ar, ai);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// block-cooperative window loader: dst[0..count) = samples [start, start+count) (0-based) of the stream
+// the stage works on.  X, Y: scratch of (count + GSMCAL_MAX_TAPS + 8) and (count + 8) double2.
+// Lazy levels restate, per sample, FCCH_fine_correction.m:123-125 (interp1), :165 (derotation) and
+// SCH_corr_rate_correction.m:126-127 (second interp1) on top of raw2iq + filter.
+// ---------------------------------------------------------------------------------------------------
+__device__ void load_window(const WinSrc &src, const StreamCtl &c, int stream, i64 start, int count,
+                            double2 *dst, double2 *X, double2 *Y) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (!src.lazy) {
+        const double2 *b = src.base + (i64)stream * src.base_stride;
+        if (src.mat_interp && c.interp1_on) {
+            const double scale = 1.0 + c.e1;
+            for (int i = tid; i < count; i += nt) {
+                double xq = (double)(start + i) * scale;
+                i64 i0 = (i64)floor(xq);
+                if (i0 > src.base_len - 1) i0 = src.base_len - 1;
+                if (i0 < 0) i0 = 0;
+                i64 i1 = (i0 + 1 > src.base_len - 1) ? src.base_len - 1 : i0 + 1;
+                dst[i] = lerp_ref(b[i0], b[i1], xq - (double)i0);
+            }
+        } else {
+            for (int i = tid; i < count; i += nt) {
+                i64 j = start + i;
+                dst[i] = (j >= 0 && j < src.base_len) ? b[j] : make_double2(0.0, 0.0);
+            }
+        }
+        __syncthreads();
+        return;
+    }
+    const uint8_t *raw = src.raw + (i64)stream * 2 * src.n_iq;
+    const i64 n0 = src.n_iq;
+    const double mur = stream_mean(c.sum_i, n0), mui = stream_mean(c.sum_q, n0);
+    const bool use2 = (src.level == 3) && c.interp2_on;
+    const bool use1 = (src.level >= 1) && c.interp1_on;
+    const bool derot = (src.level >= 2) && c.derot1_on;
+    const double s1 = 1.0 + c.e1, s2 = 1.0 + c.e2;
+    const i64 len1 = use1 ? c.len1 : n0;
+    i64 a2 = start, b2 = start + count - 1, a1 = a2, b1 = b2, a0, b0;
+    if (use2) {
+        a1 = (i64)floor((double)a2 * s2);
+        b1 = (i64)floor((double)b2 * s2) + 1;
+        if (b1 > len1 - 1) b1 = len1 - 1;
+        if (a1 > b1) a1 = b1;
+    }
+    a0 = a1; b0 = b1;
+    if (use1) {
+        a0 = (i64)floor((double)a1 * s1);
+        b0 = (i64)floor((double)b1 * s1) + 1;
+        if (b0 > n0 - 1) b0 = n0 - 1;
+        if (a0 > b0) a0 = b0;
+    }
+    if (a0 < 0) a0 = 0;
+    if (b0 > n0 - 1) b0 = n0 - 1;
+    const int nt1 = src.n_taps - 1;
+    const int n_l0 = (int)(b0 - a0 + 1);
+    const int n_raw = n_l0 + nt1;
+    // stage the DC-removed capture once (zero before the first sample: zero initial filter state)
+    for (int i = tid; i < n_raw; i += nt) {
+        i64 j = a0 - nt1 + i;
+        double2 v = make_double2(0.0, 0.0);
+        if (j >= 0) {
+            uchar2 u = *reinterpret_cast<const uchar2 *>(raw + 2 * j);
+            v = make_double2((double)u.x - mur, (double)u.y - mui);
+        }
+        X[i] = v;
+    }
+    __syncthreads();
+    double2 *l0 = (use1 || use2) ? Y : dst;
+    for (int i = tid; i < n_l0; i += nt) {
+        double ar = 0.0, ai = 0.0;
+        for (int k = nt1; k >= 0; --k) {
+            double h = c_taps[k];
+            double2 x = X[i + nt1 - k];
+            ar = fma(h, x.x, ar);
+            ai = fma(h, x.y, ai);
+        }
+        l0[i] = make_double2(ar, ai);
+    }
+    __syncthreads();
+    if (!use1 && !use2) {
+        if (derot) {   // not reachable in the reference flow (derotation implies resampling) but keep it total
+            for (int i = tid; i < count; i += nt) {
+                double sn, cs; sincos((double)(start + i) * c.dphi1, &sn, &cs);
+                dst[i] = cmul(dst[i], make_double2(cs, sn));
+            }
+            __syncthreads();
+        }
+        return;
+    }
+    if (use1) {
+        double2 *l1 = use2 ? X : dst;
+        const int n_l1 = (int)(b1 - a1 + 1);
+        for (int i = tid; i < n_l1; i += nt) {
+            i64 j = a1 + i;
+            double xq = (double)j * s1;
+            i64 i0 = (i64)floor(xq);
+            if (i0 > n0 - 1) i0 = n0 - 1;
+            i64 i1 = (i0 + 1 > n0 - 1) ? n0 - 1 : i0 + 1;
+            double2 v = lerp_ref(Y[i0 - a0], Y[i1 - a0], xq - (double)i0);
+            if (derot) {
+                double sn, cs; sincos((double)j * c.dphi1, &sn, &cs);
+                v = cmul(v, make_double2(cs, sn));
+            }
+            l1[i] = v;
+        }
+        __syncthreads();
+    } else {   // level 3 with interp2 only (e1 path off): L1 == L0 (+derot)
+        for (int i = tid; i < n_l0; i += nt) {
+            double2 v = Y[i];
+            if (derot) {
+                double sn, cs; sincos((double)(a0 + i) * c.dphi1, &sn, &cs);
+                v = cmul(v, make_double2(cs, sn));
+            }
+            X[i] = v;
+        }
+        __syncthreads();
+    }
+    if (use2) {
+        for (int i = tid; i < count; i += nt) {
+            double xq = (double)(a2 + i) * s2;
+            i64 i0 = (i64)floor(xq);
+            if (i0 > len1 - 1) i0 = len1 - 1;
+            i64 i1 = (i0 + 1 > len1 - 1) ? len1 - 1 : i0 + 1;
+            dst[i] = lerp_ref(X[i0 - a1], X[i1 - a1], xq - (double)i0);
+        }
+        __syncthreads();
+    }
+}
+
+// one decimated sample of the stream the coarse stage sees: s(1:dec:end) - gsm_sync_demod.m:117
+__device__ __forceinline__ double2 coarse_sample(const WinSrc &src, const StreamCtl &c, int stream, i64 idx0) {
+    if (!src.lazy) return src.base[(i64)stream * src.base_stride + idx0];
+    const uint8_t *raw = src.raw + (i64)stream * 2 * src.n_iq;
+    return fir_from_raw(raw, idx0 * src.dec, src.n_taps, stream_mean(c.sum_i, src.n_iq), stream_mean(c.sum_q, src.n_iq));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// block reductions
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+// first-maximum argmax: larger value wins, equal values -> smaller index (MATLAB max returns the first)
+__device__ __forceinline__ void argmax_combine(double &v, int &i, double v2, int i2) {
+    if (v2 > v || (v2 == v && i2 < i)) { v = v2; i = i2; }
+}
+__device__ void block_argmax(double &v, int &i, double *sv, int *si) {
+    for (int o = 16; o > 0; o >>= 1) {
+        double v2 = __shfl_down_sync(0xffffffffu, v, o);
+        int i2 = __shfl_down_sync(0xffffffffu, i, o);
+        argmax_combine(v, i, v2, i2);
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) { sv[w] = v; si[w] = i; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double bv = sv[0]; int bi = si[0];
+        for (int k = 1; k < nw; ++k) argmax_combine(bv, bi, sv[k], si[k]);
+        sv[0] = bv; si[0] = bi;
+    }
+    __syncthreads();
+    v = sv[0]; i = si[0];
+    __syncthreads();
+}
+__device__ double block_sum(double v, double *sv) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) sv[w] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < nw; ++k) t += sv[k];
+        sv[0] = t;
+    }
+    __syncthreads();
+    double r = sv[0];
+    __syncthreads();
+    return r;
+}
+
+// ===================================================================================================
+// K1  raw2iq.m:5-8
+// ===================================================================================================
+// exact integer column sums: 16-byte loads, dp4a byte sums, one 64-bit atomic per warp.
+// grid (chunks, streams); each block owns `chunk_bytes` (multiple of 16) of one stream.
+__global__ void __launch_bounds__(256) colsum_u8_kernel(const uint8_t *__restrict__ raw, i64 n_iq, i64 chunk_bytes, StreamCtl *ctl) {
+    const int stream = blockIdx.y;
+    const uint8_t *p = raw + (i64)stream * 2 * n_iq;
+    const i64 total = 2 * n_iq;
+    const i64 head = (16 - ((uintptr_t)p & 15)) & 15;            // even, since every stream starts on an even byte
+    const i64 body = ((total - (head < total ? head : total)) / 16) * 16;
+    unsigned si = 0, sq = 0;
+    u64 li = 0, lq = 0;
+    {
+        const i64 c0 = (i64)blockIdx.x * chunk_bytes;
+        i64 c1 = c0 + chunk_bytes; if (c1 > body) c1 = body;
+        const uint4 *v = reinterpret_cast<const uint4 *>(p + head);
+        const i64 i0 = c0 / 16, i1 = c1 / 16;
+        i64 i = i0 + threadIdx.x;
+        for (; i + 3 * 256 < i1; i += 4 * 256) {
+            uint4 a = __ldg(v + i), b = __ldg(v + i + 256), c = __ldg(v + i + 512), d = __ldg(v + i + 768);
+#define GSMCAL_ACC(w) si = __dp4a((w), 0x00010001u, si); sq = __dp4a((w), 0x01000100u, sq);
+            GSMCAL_ACC(a.x) GSMCAL_ACC(a.y) GSMCAL_ACC(a.z) GSMCAL_ACC(a.w)
+            GSMCAL_ACC(b.x) GSMCAL_ACC(b.y) GSMCAL_ACC(b.z) GSMCAL_ACC(b.w)
+            GSMCAL_ACC(c.x) GSMCAL_ACC(c.y) GSMCAL_ACC(c.z) GSMCAL_ACC(c.w)
+            GSMCAL_ACC(d.x) GSMCAL_ACC(d.y) GSMCAL_ACC(d.z) GSMCAL_ACC(d.w)
+        }
+        for (; i < i1; i += 256) {
+            uint4 a = __ldg(v + i);
+            GSMCAL_ACC(a.x) GSMCAL_ACC(a.y) GSMCAL_ACC(a.z) GSMCAL_ACC(a.w)
+        }
+#undef GSMCAL_ACC
+    }
+    li = si; lq = sq;
+    if (blockIdx.x == 0) {                                        // ragged head / tail bytes, scalar
+        const i64 hb = (head < total) ? head : total;
+        for (i64 j = threadIdx.x; j < hb; j += 256) { if (j & 1) lq += p[j]; else li += p[j]; }
+        for (i64 j = hb + body + threadIdx.x; j < total; j += 256) { if (j & 1) lq += p[j]; else li += p[j]; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        li += __shfl_down_sync(0xffffffffu, li, o);
+        lq += __shfl_down_sync(0xffffffffu, lq, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (li) atomicAdd(&ctl[stream].sum_i, li);
+        if (lq) atomicAdd(&ctl[stream].sum_q, lq);
+    }
+}
+
+// b = c - mean: one thread per IQ pair, 2-byte load, 16-byte store (warp stores 512 contiguous bytes)
+__global__ void __launch_bounds__(256) raw2iq_store_kernel(const uint8_t *__restrict__ raw, i64 n_iq, const StreamCtl *__restrict__ ctl, double2 *__restrict__ out) {
+    const int stream = blockIdx.y;
+    const uchar2 *p = reinterpret_cast<const uchar2 *>(raw + (i64)stream * 2 * n_iq);
+    double2 *o = out + (i64)stream * n_iq;
+    const double mur = stream_mean(ctl[stream].sum_i, n_iq), mui = stream_mean(ctl[stream].sum_q, n_iq);
+    const i64 stride = (i64)gridDim.x * 256;
+    for (i64 i = (i64)blockIdx.x * 256 + threadIdx.x; i < n_iq; i += stride) {
+        uchar2 u = p[i];
+        __stcs(o + i, make_double2((double)u.x - mur, (double)u.y - mui));
+    }
+}
+
+// double-typed input (fread returns double, gsm_sync_demod.m:96): exact sums as long as values are 0..255 integers;
+// done in fp64 with a fixed tree so the result is order-independent only for integer data (documented).
+__global__ void __launch_bounds__(256) colsum_f64_kernel(const double *__restrict__ a, i64 n_iq, StreamCtl *ctl) {
+    const int stream = blockIdx.y;
+    const double2 *p = reinterpret_cast<const double2 *>(a + (i64)stream * 2 * n_iq);
+    u64 li = 0, lq = 0;
+    const i64 stride = (i64)gridDim.x * 256;
+    for (i64 i = (i64)blockIdx.x * 256 + threadIdx.x; i < n_iq; i += stride) {
+        double2 v = p[i];
+        li += (u64)(i64)v.x; lq += (u64)(i64)v.y;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        li += __shfl_down_sync(0xffffffffu, li, o);
+        lq += __shfl_down_sync(0xffffffffu, lq, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&ctl[stream].sum_i, li); atomicAdd(&ctl[stream].sum_q, lq); }
+}
+__global__ void __launch_bounds__(256) raw2iq_store_f64_kernel(const double *__restrict__ a, i64 n_iq, const StreamCtl *__restrict__ ctl, double2 *__restrict__ out) {
+    const int stream = blockIdx.y;
+    const double2 *p = reinterpret_cast<const double2 *>(a + (i64)stream * 2 * n_iq);
+    double2 *o = out + (i64)stream * n_iq;
+    const double mur = stream_mean(ctl[stream].sum_i, n_iq), mui = stream_mean(ctl[stream].sum_q, n_iq);
+    const i64 stride = (i64)gridDim.x * 256;
+    for (i64 i = (i64)blockIdx.x * 256 + threadIdx.x; i < n_iq; i += stride) {
+        double2 v = p[i];
+        o[i] = make_double2(v.x - mur, v.y - mui);
+    }
+}
+
+// ===================================================================================================
+// K2  filter(coef,1,s) [+ s(1:decim:end)]   gsm_sync_demod.m:110, chn_filter_8x_4x.m:13-15
+// ===================================================================================================
+// Full-rate FIR, complex128 in/out (or uint8 in with DC removal fused).  Each thread produces R=8
+// consecutive outputs from a register-blocked sliding window, so every staged input is read from shared
+// memory once per 8 outputs.  Shared rows are padded (one slot per 8) to keep the 128-byte-strided
+// per-thread reads bank-conflict free.  NT = taps rounded up (zero-padded on the old side: adds exact 0).
+#define FIR_R 8
+#define FIR_THREADS 128
+#define FIR_TILE (FIR_R * FIR_THREADS)
+__device__ __forceinline__ int fir_pad(int i) { return i + (i >> 3); }
+
+template <int NT, bool FROM_U8>
+__global__ void __launch_bounds__(FIR_THREADS) fir_full_kernel(const void *__restrict__ in_, i64 n, i64 in_stride, const StreamCtl *__restrict__ ctl,
+                                                              double2 *__restrict__ out, i64 out_stride) {
+    extern __shared__ double2 sm[];
+    const int stream = blockIdx.y;
+    const i64 t0 = (i64)blockIdx.x * FIR_TILE;                    // first output of the tile
+    const int n_in = FIR_TILE + NT - 1;
+    double mur = 0.0, mui = 0.0;
+    if (FROM_U8) { mur = stream_mean(ctl[stream].sum_i, n); mui = stream_mean(ctl[stream].sum_q, n); }
+    for (int i = threadIdx.x; i < n_in; i += FIR_THREADS) {
+        i64 j = t0 - (NT - 1) + i;
+        double2 v = make_double2(0.0, 0.0);
+        if (j >= 0 && j < n) {
+            if (FROM_U8) {
+                uchar2 u = reinterpret_cast<const uchar2 *>(static_cast<const uint8_t *>(in_) + (i64)stream * in_stride)[j];
+                v = make_double2((double)u.x - mur, (double)u.y - mui);
+            } else {
+                v = __ldcs(static_cast<const double2 *>(in_) + (i64)stream * in_stride + j);
+            }
+        }
+        sm[fir_pad(i)] = v;
+    }
+    __syncthreads();
+    double ar[FIR_R], ai[FIR_R];
+#pragma unroll
+    for (int r = 0; r < FIR_R; ++r) { ar[r] = 0.0; ai[r] = 0.0; }
+    const int base = threadIdx.x * FIR_R;                         // staged index of the oldest input of output 0
+#pragma unroll
+    for (int k = 0; k < NT - 1 + FIR_R; ++k) {
+        double2 x = sm[fir_pad(base + k)];
+#pragma unroll
+        for (int r = 0; r < FIR_R; ++r) {
+            const int tap = (NT - 1) + r - k;                     // oldest input first: h[NT-1] ... h[0]
+            if (tap >= 0 && tap < NT) {
+                ar[r] = fma(c_taps[tap], x.x, ar[r]);
+                ai[r] = fma(c_taps[tap], x.y, ai[r]);
+            }
+        }
+    }
+    double2 *o = out + (i64)stream * out_stride;
+#pragma unroll
+    for (int r = 0; r < FIR_R; ++r) {
+        i64 j = t0 + base + r;
+        if (j < n) __stcs(o + j, make_double2(ar[r], ai[r]));
+    }
+}
+
+// Decimating FIR: one thread per kept output r(1+m*decim); input tile staged contiguously (coalesced) in
+// shared memory.  Used for decim > 1 (2: chn_filter_8x_4x, 20: split scanner, 64: coarse stream).
+#define FIRD_THREADS 128
+template <bool FROM_U8>
+__global__ void __launch_bounds__(FIRD_THREADS) fir_decim_kernel(const void *__restrict__ in_, i64 n, i64 in_stride, const StreamCtl *__restrict__ ctl, int n_taps,
+                                                                int decim, int outs_per_block, double2 *__restrict__ out, i64 n_out, i64 out_stride,
+                                                                double *__restrict__ power_acc) {
+    extern __shared__ double2 sm[];
+    const int stream = blockIdx.y;
+    const i64 m0 = (i64)blockIdx.x * outs_per_block;
+    i64 m1 = m0 + outs_per_block; if (m1 > n_out) m1 = n_out;
+    const int n_o = (int)(m1 - m0);
+    const i64 j0 = m0 * decim - (n_taps - 1);
+    const int n_in = (n_o - 1) * decim + n_taps;
+    double mur = 0.0, mui = 0.0;
+    if (FROM_U8) { mur = stream_mean(ctl[stream].sum_i, n); mui = stream_mean(ctl[stream].sum_q, n); }
+    const bool sparse = decim >= n_taps;          // windows do not overlap: skip the unused inputs between them
+    for (int i = threadIdx.x; i < n_in; i += FIRD_THREADS) {
+        if (sparse && ((i % decim) >= n_taps)) continue;
+        i64 j = j0 + i;
+        double2 v = make_double2(0.0, 0.0);
+        if (j >= 0 && j < n) {
+            if (FROM_U8) {
+                uchar2 u = reinterpret_cast<const uchar2 *>(static_cast<const uint8_t *>(in_) + (i64)stream * in_stride)[j];
+                v = make_double2((double)u.x - mur, (double)u.y - mui);
+            } else {
+                v = static_cast<const double2 *>(in_)[(i64)stream * in_stride + j];
+            }
+        }
+        sm[i + i / 8] = v;
+    }
+    __syncthreads();
+    double pw = 0.0;
+    for (int o = threadIdx.x; o < n_o; o += FIRD_THREADS) {
+        const int b = o * decim;
+        double ar = 0.0, ai = 0.0;
+        for (int k = n_taps - 1; k >= 0; --k) {
+            int idx = b + (n_taps - 1 - k);
+            double2 x = sm[idx + idx / 8];
+            ar = fma(c_taps[k], x.x, ar);
+            ai = fma(c_taps[k], x.y, ai);
+        }
+        if (out) out[(i64)stream * out_stride + m0 + o] = make_double2(ar, ai);
+        if (power_acc) { double h = hypot(ar, ai); pw += h * h; }
+    }
+    if (power_acc) {
+        __shared__ double red[8];
+        double t = block_sum(pw, red);
+        if (threadIdx.x == 0) atomicAdd(&power_acc[stream], t);
+    }
+}
+
+// mean(abs(raw2iq(a)).^2) without a filter: scan_band_power_spectrum.m:80-85
+__global__ void __launch_bounds__(256) power_u8_kernel(const uint8_t *__restrict__ raw, i64 n_iq, const StreamCtl *__restrict__ ctl, int decim, double *__restrict__ power_acc) {
+    __shared__ double red[8];
+    const int stream = blockIdx.y;
+    const uchar2 *p = reinterpret_cast<const uchar2 *>(raw + (i64)stream * 2 * n_iq);
+    const double mur = stream_mean(ctl[stream].sum_i, n_iq), mui = stream_mean(ctl[stream].sum_q, n_iq);
+    const i64 n_out = (n_iq + decim - 1) / decim;
+    double pw = 0.0;
+    for (i64 m = (i64)blockIdx.x * 256 + threadIdx.x; m < n_out; m += (i64)gridDim.x * 256) {
+        uchar2 u = p[m * decim];
+        double h = hypot((double)u.x - mur, (double)u.y - mui);
+        pw += h * h;
+    }
+    double t = block_sum(pw, red);
+    if (threadIdx.x == 0) atomicAdd(&power_acc[stream], t);
+}
+
+// ===================================================================================================
+// K6 / K7  whole-stream resample (interp1 'linear') and derotation
+//          FCCH_fine_correction.m:118-125,163-165; SCH_corr_rate_correction.m:120-128; carrier_correct_post_SCH.m:81-83
+// ===================================================================================================
+// out[j] = lerp(in, j*(1+e)) * exp(1i*j*dphi).  The phasor is evaluated exactly (fp64 sincos of the rounded
+// product, as the reference does) for the first of each thread's DEROT_K samples and advanced by a fixed
+// complex step for the others; the error is < 1e-15 per step and the samples stay coalesced.
+#define DEROT_K 8
+__global__ void __launch_bounds__(256) resample_derotate_kernel(const double2 *__restrict__ in, i64 len_in, double e, int do_interp,
+                                                               double dphi, int do_derot, double2 *__restrict__ out, i64 len_out) {
+    const i64 blk0 = (i64)blockIdx.x * (256 * DEROT_K);
+    const double scale = 1.0 + e;
+    double2 ph = make_double2(1.0, 0.0), step = make_double2(1.0, 0.0);
+    if (do_derot) {
+        double sn, cs;
+        sincos((double)(blk0 + threadIdx.x) * dphi, &sn, &cs); ph = make_double2(cs, sn);
+        sincos(256.0 * dphi, &sn, &cs); step = make_double2(cs, sn);
+    }
+#pragma unroll
+    for (int k = 0; k < DEROT_K; ++k) {
+        i64 j = blk0 + (i64)k * 256 + threadIdx.x;
+        if (j < len_out) {
+            double2 v;
+            if (do_interp) {
+                double xq = (double)j * scale;
+                i64 i0 = (i64)floor(xq);
+                if (i0 > len_in - 1) i0 = len_in - 1;
+                i64 i1 = (i0 + 1 > len_in - 1) ? len_in - 1 : i0 + 1;
+                v = lerp_ref(in[i0], in[i1], xq - (double)i0);
+            } else {
+                v = in[j];
+            }
+            if (do_derot) v = cmul(v, ph);
+            __stcs(out + j, v);
+        }
+        if (do_derot) ph = cmul(ph, step);
+    }
+}
+
+// ===================================================================================================
+// K3  moving-FFT SNR statistic   move_fft_snr_runtime_avg.m:17-28, specific_fft_snr_fix_avg.m:10-20
+// ===================================================================================================
+// SNR of one fft_len-point window held in w[] (fft_len <= 128): direct DFT with an exact twiddle table.
+__device__ double window_snr(const double2 *w, int fft_len, const double2 *tw /* exp(-2*pi*i*j/fft_len) */) {
+    double p[128];
+    double tot = 0.0, best = -1.0;
+    int kbest = 0;
+    for (int k = 0; k < fft_len; ++k) {
+        double xr = 0.0, xi = 0.0;
+        int idx = 0;
+        for (int n = 0; n < fft_len; ++n) {
+            double2 t = tw[idx];
+            xr += w[n].x * t.x - w[n].y * t.y;
+            xi += w[n].x * t.y + w[n].y * t.x;
+            idx += k; if (idx >= fft_len) idx -= fft_len;
+        }
+        double h = hypot(xr, xi);
+        p[k] = h * h;
+        tot += p[k];
+        if (p[k] > best) { best = p[k]; kbest = k; }             // first maximum
+    }
+    double sig = p[(kbest + fft_len - 1) % fft_len] + p[kbest] + p[(kbest + 1) % fft_len];
+    double noise = tot - sig;
+    return 10.0 * log10(sig / noise);
+}
+
+// SNR of windows [w0, w0+n_win) (0-based window starts) of each stream -> snr[stream][0..n_win)
+#define SNR_THREADS 128
+__global__ void __launch_bounds__(SNR_THREADS) snr_map_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, i64 w0, i64 n_win, int fft_len,
+                                                             double *__restrict__ snr, i64 snr_stride) {
+    extern __shared__ double2 sm[];
+    double2 *tw = sm;                       // fft_len
+    double2 *buf = sm + fft_len;            // SNR_THREADS + fft_len - 1 samples
+    const int stream = blockIdx.y;
+    const i64 b0 = (i64)blockIdx.x * SNR_THREADS;
+    if (b0 >= n_win) return;
+    for (int j = threadIdx.x; j < fft_len; j += SNR_THREADS) {
+        double sn, cs; sincospi(-2.0 * (double)j / (double)fft_len, &sn, &cs);
+        tw[j] = make_double2(cs, sn);
+    }
+    i64 rem = n_win - b0;
+    const int nw = rem < SNR_THREADS ? (int)rem : SNR_THREADS;
+    const int ns = nw + fft_len - 1;
+    StreamCtl c = ctl[stream];
+    for (int i = threadIdx.x; i < ns; i += SNR_THREADS) buf[i] = coarse_sample(src, c, stream, w0 + b0 + i);
+    __syncthreads();
+    if (threadIdx.x < nw) snr[(i64)stream * snr_stride + b0 + threadIdx.x] = window_snr(buf + threadIdx.x, fft_len, tw);
+}
+
+// sequential first-hit scan, one warp per stream, every lane runs the identical recurrence
+//   move_fft_snr_runtime_avg.m:11-12,30-41 (sum_snr updated as "subtract oldest, add newest", FIFO seeded with 999)
+__global__ void first_hit_scan_kernel(const double *__restrict__ snr, i64 snr_stride, i64 n_win, int mv_len, double th, StreamCtl *ctl, int n_streams) {
+    const int stream = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (stream >= n_streams) return;
+    const double *s = snr + (i64)stream * snr_stride;
+    double sum_snr = 999.0 * (double)mv_len;
+    int hit = -1; double hit_snr = 0.0, hit_avg = 0.0;
+    for (i64 c0 = 0; c0 < n_win && hit < 0; c0 += 32) {
+        i64 i = c0 + lane;
+        double cur = (i < n_win) ? s[i] : 0.0;
+        double old = (i < n_win) ? ((i >= mv_len) ? s[i - mv_len] : 999.0) : 0.0;
+        const int m = (n_win - c0 < 32) ? (int)(n_win - c0) : 32;
+        for (int k = 0; k < m; ++k) {
+            double v = __shfl_sync(0xffffffffu, cur, k);
+            double o = __shfl_sync(0xffffffffu, old, k);
+            double peak_to_avg = v - (sum_snr / (double)mv_len);
+            if (peak_to_avg > th) { hit = (int)(c0 + k) + 1; hit_snr = v; hit_avg = v - peak_to_avg; break; }
+            sum_snr = sum_snr - o;
+            sum_snr = sum_snr + v;
+        }
+    }
+    if (lane == 0) {
+        ctl[stream].first_hit = hit;
+        ctl[stream].hit_snr = hit_snr;
+        ctl[stream].hit_avg_snr = hit_avg;
+    }
+}
+
+// specific_fft_snr_fix_avg.m:10-29 for one stream (drop-in entry point): first window in [t0,t1] over threshold
+__global__ void specific_hit_kernel(const double *__restrict__ snr, i64 n, double th, double avg, int *hit_off, double *hit_snr) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        *hit_off = -1;
+        for (i64 i = 0; i < n; ++i)
+            if (snr[i] - avg > th) { *hit_off = (int)i; *hit_snr = snr[i]; break; }
+    }
+}
+
+// ===================================================================================================
+// K4  burst chain  FCCH_coarse_position.m:32-91 - one warp per stream, 11 candidate windows per step
+// ===================================================================================================
+__global__ void __launch_bounds__(32) coarse_chain_kernel(WinSrc src, StreamCtl *ctl, i64 len, int fft_len, double th, int step10, int step11,
+                                                          int dr, int cap, double *__restrict__ position, double *__restrict__ snr_out) {
+    __shared__ double2 tw[128];
+    __shared__ double2 buf[128 + 16];
+    const int stream = blockIdx.x, lane = threadIdx.x;
+    StreamCtl c = ctl[stream];
+    double *pos_o = position + (i64)stream * cap;
+    double *snr_o = snr_out + (i64)stream * cap;
+    if (c.first_hit < 0) {
+        if (lane == 0) ctl[stream].n_coarse = -1;
+        return;
+    }
+    for (int j = lane; j < fft_len; j += 32) {
+        double sn, cs; sincospi(-2.0 * (double)j / (double)fft_len, &sn, &cs);
+        tw[j] = make_double2(cs, sn);
+    }
+    const int max_offset = 5;
+    const i64 limit = (len - (fft_len - 1)) - max_offset;
+    i64 pos = c.first_hit;
+    int count = 1;
+    if (lane == 0) { pos_o[0] = (double)((pos - 1) * dr + 1); snr_o[0] = c.hit_snr; }
+    while (count < cap) {
+        bool found = false;
+        for (int attempt = 0; attempt < 2 && !found; ++attempt) {
+            i64 next = pos + (attempt == 0 ? step10 : step11);
+            if (next > limit) { attempt = 2; break; }
+            const i64 first = next - max_offset;                 // 1-based window start
+            const int ns = 2 * max_offset + fft_len;
+            __syncwarp();
+            for (int i = lane; i < ns; i += 32) buf[i] = coarse_sample(src, c, stream, first - 1 + i);
+            __syncwarp();
+            double v = 0.0; bool h = false;
+            if (lane <= 2 * max_offset) { v = window_snr(buf + lane, fft_len, tw); h = (v - c.hit_avg_snr) > th; }
+            unsigned mask = __ballot_sync(0xffffffffu, h);
+            if (mask) {
+                int l = __ffs(mask) - 1;
+                double hv = __shfl_sync(0xffffffffu, v, l);
+                pos = first + l;
+                if (lane == 0) { pos_o[count] = (double)((pos - 1) * dr + 1); snr_o[count] = hv; }
+                ++count;
+                found = true;
+            }
+        }
+        if (!found) break;
+    }
+    if (lane == 0) ctl[stream].n_coarse = count;
+}
+
+// ===================================================================================================
+// K5  fine FCCH position  FCCH_fine_correction.m:32-64
+// ===================================================================================================
+// One block per (burst, stream).  All n_win sliding windows' max-bin power by a sliding DFT:
+//   X_{m+1}[k] = (X_m[k] - s[m] + s[m+N]) * exp(+2*pi*i*k/N)
+// each thread owns FP_BPT bins in registers and remembers the first window where its bins peak; the block
+// then takes the first-maximum over bins.  (max_m max_k == max_k max_m, and the first window attaining the
+// global maximum is the same either way, so no per-window reduction is needed.)
+#define FP_BPT 4
+__global__ void __launch_bounds__(320) fine_peak_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ base_pos, int cap,
+                                                        int osr, i64 len_s_ov, const double2 *__restrict__ tw /* exp(-2*pi*i*j/N) */,
+                                                        double *__restrict__ fine_raw) {
+    extern __shared__ double2 sm[];
+    __shared__ double red_v[16];
+    __shared__ int red_i[16];
+    const int burst = blockIdx.x, stream = blockIdx.y;
+    const StreamCtl c = ctl[stream];
+    if (c.n_coarse < 5 || burst >= c.n_coarse) return;
+    const int N = 148 * osr;
+    const int max_offset = 64;
+    const int n_win = 2 * max_offset * osr + 1;
+    const int n_smp = n_win + N - 1;
+    const i64 len_s = len_s_ov / osr;
+    const i64 position = (i64)base_pos[(i64)stream * cap + burst];
+    double *o = fine_raw + (i64)stream * cap + burst;
+    if (position + max_offset > len_s - 148 + 1) {            // run out of sampled signal (:35-38)
+        if (threadIdx.x == 0) *o = INFINITY;
+        return;
+    }
+    const i64 sp = (position - max_offset - 1) * osr + 1;     // 1-based
+    double2 *win = sm;
+    double2 *X = win + n_smp;
+    double2 *Y = X + n_smp + GSMCAL_MAX_TAPS + 8;
+    load_window(src, c, stream, sp - 1, n_smp, win, X, Y);
+
+    double xr[FP_BPT], xi[FP_BPT], wr[FP_BPT], wi[FP_BPT], best[FP_BPT];
+    int bestm[FP_BPT];
+    const int T = blockDim.x;
+#pragma unroll
+    for (int b = 0; b < FP_BPT; ++b) {
+        const int k = threadIdx.x + b * T;
+        xr[b] = 0.0; xi[b] = 0.0; best[b] = -1.0; bestm[b] = 0;
+        double2 w = (k < N) ? tw[k] : make_double2(1.0, 0.0);
+        wr[b] = w.x; wi[b] = -w.y;                               // exp(+2*pi*i*k/N)
+    }
+    // X_0[k] by direct DFT
+    {
+        int idx[FP_BPT];
+#pragma unroll
+        for (int b = 0; b < FP_BPT; ++b) idx[b] = 0;
+        for (int n = 0; n < N; ++n) {
+            const double2 s = win[n];
+#pragma unroll
+            for (int b = 0; b < FP_BPT; ++b) {
+                const int k = threadIdx.x + b * T;
+                if (k < N) {
+                    const double2 t = tw[idx[b]];
+                    xr[b] = fma(s.x, t.x, fma(-s.y, t.y, xr[b]));
+                    xi[b] = fma(s.x, t.y, fma(s.y, t.x, xi[b]));
+                    idx[b] += k; if (idx[b] >= N) idx[b] -= N;
+                }
+            }
+        }
+    }
+    for (int m = 0; m < n_win; ++m) {
+#pragma unroll
+        for (int b = 0; b < FP_BPT; ++b) {
+            const double p = fma(xr[b], xr[b], xi[b] * xi[b]);
+            if (p > best[b]) { best[b] = p; bestm[b] = m; }
+        }
+        if (m + 1 < n_win) {
+            const double2 s_old = win[m], s_new = win[m + N];
+            const double dr_ = s_new.x - s_old.x, di_ = s_new.y - s_old.y;
+#pragma unroll
+            for (int b = 0; b < FP_BPT; ++b) {
+                const double tr = xr[b] + dr_, ti = xi[b] + di_;
+                xr[b] = fma(tr, wr[b], -(ti * wi[b]));
+                xi[b] = fma(tr, wi[b], ti * wr[b]);
+            }
+        }
+    }
+    double v = -1.0; int mi = 0x7fffffff;
+#pragma unroll
+    for (int b = 0; b < FP_BPT; ++b) {
+        const int k = threadIdx.x + b * T;
+        if (k < N) argmax_combine(v, mi, best[b], bestm[b]);
+    }
+    block_argmax(v, mi, red_v, red_i);
+    if (threadIdx.x == 0) *o = (double)(sp + mi);              // sp + max_idx - 1, max_idx = mi + 1
+}
+
+// ===================================================================================================
+// N = 37 * M point DFT of a shared-memory vector (M = 4*osr): two direct stages, exact twiddle table.
+//   X[k1 + 37*k2] = sum_{n2<M} W_N^{n2*k1} W_M^{n2*k2} sum_{n1<37} x[M*n1+n2] W_37^{n1*k1}
+// ===================================================================================================
+__device__ void dft_37xM(const double2 *in, double2 *tmp, double2 *out, int N, const double2 *__restrict__ tw) {
+    const int M = N / 37;
+    for (int idx = threadIdx.x; idx < N; idx += blockDim.x) {
+        const int n2 = idx % M, k1 = idx / M;
+        double ar = 0.0, ai = 0.0;
+        int t = 0; const int stp = (M * k1) % N;
+        for (int n1 = 0; n1 < 37; ++n1) {
+            const double2 x = in[M * n1 + n2], w = tw[t];
+            ar = fma(x.x, w.x, fma(-x.y, w.y, ar));
+            ai = fma(x.x, w.y, fma(x.y, w.x, ai));
+            t += stp; if (t >= N) t -= N;
+        }
+        tmp[idx] = cmul(make_double2(ar, ai), tw[(n2 * k1) % N]);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < N; idx += blockDim.x) {
+        const int k1 = idx % 37, k2 = idx / 37;
+        double ar = 0.0, ai = 0.0;
+        int t = 0; const int stp = (37 * k2) % N;
+        const double2 *a = tmp + M * k1;
+        for (int n2 = 0; n2 < M; ++n2) {
+            const double2 x = a[n2], w = tw[t];
+            ar = fma(x.x, w.x, fma(-x.y, w.y, ar));
+            ai = fma(x.x, w.y, fma(x.y, w.x, ai));
+            t += stp; if (t >= N) t -= N;
+        }
+        out[k1 + 37 * k2] = make_double2(ar, ai);
+    }
+    __syncthreads();
+}
+
+// ===================================================================================================
+// K8  per-burst tone frequency (+ SNR gate)   FCCH_fine_correction.m:143-155,185-189; carrier_correct_post_SCH.m:58-72
+// ===================================================================================================
+#define TONE_THREADS 256
+__global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, int which /* 1: fine stage, 2: post-SCH */,
+                                                               const double *__restrict__ pos, int cap, int osr, const double2 *__restrict__ tw,
+                                                               double *__restrict__ fo_out, double *__restrict__ gate_out) {
+    extern __shared__ double2 sm[];
+    __shared__ double red_v[8];
+    __shared__ int red_i[8];
+    const int burst = blockIdx.x, stream = blockIdx.y;
+    const StreamCtl c = ctl[stream];
+    const int nb = (which == 1) ? (c.tone1_enable ? c.n_fcch : 0) : (c.post_enable ? c.n_post_fcch : 0);
+    if (burst >= nb) return;
+    const int N = 148 * osr;
+    const double sampling_rate = ((1625.0 / 6.0) * 1e3) * (double)osr;
+    double2 *u = sm, *A = u + N, *F = A + N;
+    double2 *X = F + N, *Y = X + N + GSMCAL_MAX_TAPS + 8;
+    const i64 sp = (i64)pos[(i64)stream * cap + burst];
+    load_window(src, c, stream, sp - 1, N, u, X, Y);
+    dft_37xM(u, A, F, N, tw);
+    // fftshift ordering then first max (:149-150): shifted index j <-> bin (j + N/2) mod N
+    double v = -1.0; int j_best = 0x7fffffff;
+    for (int j = threadIdx.x; j < N; j += TONE_THREADS) {
+        int k = j + N / 2; if (k >= N) k -= N;
+        argmax_combine(v, j_best, abs2_ref(F[k]), j);
+    }
+    block_argmax(v, j_best, red_v, red_i);
+    const double int_phase_rotate = 2.0 * GSMCAL_PI * (double)(j_best + 1 - ((N / 2) + 1)) / (double)N;
+    // integer-bin derotation, unit phasors (:152-153)
+    for (int n = threadIdx.x; n < N; n += TONE_THREADS) {
+        double sn, cs; sincos((double)n * int_phase_rotate, &sn, &cs);
+        double2 w = cmul(u[n], make_double2(cs, -sn));
+        u[n] = w;
+        double ang = atan2(w.y, w.x);
+        sincos(ang, &sn, &cs);
+        A[n] = make_double2(cs, sn);
+    }
+    __syncthreads();
+    double rr = 0.0, ri = 0.0;
+    for (int n = threadIdx.x; n < N - 1; n += TONE_THREADS) {
+        const double2 a = A[n + 1], b = A[n];
+        const double den = b.x * b.x + b.y * b.y;
+        rr += (a.x * b.x + a.y * b.y) / den;
+        ri += (a.y * b.x - a.x * b.y) / den;
+    }
+    rr = block_sum(rr, red_v);
+    ri = block_sum(ri, red_v);
+    const double phase_rotate = atan2(ri / (double)(N - 1), rr / (double)(N - 1));
+    const double fo = sampling_rate * (int_phase_rotate + phase_rotate) / (2 * GSMCAL_PI);
+    if (threadIdx.x == 0) fo_out[(i64)stream * cap + burst] = fo;
+    if (which != 1) return;
+    // SNR gate (:185-189): fine derotation, spectrum, bins [1:3,end-1:end] vs [4:hnl, end-hnl+1:end-2]
+    for (int n = threadIdx.x; n < N; n += TONE_THREADS) {
+        double sn, cs; sincos((double)n * phase_rotate, &sn, &cs);
+        u[n] = cmul(u[n], make_double2(cs, -sn));
+    }
+    __syncthreads();
+    dft_37xM(u, A, F, N, tw);
+    const int hnl = (int)ceil(((double)N * 200e3 / sampling_rate) / 2.0);
+    double sig = 0.0, noise = 0.0;
+    for (int k = threadIdx.x; k < N; k += TONE_THREADS) {
+        const bool is_sig = (k < 3) || (k >= N - 2);
+        const bool is_noise = (k >= 3 && k < hnl) || (k >= N - hnl && k < N - 2);
+        if (is_sig) sig += abs2_ref(F[k]);
+        else if (is_noise) noise += abs2_ref(F[k]);
+    }
+    sig = block_sum(sig, red_v);
+    noise = block_sum(noise, red_v);
+    if (threadIdx.x == 0) gate_out[(i64)stream * cap + burst] = 10.0 * log10(sig / noise);
+}
+
+// ===================================================================================================
+// K9  SCH training-sequence correlation   SCH_corr_rate_correction.m:37-63
+// ===================================================================================================
+#define SCH_THREADS 256
+__global__ void __launch_bounds__(SCH_THREADS) sch_corr_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ fcch_pos, int cap,
+                                                              int osr, const double2 *__restrict__ tpl, double *__restrict__ sch_raw, int *__restrict__ sch_edge) {
+    extern __shared__ double2 sm[];
+    __shared__ double red_v[8];
+    __shared__ int red_i[8];
+    __shared__ double corr[160];
+    const int burst = blockIdx.x, stream = blockIdx.y;
+    const StreamCtl c = ctl[stream];
+    if (!c.sch_enable || burst >= c.n_fcch) return;
+    const int L = 64 * osr;
+    const int max_offset = 8 * osr;
+    const i64 len_s = c.len1;
+    const int slot_ov = (625 * osr) / 4;
+    const int fix_off = slot_ov * 8 + 42 * osr;
+    const i64 training_sp = (i64)fcch_pos[(i64)stream * cap + burst] + fix_off;
+    double *o = sch_raw + (i64)stream * cap + burst;
+    if (training_sp + max_offset > len_s - L + 1) {            // run out (:40-43)
+        if (threadIdx.x == 0) { *o = INFINITY; sch_edge[(i64)stream * cap + burst] = 0; }
+        return;
+    }
+    const i64 sp = training_sp - max_offset;
+    const int n_lag = 2 * max_offset - 5 * osr + 1;            // 89 at osr 8
+    const int n_smp = n_lag + L - 1;
+    double2 *win = sm, *t = win + n_smp, *X = t + L, *Y = X + n_smp + GSMCAL_MAX_TAPS + 8;
+    for (int i = threadIdx.x; i < L; i += SCH_THREADS) t[i] = tpl[i];
+    load_window(src, c, stream, sp - 1, n_smp, win, X, Y);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = SCH_THREADS >> 5;
+    for (int lag = w; lag < n_lag; lag += nw) {
+        double ar = 0.0, ai = 0.0;
+        for (int n = lane; n < L; n += 32) {
+            const double2 p = cmulc(win[lag + n], t[n]);        // conj(ts) .* window
+            ar += p.x; ai += p.y;
+        }
+        ar = warp_sum(ar); ai = warp_sum(ai);
+        if (lane == 0) corr[lag] = abs2_ref(make_double2(ar, ai));
+    }
+    __syncthreads();
+    double v = -1.0; int bi = 0x7fffffff;
+    for (int lag = threadIdx.x; lag < n_lag; lag += SCH_THREADS) argmax_combine(v, bi, corr[lag], lag);
+    block_argmax(v, bi, red_v, red_i);
+    if (threadIdx.x == 0) {
+        *o = (double)(sp + bi);
+        sch_edge[(i64)stream * cap + burst] = (bi == 0 || bi == n_lag - 1) ? 1 : 0;
+    }
+}
+
+// ===================================================================================================
+// sequential per-stream stages (one thread per stream): ppm solves, regridding, pos_info
+// ===================================================================================================
+__device__ __forceinline__ double mround(double x) { return (x >= 0.0) ? floor(x + 0.5) : -floor(-x + 0.5); }   // MATLAB round
+
+// 10-frame / 11-frame spacing classification - FCCH_fine_correction.m:74-113 == SCH_corr_rate_correction.m:89-116.
+// kind[i] = 0 (10 frames) / 1 (11 frames) / 2 (both windows, cannot happen with these thresholds).
+__device__ bool classify_spacing(const double *pos, int n, int osr, double max_ppm, double *expected, double *d10o, double *d11o, unsigned char *kind) {
+    const double num_sym_per_frame = (625.0 / 4.0) * 8.0;
+    const double d10 = 10.0 * num_sym_per_frame * osr, d11 = 11.0 * num_sym_per_frame * osr;
+    const double th10 = floor(d10 * max_ppm * 1e-6), th11 = floor(d11 * max_ppm * 1e-6);
+    int na = 0, nb = 0;
+    for (int i = 0; i + 1 < n; ++i) {
+        const double d = pos[i + 1] - pos[i];
+        const bool a = fabs(d - d10) < th10, b = fabs(d - d11) < th11;
+        na += a; nb += b;
+        kind[i] = b ? 1 : 0;
+        if (a && b) kind[i] = 2;
+    }
+    *expected = (double)na * d10 + (double)nb * d11;
+    *d10o = d10; *d11o = d11;
+    return (na + nb) == n - 1;
+}
+
+__global__ void fine_ppm_kernel(StreamCtl *ctl, int n_streams, int cap, int osr, i64 n_iq, const double *__restrict__ fine_raw,
+                                double *__restrict__ fcch_pos, unsigned char *__restrict__ kind_scratch) {
+    const int stream = blockIdx.x * blockDim.x + threadIdx.x;
+    if (stream >= n_streams) return;
+    StreamCtl c = ctl[stream];
+    const double *fr = fine_raw + (i64)stream * cap;
+    double *fp = fcch_pos + (i64)stream * cap;
+    unsigned char *kind = kind_scratch + (i64)stream * cap;
+    c.n_fcch = -1; c.len1 = -1; c.sppm1 = INFINITY; c.cppm1 = INFINITY; c.interp1_on = 0; c.tone1_enable = 0; c.derot1_on = 0;
+    c.e1 = 0.0; c.dphi1 = 0.0; c.n_fine = 0;
+    const int fft_len = 148 * osr;
+    if (c.n_coarse >= 5) {
+        int last_idx = c.n_coarse;
+        for (int i = 0; i < c.n_coarse; ++i) if (isinf(fr[i])) { last_idx = i; break; }
+        c.n_fine = last_idx;
+        c.n_fcch = last_idx;
+        for (int i = 0; i < last_idx; ++i) fp[i] = fr[i];
+        if (last_idx >= 5) {
+            c.len1 = n_iq;                                        // r = s (:72)
+            double expected, d10, d11;
+            if (!classify_spacing(fr, last_idx, osr, 4000.0, &expected, &d10, &d11, kind)) {
+                c.n_fcch = -1; c.flags |= 1;                      // :95-102
+            } else {
+                const double actual = fr[last_idx - 1] - fr[0];
+                const double e = (actual - expected) / expected;
+                c.e1 = e; c.sppm1 = e * 1e6; c.interp1_on = 1;
+                c.len1 = (e >= 0.0) ? (i64)floor((double)n_iq / (1.0 + e)) : n_iq;
+                const double first = mround((fr[0] - 1.0) / (1.0 + e)) + 1.0;
+                double acc = 1.0;
+                fp[0] = acc + first - 1.0;
+                for (int i = 0; i + 1 < last_idx; ++i) { acc += (kind[i] == 1) ? d11 : d10; fp[i + 1] = acc + first - 1.0; }
+                int n = last_idx;
+                if (fp[n - 1] + fft_len - 1 > (double)c.len1) n -= 1;     // :135-137
+                c.n_fcch = n;
+                c.tone1_enable = (n >= 5);
+            }
+        }
+    }
+    ctl[stream] = c;
+}
+
+__global__ void fine_carrier_kernel(StreamCtl *ctl, int n_streams, int cap, int osr, double carrier_freq, const double *__restrict__ fo, const double *__restrict__ gate) {
+    const int stream = blockIdx.x * blockDim.x + threadIdx.x;
+    if (stream >= n_streams) return;
+    StreamCtl c = ctl[stream];
+    if (c.tone1_enable) {
+        const double symbol_rate = (1625.0 / 6.0) * 1e3, sampling_rate = symbol_rate * osr, target = symbol_rate / 4.0;
+        double acc = 0.0;
+        for (int i = 0; i < c.n_fcch; ++i) acc += fo[(i64)stream * cap + i];
+        const double fom = acc / (double)c.n_fcch;
+        c.cppm1 = 1e6 * (fom - target) / carrier_freq;
+        c.dphi1 = (target - fom) * 2 * GSMCAL_PI / sampling_rate;
+        c.derot1_on = 1;
+        int low = 0;
+        for (int i = 0; i < c.n_fcch; ++i) low += (gate[(i64)stream * cap + i] < 5.0);
+        if (low > 0) { c.n_fcch = -1; c.flags |= 2; }             // :192-196
+    }
+    c.sch_enable = (c.n_fcch >= 5);
+    ctl[stream] = c;
+}
+
+__global__ void sch_ppm_kernel(StreamCtl *ctl, int n_streams, int cap, int osr, const double *__restrict__ sch_raw, const int *__restrict__ sch_edge,
+                               double *__restrict__ sch_pos_scratch, unsigned char *__restrict__ kind_scratch, double *__restrict__ pos_info /* [stream][6*cap][2] */,
+                               double *__restrict__ post_pos) {
+    const int stream = blockIdx.x * blockDim.x + threadIdx.x;
+    if (stream >= n_streams) return;
+    StreamCtl c = ctl[stream];
+    double *pi = pos_info + (i64)stream * 6 * cap * 2;
+    double *pp = post_pos + (i64)stream * cap;
+    double *sp_ = sch_pos_scratch + (i64)stream * cap;
+    unsigned char *kind = kind_scratch + (i64)stream * cap;
+    c.n_pos_info = -1; c.len2 = -1; c.sppm2 = INFINITY; c.interp2_on = 0; c.e2 = 0.0; c.n_sch = 0; c.post_enable = 0; c.n_post_fcch = 0;
+    c.cppm2 = INFINITY; c.dphi2 = 0.0; c.len3 = -1;
+    if (c.sch_enable) {
+        const int H = c.n_fcch;
+        const double *sr = sch_raw + (i64)stream * cap;
+        const int *se = sch_edge + (i64)stream * cap;
+        int num_sch = H; bool edge = false;
+        for (int i = 0; i < H; ++i) {
+            if (isinf(sr[i])) { num_sch = i; break; }
+            if (se[i]) { edge = true; break; }
+        }
+        if (edge) {
+            c.flags |= 4;                                         // pos_info = [-1,-1], r = -1 (:59-63)
+        } else {
+            c.n_sch = num_sch;
+            c.n_pos_info = 3 * H;                                 // -1.*ones(3*num_fcch_hit,2) (:32)
+            for (int i = 0; i < 3 * H; ++i) { pi[2 * i] = -1.0; pi[2 * i + 1] = -1.0; }
+            if (num_sch >= 5) {
+                c.len2 = c.len1;                                  // r = s (:87)
+                double expected, d10, d11;
+                if (!classify_spacing(sr, num_sch, osr, 400.0, &expected, &d10, &d11, kind)) {
+                    c.flags |= 8;                                 // :106-112
+                } else {
+                    const double actual = sr[num_sch - 1] - sr[0];
+                    const double e = (actual - expected) / expected;
+                    c.e2 = e; c.sppm2 = e * 1e6;
+                    if (e != 0.0) {
+                        c.interp2_on = 1;
+                        c.len2 = (e > 0.0) ? (i64)floor((double)c.len1 / (1.0 + e)) : c.len1;
+                    }
+                    const double first = mround((sr[0] - 1.0) / (1.0 + e)) + 1.0;
+                    double acc = 1.0;
+                    sp_[0] = acc + first - 1.0;
+                    for (int i = 0; i + 1 < num_sch; ++i) { acc += (kind[i] == 1) ? d11 : d10; sp_[i + 1] = acc + first - 1.0; }
+                    // BCCH_flag (:138-141): 1-based b_idx = i+1 for kind[i]==1; flag(b_idx+1), flag(b_idx-4) if b_idx>=5
+                    // flags are consulted for i = 1..num_sch (1-based) -> reuse kind[] upper bits
+                    const int slot_ov = (625 * osr) / 4, frame_ov = slot_ov * 8;
+                    const double fix_off = (double)(frame_ov + 42 * osr), pre_ov = (double)(42 * osr);
+                    const double len_r = (double)c.len2;
+                    int row = 0, n_f = 0, n_b = 0;
+                    for (int i = 0; i < num_sch; ++i) {           // i 0-based; 1-based index i+1
+                        // flag(i+1) set if (b_idx+1 == i+1 -> kind[i-1]==1) or (b_idx-4 == i+1, b_idx>=5 -> kind[i+4]==1)
+                        bool flag = (i >= 1 && kind[i - 1] == 1) || (i + 4 < num_sch - 1 && kind[i + 4] == 1);
+                        pi[2 * row] = sp_[i] - fix_off; pi[2 * row + 1] = 0.0; pp[n_f++] = sp_[i] - fix_off; ++row;
+                        const double s0 = sp_[i] - pre_ov;
+                        if (s0 + slot_ov - 1 <= len_r) { pi[2 * row] = s0; pi[2 * row + 1] = 1.0; ++row; } else break;
+                        if (flag) {
+                            bool runout = false;
+                            for (int k = 1; k <= 4; ++k) {
+                                const double b0 = s0 + (double)k * frame_ov;
+                                if (b0 + slot_ov - 1 <= len_r) { pi[2 * row] = b0; pi[2 * row + 1] = 2.0; ++row; ++n_b; }
+                                else { runout = true; break; }
+                            }
+                            if (runout) break;
+                        }
+                    }
+                    c.n_pos_info = row;
+                    c.n_post_fcch = n_f;
+                    // carrier_correct_post_SCH.m:10-19: all -1 cannot happen here; needs >= 4 BCCH rows
+                    if (n_b >= 4) { c.post_enable = 1; c.len3 = c.len2; } else c.flags |= 16;
+                }
+            }
+        }
+    }
+    ctl[stream] = c;
+}
+
+__device__ __forceinline__ double total_ppm2(double a, double b) {     // total_ppm_calculation.m:5-21
+    if (isinf(a) && a > 0 && isinf(b) && b > 0) return INFINITY;
+    double acc = 1.0;
+    acc = acc * (1.0 + a * 1e-6);
+    acc = acc * (1.0 + b * 1e-6);
+    return (acc - 1.0) * 1e6;
+}
+
+struct StreamResultDev {            // mirrors gsmcal_stream_result (include/gsmcal.h)
+    int n_coarse, n_fcch, n_pos_info, flags;
+    i64 r_len[3];
+    double sampling_ppm[2], carrier_ppm[2], total_sampling_ppm, total_carrier_ppm;
+};
+
+__global__ void post_carrier_kernel(StreamCtl *ctl, int n_streams, int cap, int osr, double carrier_freq, const double *__restrict__ fo, StreamResultDev *res) {
+    const int stream = blockIdx.x * blockDim.x + threadIdx.x;
+    if (stream >= n_streams) return;
+    StreamCtl c = ctl[stream];
+    if (c.post_enable) {
+        const double symbol_rate = (1625.0 / 6.0) * 1e3, sampling_rate = symbol_rate * osr, target = symbol_rate / 4.0;
+        double acc = 0.0;
+        for (int i = 0; i < c.n_post_fcch; ++i) acc += fo[(i64)stream * cap + i];
+        const double fom = acc / (double)c.n_post_fcch;
+        c.cppm2 = 1e6 * (fom - target) / carrier_freq;
+        c.dphi2 = (target - fom) * 2 * GSMCAL_PI / sampling_rate;
+    }
+    ctl[stream] = c;
+    if (res) {
+        StreamResultDev r;
+        r.n_coarse = c.n_coarse; r.n_fcch = c.n_fcch; r.n_pos_info = c.n_pos_info; r.flags = c.flags;
+        r.r_len[0] = c.len1; r.r_len[1] = c.len2; r.r_len[2] = c.len3;
+        r.sampling_ppm[0] = c.sppm1; r.sampling_ppm[1] = c.sppm2;
+        r.carrier_ppm[0] = c.cppm1; r.carrier_ppm[1] = c.cppm2;
+        r.total_sampling_ppm = total_ppm2(c.sppm1, c.sppm2);
+        r.total_carrier_ppm = total_ppm2(c.cppm1, c.cppm2);
+        res[stream] = r;
+    }
+}
+
+// FCCH scanner acceptance: multi_rtl_sdr_gsm_FCCH_scanner.m:165-186
+__global__ void scan_accept_kernel(const StreamCtl *ctl, int n_chan, int cap, const double *__restrict__ position, const double *__restrict__ snr,
+                                   double *__restrict__ snr_out, double *__restrict__ num_hit) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= n_chan) return;
+    const int n = ctl[ch].n_coarse;
+    double s = 0.0, h = 0.0;
+    if (n >= 3) {
+        const double *p = position + (i64)ch * cap;
+        bool all_a = true, all_b = true;
+        for (int i = 0; i + 1 < n; ++i) {
+            const double d = p[i + 1] - p[i];
+            const bool a = fabs(d - 12500.0) > 50.0;
+            if (a) { all_a = false; if (fabs(d - 13750.0) > 50.0) all_b = false; }
+        }
+        if (all_a || all_b) {
+            double acc = 0.0;
+            for (int i = 0; i < n; ++i) acc += snr[(i64)ch * cap + i];
+            s = acc / (double)n; h = (double)n;
+        }
+    }
+    snr_out[ch] = s; num_hit[ch] = h;
+}
+
+__global__ void twiddle_init_kernel(double2 *tw, int N) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < N) {
+        double sn, cs; sincospi(-2.0 * (double)j / (double)N, &sn, &cs);
+        tw[j] = make_double2(cs, sn);
+    }
+}

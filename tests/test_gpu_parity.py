@@ -1,0 +1,329 @@
+"""Parity of the CUDA hot path (through the C ABI) against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): burst indices / pos_info / hit_idx / raw2iq bit-exact; ppm within 1e-3 ppm;
+floating-point streams within the relative tolerance written in each test.
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import gsmcal_oracle as oracle
+from gsmcal import synth
+
+pytestmark = pytest.mark.gpu
+
+FS = oracle.SYMBOL_RATE * 8
+CARRIER = 957.4e6
+N_SYNC = 1020000                       # gsm_sync_demod.m:23-29
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def coef47():
+    return oracle.fir1(46, 200e3 / FS)
+
+
+@pytest.fixture(scope="module")
+def tpl():
+    return oracle.gsm_SCH_training_sequence_gen(8)
+
+
+@pytest.fixture(scope="module")
+def captures():
+    specs = [synth.random_spec(seed, N_SYNC) for seed in (1, 2, 3, 4, 5)]
+    return specs, synth.generate_batch(specs).numpy()
+
+
+@pytest.fixture(scope="module")
+def oracle_chain(captures, coef47, tpl):
+    """Oracle intermediates for seed 1, shared by the per-function tests."""
+    _, raw = captures
+    r = oracle.fir_filter(coef47, oracle.raw2iq(raw[0])[:, 0])
+    coarse, coarse_snr = oracle.FCCH_coarse_position(r[::64], 8)
+    fpos, r1, sppm1, cppm1 = oracle.FCCH_fine_correction(r, coarse, 8, CARRIER)
+    pinfo, r2, sppm2 = oracle.SCH_corr_rate_correction(r1, fpos, tpl, 8)
+    r3, cppm2 = oracle.carrier_correct_post_SCH(r2, pinfo, 8, CARRIER)
+    return dict(r=r, coarse=coarse, coarse_snr=coarse_snr, fpos=fpos, r1=r1, sppm1=sppm1, cppm1=cppm1,
+                pinfo=pinfo, r2=r2, sppm2=sppm2, r3=r3, cppm2=cppm2)
+
+
+# ---- K1 ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_iq,cols", [(1, 1), (7, 3), (4096, 2), (100003, 5), (1020000, 2)])
+def test_raw2iq_u8_bit_exact(gpu, n_iq, cols):
+    rng = np.random.default_rng(n_iq)
+    a = rng.integers(0, 256, size=(2 * n_iq, cols), dtype=np.uint8)
+    got = gpu.raw2iq(a)
+    ref = oracle.raw2iq(a)
+    assert got.shape == ref.shape
+    assert np.array_equal(got, ref)
+
+
+def test_raw2iq_double_input_bit_exact(gpu):
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 256, size=(2 * 5001, 2)).astype(np.float64)      # what fread(...,'uint8') returns
+    assert np.array_equal(gpu.raw2iq(a), oracle.raw2iq(a))
+
+
+def test_raw2iq_extremes(gpu):
+    for v in (0, 255):
+        a = np.full((2 * 1000, 1), v, dtype=np.uint8)
+        assert np.array_equal(gpu.raw2iq(a), oracle.raw2iq(a))
+
+
+# ---- K2 ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("order,decim", [(46, 1), (30, 1), (63, 1), (127, 1), (46, 64), (30, 64), (63, 20), (46, 2), (46, 3)])
+def test_fir_filter_matches_lfilter(gpu, order, decim):
+    rng = np.random.default_rng(order * 100 + decim)
+    n = 50021
+    s = rng.standard_normal((n, 2)) * 40 + 1j * rng.standard_normal((n, 2)) * 40
+    coef = oracle.fir1(order, 0.09)
+    got = gpu.fir_filter(coef, s, decim)
+    ref = oracle.fir_filter(coef, s, decim)
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < 1e-14            # same nesting order as direct-form-II-transposed, FMA instead of mul+add
+
+
+def test_fir_short_input_startup_transient(gpu):
+    coef = oracle.fir1(46, 0.09)
+    s = (np.arange(10) + 1j * np.arange(10)).astype(np.complex128)       # shorter than the filter
+    assert rel_err(gpu.fir_filter(coef, s), oracle.fir_filter(coef, s)) < 1e-14
+
+
+def test_fir1_matches_firwin(gpu):
+    for order, wn in ((46, 200e3 / FS), (30, 200e3 / FS), (63, 0.05 / 2.048), (127, 0.01)):
+        assert np.max(np.abs(gpu.fir1(order, wn) - oracle.fir1(order, wn))) < 2e-16
+
+
+def test_fused_raw2iq_fir(gpu, captures, coef47):
+    _, raw = captures
+    a = raw[:2, :2 * 200000].T.copy()
+    ref = oracle.fir_filter(coef47, oracle.raw2iq(a))
+    assert rel_err(gpu.raw2iq_fir(a, coef47, 1), ref) < 1e-14
+    assert rel_err(gpu.raw2iq_fir(a, coef47, 64), ref[::64]) < 1e-14
+
+
+def test_chn_filters_with_fda_taps(gpu):
+    with open(os.path.join(GOLDEN, "chn_filter_taps.json")) as f:
+        g = json.load(f)
+    num8 = np.array([float.fromhex(h) for h in g["Num_8x"]["hex"]])
+    num4 = np.array([float.fromhex(h) for h in g["Num_4x"]["hex"]])
+    assert np.array_equal(gpu.chn_filter_taps(8), num8)
+    assert np.array_equal(gpu.chn_filter_taps(4), num4)
+    rng = np.random.default_rng(7)
+    s = rng.standard_normal((20001, 2)) + 1j * rng.standard_normal((20001, 2))
+    assert rel_err(gpu.chn_filter_8x_4x(s), oracle.chn_filter_8x_4x(s, num8)) < 1e-14
+    assert rel_err(gpu.chn_filter_4x(s), oracle.chn_filter_4x(s, num4)) < 1e-14
+
+
+def test_band_power_scanners(gpu):
+    rng = np.random.default_rng(11)
+    a = np.clip(np.round(rng.standard_normal((2 * 12288, 4)) * 20 + 127.5), 0, 255).astype(np.uint8)
+    assert rel_err(gpu.band_power(a), oracle.band_power(a)) < 1e-12                 # scan_band_power_spectrum.m
+    a = np.clip(np.round(rng.standard_normal((2 * 204800, 3)) * 20 + 127.5), 0, 255).astype(np.uint8)
+    coef = oracle.fir1(63, 0.05 / 2.048)
+    assert rel_err(gpu.band_power(a, coef, 20), oracle.band_power(a, coef, 20)) < 1e-12   # split scanner
+
+
+# ---- K3 / K4 ---------------------------------------------------------------------------------------
+def test_move_fft_snr_runtime_avg(gpu, oracle_chain):
+    s = oracle_chain["r"][::64][:3594]
+    ref = oracle.move_fft_snr_runtime_avg(s, 160, 16, 10)
+    got = gpu.move_fft_snr_runtime_avg(s, 160, 16, 10)
+    assert got[0] == ref[0] and got[1] == ref[1]
+    assert abs(got[2] - ref[2]) < 1e-9 and abs(got[3] - ref[3]) < 1e-9
+    _, trace = oracle.move_fft_snr_runtime_avg(s, 160, 16, 10, return_trace=True)
+    assert np.max(np.abs(gpu.move_fft_snr_trace(s, 16) - trace)) < 1e-9
+
+
+def test_move_fft_no_hit_sentinel(gpu):
+    rng = np.random.default_rng(5)
+    s = rng.standard_normal(2000) + 1j * rng.standard_normal(2000)
+    assert gpu.move_fft_snr_runtime_avg(s, 160, 16, 10) == oracle.move_fft_snr_runtime_avg(s, 160, 16, 10) == (False, -1.0, math.inf, math.inf)
+
+
+def test_specific_fft_snr_fix_avg(gpu, oracle_chain):
+    s = oracle_chain["r"][::64]
+    p = int((oracle_chain["coarse"][1] - 1) / 8 + 1)
+    for avg in (0.0, 30.0):
+        ref = oracle.specific_fft_snr_fix_avg(s, (p - 5, p + 5), 16, 10, avg)
+        got = gpu.specific_fft_snr_fix_avg(s, (p - 5, p + 5), 16, 10, avg)
+        assert got[0] == ref[0] and got[1] == ref[1]
+        if ref[0]:
+            assert abs(got[2] - ref[2]) < 1e-9
+        else:
+            assert got[2] == math.inf
+
+
+def test_fcch_coarse_position(gpu, oracle_chain):
+    pos, snr = gpu.FCCH_coarse_position(oracle_chain["r"][::64], 8)
+    assert np.array_equal(pos, oracle_chain["coarse"])
+    assert np.max(np.abs(snr - oracle_chain["coarse_snr"])) < 1e-9
+
+
+def test_fcch_coarse_noise_only_sentinel(gpu):
+    rng = np.random.default_rng(9)
+    s = rng.standard_normal(16000) + 1j * rng.standard_normal(16000)
+    pos, snr = gpu.FCCH_coarse_position(s, 8)
+    ref = oracle.FCCH_coarse_position(s, 8)
+    assert np.array_equal(pos, ref[0]) and np.array_equal(snr, ref[1]) and pos[0] == -1
+
+
+# ---- K5-K8 -----------------------------------------------------------------------------------------
+def test_fcch_fine_correction(gpu, oracle_chain):
+    fpos, r1, sppm, cppm = gpu.FCCH_fine_correction(oracle_chain["r"], oracle_chain["coarse"], 8, CARRIER)
+    assert np.array_equal(fpos, oracle_chain["fpos"])
+    assert sppm == oracle_chain["sppm1"]                      # integer differences -> identical fp64
+    assert abs(cppm - oracle_chain["cppm1"]) < 1e-3
+    assert len(r1) == len(oracle_chain["r1"])
+    assert rel_err(r1, oracle_chain["r1"]) < 1e-8             # derotation phase: n*dphi reaches 1e5..1e6 rad
+
+
+def test_fcch_fine_fewer_than_5_hits_sentinel(gpu, oracle_chain):
+    fpos, r1, sppm, cppm = gpu.FCCH_fine_correction(oracle_chain["r"], oracle_chain["coarse"][:4], 8, CARRIER)
+    assert np.array_equal(fpos, [-1.0]) and r1 is None and sppm == math.inf and cppm == math.inf
+
+
+def test_fcch_fine_runout_keeps_first_round_positions(gpu, oracle_chain):
+    # truncate the stream so only 3 coarse hits survive the run-out check: FCCH_pos = first-round positions, r = -1
+    n_cut = int(oracle_chain["coarse"][3] * 8)
+    s = oracle_chain["r"][:n_cut]
+    ref = oracle.FCCH_fine_correction(s, oracle_chain["coarse"], 8, CARRIER)
+    got = gpu.FCCH_fine_correction(s, oracle_chain["coarse"], 8, CARRIER)
+    assert len(ref[0]) < 5 and np.array_equal(got[0], ref[0]) and got[1] is None and ref[1] is None
+    assert got[2] == math.inf and got[3] == math.inf
+
+
+def test_fcch_fine_bad_spacing_returns_s(gpu, oracle_chain):
+    base = oracle_chain["coarse"].copy()
+    base[2] += 700                                             # > 4000 ppm of 10 frames: spacing classification fails
+    ref = oracle.FCCH_fine_correction(oracle_chain["r"], base, 8, CARRIER)
+    got = gpu.FCCH_fine_correction(oracle_chain["r"], base, 8, CARRIER)
+    assert np.array_equal(ref[0], [-1.0]) and np.array_equal(got[0], [-1.0])
+    assert np.array_equal(got[1], oracle_chain["r"]) and got[2] == math.inf
+
+
+# ---- K9-K10 ----------------------------------------------------------------------------------------
+def test_sch_template_generator(gpu, tpl):
+    assert np.max(np.abs(gpu.gsm_SCH_training_sequence_gen(8) - tpl)) < 1e-12
+    assert np.max(np.abs(gpu.gsm_SCH_training_sequence_gen(4) - oracle.gsm_SCH_training_sequence_gen(4))) < 1e-12
+
+
+def test_sch_corr_rate_correction(gpu, oracle_chain, tpl):
+    pinfo, r2, sppm = gpu.SCH_corr_rate_correction(oracle_chain["r1"], oracle_chain["fpos"], tpl, 8)
+    assert np.array_equal(pinfo, oracle_chain["pinfo"])
+    assert sppm == oracle_chain["sppm2"]
+    assert rel_err(r2, oracle_chain["r2"]) < 1e-13
+
+
+def test_sch_sentinels(gpu, oracle_chain, tpl):
+    r1, fpos = oracle_chain["r1"], oracle_chain["fpos"]
+    got = gpu.SCH_corr_rate_correction(r1, fpos[:4], tpl, 8)
+    assert np.array_equal(got[0], [[-1.0, -1.0]]) and got[1] is None and got[2] == math.inf
+    # shifted FCCH positions push the correlation peak to the window edge -> pos_info=[-1,-1]
+    ref = oracle.SCH_corr_rate_correction(r1, fpos - 41, tpl, 8)
+    got = gpu.SCH_corr_rate_correction(r1, fpos - 41, tpl, 8)
+    assert ref[0].shape == (1, 2) and np.array_equal(got[0], ref[0]) and got[1] is None and ref[1] is None
+    # positions 200 samples off: peaks are spurious, the spacing test fails -> pos_info=-ones(3H,2), r=s
+    ref = oracle.SCH_corr_rate_correction(r1, fpos - 200, tpl, 8)
+    got = gpu.SCH_corr_rate_correction(r1, fpos - 200, tpl, 8)
+    assert np.array_equal(got[0], ref[0]) and (got[1] is None) == (ref[1] is None)
+    # stream cut so fewer than 5 SCH fit: pos_info = -ones(3H,2)
+    n_cut = int(fpos[4] + 5000)
+    ref = oracle.SCH_corr_rate_correction(r1[:n_cut], fpos, tpl, 8)
+    got = gpu.SCH_corr_rate_correction(r1[:n_cut], fpos, tpl, 8)
+    assert ref[0].shape == (3 * len(fpos), 2) and np.array_equal(got[0], ref[0]) and got[1] is None and ref[1] is None
+
+
+def test_carrier_correct_post_sch(gpu, oracle_chain):
+    r3, cppm = gpu.carrier_correct_post_SCH(oracle_chain["r2"], oracle_chain["pinfo"], 8, CARRIER)
+    assert abs(cppm - oracle_chain["cppm2"]) < 1e-3
+    assert rel_err(r3, oracle_chain["r3"]) < 1e-8
+    for bad in (np.array([[-1.0, -1.0]]), -np.ones((30, 2)), oracle_chain["pinfo"][:3]):
+        r, c = gpu.carrier_correct_post_SCH(oracle_chain["r2"], bad, 8, CARRIER)
+        rr, cc = oracle.carrier_correct_post_SCH(oracle_chain["r2"], bad, 8, CARRIER)
+        assert r is None and rr is None and c == math.inf and cc == math.inf
+
+
+def test_total_ppm_calculation(gpu):
+    for v in ([-35.0, 1.2], [math.inf, math.inf], [3.0, math.inf], [0.0, 0.0]):
+        assert gpu.total_ppm_calculation(v) == oracle.total_ppm_calculation(v)
+
+
+# ---- batched pipeline ------------------------------------------------------------------------------
+def _check_stream(got, ref):
+    assert np.array_equal(got["coarse_pos"], ref["coarse_pos"])
+    assert np.array_equal(got["fcch_pos"], ref["fcch_pos"])
+    assert np.array_equal(got["pos_info"], ref["pos_info"])
+    for k in ("sampling_ppm", "carrier_ppm"):
+        for a, b in zip(got[k], ref[k]):
+            assert (a == b) if math.isinf(b) else abs(a - b) < 1e-3
+    for k in ("total_sampling_ppm", "total_carrier_ppm"):
+        assert (got[k] == ref[k]) if math.isinf(ref[k]) else abs(got[k] - ref[k]) < 1e-3
+
+
+def test_calibrate_batch_matches_function_chain(gpu, captures, coef47, tpl):
+    _, raw = captures
+    got = gpu.calibrate_batch(raw, CARRIER, tpl, coef47)
+    for d in range(raw.shape[0]):
+        _check_stream(got[d], oracle.calibrate_stream(raw[d], CARRIER, tpl, coef47))
+
+
+def test_calibrate_batch_matches_golden(gpu, captures, coef47, tpl):
+    _, raw = captures
+    with open(os.path.join(GOLDEN, "pipeline_golden.json")) as f:
+        g = json.load(f)["cases"]
+    got = gpu.calibrate_batch(raw, CARRIER, tpl, coef47)
+    for d, seed in enumerate((1, 2, 3, 4, 5)):
+        c = g[str(seed)]
+        assert np.array_equal(got[d]["fcch_pos"], c["fcch_pos"])
+        assert np.array_equal(got[d]["pos_info"], np.array(c["pos_info"]))
+        assert abs(got[d]["total_sampling_ppm"] - c["total_sampling_ppm"]) < 1e-3
+        assert abs(got[d]["total_carrier_ppm"] - c["total_carrier_ppm"]) < 1e-3
+
+
+def test_calibrate_batch_negative_fixtures(gpu, coef47, tpl):
+    n = N_SYNC
+    specs = [
+        synth.StreamSpec(seed=21, n_samples=n, noise_only=True),                                  # coarse -1
+        synth.StreamSpec(seed=22, n_samples=n, snr_db=0.0, sampling_ppm=5, carrier_ppm=3),        # weak: sentinel chain
+        synth.StreamSpec(seed=23, n_samples=n, sampling_ppm=-12, carrier_ppm=8, drop_fcch=(2,)),  # dropped FCCH: chain stops early
+        synth.StreamSpec(seed=24, n_samples=n, sampling_ppm=10, carrier_ppm=-20, start_offset=123456.0),
+    ]
+    raw = synth.generate_batch(specs).numpy()
+    got = gpu.calibrate_batch(raw, CARRIER, tpl, coef47)
+    for d in range(len(specs)):
+        _check_stream(got[d], oracle.calibrate_stream(raw[d], CARRIER, tpl, coef47))
+    assert got[0]["coarse_pos"][0] == -1 and math.isinf(got[0]["total_sampling_ppm"])
+
+
+def test_fcch_scan_channels(gpu):
+    n = 640000                                      # multi_rtl_sdr_gsm_FCCH_scanner.m:39-49
+    coef = oracle.fir1(30, 200e3 / FS)
+    specs = [synth.StreamSpec(seed=31, n_samples=n, sampling_ppm=7, carrier_ppm=-4, start_offset=4000.0),
+             synth.StreamSpec(seed=32, n_samples=n, noise_only=True),
+             synth.StreamSpec(seed=33, n_samples=n, sampling_ppm=-20, carrier_ppm=15, snr_db=12, start_offset=250000.0)]
+    raw = synth.generate_batch(specs).numpy()
+    snr, num_hit, positions = gpu.fcch_scan(raw, coef)
+    for c in range(len(specs)):
+        rs, rn, rp, _ = oracle.fcch_scan_channel(raw[c], coef)
+        assert np.array_equal(positions[c], rp)
+        assert num_hit[c] == rn and abs(snr[c] - rs) < 1e-9
+
+
+def test_device_resident_batch_equals_host_batch(gpu, captures, coef47, tpl):
+    torch = pytest.importorskip("torch")
+    _, raw = captures
+    dev = torch.from_numpy(raw[:2].copy()).cuda()
+    torch.cuda.synchronize()
+    a = gpu.calibrate_batch(None, CARRIER, tpl, coef47, device_ptr=dev.data_ptr(), n_iq=raw.shape[1] // 2, n_streams=2)
+    b = gpu.calibrate_batch(raw[:2], CARRIER, tpl, coef47)
+    for x, y in zip(a, b):
+        assert np.array_equal(x["pos_info"], y["pos_info"]) and x["total_carrier_ppm"] == y["total_carrier_ppm"]
