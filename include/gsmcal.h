@@ -154,6 +154,12 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
                            double *coarse_pos, double *coarse_snr, double *fcch_pos, double *pos_info,
                            void *cuda_stream);
 
+/* CUDA-event times (ms) of the stages of the last gsmcal_calibrate_batch call on this process:
+ * [0] uint8 column sums (+ H2D when raw is on the host) [1] coarse FCCH [2] fine FCCH sliding-DFT peak search
+ * [3] fine ppm + tone estimate + gate [4] SCH correlation + pos_info [5] post-SCH tone estimate + result records.
+ * Returns the number of stages written. */
+int gsmcal_last_batch_stage_ms(double *ms, int cap);
+
 /* FCCH scanner per-channel processing, multi_rtl_sdr_gsm_FCCH_scanner.m:132-135,163-186, for n_chan
  * captures in one call: raw2iq -> filter(coef) -> r(1:osr*dr:end) -> FCCH_coarse_position -> spacing
  * acceptance.  snr[c]/num_hit[c] as the script computes them (0 when rejected). */

@@ -65,6 +65,21 @@ struct Ctx {
 };
 std::map<int, Ctx> g_ctx;
 
+// per-stage CUDA-event timing of the last gsmcal_calibrate_batch call (events are recorded on the call's stream)
+constexpr int kNumStageEvents = 8;
+cudaEvent_t g_stage_ev[kNumStageEvents];
+bool g_stage_ev_ok = false;
+int g_stage_n = 0;
+float g_stage_ms[kNumStageEvents];
+int stage_mark(cudaStream_t st) {
+    if (!g_stage_ev_ok) {
+        for (int i = 0; i < kNumStageEvents; ++i) CU(cudaEventCreate(&g_stage_ev[i]));
+        g_stage_ev_ok = true;
+    }
+    if (g_stage_n < kNumStageEvents) CU(cudaEventRecord(g_stage_ev[g_stage_n++], st));
+    return GSMCAL_OK;
+}
+
 int ensure_device() {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -190,13 +205,22 @@ int run_coarse(WinSrc src, i64 len, const CoarseParams &p, i64 D, int cap, Work 
     return GSMCAL_OK;
 }
 
-int run_fine(Ctx &c, WinSrc src_peak, WinSrc src_tone, i64 n_iq, int osr, double carrier_freq, i64 D, int cap, Work &w, cudaStream_t st) {
+int run_fine_peak(Ctx &c, WinSrc src_peak, i64 n_iq, int osr, i64 D, int cap, Work &w, cudaStream_t st) {
     const double2 *tw; TRY(get_twiddle(c, 148 * osr, st, &tw));
     LAUNCH(fine_peak_kernel, dim3((unsigned)cap, (unsigned)D), kFineThreads, fine_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw);
+    return GSMCAL_OK;
+}
+int run_fine_rest(Ctx &c, WinSrc src_tone, i64 n_iq, int osr, double carrier_freq, i64 D, int cap, Work &w, cudaStream_t st) {
+    const double2 *tw; TRY(get_twiddle(c, 148 * osr, st, &tw));
     LAUNCH(fine_ppm_kernel, (unsigned)((D + 63) / 64), 64, 0, st, w.ctl, (int)D, cap, osr, n_iq, w.fine_raw, w.fcch_pos, w.kind);
     LAUNCH(tone_est_kernel, dim3((unsigned)cap, (unsigned)D), TONE_THREADS, tone_smem(osr), st, src_tone, w.ctl, 1, w.fcch_pos, cap, osr, tw, w.fo, w.gate);
     LAUNCH(fine_carrier_kernel, (unsigned)((D + 63) / 64), 64, 0, st, w.ctl, (int)D, cap, osr, carrier_freq, w.fo, w.gate);
     return GSMCAL_OK;
+}
+
+int run_fine(Ctx &c, WinSrc src_peak, WinSrc src_tone, i64 n_iq, int osr, double carrier_freq, i64 D, int cap, Work &w, cudaStream_t st) {
+    TRY(run_fine_peak(c, src_peak, n_iq, osr, D, cap, w, st));
+    return run_fine_rest(c, src_tone, n_iq, osr, carrier_freq, D, cap, w, st);
 }
 
 int run_sch(WinSrc src, int osr, i64 D, int cap, Work &w, cudaStream_t st) {
@@ -686,6 +710,8 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
     }
     CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * D, st));
     CU(cudaMemcpyAsync(w.tpl, tpl, sizeof(double2) * 64 * osr, cudaMemcpyHostToDevice, st));
+    g_stage_n = 0;
+    TRY(stage_mark(st));
     if (raw_mem == GSMCAL_MEM_HOST) {
         // copy and reduce in slices of streams so the column sums overlap the PCIe transfer of the next slice
         const size_t per = (size_t)2 * n_iq;
@@ -704,17 +730,32 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
     } else {
         TRY(run_colsum_u8(draw, n_iq, D, w.ctl, st));
     }
+    TRY(stage_mark(st));
     TRY(run_coarse(lazy_src(draw, n_iq, n_taps, 0, dec), len_dec, p, D, cap, w, st));
-    TRY(run_fine(*c, lazy_src(draw, n_iq, n_taps, 0, 1), lazy_src(draw, n_iq, n_taps, 1, 1), n_iq, osr, carrier_freq, D, cap, w, st));
+    TRY(stage_mark(st));
+    TRY(run_fine_peak(*c, lazy_src(draw, n_iq, n_taps, 0, 1), n_iq, osr, D, cap, w, st));
+    TRY(stage_mark(st));
+    TRY(run_fine_rest(*c, lazy_src(draw, n_iq, n_taps, 1, 1), n_iq, osr, carrier_freq, D, cap, w, st));
+    TRY(stage_mark(st));
     TRY(run_sch(lazy_src(draw, n_iq, n_taps, 2, 1), osr, D, cap, w, st));
+    TRY(stage_mark(st));
     TRY(run_post(*c, lazy_src(draw, n_iq, n_taps, 3, 1), osr, carrier_freq, D, cap, w, true, st));
+    TRY(stage_mark(st));
     CU(cudaMemcpyAsync(results, w.res, sizeof(StreamResultDev) * D, cudaMemcpyDeviceToHost, st));
     if (coarse_pos) CU(cudaMemcpyAsync(coarse_pos, w.coarse_pos, sizeof(double) * D * cap, cudaMemcpyDeviceToHost, st));
     if (coarse_snr) CU(cudaMemcpyAsync(coarse_snr, w.coarse_snr, sizeof(double) * D * cap, cudaMemcpyDeviceToHost, st));
     if (fcch_pos) CU(cudaMemcpyAsync(fcch_pos, w.fcch_pos, sizeof(double) * D * cap, cudaMemcpyDeviceToHost, st));
     if (pos_info) CU(cudaMemcpyAsync(pos_info, w.pos_info, sizeof(double) * D * cap * 12, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    for (int i = 0; i + 1 < g_stage_n; ++i) CU(cudaEventElapsedTime(&g_stage_ms[i], g_stage_ev[i], g_stage_ev[i + 1]));
     return GSMCAL_OK;
+}
+
+int gsmcal_last_batch_stage_ms(double *ms, int cap_n) {
+    // colsum(+H2D), coarse, fine_peak, fine ppm+tone+carrier, SCH, post-SCH - of the last gsmcal_calibrate_batch call
+    int n = g_stage_n > 0 ? g_stage_n - 1 : 0;
+    for (int i = 0; i < n && i < cap_n; ++i) ms[i] = g_stage_ms[i];
+    return n;
 }
 
 int gsmcal_fcch_scan(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t n_chan, const double *coef, int n_taps, int osr, int coarse_dr,

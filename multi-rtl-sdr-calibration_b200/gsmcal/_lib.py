@@ -49,6 +49,7 @@ SIGNATURES = {
     "gsmcal_total_ppm_calculation": (C.c_int, [C.c_void_p, c_i64, c_dp]),
     "gsmcal_calibrate_batch": (C.c_int, [C.c_void_p, C.c_int, c_i64, c_i64, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gsmcal_last_batch_stage_ms": (C.c_int, [C.c_void_p, C.c_int]),
     "gsmcal_fcch_scan": (C.c_int, [C.c_void_p, C.c_int, c_i64, c_i64, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsmcal_launch_count": (c_i64, [C.c_int]),

@@ -283,6 +283,15 @@ def calibrate_batch(raw, carrier_freq: float, sch_training_sequence, coef, osr: 
     return _unpack_results(res, D, cap, coarse_pos, coarse_snr, fcch_pos, pos_info)
 
 
+STAGE_NAMES = ("colsum_u8", "coarse", "fine_peak", "fine_tone", "sch", "post")
+
+
+def last_batch_stage_ms() -> dict:
+    ms = np.zeros(8)
+    n = lib().gsmcal_last_batch_stage_ms(_ptr(ms), 8)
+    return {STAGE_NAMES[i]: float(ms[i]) for i in range(n)}
+
+
 def fcch_scan(raw, coef, osr: int = 8, coarse_dr: int = 8):
     """Per-channel FCCH detection of multi_rtl_sdr_gsm_FCCH_scanner.m:132-135,163-186.  raw: [n_chan, 2N] uint8."""
     raw = np.ascontiguousarray(raw, dtype=np.uint8)
