@@ -225,6 +225,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_acc = {}
     barrier()
+    torch.cuda.profiler.start()          # ncu --profile-from-start off sees only the timed region
     ev0.record(stream)
     for _ in range(args.steps):
         res = step_device()
@@ -232,6 +233,7 @@ def main():
             stage_acc[k] = stage_acc.get(k, 0.0) + v
     ev1.record(stream)
     barrier()
+    torch.cuda.profiler.stop()
     clocks = sampler.stop()
     launches = gsmcal.launch_count()
     ms = ev0.elapsed_time(ev1)

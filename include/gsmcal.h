@@ -168,6 +168,9 @@ int gsmcal_fcch_scan(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t n_ch
                      double *snr, double *num_hit, double *position /* [n_chan][B] or NULL */,
                      int32_t *n_position /* [n_chan] or NULL */, void *cuda_stream);
 
+/* test hook: key 0, value 1 = run the all-bin fine FCCH search for every burst (no band-limited fast path) */
+int gsmcal_debug_set(int key, int value);
+
 /* kernel-launch counter (all launches since the last reset, this process) - for bench.py's gpu_launches */
 int64_t gsmcal_launch_count(int reset);
 

@@ -23,6 +23,7 @@ std::mutex g_mu;
 thread_local std::string g_err;
 thread_local int g_device = 0;
 std::atomic<long long> g_launches{0};
+int g_debug_force_full = 0;       // tests: run the all-bin fine search for every burst
 
 int fail(int code, const char *fmt, ...) {
     char buf[512];
@@ -90,6 +91,7 @@ int ensure_device() {
 
 constexpr int kFineThreads = 320;
 size_t fine_smem(int osr) { int N = 148 * osr, ns = 2 * 64 * osr + 1 + N - 1; return (size_t)(3 * ns + GSMCAL_MAX_TAPS + 16) * sizeof(double2); }
+size_t fine_band_smem(int osr) { int N = 148 * osr, ns = 2 * 64 * osr + 1 + N - 1; return (size_t)(2 * ns + GSMCAL_MAX_TAPS + 16) * sizeof(double2); }
 size_t tone_smem(int osr) { int N = 148 * osr; return (size_t)(5 * N + GSMCAL_MAX_TAPS + 16) * sizeof(double2); }
 size_t sch_smem(int osr) { int L = 64 * osr, ns = 16 * osr - 5 * osr + 1 + L - 1; return (size_t)(3 * ns + L + GSMCAL_MAX_TAPS + 16) * sizeof(double2); }
 
@@ -97,7 +99,8 @@ int get_ctx(Ctx **out) {
     TRY(ensure_device());
     Ctx &c = g_ctx[g_device];
     if (!c.attrs) {
-        CU(cudaFuncSetAttribute(fine_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(cudaFuncSetAttribute(fine_peak_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(cudaFuncSetAttribute(fine_peak_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(tone_est_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(sch_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CU(cudaFuncSetAttribute(fir_decim_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -134,7 +137,7 @@ int set_taps(const double *coef, int n_taps, cudaStream_t st) {
 struct Work {
     StreamCtl *ctl; StreamResultDev *res;
     double *coarse_pos, *coarse_snr, *fine_raw, *fcch_pos, *fo, *gate, *sch_raw, *sch_pos, *post_pos, *pos_info, *snr_map, *power;
-    int *sch_edge; unsigned char *kind; double2 *tpl;
+    int *sch_edge, *need_full; unsigned char *kind; double2 *tpl;
     i64 snr_stride;
 };
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -146,7 +149,7 @@ int make_work(Ctx &c, i64 D, int cap, i64 snr_len, int tpl_len, Work *w) {
     size_t per = sizeof(double) * D * cap;
     size_t o_cp = take(per), o_cs = take(per), o_fr = take(per), o_fp = take(per), o_fo = take(per), o_g = take(per), o_sr = take(per), o_sp = take(per), o_pp = take(per);
     size_t o_pi = take(per * 12), o_snr = take(sizeof(double) * D * snr_len), o_pw = take(sizeof(double) * D);
-    size_t o_se = take(sizeof(int) * D * cap), o_k = take(D * cap), o_tpl = take(sizeof(double2) * (tpl_len > 0 ? tpl_len : 1));
+    size_t o_se = take(sizeof(int) * D * cap), o_nf = take(sizeof(int) * D * cap), o_k = take(D * cap), o_tpl = take(sizeof(double2) * (tpl_len > 0 ? tpl_len : 1));
     void *base;
     TRY(c.work.get(off, &base));
     char *b = static_cast<char *>(base);
@@ -154,7 +157,7 @@ int make_work(Ctx &c, i64 D, int cap, i64 snr_len, int tpl_len, Work *w) {
     w->coarse_pos = (double *)(b + o_cp); w->coarse_snr = (double *)(b + o_cs); w->fine_raw = (double *)(b + o_fr); w->fcch_pos = (double *)(b + o_fp);
     w->fo = (double *)(b + o_fo); w->gate = (double *)(b + o_g); w->sch_raw = (double *)(b + o_sr); w->sch_pos = (double *)(b + o_sp); w->post_pos = (double *)(b + o_pp);
     w->pos_info = (double *)(b + o_pi); w->snr_map = (double *)(b + o_snr); w->power = (double *)(b + o_pw);
-    w->sch_edge = (int *)(b + o_se); w->kind = (unsigned char *)(b + o_k); w->tpl = (double2 *)(b + o_tpl);
+    w->sch_edge = (int *)(b + o_se); w->need_full = (int *)(b + o_nf); w->kind = (unsigned char *)(b + o_k); w->tpl = (double2 *)(b + o_tpl);
     w->snr_stride = snr_len;
     return GSMCAL_OK;
 }
@@ -201,13 +204,19 @@ int run_coarse(WinSrc src, i64 len, const CoarseParams &p, i64 D, int cap, Work 
     LAUNCH(snr_map_kernel, dim3((unsigned)((n_win + SNR_THREADS - 1) / SNR_THREADS), (unsigned)D), SNR_THREADS, smem, st,
            src, w.ctl, (i64)0, n_win, p.fft_len, w.snr_map, w.snr_stride);
     LAUNCH(first_hit_scan_kernel, (unsigned)((D + 3) / 4), 128, 0, st, w.snr_map, w.snr_stride, n_win, p.mv_len, p.th, w.ctl, (int)D);
-    LAUNCH(coarse_chain_kernel, (unsigned)D, 32, 0, st, src, w.ctl, len, p.fft_len, p.th, p.step10, p.step11, p.dr, cap, w.coarse_pos, w.coarse_snr);
+    LAUNCH(coarse_chain_kernel, (unsigned)D, CHAIN_THREADS, 0, st, src, w.ctl, len, p.fft_len, p.th, p.step10, p.step11, p.dr, cap, w.coarse_pos, w.coarse_snr);
     return GSMCAL_OK;
 }
 
 int run_fine_peak(Ctx &c, WinSrc src_peak, i64 n_iq, int osr, i64 D, int cap, Work &w, cudaStream_t st) {
     const double2 *tw; TRY(get_twiddle(c, 148 * osr, st, &tw));
-    LAUNCH(fine_peak_kernel, dim3((unsigned)cap, (unsigned)D), kFineThreads, fine_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw);
+    if (g_debug_force_full) {
+        LAUNCH(fine_peak_full_kernel, dim3((unsigned)cap, (unsigned)D), kFineThreads, fine_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, (const int *)nullptr);
+        return GSMCAL_OK;
+    }
+    CU(cudaMemsetAsync(w.need_full, 0, sizeof(int) * D * cap, st));
+    LAUNCH(fine_peak_band_kernel, dim3((unsigned)cap, (unsigned)D), FB_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, w.need_full);
+    LAUNCH(fine_peak_full_kernel, dim3((unsigned)cap, (unsigned)D), kFineThreads, fine_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, (const int *)w.need_full);
     return GSMCAL_OK;
 }
 int run_fine_rest(Ctx &c, WinSrc src_tone, i64 n_iq, int osr, double carrier_freq, i64 D, int cap, Work &w, cudaStream_t st) {
@@ -298,6 +307,10 @@ void gsmcal_release(void) {
         for (auto &t : kv.second.tw) cudaFree(t.second);
         kv.second.tw.clear();
     }
+}
+int gsmcal_debug_set(int key, int value) {
+    if (key == 0) { g_debug_force_full = value; return GSMCAL_OK; }
+    return fail(GSMCAL_ERR_ARG, "debug_set: unknown key");
 }
 int64_t gsmcal_launch_count(int reset) { long long v = g_launches.load(); if (reset) g_launches = 0; return v; }
 

@@ -81,11 +81,13 @@ __device__ __forceinline__ double stream_mean(u64 sum, i64 n) { return (double)s
 __device__ __forceinline__ double2 fir_from_raw(const uint8_t *__restrict__ raw, i64 i, int n_taps, double mur, double mui) {
     double ar = 0.0, ai = 0.0;
     int kmax = (i < (i64)(n_taps - 1)) ? (int)i : n_taps - 1;
-    const uint8_t *p = raw + 2 * (i - kmax);
-    for (int k = kmax; k >= 0; --k, p += 2) {
-        double h = c_taps[k];
-        ar = fma(h, (double)p[0] - mur, ar);
-        ai = fma(h, (double)p[1] - mui, ai);
+    const uchar2 *p = reinterpret_cast<const uchar2 *>(raw + 2 * (i - kmax));
+#pragma unroll 8
+    for (int k = kmax; k >= 0; --k, ++p) {
+        const double h = c_taps[k];
+        const uchar2 u = *p;
+        ar = fma(h, (double)u.x - mur, ar);
+        ai = fma(h, (double)u.y - mui, ai);
     }
     return make_double2(ar, ai);
 }
@@ -534,27 +536,50 @@ __global__ void __launch_bounds__(256) resample_derotate_kernel(const double2 *_
 // K3  moving-FFT SNR statistic   move_fft_snr_runtime_avg.m:17-28, specific_fft_snr_fix_avg.m:10-20
 // ===================================================================================================
 // SNR of one fft_len-point window held in w[] (fft_len <= 128): direct DFT with an exact twiddle table.
-__device__ double window_snr(const double2 *w, int fft_len, const double2 *tw /* exp(-2*pi*i*j/fft_len) */) {
-    double p[128];
+// FL > 0: compile-time length, powers stay in registers; FL == 0: runtime length.
+template <int FL>
+__device__ double window_snr_t(const double2 *w, int fft_len_rt, const double2 *tw /* exp(-2*pi*i*j/fft_len) */) {
+    const int fft_len = FL > 0 ? FL : fft_len_rt;
+    double p[FL > 0 ? FL : 128];
+    double2 x[FL > 0 ? FL : 1];
+    if (FL > 0) {
+#pragma unroll
+        for (int n = 0; n < FL; ++n) x[n] = w[n];
+    }
     double tot = 0.0, best = -1.0;
     int kbest = 0;
+#pragma unroll
     for (int k = 0; k < fft_len; ++k) {
         double xr = 0.0, xi = 0.0;
-        int idx = 0;
+#pragma unroll
         for (int n = 0; n < fft_len; ++n) {
-            double2 t = tw[idx];
-            xr += w[n].x * t.x - w[n].y * t.y;
-            xi += w[n].x * t.y + w[n].y * t.x;
-            idx += k; if (idx >= fft_len) idx -= fft_len;
+            const double2 t = tw[(k * n) % fft_len];
+            const double2 v = FL > 0 ? x[n] : w[n];
+            xr += v.x * t.x - v.y * t.y;
+            xi += v.x * t.y + v.y * t.x;
         }
         double h = hypot(xr, xi);
         p[k] = h * h;
         tot += p[k];
         if (p[k] > best) { best = p[k]; kbest = k; }             // first maximum
     }
-    double sig = p[(kbest + fft_len - 1) % fft_len] + p[kbest] + p[(kbest + 1) % fft_len];
+    double sig;
+    if (FL > 0) {
+        double pm = 0.0, pp = 0.0;
+#pragma unroll
+        for (int k = 0; k < fft_len; ++k) {
+            if (k == (kbest + fft_len - 1) % fft_len) pm = p[k];
+            if (k == (kbest + 1) % fft_len) pp = p[k];
+        }
+        sig = pm + best + pp;
+    } else {
+        sig = p[(kbest + fft_len - 1) % fft_len] + p[kbest] + p[(kbest + 1) % fft_len];
+    }
     double noise = tot - sig;
     return 10.0 * log10(sig / noise);
+}
+__device__ __forceinline__ double window_snr(const double2 *w, int fft_len, const double2 *tw) {
+    return (fft_len == 16) ? window_snr_t<16>(w, 16, tw) : window_snr_t<0>(w, fft_len, tw);
 }
 
 // SNR of windows [w0, w0+n_win) (0-based window starts) of each stream -> snr[stream][0..n_win)
@@ -622,52 +647,62 @@ __global__ void specific_hit_kernel(const double *__restrict__ snr, i64 n, doubl
 // ===================================================================================================
 // K4  burst chain  FCCH_coarse_position.m:32-91 - one warp per stream, 11 candidate windows per step
 // ===================================================================================================
-__global__ void __launch_bounds__(32) coarse_chain_kernel(WinSrc src, StreamCtl *ctl, i64 len, int fft_len, double th, int step10, int step11,
-                                                          int dr, int cap, double *__restrict__ position, double *__restrict__ snr_out) {
+#define CHAIN_THREADS 64
+__global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src, StreamCtl *ctl, i64 len, int fft_len, double th, int step10, int step11,
+                                                                    int dr, int cap, double *__restrict__ position, double *__restrict__ snr_out) {
+    // Each step evaluates the 11 windows around the 10-frame prediction (:47-58) AND the 11 around the 11-frame
+    // prediction (:65-76) at once; the second set is only consulted when the first has no hit, as in the reference.
     __shared__ double2 tw[128];
-    __shared__ double2 buf[128 + 16];
-    const int stream = blockIdx.x, lane = threadIdx.x;
+    __shared__ double2 buf[2][128 + 16];
+    __shared__ int sh_hit; __shared__ double sh_snr;
+    const int stream = blockIdx.x, tid = threadIdx.x;
     StreamCtl c = ctl[stream];
     double *pos_o = position + (i64)stream * cap;
     double *snr_o = snr_out + (i64)stream * cap;
     if (c.first_hit < 0) {
-        if (lane == 0) ctl[stream].n_coarse = -1;
+        if (tid == 0) ctl[stream].n_coarse = -1;
         return;
     }
-    for (int j = lane; j < fft_len; j += 32) {
+    for (int j = tid; j < fft_len; j += CHAIN_THREADS) {
         double sn, cs; sincospi(-2.0 * (double)j / (double)fft_len, &sn, &cs);
         tw[j] = make_double2(cs, sn);
     }
     const int max_offset = 5;
+    const int n_cand = 2 * max_offset + 1;
     const i64 limit = (len - (fft_len - 1)) - max_offset;
+    const int ns = 2 * max_offset + fft_len;
     i64 pos = c.first_hit;
     int count = 1;
-    if (lane == 0) { pos_o[0] = (double)((pos - 1) * dr + 1); snr_o[0] = c.hit_snr; }
+    if (tid == 0) { pos_o[0] = (double)((pos - 1) * dr + 1); snr_o[0] = c.hit_snr; }
     while (count < cap) {
-        bool found = false;
-        for (int attempt = 0; attempt < 2 && !found; ++attempt) {
-            i64 next = pos + (attempt == 0 ? step10 : step11);
-            if (next > limit) { attempt = 2; break; }
-            const i64 first = next - max_offset;                 // 1-based window start
-            const int ns = 2 * max_offset + fft_len;
-            __syncwarp();
-            for (int i = lane; i < ns; i += 32) buf[i] = coarse_sample(src, c, stream, first - 1 + i);
-            __syncwarp();
-            double v = 0.0; bool h = false;
-            if (lane <= 2 * max_offset) { v = window_snr(buf + lane, fft_len, tw); h = (v - c.hit_avg_snr) > th; }
-            unsigned mask = __ballot_sync(0xffffffffu, h);
-            if (mask) {
-                int l = __ffs(mask) - 1;
-                double hv = __shfl_sync(0xffffffffu, v, l);
-                pos = first + l;
-                if (lane == 0) { pos_o[count] = (double)((pos - 1) * dr + 1); snr_o[count] = hv; }
-                ++count;
-                found = true;
-            }
+        const i64 nextA = pos + step10, nextB = pos + step11;
+        if (nextA > limit) break;                                // run out of sampled signal (:49-51)
+        const bool b_ok = nextB <= limit;                        // (:67-69)
+        __syncthreads();
+        for (int i = tid; i < 2 * ns; i += CHAIN_THREADS) {
+            const int g = i / ns, r = i % ns;
+            if (g == 0 || b_ok) buf[g][r] = coarse_sample(src, c, stream, (g == 0 ? nextA : nextB) - max_offset - 1 + r);
         }
-        if (!found) break;
+        __syncthreads();
+        if (tid < 32) {
+            double v = 0.0; bool h = false;
+            const int g = tid / n_cand, r = tid % n_cand;
+            if (tid < 2 * n_cand && (g == 0 || b_ok)) { v = window_snr(buf[g] + r, fft_len, tw); h = (v - c.hit_avg_snr) > th; }
+            const unsigned mask = __ballot_sync(0xffffffffu, h);
+            const unsigned mA = mask & ((1u << n_cand) - 1), mB = (mask >> n_cand) & ((1u << n_cand) - 1);
+            int l = -1;
+            if (mA) l = __ffs(mA) - 1; else if (mB) l = n_cand + __ffs(mB) - 1;
+            const double hv = __shfl_sync(0xffffffffu, v, l < 0 ? 0 : l);
+            if (tid == 0) { sh_hit = l; sh_snr = hv; }
+        }
+        __syncthreads();
+        const int l = sh_hit;
+        if (l < 0) break;
+        pos = (l < n_cand) ? nextA - max_offset + l : nextB - max_offset + (l - n_cand);
+        if (tid == 0) { pos_o[count] = (double)((pos - 1) * dr + 1); snr_o[count] = sh_snr; }
+        ++count;
     }
-    if (lane == 0) ctl[stream].n_coarse = count;
+    if (tid == 0) ctl[stream].n_coarse = count;
 }
 
 // ===================================================================================================
@@ -679,9 +714,9 @@ __global__ void __launch_bounds__(32) coarse_chain_kernel(WinSrc src, StreamCtl 
 // then takes the first-maximum over bins.  (max_m max_k == max_k max_m, and the first window attaining the
 // global maximum is the same either way, so no per-window reduction is needed.)
 #define FP_BPT 4
-__global__ void __launch_bounds__(320) fine_peak_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ base_pos, int cap,
-                                                        int osr, i64 len_s_ov, const double2 *__restrict__ tw /* exp(-2*pi*i*j/N) */,
-                                                        double *__restrict__ fine_raw) {
+__global__ void __launch_bounds__(320) fine_peak_full_kernel(WinSrc src, StreamCtl *__restrict__ ctl, const double *__restrict__ base_pos, int cap,
+                                                             int osr, i64 len_s_ov, const double2 *__restrict__ tw /* exp(-2*pi*i*j/N) */,
+                                                             double *__restrict__ fine_raw, const int *__restrict__ need_full) {
     extern __shared__ double2 sm[];
     __shared__ double red_v[16];
     __shared__ int red_i[16];
@@ -699,6 +734,8 @@ __global__ void __launch_bounds__(320) fine_peak_kernel(WinSrc src, const Stream
         if (threadIdx.x == 0) *o = INFINITY;
         return;
     }
+    if (need_full && !need_full[(i64)stream * cap + burst]) return;   // the band-limited search already certified this burst
+    if (need_full && threadIdx.x == 0) atomicOr(&ctl[stream].flags, 32);
     const i64 sp = (position - max_offset - 1) * osr + 1;     // 1-based
     double2 *win = sm;
     double2 *X = win + n_smp;
@@ -761,6 +798,134 @@ __global__ void __launch_bounds__(320) fine_peak_kernel(WinSrc src, const Stream
     if (threadIdx.x == 0) *o = (double)(sp + mi);              // sp + max_idx - 1, max_idx = mi + 1
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K5, fast path: the same argmax from a 64-bin band around the FCCH tone, with a proof that no other bin
+// can matter.  For every window m the reference takes max_k |X_m[k]|^2 over ALL N bins; here
+//   * the band S = [k0-48, k0+16) (k0 from a phase-slope estimate of the centre window; the GMSK data
+//     energy sits ~37 bins below the tone, hence the asymmetry) is tracked exactly by the sliding DFT,
+//   * every 16th window c is "certified": by Parseval sum_{k not in S} |X_c[k]|^2 = N*E_c - sum_{k in S} |X_c[k]|^2
+//     =: R_c bounds every out-of-band bin, and since |X_{m+1}[k]| <= |X_m[k]| + |s[m]| + |s[m+N]| the bound
+//     sqrt(R_c) + sum_{i=c}^{c+14} (|s[i]|+|s[i+N]|) holds for windows c..c+15.
+// If that bound squared stays below the best in-band power G for all windows, no out-of-band bin reaches G,
+// so the first window attaining the maximum - the reference's answer - is the in-band one.  Otherwise the
+// burst is flagged and fine_peak_full_kernel recomputes it over all bins.  Work drops ~18x.
+#define FB_BINS 64
+#define FB_SEGS 4
+#define FB_THREADS (FB_BINS * FB_SEGS)
+#define FB_LO 48
+#define FB_CERT 16
+__global__ void __launch_bounds__(FB_THREADS) fine_peak_band_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ base_pos, int cap,
+                                                                   int osr, i64 len_s_ov, const double2 *__restrict__ tw, double *__restrict__ fine_raw,
+                                                                   int *__restrict__ need_full) {
+    extern __shared__ double2 sm[];
+    __shared__ double red_v[8];
+    __shared__ int red_i[8];
+    __shared__ double part[2 * (8 * 128 / FB_CERT + 2)];
+    __shared__ double scan_e[8], scan_a[8];
+    const int burst = blockIdx.x, stream = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const StreamCtl c = ctl[stream];
+    if (c.n_coarse < 5 || burst >= c.n_coarse) return;
+    const int N = 148 * osr;
+    const int max_offset = 64;
+    const int n_win = 2 * max_offset * osr + 1;
+    const int n_smp = n_win + N - 1;
+    const i64 len_s = len_s_ov / osr;
+    const i64 position = (i64)base_pos[(i64)stream * cap + burst];
+    double *o = fine_raw + (i64)stream * cap + burst;
+    if (position + max_offset > len_s - 148 + 1) {            // run out of sampled signal (:35-38)
+        if (tid == 0) *o = INFINITY;
+        return;
+    }
+    const i64 sp = (position - max_offset - 1) * osr + 1;
+    double2 *win = sm;
+    double2 *X = win + n_smp;
+    load_window(src, c, stream, sp - 1, n_smp, win, X, X);      // level 0: only the staging scratch X is used
+    // ---- prefix sums of |s|^2 and |s| (window energies E_m and the triangle-inequality slack) ----
+    double *PE = reinterpret_cast<double *>(X), *PA = PE + (n_smp + 1);
+    {
+        const int per = (n_smp + FB_THREADS - 1) / FB_THREADS;
+        const int a = tid * per, b = (a + per < n_smp) ? a + per : n_smp;
+        double se = 0.0, sa = 0.0;
+        for (int n = a; n < b; ++n) { const double2 v = win[n]; const double e = v.x * v.x + v.y * v.y; se += e; sa += sqrt(e); }
+        double ie = se, ia = sa;                                // inclusive warp scan
+        for (int d = 1; d < 32; d <<= 1) {
+            const double te = __shfl_up_sync(0xffffffffu, ie, d), ta = __shfl_up_sync(0xffffffffu, ia, d);
+            if (lane >= d) { ie += te; ia += ta; }
+        }
+        if (lane == 31) { scan_e[warp] = ie; scan_a[warp] = ia; }
+        __syncthreads();
+        double oe = ie - se, oa = ia - sa;
+        for (int w2 = 0; w2 < warp; ++w2) { oe += scan_e[w2]; oa += scan_a[w2]; }
+        __syncthreads();                                        // X (staging) is dead, PE/PA may overwrite it
+        for (int n = a; n < b; ++n) {
+            PE[n] = oe; PA[n] = oa;
+            const double2 v = win[n]; const double e = v.x * v.x + v.y * v.y; oe += e; oa += sqrt(e);
+        }
+        if (b == n_smp && a < b) { PE[n_smp] = oe; PA[n_smp] = oa; }
+    }
+    // ---- band centre from the phase slope of the centre window ----
+    const int mc = (n_win - 1) / 2;
+    double pr = 0.0, pi_ = 0.0;
+    for (int n = mc + tid; n < mc + N - 1; n += FB_THREADS) {
+        const double2 q = cmulc(win[n + 1], win[n]);
+        pr += q.x; pi_ += q.y;
+    }
+    pr = block_sum(pr, red_v);
+    pi_ = block_sum(pi_, red_v);
+    int k0 = (int)floor(atan2(pi_, pr) * (double)N / (2.0 * GSMCAL_PI) + 0.5);
+    // ---- sliding DFT of the band: thread = (segment of windows, bin) ----
+    const int seg = tid / FB_BINS, j = tid % FB_BINS;
+    int k = (k0 - FB_LO + j) % N; if (k < 0) k += N;
+    const int q = (n_win - 1) / FB_SEGS;
+    const int m0 = seg * q, m_end = (seg == FB_SEGS - 1) ? n_win : m0 + q;
+    double xr = 0.0, xi = 0.0;
+    {
+        int idx = 0;
+        const double2 *w0 = win + m0;
+        for (int n = 0; n < N; ++n) {
+            const double2 s = w0[n], t = tw[idx];
+            xr = fma(s.x, t.x, fma(-s.y, t.y, xr));
+            xi = fma(s.x, t.y, fma(s.y, t.x, xi));
+            idx += k; if (idx >= N) idx -= N;
+        }
+    }
+    const double2 wk = tw[k];
+    const double wr = wk.x, wi = -wk.y;                          // exp(+2*pi*i*k/N)
+    double best = -1.0; int bestm = 0;
+    for (int m = m0; m < m_end; ++m) {
+        const double p = fma(xr, xr, xi * xi);
+        if (p > best) { best = p; bestm = m; }
+        if ((m % FB_CERT) == 0) {
+            double s = p;
+            for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+            if (lane == 0) part[2 * (m / FB_CERT) + (warp & 1)] = s;
+        }
+        if (m + 1 < m_end) {
+            const double2 s_old = win[m], s_new = win[m + N];
+            const double tr = xr + (s_new.x - s_old.x), ti = xi + (s_new.y - s_old.y);
+            xr = fma(tr, wr, -(ti * wi));
+            xi = fma(tr, wi, ti * wr);
+        }
+    }
+    block_argmax(best, bestm, red_v, red_i);                     // also orders the part[] writes before the reads below
+    const int n_cert = (n_win - 1) / FB_CERT + 1;
+    int ok = 1;
+    if (tid < n_cert) {
+        const int cw = tid * FB_CERT;
+        const double sum_s = part[2 * tid] + part[2 * tid + 1];
+        const double R = (double)N * (PE[cw + N] - PE[cw]) - sum_s;
+        int span = n_win - cw; if (span > FB_CERT) span = FB_CERT;
+        const double A = (PA[cw + span - 1] - PA[cw]) + (PA[cw + N + span - 1] - PA[cw + N]);
+        const double bound = sqrt(R > 0.0 ? R : 0.0) + A;
+        ok = (bound * bound < best * (1.0 - 1e-6)) ? 1 : 0;
+    }
+    ok = __syncthreads_and(ok);
+    if (tid == 0) {
+        *o = (double)(sp + bestm);
+        need_full[(i64)stream * cap + burst] = ok ? 0 : 1;
+    }
+}
+
 // ===================================================================================================
 // N = 37 * M point DFT of a shared-memory vector (M = 4*osr): two direct stages, exact twiddle table.
 //   X[k1 + 37*k2] = sum_{n2<M} W_N^{n2*k1} W_M^{n2*k2} sum_{n1<37} x[M*n1+n2] W_37^{n1*k1}
@@ -797,16 +962,81 @@ __device__ void dft_37xM(const double2 *in, double2 *tmp, double2 *out, int N, c
 }
 
 // ===================================================================================================
+// N = M * 37 point DFT, second factorisation (n = 37*n1 + n2, k = k1 + M*k2):
+//   X[k1 + M*k2] = sum_{n2<37} W_37^{n2*k2} * T[n2][k1],   T[n2][k1] = W_N^{n2*k1} * FFT_M(x[37*n1+n2])[k1]
+// fft_rows computes T (37 M-point FFTs, Stockham radix-2 when M is a power of two); dft_col then yields any
+// single bin in 37 MACs, so a stage that needs few bins (band around the tone, the SNR-gate bins) never pays
+// for all N.
+// ===================================================================================================
+__device__ double2 *fft_rows(const double2 *in, double2 *a, double2 *b, int N, const double2 *__restrict__ tw) {
+    const int M = N / 37, T = blockDim.x, tid = threadIdx.x;
+    double2 *src = a, *dst = b;
+    if ((M & (M - 1)) == 0) {
+        for (int i = tid; i < N; i += T) { const int n2 = i / M, n1 = i % M; src[i] = in[37 * n1 + n2]; }
+        __syncthreads();
+        const int half = M / 2;
+        for (int Ns = 1; Ns < M; Ns <<= 1) {
+            const int tstep = N / (2 * Ns);
+            for (int i = tid; i < 37 * half; i += T) {
+                const int row = i / half, j = i % half, k = j & (Ns - 1);
+                const double2 x0 = src[row * M + j];
+                const double2 x1 = cmul(src[row * M + j + half], tw[k * tstep]);
+                const int o = row * M + ((j - k) << 1) + k;
+                dst[o] = make_double2(x0.x + x1.x, x0.y + x1.y);
+                dst[o + Ns] = make_double2(x0.x - x1.x, x0.y - x1.y);
+            }
+            __syncthreads();
+            double2 *t = src; src = dst; dst = t;
+        }
+    } else {                                                  // generic M: direct row DFTs
+        for (int i = tid; i < N; i += T) {
+            const int n2 = i / M, k1 = i % M;
+            double ar = 0.0, ai = 0.0;
+            int t = 0; const int stp = (37 * k1) % N;
+            for (int n1 = 0; n1 < M; ++n1) {
+                const double2 x = in[37 * n1 + n2], w = tw[t];
+                ar = fma(x.x, w.x, fma(-x.y, w.y, ar));
+                ai = fma(x.x, w.y, fma(x.y, w.x, ai));
+                t += stp; if (t >= N) t -= N;
+            }
+            dst[i] = make_double2(ar, ai);
+        }
+        __syncthreads();
+        double2 *t = src; src = dst; dst = t;
+    }
+    for (int i = tid; i < N; i += T) { const int n2 = i / M, k1 = i % M; src[i] = cmul(src[i], tw[(n2 * k1) % N]); }
+    __syncthreads();
+    return src;
+}
+__device__ __forceinline__ double2 dft_col(const double2 *Tm, int k, int N, const double2 *__restrict__ tw) {
+    const int M = N / 37, k1 = k % M, k2 = k / M;
+    double ar = 0.0, ai = 0.0;
+    int t = 0; const int stp = (M * k2) % N;
+    for (int n2 = 0; n2 < 37; ++n2) {
+        const double2 x = Tm[n2 * M + k1], w = tw[t];
+        ar = fma(x.x, w.x, fma(-x.y, w.y, ar));
+        ai = fma(x.x, w.y, fma(x.y, w.x, ai));
+        t += stp; if (t >= N) t -= N;
+    }
+    return make_double2(ar, ai);
+}
+
+// ===================================================================================================
 // K8  per-burst tone frequency (+ SNR gate)   FCCH_fine_correction.m:143-155,185-189; carrier_correct_post_SCH.m:58-72
 // ===================================================================================================
+// The integer bin is the first maximum of the fftshift-ed power spectrum (:148-150).  It is found from a 16-bin
+// band around a phase-slope estimate and accepted only if Parseval proves every other bin smaller
+// (N*sum|u|^2 - sum_band P < max_band P); otherwise all N bins are evaluated.
 #define TONE_THREADS 256
+#define TONE_BAND 16
 __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, int which /* 1: fine stage, 2: post-SCH */,
                                                                const double *__restrict__ pos, int cap, int osr, const double2 *__restrict__ tw,
                                                                double *__restrict__ fo_out, double *__restrict__ gate_out) {
     extern __shared__ double2 sm[];
     __shared__ double red_v[8];
     __shared__ int red_i[8];
-    const int burst = blockIdx.x, stream = blockIdx.y;
+    __shared__ double2 step_sh;
+    const int burst = blockIdx.x, stream = blockIdx.y, tid = threadIdx.x;
     const StreamCtl c = ctl[stream];
     const int nb = (which == 1) ? (c.tone1_enable ? c.n_fcch : 0) : (c.post_enable ? c.n_post_fcch : 0);
     if (burst >= nb) return;
@@ -816,27 +1046,46 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
     double2 *X = F + N, *Y = X + N + GSMCAL_MAX_TAPS + 8;
     const i64 sp = (i64)pos[(i64)stream * cap + burst];
     load_window(src, c, stream, sp - 1, N, u, X, Y);
-    dft_37xM(u, A, F, N, tw);
-    // fftshift ordering then first max (:149-150): shifted index j <-> bin (j + N/2) mod N
-    double v = -1.0; int j_best = 0x7fffffff;
-    for (int j = threadIdx.x; j < N; j += TONE_THREADS) {
-        int k = j + N / 2; if (k >= N) k -= N;
-        argmax_combine(v, j_best, abs2_ref(F[k]), j);
+    // energy and phase slope -> band centre
+    double e = 0.0, pr = 0.0, pi_ = 0.0;
+    for (int n = tid; n < N; n += TONE_THREADS) {
+        const double2 v = u[n];
+        e = fma(v.x, v.x, fma(v.y, v.y, e));
+        if (n + 1 < N) { const double2 q = cmulc(u[n + 1], v); pr += q.x; pi_ += q.y; }
     }
+    e = block_sum(e, red_v); pr = block_sum(pr, red_v); pi_ = block_sum(pi_, red_v);
+    const int k0 = (int)floor(atan2(pi_, pr) * (double)N / (2.0 * GSMCAL_PI) + 0.5);
+    const double2 *Tm = fft_rows(u, A, F, N, tw);
+    // band search, shifted index j <-> bin (j + N/2) mod N; first maximum in j order (:149-150)
+    double v = -1.0; int j_best = 0x7fffffff; double band_sum = 0.0;
+    if (tid < TONE_BAND) {
+        int k = (k0 - TONE_BAND / 2 + tid) % N; if (k < 0) k += N;
+        int j = k - N / 2; if (j < 0) j += N;
+        v = abs2_ref(dft_col(Tm, k, N, tw)); j_best = j; band_sum = v;
+    }
+    band_sum = block_sum(band_sum, red_v);
     block_argmax(v, j_best, red_v, red_i);
-    const double int_phase_rotate = 2.0 * GSMCAL_PI * (double)(j_best + 1 - ((N / 2) + 1)) / (double)N;
-    // integer-bin derotation, unit phasors (:152-153)
-    for (int n = threadIdx.x; n < N; n += TONE_THREADS) {
-        double sn, cs; sincos((double)n * int_phase_rotate, &sn, &cs);
-        double2 w = cmul(u[n], make_double2(cs, -sn));
+    if (!((double)N * e - band_sum < v * (1.0 - 1e-9))) {     // not certified: every bin (uniform branch)
+        v = -1.0; j_best = 0x7fffffff;
+        for (int j = tid; j < N; j += TONE_THREADS) {
+            int k = j + N / 2; if (k >= N) k -= N;
+            argmax_combine(v, j_best, abs2_ref(dft_col(Tm, k, N, tw)), j);
+        }
+        block_argmax(v, j_best, red_v, red_i);
+    }
+    const int jr = j_best + 1 - ((N / 2) + 1);                 // max_idx - (fft_len/2 + 1)
+    const double int_phase_rotate = 2.0 * GSMCAL_PI * (double)jr / (double)N;
+    // integer-bin derotation exp(-1i*n*int_phase_rotate) == twiddle table entry (n*jr mod N); unit phasors (:152-153)
+    int jm = jr % N; if (jm < 0) jm += N;
+    for (int n = tid; n < N; n += TONE_THREADS) {
+        const double2 w = cmul(u[n], tw[(int)(((i64)n * jm) % N)]);
         u[n] = w;
-        double ang = atan2(w.y, w.x);
-        sincos(ang, &sn, &cs);
-        A[n] = make_double2(cs, sn);
+        const double h = hypot(w.x, w.y);
+        A[n] = (h > 0.0) ? make_double2(w.x / h, w.y / h) : make_double2(1.0, 0.0);
     }
     __syncthreads();
     double rr = 0.0, ri = 0.0;
-    for (int n = threadIdx.x; n < N - 1; n += TONE_THREADS) {
+    for (int n = tid; n < N - 1; n += TONE_THREADS) {
         const double2 a = A[n + 1], b = A[n];
         const double den = b.x * b.x + b.y * b.y;
         rr += (a.x * b.x + a.y * b.y) / den;
@@ -846,26 +1095,29 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
     ri = block_sum(ri, red_v);
     const double phase_rotate = atan2(ri / (double)(N - 1), rr / (double)(N - 1));
     const double fo = sampling_rate * (int_phase_rotate + phase_rotate) / (2 * GSMCAL_PI);
-    if (threadIdx.x == 0) fo_out[(i64)stream * cap + burst] = fo;
+    if (tid == 0) fo_out[(i64)stream * cap + burst] = fo;
     if (which != 1) return;
-    // SNR gate (:185-189): fine derotation, spectrum, bins [1:3,end-1:end] vs [4:hnl, end-hnl+1:end-2]
-    for (int n = threadIdx.x; n < N; n += TONE_THREADS) {
-        double sn, cs; sincos((double)n * phase_rotate, &sn, &cs);
-        u[n] = cmul(u[n], make_double2(cs, -sn));
+    // SNR gate (:185-189): fine derotation, then only the bins the gate reads: [1:3,end-1:end] vs [4:hnl, end-hnl+1:end-2]
+    if (tid == 0) { double sn, cs; sincos((double)TONE_THREADS * phase_rotate, &sn, &cs); step_sh = make_double2(cs, -sn); }
+    __syncthreads();
+    {
+        double sn, cs; sincos((double)tid * phase_rotate, &sn, &cs);
+        double2 ph = make_double2(cs, -sn);
+        const double2 st = step_sh;
+        for (int n = tid; n < N; n += TONE_THREADS) { u[n] = cmul(u[n], ph); ph = cmul(ph, st); }
     }
     __syncthreads();
-    dft_37xM(u, A, F, N, tw);
+    Tm = fft_rows(u, A, F, N, tw);
     const int hnl = (int)ceil(((double)N * 200e3 / sampling_rate) / 2.0);
     double sig = 0.0, noise = 0.0;
-    for (int k = threadIdx.x; k < N; k += TONE_THREADS) {
-        const bool is_sig = (k < 3) || (k >= N - 2);
-        const bool is_noise = (k >= 3 && k < hnl) || (k >= N - hnl && k < N - 2);
-        if (is_sig) sig += abs2_ref(F[k]);
-        else if (is_noise) noise += abs2_ref(F[k]);
+    for (int i = tid; i < 2 * hnl; i += TONE_THREADS) {
+        const int k = (i < hnl) ? i : N - 2 * hnl + i;           // 0..hnl-1 and N-hnl..N-1
+        const double p = abs2_ref(dft_col(Tm, k, N, tw));
+        if (k < 3 || k >= N - 2) sig += p; else noise += p;
     }
     sig = block_sum(sig, red_v);
     noise = block_sum(noise, red_v);
-    if (threadIdx.x == 0) gate_out[(i64)stream * cap + burst] = 10.0 * log10(sig / noise);
+    if (tid == 0) gate_out[(i64)stream * cap + burst] = 10.0 * log10(sig / noise);
 }
 
 // ===================================================================================================

@@ -327,3 +327,21 @@ def test_device_resident_batch_equals_host_batch(gpu, captures, coef47, tpl):
     b = gpu.calibrate_batch(raw[:2], CARRIER, tpl, coef47)
     for x, y in zip(a, b):
         assert np.array_equal(x["pos_info"], y["pos_info"]) and x["total_carrier_ppm"] == y["total_carrier_ppm"]
+
+
+def test_band_limited_fine_search_equals_all_bin_search(gpu, captures, coef47, tpl):
+    """The certified 64-bin sliding DFT must return exactly what the all-bin search returns (it falls back when unsure)."""
+    from gsmcal._lib import lib
+    _, raw = captures
+    fast = gpu.calibrate_batch(raw, CARRIER, tpl, coef47)
+    lib().gsmcal_debug_set(0, 1)
+    try:
+        full = gpu.calibrate_batch(raw, CARRIER, tpl, coef47)
+    finally:
+        lib().gsmcal_debug_set(0, 0)
+    n_fallback = 0
+    for a, b in zip(fast, full):
+        assert np.array_equal(a["fcch_pos"], b["fcch_pos"]) and np.array_equal(a["pos_info"], b["pos_info"])
+        assert a["sampling_ppm"] == b["sampling_ppm"]
+        n_fallback += 1 if (a["flags"] & 32) else 0
+    assert n_fallback <= 1, "the band certificate should hold for clean captures"
