@@ -236,6 +236,7 @@ def main():
     torch.cuda.profiler.stop()
     clocks = sampler.stop()
     launches = gsmcal.launch_count()
+    n_fallback = int(lib().gsmcal_debug_get(1))
     ms = ev0.elapsed_time(ev1)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -321,7 +322,8 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "stage_ms": stage_ms,
-                "streams_fully_calibrated": f"{n_ok}/{D} on rank 0"}
+                "streams_fully_calibrated": f"{n_ok}/{D} on rank 0",
+                "fine_search_allbin_fallback_bursts": n_fallback}
         if stages is not None:
             line["stage_rooflines"] = stages
         print(json.dumps(line), flush=True)

@@ -170,6 +170,8 @@ int gsmcal_fcch_scan(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t n_ch
 
 /* test hook: key 0, value 1 = run the all-bin fine FCCH search for every burst (no band-limited fast path) */
 int gsmcal_debug_set(int key, int value);
+/* key 1: number of bursts of the last fine FCCH search whose band certificate failed (all-bin fallback ran) */
+int64_t gsmcal_debug_get(int key);
 
 /* kernel-launch counter (all launches since the last reset, this process) - for bench.py's gpu_launches */
 int64_t gsmcal_launch_count(int reset);

@@ -23,6 +23,7 @@ std::mutex g_mu;
 thread_local std::string g_err;
 thread_local int g_device = 0;
 std::atomic<long long> g_launches{0};
+int *g_last_need_full = nullptr; long long g_last_need_full_n = 0;
 int g_debug_force_full = 0;       // tests: run the all-bin fine search for every burst
 
 int fail(int code, const char *fmt, ...) {
@@ -90,10 +91,18 @@ int ensure_device() {
 }
 
 constexpr int kFineThreads = 320;
-size_t fine_smem(int osr) { int N = 148 * osr, ns = 2 * 64 * osr + 1 + N - 1; return (size_t)(3 * ns + GSMCAL_MAX_TAPS + 16) * sizeof(double2); }
-size_t fine_band_smem(int osr) { int N = 148 * osr, ns = 2 * 64 * osr + 1 + N - 1; return (size_t)(2 * ns + GSMCAL_MAX_TAPS + 16) * sizeof(double2); }
-size_t tone_smem(int osr) { int N = 148 * osr; return (size_t)(5 * N + GSMCAL_MAX_TAPS + 16) * sizeof(double2); }
-size_t sch_smem(int osr) { int L = 64 * osr, ns = 16 * osr - 5 * osr + 1 + L - 1; return (size_t)(3 * ns + L + GSMCAL_MAX_TAPS + 16) * sizeof(double2); }
+size_t fine_smem(int osr) { int N = 148 * osr, ns = 2 * 64 * osr + 1 + N - 1; return (size_t)(2 * ns + 8 + GSMCAL_XCAP(ns)) * sizeof(double2); }
+size_t fine_band_smem(int osr) {
+    int N = 148 * osr, ns = 2 * 64 * osr + 1 + N - 1, x = GSMCAL_XCAP((ns + 2) / 3);
+    if (x < 8 * FB_BINS) x = 8 * FB_BINS;                     // the piece sums reuse the staging scratch
+    return (size_t)(ns + x) * sizeof(double2);
+}
+size_t tone_smem(int osr) {
+    int N = 148 * osr, work = GSMCAL_XCAP(N) + N + 8;
+    if (work < 2 * N) work = 2 * N;
+    return (size_t)(N + work) * sizeof(double2);
+}
+size_t sch_smem(int osr) { int L = 64 * osr, ns = 16 * osr - 5 * osr + 1 + L - 1; return (size_t)(2 * ns + L + 8 + GSMCAL_XCAP(ns)) * sizeof(double2); }
 
 int get_ctx(Ctx **out) {
     TRY(ensure_device());
@@ -210,11 +219,12 @@ int run_coarse(WinSrc src, i64 len, const CoarseParams &p, i64 D, int cap, Work 
 
 int run_fine_peak(Ctx &c, WinSrc src_peak, i64 n_iq, int osr, i64 D, int cap, Work &w, cudaStream_t st) {
     const double2 *tw; TRY(get_twiddle(c, 148 * osr, st, &tw));
-    if (g_debug_force_full) {
+    if (g_debug_force_full || (osr % 4) != 0) {      // the band kernel's 16-sample certificate grid needs osr % 4 == 0
         LAUNCH(fine_peak_full_kernel, dim3((unsigned)cap, (unsigned)D), kFineThreads, fine_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, (const int *)nullptr);
         return GSMCAL_OK;
     }
     CU(cudaMemsetAsync(w.need_full, 0, sizeof(int) * D * cap, st));
+    g_last_need_full = w.need_full; g_last_need_full_n = (long long)D * cap;
     LAUNCH(fine_peak_band_kernel, dim3((unsigned)cap, (unsigned)D), FB_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, w.need_full);
     LAUNCH(fine_peak_full_kernel, dim3((unsigned)cap, (unsigned)D), kFineThreads, fine_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, (const int *)w.need_full);
     return GSMCAL_OK;
@@ -307,6 +317,19 @@ void gsmcal_release(void) {
         for (auto &t : kv.second.tw) cudaFree(t.second);
         kv.second.tw.clear();
     }
+}
+int64_t gsmcal_debug_get(int key) {
+    // key 1: bursts of the last fine search (this device) that needed the all-bin fallback
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (key == 1) {
+        if (!g_last_need_full || g_last_need_full_n <= 0) return 0;
+        std::vector<int> h((size_t)g_last_need_full_n);
+        if (cudaMemcpy(h.data(), g_last_need_full, sizeof(int) * h.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        int64_t n = 0;
+        for (int v : h) n += (v != 0);
+        return n;
+    }
+    return -1;
 }
 int gsmcal_debug_set(int key, int value) {
     if (key == 0) { g_debug_force_full = value; return GSMCAL_OK; }

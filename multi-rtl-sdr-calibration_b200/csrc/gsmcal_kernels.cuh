@@ -59,6 +59,11 @@ struct WinSrc {
     int            dec;         // decimation applied on top (coarse stage: osr*dr), else 1
 };
 
+// capacity (double2) of load_window's scratch X for a window of `count` samples; the staged capture is stored with one
+// pad slot per 4 samples so that each thread's 4-consecutive-output FIR reads are bank-conflict free
+#define GSMCAL_XCAP(count) ((((count) + GSMCAL_MAX_TAPS + 8) * 5) / 4 + 4)
+__host__ __device__ __forceinline__ int xpad(int i) { return i + (i >> 2); }
+
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -94,7 +99,7 @@ __device__ __forceinline__ double2 fir_from_raw(const uint8_t *__restrict__ raw,
 
 // ---------------------------------------------------------------------------------------------------
 // block-cooperative window loader: dst[0..count) = samples [start, start+count) (0-based) of the stream
-// the stage works on.  X, Y: scratch of (count + GSMCAL_MAX_TAPS + 8) and (count + 8) double2.
+// the stage works on.  X, Y: scratch of GSMCAL_XCAP(count) and (count + 8) double2.
 // Lazy levels restate, per sample, FCCH_fine_correction.m:123-125 (interp1), :165 (derotation) and
 // SCH_corr_rate_correction.m:126-127 (second interp1) on top of raw2iq + filter.
 // ---------------------------------------------------------------------------------------------------
@@ -157,19 +162,27 @@ __device__ void load_window(const WinSrc &src, const StreamCtl &c, int stream, i
             uchar2 u = *reinterpret_cast<const uchar2 *>(raw + 2 * j);
             v = make_double2((double)u.x - mur, (double)u.y - mui);
         }
-        X[i] = v;
+        X[xpad(i)] = v;
     }
     __syncthreads();
+    // FIR, 4 consecutive outputs per thread from a sliding register window of taps (oldest input first, as
+    // direct-form-II-transposed nests the sum); every staged sample is read once per 4 outputs
     double2 *l0 = (use1 || use2) ? Y : dst;
-    for (int i = tid; i < n_l0; i += nt) {
-        double ar = 0.0, ai = 0.0;
-        for (int k = nt1; k >= 0; --k) {
-            double h = c_taps[k];
-            double2 x = X[i + nt1 - k];
-            ar = fma(h, x.x, ar);
-            ai = fma(h, x.y, ai);
+    const int n_grp = (n_l0 + 3) >> 2;
+    for (int gi = tid; gi < n_grp; gi += nt) {
+        double ar[4] = {0.0, 0.0, 0.0, 0.0}, ai[4] = {0.0, 0.0, 0.0, 0.0};
+        double hw[4] = {c_taps[nt1], 0.0, 0.0, 0.0};
+        const int base = 4 * gi;
+        for (int kk = 0; kk <= nt1 + 3; ++kk) {
+            const int ii = base + kk;
+            const double2 x = (ii < n_raw) ? X[xpad(ii)] : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { ar[r] = fma(hw[r], x.x, ar[r]); ai[r] = fma(hw[r], x.y, ai[r]); }
+            hw[3] = hw[2]; hw[2] = hw[1]; hw[1] = hw[0];
+            hw[0] = (nt1 - kk - 1 >= 0) ? c_taps[nt1 - kk - 1] : 0.0;
         }
-        l0[i] = make_double2(ar, ai);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) if (base + r < n_l0) l0[base + r] = make_double2(ar[r], ai[r]);
     }
     __syncthreads();
     if (!use1 && !use2) {
@@ -739,7 +752,7 @@ __global__ void __launch_bounds__(320) fine_peak_full_kernel(WinSrc src, StreamC
     const i64 sp = (position - max_offset - 1) * osr + 1;     // 1-based
     double2 *win = sm;
     double2 *X = win + n_smp;
-    double2 *Y = X + n_smp + GSMCAL_MAX_TAPS + 8;
+    double2 *Y = X + GSMCAL_XCAP(n_smp);
     load_window(src, c, stream, sp - 1, n_smp, win, X, Y);
 
     double xr[FP_BPT], xi[FP_BPT], wr[FP_BPT], wi[FP_BPT], best[FP_BPT];
@@ -821,7 +834,7 @@ __global__ void __launch_bounds__(FB_THREADS) fine_peak_band_kernel(WinSrc src, 
     __shared__ double red_v[8];
     __shared__ int red_i[8];
     __shared__ double part[2 * (8 * 128 / FB_CERT + 2)];
-    __shared__ double scan_e[8], scan_a[8];
+    __shared__ double pe16[8 * 148 * 2 / FB_CERT + 12], pa16[8 * 148 * 2 / FB_CERT + 12], pa15[8 * 148 * 2 / FB_CERT + 12];
     const int burst = blockIdx.x, stream = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const StreamCtl c = ctl[stream];
     if (c.n_coarse < 5 || burst >= c.n_coarse) return;
@@ -839,70 +852,101 @@ __global__ void __launch_bounds__(FB_THREADS) fine_peak_band_kernel(WinSrc src, 
     const i64 sp = (position - max_offset - 1) * osr + 1;
     double2 *win = sm;
     double2 *X = win + n_smp;
-    load_window(src, c, stream, sp - 1, n_smp, win, X, X);      // level 0: only the staging scratch X is used
-    // ---- prefix sums of |s|^2 and |s| (window energies E_m and the triangle-inequality slack) ----
-    double *PE = reinterpret_cast<double *>(X), *PA = PE + (n_smp + 1);
-    {
-        const int per = (n_smp + FB_THREADS - 1) / FB_THREADS;
-        const int a = tid * per, b = (a + per < n_smp) ? a + per : n_smp;
-        double se = 0.0, sa = 0.0;
-        for (int n = a; n < b; ++n) { const double2 v = win[n]; const double e = v.x * v.x + v.y * v.y; se += e; sa += sqrt(e); }
-        double ie = se, ia = sa;                                // inclusive warp scan
-        for (int d = 1; d < 32; d <<= 1) {
-            const double te = __shfl_up_sync(0xffffffffu, ie, d), ta = __shfl_up_sync(0xffffffffu, ia, d);
-            if (lane >= d) { ie += te; ia += ta; }
+    {   // level 0: only the staging scratch X is used; three passes keep it small (4 blocks per SM)
+        const int part_n = (n_smp + 2) / 3;
+        for (int off = 0; off < n_smp; off += part_n)
+            load_window(src, c, stream, sp - 1 + off, (n_smp - off < part_n) ? n_smp - off : part_n, win + off, X, X);
+    }
+    // ---- energy / magnitude sums per 16-sample chunk, prefix over chunks (N and the certified windows are multiples of 16) ----
+    const int n_chunk = n_smp / FB_CERT;                        // 138 at osr 8 (n_smp = 16*138)
+    if (tid < n_chunk) {
+        double se = 0.0, sa = 0.0, sa15 = 0.0;
+        for (int i = 0; i < FB_CERT; ++i) {
+            const double2 v = win[tid * FB_CERT + i];
+            const double e = v.x * v.x + v.y * v.y;
+            se += e;
+            const double a = sqrt(e);
+            sa += a; if (i < FB_CERT - 1) sa15 += a;
         }
-        if (lane == 31) { scan_e[warp] = ie; scan_a[warp] = ia; }
-        __syncthreads();
-        double oe = ie - se, oa = ia - sa;
-        for (int w2 = 0; w2 < warp; ++w2) { oe += scan_e[w2]; oa += scan_a[w2]; }
-        __syncthreads();                                        // X (staging) is dead, PE/PA may overwrite it
-        for (int n = a; n < b; ++n) {
-            PE[n] = oe; PA[n] = oa;
-            const double2 v = win[n]; const double e = v.x * v.x + v.y * v.y; oe += e; oa += sqrt(e);
-        }
-        if (b == n_smp && a < b) { PE[n_smp] = oe; PA[n_smp] = oa; }
+        pe16[tid + 1] = se; pa16[tid + 1] = sa; pa15[tid] = sa15;
+    }
+    __syncthreads();
+    if (tid == 0) {                                             // pe16[i] = sum_{n<16i}|s|^2, pa16 likewise, pa15[i] = sum_{n<16i+15}|s|
+        pe16[0] = 0.0; pa16[0] = 0.0;
+        for (int i = 1; i <= n_chunk; ++i) { pe16[i] += pe16[i - 1]; pa16[i] += pa16[i - 1]; }
+        for (int i = 0; i < n_chunk; ++i) pa15[i] += pa16[i];
     }
     // ---- band centre from the phase slope of the centre window ----
     const int mc = (n_win - 1) / 2;
     double pr = 0.0, pi_ = 0.0;
     for (int n = mc + tid; n < mc + N - 1; n += FB_THREADS) {
-        const double2 q = cmulc(win[n + 1], win[n]);
-        pr += q.x; pi_ += q.y;
+        const double2 q2 = cmulc(win[n + 1], win[n]);
+        pr += q2.x; pi_ += q2.y;
     }
     pr = block_sum(pr, red_v);
     pi_ = block_sum(pi_, red_v);
-    int k0 = (int)floor(atan2(pi_, pr) * (double)N / (2.0 * GSMCAL_PI) + 0.5);
-    // ---- sliding DFT of the band: thread = (segment of windows, bin) ----
-    const int seg = tid / FB_BINS, j = tid % FB_BINS;
+    const int k0 = (int)floor(atan2(pi_, pr) * (double)N / (2.0 * GSMCAL_PI) + 0.5);
+    // ---- thread = (segment g of windows, bin j).  Segment-start spectra from shared piece sums (absolute phase):
+    //      pieces [0,q) [q,2q) [2q,3q) [3q,4q) [4q,N) [N,N+q) [N+q,N+2q) [N+2q,N+3q); window g*q = pieces g..g+4 ----
+    const int g = tid / FB_BINS, j = tid % FB_BINS;
     int k = (k0 - FB_LO + j) % N; if (k < 0) k += N;
     const int q = (n_win - 1) / FB_SEGS;
-    const int m0 = seg * q, m_end = (seg == FB_SEGS - 1) ? n_win : m0 + q;
-    double xr = 0.0, xi = 0.0;
-    {
-        int idx = 0;
-        const double2 *w0 = win + m0;
-        for (int n = 0; n < N; ++n) {
-            const double2 s = w0[n], t = tw[idx];
-            xr = fma(s.x, t.x, fma(-s.y, t.y, xr));
-            xi = fma(s.x, t.y, fma(s.y, t.x, xi));
-            idx += k; if (idx >= N) idx -= N;
+    const double2 wk = tw[k];                                    // exp(-2*pi*i*k/N)
+    double2 *PS = X;                                             // [8][FB_BINS]
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int pc = g + 4 * half;
+        const int a = (pc <= 4) ? pc * q : N + (pc - 5) * q;
+        const int b = (pc < 4) ? a + q : (pc == 4 ? N : a + q);
+        double ar = 0.0, ai = 0.0, br = 0.0, bi = 0.0;
+        for (int n0 = a; n0 < b; n0 += 32) {
+            double2 t = tw[(int)(((i64)n0 * k) % N)];            // exact re-seed every 32 samples, recurrence in between
+            const int n1 = (n0 + 32 < b) ? n0 + 32 : b;
+            for (int n = n0; n < n1; n += 2) {
+                const double2 s0 = win[n];
+                ar = fma(s0.x, t.x, fma(-s0.y, t.y, ar));
+                ai = fma(s0.x, t.y, fma(s0.y, t.x, ai));
+                t = cmul(t, wk);
+                if (n + 1 < n1) {
+                    const double2 s1 = win[n + 1];
+                    br = fma(s1.x, t.x, fma(-s1.y, t.y, br));
+                    bi = fma(s1.x, t.y, fma(s1.y, t.x, bi));
+                    t = cmul(t, wk);
+                }
+            }
         }
+        PS[pc * FB_BINS + j] = make_double2(ar + br, ai + bi);
     }
-    const double2 wk = tw[k];
+    __syncthreads();
+    const int m0 = g * q, m_end = (g == FB_SEGS - 1) ? n_win : m0 + q;
+    double xr, xi;
+    {
+        double yr = 0.0, yi = 0.0;
+#pragma unroll
+        for (int pc = 0; pc < 5; ++pc) { const double2 v = PS[(g + pc) * FB_BINS + j]; yr += v.x; yi += v.y; }
+        const double2 t = tw[(int)(((i64)m0 * k) % N)];          // X_{m0}[k] = Y_{m0}[k] * exp(+2*pi*i*m0*k/N)
+        xr = yr * t.x + yi * t.y;
+        xi = yi * t.x - yr * t.y;
+    }
+    // ---- d[m] = s[m+N] - s[m] in place (m < 4q <= N, so the sources s[m+N] are never overwritten) ----
+    for (int m = tid; m < n_win - 1; m += FB_THREADS) {
+        const double2 s_old = win[m], s_new = win[m + N];
+        win[m] = make_double2(s_new.x - s_old.x, s_new.y - s_old.y);
+    }
+    __syncthreads();
     const double wr = wk.x, wi = -wk.y;                          // exp(+2*pi*i*k/N)
     double best = -1.0; int bestm = 0;
     for (int m = m0; m < m_end; ++m) {
         const double p = fma(xr, xr, xi * xi);
         if (p > best) { best = p; bestm = m; }
         if ((m % FB_CERT) == 0) {
-            double s = p;
-            for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-            if (lane == 0) part[2 * (m / FB_CERT) + (warp & 1)] = s;
+            double s2 = p;
+            for (int d = 16; d > 0; d >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+            if (lane == 0) part[2 * (m / FB_CERT) + (warp & 1)] = s2;
         }
         if (m + 1 < m_end) {
-            const double2 s_old = win[m], s_new = win[m + N];
-            const double tr = xr + (s_new.x - s_old.x), ti = xi + (s_new.y - s_old.y);
+            const double2 d = win[m];
+            const double tr = xr + d.x, ti = xi + d.y;
             xr = fma(tr, wr, -(ti * wi));
             xi = fma(tr, wi, ti * wr);
         }
@@ -911,11 +955,11 @@ __global__ void __launch_bounds__(FB_THREADS) fine_peak_band_kernel(WinSrc src, 
     const int n_cert = (n_win - 1) / FB_CERT + 1;
     int ok = 1;
     if (tid < n_cert) {
-        const int cw = tid * FB_CERT;
-        const double sum_s = part[2 * tid] + part[2 * tid + 1];
-        const double R = (double)N * (PE[cw + N] - PE[cw]) - sum_s;
-        int span = n_win - cw; if (span > FB_CERT) span = FB_CERT;
-        const double A = (PA[cw + span - 1] - PA[cw]) + (PA[cw + N + span - 1] - PA[cw + N]);
+        const int ci = tid, nc = N / FB_CERT;                    // window c = 16*ci covers samples [16*ci, 16*(ci+nc))
+        const double sum_s = part[2 * ci] + part[2 * ci + 1];
+        const double R = (double)N * (pe16[ci + nc] - pe16[ci]) - sum_s;
+        // windows c..c+15 (only c itself for the last one): slack = sum_{i=c}^{c+14} (|s[i]| + |s[i+N]|)
+        const double A = (ci == n_cert - 1) ? 0.0 : (pa15[ci] - pa16[ci]) + (pa15[ci + nc] - pa16[ci + nc]);
         const double bound = sqrt(R > 0.0 ? R : 0.0) + A;
         ok = (bound * bound < best * (1.0 - 1e-6)) ? 1 : 0;
     }
@@ -972,13 +1016,13 @@ __device__ double2 *fft_rows(const double2 *in, double2 *a, double2 *b, int N, c
     const int M = N / 37, T = blockDim.x, tid = threadIdx.x;
     double2 *src = a, *dst = b;
     if ((M & (M - 1)) == 0) {
-        for (int i = tid; i < N; i += T) { const int n2 = i / M, n1 = i % M; src[i] = in[37 * n1 + n2]; }
+        const int lm = 31 - __clz(M), half = M / 2;
+        for (int i = tid; i < N; i += T) { const int n2 = i >> lm, n1 = i & (M - 1); src[i] = in[37 * n1 + n2]; }
         __syncthreads();
-        const int half = M / 2;
-        for (int Ns = 1; Ns < M; Ns <<= 1) {
-            const int tstep = N / (2 * Ns);
+        int tstep = N / 2;
+        for (int Ns = 1; Ns < M; Ns <<= 1, tstep >>= 1) {
             for (int i = tid; i < 37 * half; i += T) {
-                const int row = i / half, j = i % half, k = j & (Ns - 1);
+                const int row = i >> (lm - 1), j = i & (half - 1), k = j & (Ns - 1);
                 const double2 x0 = src[row * M + j];
                 const double2 x1 = cmul(src[row * M + j + half], tw[k * tstep]);
                 const int o = row * M + ((j - k) << 1) + k;
@@ -1004,14 +1048,15 @@ __device__ double2 *fft_rows(const double2 *in, double2 *a, double2 *b, int N, c
         __syncthreads();
         double2 *t = src; src = dst; dst = t;
     }
-    for (int i = tid; i < N; i += T) { const int n2 = i / M, k1 = i % M; src[i] = cmul(src[i], tw[(n2 * k1) % N]); }
+    for (int i = tid; i < N; i += T) { const int n2 = i / M, k1 = i - n2 * M; src[i] = cmul(src[i], tw[n2 * k1]); }   // n2*k1 < 37*M = N
     __syncthreads();
     return src;
 }
 __device__ __forceinline__ double2 dft_col(const double2 *Tm, int k, int N, const double2 *__restrict__ tw) {
     const int M = N / 37, k1 = k % M, k2 = k / M;
     double ar = 0.0, ai = 0.0;
-    int t = 0; const int stp = (M * k2) % N;
+    int t = 0; const int stp = M * k2;                         // < N
+#pragma unroll 4
     for (int n2 = 0; n2 < 37; ++n2) {
         const double2 x = Tm[n2 * M + k1], w = tw[t];
         ar = fma(x.x, w.x, fma(-x.y, w.y, ar));
@@ -1043,7 +1088,7 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
     const int N = 148 * osr;
     const double sampling_rate = ((1625.0 / 6.0) * 1e3) * (double)osr;
     double2 *u = sm, *A = u + N, *F = A + N;
-    double2 *X = F + N, *Y = X + N + GSMCAL_MAX_TAPS + 8;
+    double2 *X = A, *Y = X + GSMCAL_XCAP(N);                  // the loader's scratch aliases the FFT work buffers
     const i64 sp = (i64)pos[(i64)stream * cap + burst];
     load_window(src, c, stream, sp - 1, N, u, X, Y);
     // energy and phase slope -> band centre
@@ -1077,8 +1122,10 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
     const double int_phase_rotate = 2.0 * GSMCAL_PI * (double)jr / (double)N;
     // integer-bin derotation exp(-1i*n*int_phase_rotate) == twiddle table entry (n*jr mod N); unit phasors (:152-153)
     int jm = jr % N; if (jm < 0) jm += N;
-    for (int n = tid; n < N; n += TONE_THREADS) {
-        const double2 w = cmul(u[n], tw[(int)(((i64)n * jm) % N)]);
+    int tidx = (int)(((i64)tid * jm) % N);
+    const int tinc = (int)(((i64)TONE_THREADS * jm) % N);
+    for (int n = tid; n < N; n += TONE_THREADS, tidx = (tidx + tinc >= N) ? tidx + tinc - N : tidx + tinc) {
+        const double2 w = cmul(u[n], tw[tidx]);
         u[n] = w;
         const double h = hypot(w.x, w.y);
         A[n] = (h > 0.0) ? make_double2(w.x / h, w.y / h) : make_double2(1.0, 0.0);
@@ -1147,7 +1194,7 @@ __global__ void __launch_bounds__(SCH_THREADS) sch_corr_kernel(WinSrc src, const
     const i64 sp = training_sp - max_offset;
     const int n_lag = 2 * max_offset - 5 * osr + 1;            // 89 at osr 8
     const int n_smp = n_lag + L - 1;
-    double2 *win = sm, *t = win + n_smp, *X = t + L, *Y = X + n_smp + GSMCAL_MAX_TAPS + 8;
+    double2 *win = sm, *t = win + n_smp, *X = t + L, *Y = X + GSMCAL_XCAP(n_smp);
     for (int i = threadIdx.x; i < L; i += SCH_THREADS) t[i] = tpl[i];
     load_window(src, c, stream, sp - 1, n_smp, win, X, Y);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = SCH_THREADS >> 5;
