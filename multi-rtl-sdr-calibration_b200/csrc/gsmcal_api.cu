@@ -112,6 +112,11 @@ int get_ctx(Ctx **out) {
         CU(cudaFuncSetAttribute(fine_peak_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(tone_est_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(sch_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CU(cudaFuncSetAttribute(coarse_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CU(cudaFuncSetAttribute(fine_ppm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CU(cudaFuncSetAttribute(fine_carrier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CU(cudaFuncSetAttribute(sch_ppm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CU(cudaFuncSetAttribute(post_carrier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CU(cudaFuncSetAttribute(fir_decim_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CU(cudaFuncSetAttribute(fir_decim_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         c.attrs = true;
@@ -213,7 +218,8 @@ int run_coarse(WinSrc src, i64 len, const CoarseParams &p, i64 D, int cap, Work 
     LAUNCH(snr_map_kernel, dim3((unsigned)((n_win + SNR_THREADS - 1) / SNR_THREADS), (unsigned)D), SNR_THREADS, smem, st,
            src, w.ctl, (i64)0, n_win, p.fft_len, w.snr_map, w.snr_stride);
     LAUNCH(first_hit_scan_kernel, (unsigned)((D + 3) / 4), 128, 0, st, w.snr_map, w.snr_stride, n_win, p.mv_len, p.th, w.ctl, (int)D);
-    LAUNCH(coarse_chain_kernel, (unsigned)D, CHAIN_THREADS, 0, st, src, w.ctl, len, p.fft_len, p.th, p.step10, p.step11, p.dr, cap, w.coarse_pos, w.coarse_snr);
+    size_t chain_smem = src.lazy ? sizeof(double2) * 2 * (CHAIN_MAXSTAGE + CHAIN_MAXSTAGE / 32 + 4) : 0;
+    LAUNCH(coarse_chain_kernel, (unsigned)D, CHAIN_THREADS, chain_smem, st, src, w.ctl, len, p.fft_len, p.th, p.step10, p.step11, p.dr, cap, w.coarse_pos, w.coarse_snr);
     return GSMCAL_OK;
 }
 
@@ -231,9 +237,9 @@ int run_fine_peak(Ctx &c, WinSrc src_peak, i64 n_iq, int osr, i64 D, int cap, Wo
 }
 int run_fine_rest(Ctx &c, WinSrc src_tone, i64 n_iq, int osr, double carrier_freq, i64 D, int cap, Work &w, cudaStream_t st) {
     const double2 *tw; TRY(get_twiddle(c, 148 * osr, st, &tw));
-    LAUNCH(fine_ppm_kernel, (unsigned)((D + 63) / 64), 64, 0, st, w.ctl, (int)D, cap, osr, n_iq, w.fine_raw, w.fcch_pos, w.kind);
+    LAUNCH(fine_ppm_kernel, (unsigned)D, PS_THREADS, (size_t)cap * 17 + 16, st, w.ctl, (int)D, cap, osr, n_iq, w.fine_raw, w.fcch_pos, w.kind);
     LAUNCH(tone_est_kernel, dim3((unsigned)cap, (unsigned)D), TONE_THREADS, tone_smem(osr), st, src_tone, w.ctl, 1, w.fcch_pos, cap, osr, tw, w.fo, w.gate);
-    LAUNCH(fine_carrier_kernel, (unsigned)((D + 63) / 64), 64, 0, st, w.ctl, (int)D, cap, osr, carrier_freq, w.fo, w.gate);
+    LAUNCH(fine_carrier_kernel, (unsigned)D, PS_THREADS, (size_t)cap * 16, st, w.ctl, (int)D, cap, osr, carrier_freq, w.fo, w.gate);
     return GSMCAL_OK;
 }
 
@@ -244,14 +250,14 @@ int run_fine(Ctx &c, WinSrc src_peak, WinSrc src_tone, i64 n_iq, int osr, double
 
 int run_sch(WinSrc src, int osr, i64 D, int cap, Work &w, cudaStream_t st) {
     LAUNCH(sch_corr_kernel, dim3((unsigned)cap, (unsigned)D), SCH_THREADS, sch_smem(osr), st, src, w.ctl, w.fcch_pos, cap, osr, w.tpl, w.sch_raw, w.sch_edge);
-    LAUNCH(sch_ppm_kernel, (unsigned)((D + 63) / 64), 64, 0, st, w.ctl, (int)D, cap, osr, w.sch_raw, w.sch_edge, w.sch_pos, w.kind, w.pos_info, w.post_pos);
+    LAUNCH(sch_ppm_kernel, (unsigned)D, PS_THREADS, (size_t)cap * 21 + 16, st, w.ctl, (int)D, cap, osr, w.sch_raw, w.sch_edge, w.sch_pos, w.kind, w.pos_info, w.post_pos);
     return GSMCAL_OK;
 }
 
 int run_post(Ctx &c, WinSrc src, int osr, double carrier_freq, i64 D, int cap, Work &w, bool want_res, cudaStream_t st) {
     const double2 *tw; TRY(get_twiddle(c, 148 * osr, st, &tw));
     LAUNCH(tone_est_kernel, dim3((unsigned)cap, (unsigned)D), TONE_THREADS, tone_smem(osr), st, src, w.ctl, 2, w.post_pos, cap, osr, tw, w.fo, w.gate);
-    LAUNCH(post_carrier_kernel, (unsigned)((D + 63) / 64), 64, 0, st, w.ctl, (int)D, cap, osr, carrier_freq, w.fo, want_res ? w.res : nullptr);
+    LAUNCH(post_carrier_kernel, (unsigned)D, PS_THREADS, (size_t)cap * 8, st, w.ctl, (int)D, cap, osr, carrier_freq, w.fo, want_res ? w.res : nullptr);
     return GSMCAL_OK;
 }
 

@@ -276,10 +276,10 @@ __device__ double block_sum(double v, double *sv) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     if (lane == 0) sv[w] = v;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int k = 0; k < nw; ++k) t += sv[k];
-        sv[0] = t;
+    if (w == 0) {
+        double t = (lane < nw) ? sv[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) sv[0] = t;
     }
     __syncthreads();
     double r = sv[0];
@@ -618,8 +618,11 @@ __global__ void __launch_bounds__(SNR_THREADS) snr_map_kernel(WinSrc src, const 
     if (threadIdx.x < nw) snr[(i64)stream * snr_stride + b0 + threadIdx.x] = window_snr(buf + threadIdx.x, fft_len, tw);
 }
 
-// sequential first-hit scan, one warp per stream, every lane runs the identical recurrence
-//   move_fft_snr_runtime_avg.m:11-12,30-41 (sum_snr updated as "subtract oldest, add newest", FIFO seeded with 999)
+// sequential first-hit scan, one warp per stream
+//   move_fft_snr_runtime_avg.m:11-12,30-41 (sum_snr updated as "subtract oldest, add newest", FIFO seeded with 999).
+// Until the first hit every window is pushed, so the running sum S_i seen by window i does not depend on any decision:
+// all lanes replay the two-add recurrence for 32 windows (same order of operations as the reference), lane k keeps
+// S_k, and the 32 threshold tests (with their divisions) are then evaluated in parallel; the first set lane wins.
 __global__ void first_hit_scan_kernel(const double *__restrict__ snr, i64 snr_stride, i64 n_win, int mv_len, double th, StreamCtl *ctl, int n_streams) {
     const int stream = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -628,17 +631,25 @@ __global__ void first_hit_scan_kernel(const double *__restrict__ snr, i64 snr_st
     double sum_snr = 999.0 * (double)mv_len;
     int hit = -1; double hit_snr = 0.0, hit_avg = 0.0;
     for (i64 c0 = 0; c0 < n_win && hit < 0; c0 += 32) {
-        i64 i = c0 + lane;
-        double cur = (i < n_win) ? s[i] : 0.0;
-        double old = (i < n_win) ? ((i >= mv_len) ? s[i - mv_len] : 999.0) : 0.0;
-        const int m = (n_win - c0 < 32) ? (int)(n_win - c0) : 32;
-        for (int k = 0; k < m; ++k) {
-            double v = __shfl_sync(0xffffffffu, cur, k);
-            double o = __shfl_sync(0xffffffffu, old, k);
-            double peak_to_avg = v - (sum_snr / (double)mv_len);
-            if (peak_to_avg > th) { hit = (int)(c0 + k) + 1; hit_snr = v; hit_avg = v - peak_to_avg; break; }
+        const i64 i = c0 + lane;
+        const double cur = (i < n_win) ? s[i] : 0.0;
+        const double old = (i < n_win) ? ((i >= mv_len) ? s[i - mv_len] : 999.0) : 0.0;
+        double mine = 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const double v = __shfl_sync(0xffffffffu, cur, k);
+            const double o = __shfl_sync(0xffffffffu, old, k);
+            if (lane == k) mine = sum_snr;
             sum_snr = sum_snr - o;
             sum_snr = sum_snr + v;
+        }
+        const double peak_to_avg = cur - (mine / (double)mv_len);
+        const unsigned mask = __ballot_sync(0xffffffffu, (i < n_win) && (peak_to_avg > th));
+        if (mask) {
+            const int l = __ffs(mask) - 1;
+            hit = (int)(c0 + l) + 1;
+            hit_snr = __shfl_sync(0xffffffffu, cur, l);
+            hit_avg = hit_snr - __shfl_sync(0xffffffffu, peak_to_avg, l);
         }
     }
     if (lane == 0) {
@@ -661,10 +672,14 @@ __global__ void specific_hit_kernel(const double *__restrict__ snr, i64 n, doubl
 // K4  burst chain  FCCH_coarse_position.m:32-91 - one warp per stream, 11 candidate windows per step
 // ===================================================================================================
 #define CHAIN_THREADS 64
+#define CHAIN_MAXSTAGE 2200        // staged DC-removed samples per candidate group (lazy path, dec*(2*5+fft_len-1)+n_taps <= this)
 __global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src, StreamCtl *ctl, i64 len, int fft_len, double th, int step10, int step11,
                                                                     int dr, int cap, double *__restrict__ position, double *__restrict__ snr_out) {
     // Each step evaluates the 11 windows around the 10-frame prediction (:47-58) AND the 11 around the 11-frame
     // prediction (:65-76) at once; the second set is only consulted when the first has no hit, as in the reference.
+    // Lazy source: the uint8 samples both groups need are staged with coalesced loads (one memory latency per step),
+    // then every decimated sample is a FIR over shared memory.
+    extern __shared__ double2 stage[];                           // [2][CHAIN_MAXSTAGE + pad] when src.lazy
     __shared__ double2 tw[128];
     __shared__ double2 buf[2][128 + 16];
     __shared__ int sh_hit; __shared__ double sh_snr;
@@ -684,6 +699,12 @@ __global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src,
     const int n_cand = 2 * max_offset + 1;
     const i64 limit = (len - (fft_len - 1)) - max_offset;
     const int ns = 2 * max_offset + fft_len;
+    const int dec = src.dec, nt1 = src.n_taps - 1;
+    const int n_stage = (ns - 1) * dec + src.n_taps;             // raw samples one group touches
+    const bool can_stage = src.lazy && n_stage <= CHAIN_MAXSTAGE;
+    const int stage_cap = CHAIN_MAXSTAGE + CHAIN_MAXSTAGE / 32 + 4;
+    const uint8_t *raw = src.raw + (i64)stream * 2 * src.n_iq;
+    const double mur = stream_mean(c.sum_i, src.n_iq), mui = stream_mean(c.sum_q, src.n_iq);
     i64 pos = c.first_hit;
     int count = 1;
     if (tid == 0) { pos_o[0] = (double)((pos - 1) * dr + 1); snr_o[0] = c.hit_snr; }
@@ -692,9 +713,68 @@ __global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src,
         if (nextA > limit) break;                                // run out of sampled signal (:49-51)
         const bool b_ok = nextB <= limit;                        // (:67-69)
         __syncthreads();
-        for (int i = tid; i < 2 * ns; i += CHAIN_THREADS) {
-            const int g = i / ns, r = i % ns;
-            if (g == 0 || b_ok) buf[g][r] = coarse_sample(src, c, stream, (g == 0 ? nextA : nextB) - max_offset - 1 + r);
+        // the aligned words must stay inside this stream's row (the first samples of a capture use the scalar path)
+        const i64 lo_raw = (nextA - max_offset - 1) * (i64)dec - nt1, hi_raw = (nextB + max_offset + fft_len) * (i64)dec;
+        const bool staged = can_stage && lo_raw >= 4 && hi_raw + 4 < src.n_iq;
+        if (staged) {
+            // 8-byte aligned loads (4 IQ pairs each), all of a thread's loads for both groups in flight at once:
+            // one memory latency per step instead of one per sample
+            constexpr int MAXW = (CHAIN_MAXSTAGE + 3 + 3) / 4 / CHAIN_THREADS + 1;      // words per thread per group
+            uint2 wv[2][MAXW];
+            i64 r0g[2]; int offg[2], nwg[2];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const i64 d0 = (g == 0 ? nextA : nextB) - max_offset - 1;     // first decimated index (0-based)
+                r0g[g] = d0 * dec - nt1;                                      // first raw sample staged
+                const uintptr_t a = (uintptr_t)(raw + 2 * r0g[g]);
+                offg[g] = (int)((a & 7) >> 1);                                // samples between the aligned word and r0
+                nwg[g] = (g == 0 || b_ok) ? (n_stage + offg[g] + 3) / 4 : 0;
+                const uint2 *wp = reinterpret_cast<const uint2 *>(a & ~(uintptr_t)7);
+#pragma unroll
+                for (int q = 0; q < MAXW; ++q) {
+                    const int wi = tid + q * CHAIN_THREADS;
+                    wv[g][q] = (wi < nwg[g]) ? __ldg(wp + wi) : make_uint2(0u, 0u);
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                double2 *sg = stage + g * stage_cap;
+#pragma unroll
+                for (int q = 0; q < MAXW; ++q) {
+                    const int wi = tid + q * CHAIN_THREADS;
+                    if (wi < nwg[g]) {
+                        const unsigned w2[2] = {wv[g][q].x, wv[g][q].y};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int i = 4 * wi + e - offg[g];
+                            if (i >= 0 && i < n_stage) {
+                                const unsigned pr2 = w2[e >> 1] >> (16 * (e & 1));
+                                sg[i + (i >> 5)] = make_double2((double)(pr2 & 0xffu) - mur, (double)((pr2 >> 8) & 0xffu) - mui);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < 2 * ns; i += CHAIN_THREADS) {
+                const int g = i / ns, r = i % ns;
+                if (g == 1 && !b_ok) continue;
+                const double2 *sg = stage + g * stage_cap;
+                double ar = 0.0, ai = 0.0;
+                const int b0 = r * dec;
+                for (int k = nt1; k >= 0; --k) {                 // oldest tap first
+                    const int idx = b0 + nt1 - k;
+                    const double2 x = sg[idx + (idx >> 5)];
+                    ar = fma(c_taps[k], x.x, ar);
+                    ai = fma(c_taps[k], x.y, ai);
+                }
+                buf[g][r] = make_double2(ar, ai);
+            }
+        } else {
+            for (int i = tid; i < 2 * ns; i += CHAIN_THREADS) {
+                const int g = i / ns, r = i % ns;
+                if (g == 0 || b_ok) buf[g][r] = coarse_sample(src, c, stream, (g == 0 ? nextA : nextB) - max_offset - 1 + r);
+            }
         }
         __syncthreads();
         if (tid < 32) {
@@ -827,14 +907,13 @@ __global__ void __launch_bounds__(320) fine_peak_full_kernel(WinSrc src, StreamC
 #define FB_THREADS (FB_BINS * FB_SEGS)
 #define FB_LO 48
 #define FB_CERT 16
-__global__ void __launch_bounds__(FB_THREADS) fine_peak_band_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ base_pos, int cap,
+__global__ void __launch_bounds__(FB_THREADS, 4) fine_peak_band_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ base_pos, int cap,
                                                                    int osr, i64 len_s_ov, const double2 *__restrict__ tw, double *__restrict__ fine_raw,
                                                                    int *__restrict__ need_full) {
     extern __shared__ double2 sm[];
     __shared__ double red_v[8];
     __shared__ int red_i[8];
     __shared__ double part[2 * (8 * 128 / FB_CERT + 2)];
-    __shared__ double pe16[8 * 148 * 2 / FB_CERT + 12], pa16[8 * 148 * 2 / FB_CERT + 12], pa15[8 * 148 * 2 / FB_CERT + 12];
     const int burst = blockIdx.x, stream = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const StreamCtl c = ctl[stream];
     if (c.n_coarse < 5 || burst >= c.n_coarse) return;
@@ -859,6 +938,7 @@ __global__ void __launch_bounds__(FB_THREADS) fine_peak_band_kernel(WinSrc src, 
     }
     // ---- energy / magnitude sums per 16-sample chunk, prefix over chunks (N and the certified windows are multiples of 16) ----
     const int n_chunk = n_smp / FB_CERT;                        // 138 at osr 8 (n_smp = 16*138)
+    double *pe16 = reinterpret_cast<double *>(X + 8 * FB_BINS), *pa16 = pe16 + n_chunk + 2, *pa15 = pa16 + n_chunk + 2;   // behind the piece sums
     if (tid < n_chunk) {
         double se = 0.0, sa = 0.0, sa15 = 0.0;
         for (int i = 0; i < FB_CERT; ++i) {
@@ -893,29 +973,33 @@ __global__ void __launch_bounds__(FB_THREADS) fine_peak_band_kernel(WinSrc src, 
     const int q = (n_win - 1) / FB_SEGS;
     const double2 wk = tw[k];                                    // exp(-2*pi*i*k/N)
     double2 *PS = X;                                             // [8][FB_BINS]
+    const double2 wk2 = tw[(2 * k) % N], wk3 = tw[(3 * k) % N], wk4 = tw[(4 * k) % N];
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const int pc = g + 4 * half;
         const int a = (pc <= 4) ? pc * q : N + (pc - 5) * q;
         const int b = (pc < 4) ? a + q : (pc == 4 ? N : a + q);
-        double ar = 0.0, ai = 0.0, br = 0.0, bi = 0.0;
+        // sample n+r (r<4) carries W^{(n+r)k} = t * W^{rk}: four accumulators share one twiddle, advanced by W^{4k};
+        // t is re-seeded exactly from the table every 32 samples
+        double a0r = 0.0, a0i = 0.0, a1r = 0.0, a1i = 0.0, a2r = 0.0, a2i = 0.0, a3r = 0.0, a3i = 0.0;
         for (int n0 = a; n0 < b; n0 += 32) {
-            double2 t = tw[(int)(((i64)n0 * k) % N)];            // exact re-seed every 32 samples, recurrence in between
+            double2 t = tw[(int)(((i64)n0 * k) % N)];
             const int n1 = (n0 + 32 < b) ? n0 + 32 : b;
-            for (int n = n0; n < n1; n += 2) {
-                const double2 s0 = win[n];
-                ar = fma(s0.x, t.x, fma(-s0.y, t.y, ar));
-                ai = fma(s0.x, t.y, fma(s0.y, t.x, ai));
-                t = cmul(t, wk);
-                if (n + 1 < n1) {
-                    const double2 s1 = win[n + 1];
-                    br = fma(s1.x, t.x, fma(-s1.y, t.y, br));
-                    bi = fma(s1.x, t.y, fma(s1.y, t.x, bi));
-                    t = cmul(t, wk);
-                }
+            int n = n0;
+            for (; n + 3 < n1; n += 4) {
+                const double2 s0 = win[n], s1 = win[n + 1], s2 = win[n + 2], s3 = win[n + 3];
+                a0r = fma(s0.x, t.x, fma(-s0.y, t.y, a0r)); a0i = fma(s0.x, t.y, fma(s0.y, t.x, a0i));
+                a1r = fma(s1.x, t.x, fma(-s1.y, t.y, a1r)); a1i = fma(s1.x, t.y, fma(s1.y, t.x, a1i));
+                a2r = fma(s2.x, t.x, fma(-s2.y, t.y, a2r)); a2i = fma(s2.x, t.y, fma(s2.y, t.x, a2i));
+                a3r = fma(s3.x, t.x, fma(-s3.y, t.y, a3r)); a3i = fma(s3.x, t.y, fma(s3.y, t.x, a3i));
+                t = cmul(t, wk4);
             }
+            if (n < n1)     { const double2 s0 = win[n];     a0r = fma(s0.x, t.x, fma(-s0.y, t.y, a0r)); a0i = fma(s0.x, t.y, fma(s0.y, t.x, a0i)); }
+            if (n + 1 < n1) { const double2 s1 = win[n + 1]; a1r = fma(s1.x, t.x, fma(-s1.y, t.y, a1r)); a1i = fma(s1.x, t.y, fma(s1.y, t.x, a1i)); }
+            if (n + 2 < n1) { const double2 s2 = win[n + 2]; a2r = fma(s2.x, t.x, fma(-s2.y, t.y, a2r)); a2i = fma(s2.x, t.y, fma(s2.y, t.x, a2i)); }
         }
-        PS[pc * FB_BINS + j] = make_double2(ar + br, ai + bi);
+        const double2 c1 = cmul(make_double2(a1r, a1i), wk), c2 = cmul(make_double2(a2r, a2i), wk2), c3 = cmul(make_double2(a3r, a3i), wk3);
+        PS[pc * FB_BINS + j] = make_double2((a0r + c1.x) + (c2.x + c3.x), (a0i + c1.y) + (c2.y + c3.y));
     }
     __syncthreads();
     const int m0 = g * q, m_end = (g == FB_SEGS - 1) ? n_win : m0 + q;
@@ -1171,6 +1255,8 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
 // K9  SCH training-sequence correlation   SCH_corr_rate_correction.m:37-63
 // ===================================================================================================
 #define SCH_THREADS 256
+#define SCH_LPG 12      // lags per warp
+#define SCH_NSL 16      // template samples per lane
 __global__ void __launch_bounds__(SCH_THREADS) sch_corr_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ fcch_pos, int cap,
                                                               int osr, const double2 *__restrict__ tpl, double *__restrict__ sch_raw, int *__restrict__ sch_edge) {
     extern __shared__ double2 sm[];
@@ -1198,14 +1284,49 @@ __global__ void __launch_bounds__(SCH_THREADS) sch_corr_kernel(WinSrc src, const
     for (int i = threadIdx.x; i < L; i += SCH_THREADS) t[i] = tpl[i];
     load_window(src, c, stream, sp - 1, n_smp, win, X, Y);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = SCH_THREADS >> 5;
-    for (int lag = w; lag < n_lag; lag += nw) {
-        double ar = 0.0, ai = 0.0;
-        for (int n = lane; n < L; n += 32) {
-            const double2 p = cmulc(win[lag + n], t[n]);        // conj(ts) .* window
-            ar += p.x; ai += p.y;
+    if (L == 32 * SCH_NSL && n_lag <= nw * SCH_LPG) {
+        // register-tiled correlation: warp w owns lags [12w, 12w+12), lane owns template samples [16*lane, 16*lane+16);
+        // a 12-deep sliding register window of the burst is advanced one sample per step (2 shared loads per 12 MACs).
+        // Both arrays are re-laid out with one pad slot per 16 samples so the 256-byte lane stride is conflict free.
+        double2 *wp = X, *tp = X + (n_smp + (n_smp >> 4) + 2);      // X and Y are contiguous: 924 + 608 slots >= 640 + 544
+        for (int i = threadIdx.x; i < n_smp; i += SCH_THREADS) wp[i + (i >> 4)] = win[i];
+        for (int i = threadIdx.x; i < L; i += SCH_THREADS) tp[i + (i >> 4)] = t[i];
+        __syncthreads();
+        double ar[SCH_LPG], ai[SCH_LPG];
+        double2 wr_[SCH_LPG];
+#pragma unroll
+        for (int l = 0; l < SCH_LPG; ++l) { ar[l] = 0.0; ai[l] = 0.0; }
+        const int l0 = SCH_LPG * w, nb = SCH_NSL * lane;
+#pragma unroll
+        for (int l = 0; l < SCH_LPG - 1; ++l) { const int i = l0 + nb + l; wr_[l] = (i < n_smp) ? wp[i + (i >> 4)] : make_double2(0.0, 0.0); }
+#pragma unroll
+        for (int n = 0; n < SCH_NSL; ++n) {
+            const int iw = l0 + nb + n + SCH_LPG - 1, it = nb + n;
+            wr_[SCH_LPG - 1] = (iw < n_smp) ? wp[iw + (iw >> 4)] : make_double2(0.0, 0.0);
+            const double2 tt = tp[it + (it >> 4)];
+#pragma unroll
+            for (int l = 0; l < SCH_LPG; ++l) {                  // conj(ts) .* window
+                ar[l] = fma(wr_[l].x, tt.x, fma(wr_[l].y, tt.y, ar[l]));
+                ai[l] = fma(wr_[l].y, tt.x, fma(-wr_[l].x, tt.y, ai[l]));
+            }
+#pragma unroll
+            for (int l = 0; l < SCH_LPG - 1; ++l) wr_[l] = wr_[l + 1];
         }
-        ar = warp_sum(ar); ai = warp_sum(ai);
-        if (lane == 0) corr[lag] = abs2_ref(make_double2(ar, ai));
+#pragma unroll
+        for (int l = 0; l < SCH_LPG; ++l) {
+            const double sr_ = warp_sum(ar[l]), si_ = warp_sum(ai[l]);
+            if (lane == 0 && l0 + l < n_lag) corr[l0 + l] = abs2_ref(make_double2(sr_, si_));
+        }
+    } else {
+        for (int lag = w; lag < n_lag; lag += nw) {              // generic shapes: one warp per lag
+            double ar = 0.0, ai = 0.0;
+            for (int n = lane; n < L; n += 32) {
+                const double2 p = cmulc(win[lag + n], t[n]);      // conj(ts) .* window
+                ar += p.x; ai += p.y;
+            }
+            ar = warp_sum(ar); ai = warp_sum(ai);
+            if (lane == 0) corr[lag] = abs2_ref(make_double2(ar, ai));
+        }
     }
     __syncthreads();
     double v = -1.0; int bi = 0x7fffffff;
@@ -1241,142 +1362,178 @@ __device__ bool classify_spacing(const double *pos, int n, int osr, double max_p
     return (na + nb) == n - 1;
 }
 
-__global__ void fine_ppm_kernel(StreamCtl *ctl, int n_streams, int cap, int osr, i64 n_iq, const double *__restrict__ fine_raw,
-                                double *__restrict__ fcch_pos, unsigned char *__restrict__ kind_scratch) {
-    const int stream = blockIdx.x * blockDim.x + threadIdx.x;
+// The per-stream stages below run as ONE WARP per stream: the lanes stage the stream's small arrays in shared memory
+// with coalesced loads, lane 0 replays the reference's sequential logic on shared memory (global-memory latency was
+// the whole cost of the one-thread-per-stream version), and the lanes write the results back together.
+#define PS_THREADS 32
+__global__ void __launch_bounds__(PS_THREADS) fine_ppm_kernel(StreamCtl *ctl, int n_streams, int cap, int osr, i64 n_iq, const double *__restrict__ fine_raw,
+                                                             double *__restrict__ fcch_pos, unsigned char *__restrict__ kind_scratch) {
+    extern __shared__ double ps_sm[];
+    double *fr = ps_sm, *fp = fr + cap;
+    unsigned char *kind = reinterpret_cast<unsigned char *>(fp + cap);
+    __shared__ StreamCtl cs;
+    const int stream = blockIdx.x, lane = threadIdx.x;
     if (stream >= n_streams) return;
-    StreamCtl c = ctl[stream];
-    const double *fr = fine_raw + (i64)stream * cap;
-    double *fp = fcch_pos + (i64)stream * cap;
-    unsigned char *kind = kind_scratch + (i64)stream * cap;
-    c.n_fcch = -1; c.len1 = -1; c.sppm1 = INFINITY; c.cppm1 = INFINITY; c.interp1_on = 0; c.tone1_enable = 0; c.derot1_on = 0;
-    c.e1 = 0.0; c.dphi1 = 0.0; c.n_fine = 0;
-    const int fft_len = 148 * osr;
-    if (c.n_coarse >= 5) {
-        int last_idx = c.n_coarse;
-        for (int i = 0; i < c.n_coarse; ++i) if (isinf(fr[i])) { last_idx = i; break; }
-        c.n_fine = last_idx;
-        c.n_fcch = last_idx;
-        for (int i = 0; i < last_idx; ++i) fp[i] = fr[i];
-        if (last_idx >= 5) {
-            c.len1 = n_iq;                                        // r = s (:72)
-            double expected, d10, d11;
-            if (!classify_spacing(fr, last_idx, osr, 4000.0, &expected, &d10, &d11, kind)) {
-                c.n_fcch = -1; c.flags |= 1;                      // :95-102
-            } else {
-                const double actual = fr[last_idx - 1] - fr[0];
-                const double e = (actual - expected) / expected;
-                c.e1 = e; c.sppm1 = e * 1e6; c.interp1_on = 1;
-                c.len1 = (e >= 0.0) ? (i64)floor((double)n_iq / (1.0 + e)) : n_iq;
-                const double first = mround((fr[0] - 1.0) / (1.0 + e)) + 1.0;
-                double acc = 1.0;
-                fp[0] = acc + first - 1.0;
-                for (int i = 0; i + 1 < last_idx; ++i) { acc += (kind[i] == 1) ? d11 : d10; fp[i + 1] = acc + first - 1.0; }
-                int n = last_idx;
-                if (fp[n - 1] + fft_len - 1 > (double)c.len1) n -= 1;     // :135-137
-                c.n_fcch = n;
-                c.tone1_enable = (n >= 5);
+    if (lane == 0) cs = ctl[stream];
+    __syncwarp();
+    const int nc = cs.n_coarse;
+    for (int i = lane; i < nc; i += PS_THREADS) fr[i] = fine_raw[(i64)stream * cap + i];
+    __syncwarp();
+    if (lane == 0) {
+        StreamCtl c = cs;
+        c.n_fcch = -1; c.len1 = -1; c.sppm1 = INFINITY; c.cppm1 = INFINITY; c.interp1_on = 0; c.tone1_enable = 0; c.derot1_on = 0;
+        c.e1 = 0.0; c.dphi1 = 0.0; c.n_fine = 0;
+        const int fft_len = 148 * osr;
+        if (c.n_coarse >= 5) {
+            int last_idx = c.n_coarse;
+            for (int i = 0; i < c.n_coarse; ++i) if (isinf(fr[i])) { last_idx = i; break; }
+            c.n_fine = last_idx;
+            c.n_fcch = last_idx;
+            for (int i = 0; i < last_idx; ++i) fp[i] = fr[i];
+            if (last_idx >= 5) {
+                c.len1 = n_iq;                                        // r = s (:72)
+                double expected, d10, d11;
+                if (!classify_spacing(fr, last_idx, osr, 4000.0, &expected, &d10, &d11, kind)) {
+                    c.n_fcch = -1; c.flags |= 1;                      // :95-102
+                } else {
+                    const double actual = fr[last_idx - 1] - fr[0];
+                    const double e = (actual - expected) / expected;
+                    c.e1 = e; c.sppm1 = e * 1e6; c.interp1_on = 1;
+                    c.len1 = (e >= 0.0) ? (i64)floor((double)n_iq / (1.0 + e)) : n_iq;
+                    const double first = mround((fr[0] - 1.0) / (1.0 + e)) + 1.0;
+                    double acc = 1.0;
+                    fp[0] = acc + first - 1.0;
+                    for (int i = 0; i + 1 < last_idx; ++i) { acc += (kind[i] == 1) ? d11 : d10; fp[i + 1] = acc + first - 1.0; }
+                    int n = last_idx;
+                    if (fp[n - 1] + fft_len - 1 > (double)c.len1) n -= 1;     // :135-137
+                    c.n_fcch = n;
+                    c.tone1_enable = (n >= 5);
+                }
             }
         }
+        cs = c;
+        ctl[stream] = c;
     }
-    ctl[stream] = c;
+    __syncwarp();
+    const int n_out = cs.n_fine > cs.n_fcch ? cs.n_fine : cs.n_fcch;
+    for (int i = lane; i < n_out; i += PS_THREADS) fcch_pos[(i64)stream * cap + i] = fp[i];
+    (void)kind_scratch;
 }
 
-__global__ void fine_carrier_kernel(StreamCtl *ctl, int n_streams, int cap, int osr, double carrier_freq, const double *__restrict__ fo, const double *__restrict__ gate) {
-    const int stream = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(PS_THREADS) fine_carrier_kernel(StreamCtl *ctl, int n_streams, int cap, int osr, double carrier_freq, const double *__restrict__ fo,
+                                                                 const double *__restrict__ gate) {
+    extern __shared__ double ps_sm[];
+    double *f = ps_sm, *g = f + cap;
+    const int stream = blockIdx.x, lane = threadIdx.x;
     if (stream >= n_streams) return;
     StreamCtl c = ctl[stream];
     if (c.tone1_enable) {
+        for (int i = lane; i < c.n_fcch; i += PS_THREADS) { f[i] = fo[(i64)stream * cap + i]; g[i] = gate[(i64)stream * cap + i]; }
+        __syncwarp();
+    }
+    if (lane != 0) return;
+    if (c.tone1_enable) {
         const double symbol_rate = (1625.0 / 6.0) * 1e3, sampling_rate = symbol_rate * osr, target = symbol_rate / 4.0;
         double acc = 0.0;
-        for (int i = 0; i < c.n_fcch; ++i) acc += fo[(i64)stream * cap + i];
+        for (int i = 0; i < c.n_fcch; ++i) acc += f[i];
         const double fom = acc / (double)c.n_fcch;
         c.cppm1 = 1e6 * (fom - target) / carrier_freq;
         c.dphi1 = (target - fom) * 2 * GSMCAL_PI / sampling_rate;
         c.derot1_on = 1;
         int low = 0;
-        for (int i = 0; i < c.n_fcch; ++i) low += (gate[(i64)stream * cap + i] < 5.0);
+        for (int i = 0; i < c.n_fcch; ++i) low += (g[i] < 5.0);
         if (low > 0) { c.n_fcch = -1; c.flags |= 2; }             // :192-196
     }
     c.sch_enable = (c.n_fcch >= 5);
     ctl[stream] = c;
 }
 
-__global__ void sch_ppm_kernel(StreamCtl *ctl, int n_streams, int cap, int osr, const double *__restrict__ sch_raw, const int *__restrict__ sch_edge,
-                               double *__restrict__ sch_pos_scratch, unsigned char *__restrict__ kind_scratch, double *__restrict__ pos_info /* [stream][6*cap][2] */,
-                               double *__restrict__ post_pos) {
-    const int stream = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(PS_THREADS) sch_ppm_kernel(StreamCtl *ctl, int n_streams, int cap, int osr, const double *__restrict__ sch_raw, const int *__restrict__ sch_edge,
+                                                            double *__restrict__ sch_pos_scratch, unsigned char *__restrict__ kind_scratch, double *__restrict__ pos_info /* [stream][6*cap][2] */,
+                                                            double *__restrict__ post_pos) {
+    extern __shared__ double ps_sm[];
+    double *sr = ps_sm, *sp_ = sr + cap;
+    int *se = reinterpret_cast<int *>(sp_ + cap);
+    unsigned char *kind = reinterpret_cast<unsigned char *>(se + cap);
+    __shared__ StreamCtl cs;
+    __shared__ int sh_fill;
+    const int stream = blockIdx.x, lane = threadIdx.x;
     if (stream >= n_streams) return;
-    StreamCtl c = ctl[stream];
+    if (lane == 0) { cs = ctl[stream]; sh_fill = 0; }
+    __syncwarp();
     double *pi = pos_info + (i64)stream * 6 * cap * 2;
     double *pp = post_pos + (i64)stream * cap;
-    double *sp_ = sch_pos_scratch + (i64)stream * cap;
-    unsigned char *kind = kind_scratch + (i64)stream * cap;
-    c.n_pos_info = -1; c.len2 = -1; c.sppm2 = INFINITY; c.interp2_on = 0; c.e2 = 0.0; c.n_sch = 0; c.post_enable = 0; c.n_post_fcch = 0;
-    c.cppm2 = INFINITY; c.dphi2 = 0.0; c.len3 = -1;
-    if (c.sch_enable) {
-        const int H = c.n_fcch;
-        const double *sr = sch_raw + (i64)stream * cap;
-        const int *se = sch_edge + (i64)stream * cap;
-        int num_sch = H; bool edge = false;
-        for (int i = 0; i < H; ++i) {
-            if (isinf(sr[i])) { num_sch = i; break; }
-            if (se[i]) { edge = true; break; }
-        }
-        if (edge) {
-            c.flags |= 4;                                         // pos_info = [-1,-1], r = -1 (:59-63)
-        } else {
-            c.n_sch = num_sch;
-            c.n_pos_info = 3 * H;                                 // -1.*ones(3*num_fcch_hit,2) (:32)
-            for (int i = 0; i < 3 * H; ++i) { pi[2 * i] = -1.0; pi[2 * i + 1] = -1.0; }
-            if (num_sch >= 5) {
-                c.len2 = c.len1;                                  // r = s (:87)
-                double expected, d10, d11;
-                if (!classify_spacing(sr, num_sch, osr, 400.0, &expected, &d10, &d11, kind)) {
-                    c.flags |= 8;                                 // :106-112
-                } else {
-                    const double actual = sr[num_sch - 1] - sr[0];
-                    const double e = (actual - expected) / expected;
-                    c.e2 = e; c.sppm2 = e * 1e6;
-                    if (e != 0.0) {
-                        c.interp2_on = 1;
-                        c.len2 = (e > 0.0) ? (i64)floor((double)c.len1 / (1.0 + e)) : c.len1;
-                    }
-                    const double first = mround((sr[0] - 1.0) / (1.0 + e)) + 1.0;
-                    double acc = 1.0;
-                    sp_[0] = acc + first - 1.0;
-                    for (int i = 0; i + 1 < num_sch; ++i) { acc += (kind[i] == 1) ? d11 : d10; sp_[i + 1] = acc + first - 1.0; }
-                    // BCCH_flag (:138-141): 1-based b_idx = i+1 for kind[i]==1; flag(b_idx+1), flag(b_idx-4) if b_idx>=5
-                    // flags are consulted for i = 1..num_sch (1-based) -> reuse kind[] upper bits
-                    const int slot_ov = (625 * osr) / 4, frame_ov = slot_ov * 8;
-                    const double fix_off = (double)(frame_ov + 42 * osr), pre_ov = (double)(42 * osr);
-                    const double len_r = (double)c.len2;
-                    int row = 0, n_f = 0, n_b = 0;
-                    for (int i = 0; i < num_sch; ++i) {           // i 0-based; 1-based index i+1
-                        // flag(i+1) set if (b_idx+1 == i+1 -> kind[i-1]==1) or (b_idx-4 == i+1, b_idx>=5 -> kind[i+4]==1)
-                        bool flag = (i >= 1 && kind[i - 1] == 1) || (i + 4 < num_sch - 1 && kind[i + 4] == 1);
-                        pi[2 * row] = sp_[i] - fix_off; pi[2 * row + 1] = 0.0; pp[n_f++] = sp_[i] - fix_off; ++row;
-                        const double s0 = sp_[i] - pre_ov;
-                        if (s0 + slot_ov - 1 <= len_r) { pi[2 * row] = s0; pi[2 * row + 1] = 1.0; ++row; } else break;
-                        if (flag) {
-                            bool runout = false;
-                            for (int k = 1; k <= 4; ++k) {
-                                const double b0 = s0 + (double)k * frame_ov;
-                                if (b0 + slot_ov - 1 <= len_r) { pi[2 * row] = b0; pi[2 * row + 1] = 2.0; ++row; ++n_b; }
-                                else { runout = true; break; }
-                            }
-                            if (runout) break;
+    const int H = cs.sch_enable ? cs.n_fcch : 0;
+    for (int i = lane; i < H; i += PS_THREADS) { sr[i] = sch_raw[(i64)stream * cap + i]; se[i] = sch_edge[(i64)stream * cap + i]; }
+    __syncwarp();
+    if (lane == 0) {
+        StreamCtl c = cs;
+        c.n_pos_info = -1; c.len2 = -1; c.sppm2 = INFINITY; c.interp2_on = 0; c.e2 = 0.0; c.n_sch = 0; c.post_enable = 0; c.n_post_fcch = 0;
+        c.cppm2 = INFINITY; c.dphi2 = 0.0; c.len3 = -1;
+        if (c.sch_enable) {
+            int num_sch = H; bool edge = false;
+            for (int i = 0; i < H; ++i) {
+                if (isinf(sr[i])) { num_sch = i; break; }
+                if (se[i]) { edge = true; break; }
+            }
+            if (edge) {
+                c.flags |= 4;                                         // pos_info = [-1,-1], r = -1 (:59-63)
+            } else {
+                c.n_sch = num_sch;
+                c.n_pos_info = 3 * H;                                 // -1.*ones(3*num_fcch_hit,2) (:32)
+                sh_fill = 3 * H;
+                if (num_sch >= 5) {
+                    c.len2 = c.len1;                                  // r = s (:87)
+                    double expected, d10, d11;
+                    if (!classify_spacing(sr, num_sch, osr, 400.0, &expected, &d10, &d11, kind)) {
+                        c.flags |= 8;                                 // :106-112
+                    } else {
+                        const double actual = sr[num_sch - 1] - sr[0];
+                        const double e = (actual - expected) / expected;
+                        c.e2 = e; c.sppm2 = e * 1e6;
+                        if (e != 0.0) {
+                            c.interp2_on = 1;
+                            c.len2 = (e > 0.0) ? (i64)floor((double)c.len1 / (1.0 + e)) : c.len1;
                         }
+                        const double first = mround((sr[0] - 1.0) / (1.0 + e)) + 1.0;
+                        double acc = 1.0;
+                        sp_[0] = acc + first - 1.0;
+                        for (int i = 0; i + 1 < num_sch; ++i) { acc += (kind[i] == 1) ? d11 : d10; sp_[i + 1] = acc + first - 1.0; }
+                        // BCCH_flag (:138-141), 1-based: flag(b_idx+1) and flag(b_idx-4) for b_idx>=5, b_idx = 11-frame gaps
+                        const int slot_ov = (625 * osr) / 4, frame_ov = slot_ov * 8;
+                        const double fix_off = (double)(frame_ov + 42 * osr), pre_ov = (double)(42 * osr);
+                        const double len_r = (double)c.len2;
+                        int row = 0, n_f = 0, n_b = 0;
+                        sh_fill = 0;                                  // rows are written explicitly below
+                        for (int i = 0; i < num_sch; ++i) {
+                            const bool flag = (i >= 1 && kind[i - 1] == 1) || (i + 4 < num_sch - 1 && kind[i + 4] == 1);
+                            pi[2 * row] = sp_[i] - fix_off; pi[2 * row + 1] = 0.0; pp[n_f++] = sp_[i] - fix_off; ++row;
+                            const double s0 = sp_[i] - pre_ov;
+                            if (s0 + slot_ov - 1 <= len_r) { pi[2 * row] = s0; pi[2 * row + 1] = 1.0; ++row; } else break;
+                            if (flag) {
+                                bool runout = false;
+                                for (int k = 1; k <= 4; ++k) {
+                                    const double b0 = s0 + (double)k * frame_ov;
+                                    if (b0 + slot_ov - 1 <= len_r) { pi[2 * row] = b0; pi[2 * row + 1] = 2.0; ++row; ++n_b; }
+                                    else { runout = true; break; }
+                                }
+                                if (runout) break;
+                            }
+                        }
+                        c.n_pos_info = row;
+                        c.n_post_fcch = n_f;
+                        // carrier_correct_post_SCH.m:10-19: all -1 cannot happen here; needs >= 4 BCCH rows
+                        if (n_b >= 4) { c.post_enable = 1; c.len3 = c.len2; } else c.flags |= 16;
                     }
-                    c.n_pos_info = row;
-                    c.n_post_fcch = n_f;
-                    // carrier_correct_post_SCH.m:10-19: all -1 cannot happen here; needs >= 4 BCCH rows
-                    if (n_b >= 4) { c.post_enable = 1; c.len3 = c.len2; } else c.flags |= 16;
                 }
             }
         }
+        ctl[stream] = c;
     }
-    ctl[stream] = c;
+    __syncwarp();
+    const int fill = sh_fill;                                         // the -1 sentinel matrix (:32), written by all lanes
+    for (int i = lane; i < 2 * fill; i += PS_THREADS) pi[i] = -1.0;
+    (void)sch_pos_scratch; (void)kind_scratch;
 }
 
 __device__ __forceinline__ double total_ppm2(double a, double b) {     // total_ppm_calculation.m:5-21
@@ -1393,14 +1550,20 @@ struct StreamResultDev {            // mirrors gsmcal_stream_result (include/gsm
     double sampling_ppm[2], carrier_ppm[2], total_sampling_ppm, total_carrier_ppm;
 };
 
-__global__ void post_carrier_kernel(StreamCtl *ctl, int n_streams, int cap, int osr, double carrier_freq, const double *__restrict__ fo, StreamResultDev *res) {
-    const int stream = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(PS_THREADS) post_carrier_kernel(StreamCtl *ctl, int n_streams, int cap, int osr, double carrier_freq, const double *__restrict__ fo, StreamResultDev *res) {
+    extern __shared__ double ps_sm[];
+    const int stream = blockIdx.x, lane = threadIdx.x;
     if (stream >= n_streams) return;
     StreamCtl c = ctl[stream];
     if (c.post_enable) {
+        for (int i = lane; i < c.n_post_fcch; i += PS_THREADS) ps_sm[i] = fo[(i64)stream * cap + i];
+        __syncwarp();
+    }
+    if (lane != 0) return;
+    if (c.post_enable) {
         const double symbol_rate = (1625.0 / 6.0) * 1e3, sampling_rate = symbol_rate * osr, target = symbol_rate / 4.0;
         double acc = 0.0;
-        for (int i = 0; i < c.n_post_fcch; ++i) acc += fo[(i64)stream * cap + i];
+        for (int i = 0; i < c.n_post_fcch; ++i) acc += ps_sm[i];
         const double fom = acc / (double)c.n_post_fcch;
         c.cppm2 = 1e6 * (fom - target) / carrier_freq;
         c.dphi2 = (target - fom) * 2 * GSMCAL_PI / sampling_rate;
