@@ -237,6 +237,7 @@ def main():
     clocks = sampler.stop()
     launches = gsmcal.launch_count()
     n_fallback = int(lib().gsmcal_debug_get(1))
+    n_tier2 = int(lib().gsmcal_debug_get(2))
     ms = ev0.elapsed_time(ev1)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -323,7 +324,7 @@ def main():
                 "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "stage_ms": stage_ms,
                 "streams_fully_calibrated": f"{n_ok}/{D} on rank 0",
-                "fine_search_allbin_fallback_bursts": n_fallback}
+                "fine_search_allbin_fallback_bursts": n_fallback, "fine_search_64bin_tier2_bursts": n_tier2}
         if stages is not None:
             line["stage_rooflines"] = stages
         print(json.dumps(line), flush=True)

@@ -23,7 +23,7 @@ std::mutex g_mu;
 thread_local std::string g_err;
 thread_local int g_device = 0;
 std::atomic<long long> g_launches{0};
-int *g_last_need_full = nullptr; long long g_last_need_full_n = 0;
+int *g_last_need_full = nullptr, *g_last_need_band = nullptr; long long g_last_need_full_n = 0;
 int g_debug_force_full = 0;       // tests: run the all-bin fine search for every burst
 
 int fail(int code, const char *fmt, ...) {
@@ -110,6 +110,7 @@ int get_ctx(Ctx **out) {
     if (!c.attrs) {
         CU(cudaFuncSetAttribute(fine_peak_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(fine_peak_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(cudaFuncSetAttribute(fine_peak_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(tone_est_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(sch_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CU(cudaFuncSetAttribute(coarse_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -151,7 +152,7 @@ int set_taps(const double *coef, int n_taps, cudaStream_t st) {
 struct Work {
     StreamCtl *ctl; StreamResultDev *res;
     double *coarse_pos, *coarse_snr, *fine_raw, *fcch_pos, *fo, *gate, *sch_raw, *sch_pos, *post_pos, *pos_info, *snr_map, *power;
-    int *sch_edge, *need_full; unsigned char *kind; double2 *tpl;
+    int *sch_edge, *need_full, *need_band; unsigned char *kind; double2 *tpl;
     i64 snr_stride;
 };
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -163,7 +164,7 @@ int make_work(Ctx &c, i64 D, int cap, i64 snr_len, int tpl_len, Work *w) {
     size_t per = sizeof(double) * D * cap;
     size_t o_cp = take(per), o_cs = take(per), o_fr = take(per), o_fp = take(per), o_fo = take(per), o_g = take(per), o_sr = take(per), o_sp = take(per), o_pp = take(per);
     size_t o_pi = take(per * 12), o_snr = take(sizeof(double) * D * snr_len), o_pw = take(sizeof(double) * D);
-    size_t o_se = take(sizeof(int) * D * cap), o_nf = take(sizeof(int) * D * cap), o_k = take(D * cap), o_tpl = take(sizeof(double2) * (tpl_len > 0 ? tpl_len : 1));
+    size_t o_se = take(sizeof(int) * D * cap), o_nf = take(sizeof(int) * D * cap), o_nb = take(sizeof(int) * D * cap), o_k = take(D * cap), o_tpl = take(sizeof(double2) * (tpl_len > 0 ? tpl_len : 1));
     void *base;
     TRY(c.work.get(off, &base));
     char *b = static_cast<char *>(base);
@@ -171,7 +172,7 @@ int make_work(Ctx &c, i64 D, int cap, i64 snr_len, int tpl_len, Work *w) {
     w->coarse_pos = (double *)(b + o_cp); w->coarse_snr = (double *)(b + o_cs); w->fine_raw = (double *)(b + o_fr); w->fcch_pos = (double *)(b + o_fp);
     w->fo = (double *)(b + o_fo); w->gate = (double *)(b + o_g); w->sch_raw = (double *)(b + o_sr); w->sch_pos = (double *)(b + o_sp); w->post_pos = (double *)(b + o_pp);
     w->pos_info = (double *)(b + o_pi); w->snr_map = (double *)(b + o_snr); w->power = (double *)(b + o_pw);
-    w->sch_edge = (int *)(b + o_se); w->need_full = (int *)(b + o_nf); w->kind = (unsigned char *)(b + o_k); w->tpl = (double2 *)(b + o_tpl);
+    w->sch_edge = (int *)(b + o_se); w->need_full = (int *)(b + o_nf); w->need_band = (int *)(b + o_nb); w->kind = (unsigned char *)(b + o_k); w->tpl = (double2 *)(b + o_tpl);
     w->snr_stride = snr_len;
     return GSMCAL_OK;
 }
@@ -230,8 +231,10 @@ int run_fine_peak(Ctx &c, WinSrc src_peak, i64 n_iq, int osr, i64 D, int cap, Wo
         return GSMCAL_OK;
     }
     CU(cudaMemsetAsync(w.need_full, 0, sizeof(int) * D * cap, st));
-    g_last_need_full = w.need_full; g_last_need_full_n = (long long)D * cap;
-    LAUNCH(fine_peak_band_kernel, dim3((unsigned)cap, (unsigned)D), FB_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, w.need_full);
+    g_last_need_full = w.need_full; g_last_need_band = w.need_band; g_last_need_full_n = (long long)D * cap;
+    CU(cudaMemsetAsync(w.need_band, 0, sizeof(int) * D * cap, st));
+    LAUNCH(fine_peak_core_kernel, dim3((unsigned)cap, (unsigned)D), FC_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, w.need_band);
+    LAUNCH(fine_peak_band_kernel, dim3((unsigned)cap, (unsigned)D), FB_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, (const int *)w.need_band, w.need_full);
     LAUNCH(fine_peak_full_kernel, dim3((unsigned)cap, (unsigned)D), kFineThreads, fine_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, (const int *)w.need_full);
     return GSMCAL_OK;
 }
@@ -327,10 +330,11 @@ void gsmcal_release(void) {
 int64_t gsmcal_debug_get(int key) {
     // key 1: bursts of the last fine search (this device) that needed the all-bin fallback
     std::lock_guard<std::mutex> lk(g_mu);
-    if (key == 1) {
-        if (!g_last_need_full || g_last_need_full_n <= 0) return 0;
+    if (key == 1 || key == 2) {
+        const int *src = (key == 1) ? g_last_need_full : g_last_need_band;
+        if (!src || g_last_need_full_n <= 0) return 0;
         std::vector<int> h((size_t)g_last_need_full_n);
-        if (cudaMemcpy(h.data(), g_last_need_full, sizeof(int) * h.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        if (cudaMemcpy(h.data(), src, sizeof(int) * h.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
         int64_t n = 0;
         for (int v : h) n += (v != 0);
         return n;

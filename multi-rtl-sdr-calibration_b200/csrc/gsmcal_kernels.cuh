@@ -59,10 +59,9 @@ struct WinSrc {
     int            dec;         // decimation applied on top (coarse stage: osr*dr), else 1
 };
 
-// capacity (double2) of load_window's scratch X for a window of `count` samples; the staged capture is stored with one
-// pad slot per 4 samples so that each thread's 4-consecutive-output FIR reads are bank-conflict free
-#define GSMCAL_XCAP(count) ((((count) + GSMCAL_MAX_TAPS + 8) * 5) / 4 + 4)
-__host__ __device__ __forceinline__ int xpad(int i) { return i + (i >> 2); }
+// capacity (double2) of load_window's scratch X for a window of `count` samples
+#define GSMCAL_XCAP(count) ((count) + GSMCAL_MAX_TAPS + 8)
+__host__ __device__ __forceinline__ int xpad(int i) { return i; }   // 3 outputs per thread: 48-byte lane stride is conflict free as is
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -165,24 +164,24 @@ __device__ void load_window(const WinSrc &src, const StreamCtl &c, int stream, i
         X[xpad(i)] = v;
     }
     __syncthreads();
-    // FIR, 4 consecutive outputs per thread from a sliding register window of taps (oldest input first, as
-    // direct-form-II-transposed nests the sum); every staged sample is read once per 4 outputs
+    // FIR, 3 consecutive outputs per thread from a sliding register window of taps (oldest input first, as
+    // direct-form-II-transposed nests the sum); every staged sample is read once per 3 outputs
     double2 *l0 = (use1 || use2) ? Y : dst;
-    const int n_grp = (n_l0 + 3) >> 2;
+    const int n_grp = (n_l0 + 2) / 3;
     for (int gi = tid; gi < n_grp; gi += nt) {
-        double ar[4] = {0.0, 0.0, 0.0, 0.0}, ai[4] = {0.0, 0.0, 0.0, 0.0};
-        double hw[4] = {c_taps[nt1], 0.0, 0.0, 0.0};
-        const int base = 4 * gi;
-        for (int kk = 0; kk <= nt1 + 3; ++kk) {
+        double ar[3] = {0.0, 0.0, 0.0}, ai[3] = {0.0, 0.0, 0.0};
+        double hw[3] = {c_taps[nt1], 0.0, 0.0};
+        const int base = 3 * gi;
+        for (int kk = 0; kk <= nt1 + 2; ++kk) {
             const int ii = base + kk;
             const double2 x = (ii < n_raw) ? X[xpad(ii)] : make_double2(0.0, 0.0);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) { ar[r] = fma(hw[r], x.x, ar[r]); ai[r] = fma(hw[r], x.y, ai[r]); }
-            hw[3] = hw[2]; hw[2] = hw[1]; hw[1] = hw[0];
+            for (int r = 0; r < 3; ++r) { ar[r] = fma(hw[r], x.x, ar[r]); ai[r] = fma(hw[r], x.y, ai[r]); }
+            hw[2] = hw[1]; hw[1] = hw[0];
             hw[0] = (nt1 - kk - 1 >= 0) ? c_taps[nt1 - kk - 1] : 0.0;
         }
 #pragma unroll
-        for (int r = 0; r < 4; ++r) if (base + r < n_l0) l0[base + r] = make_double2(ar[r], ai[r]);
+        for (int r = 0; r < 3; ++r) if (base + r < n_l0) l0[base + r] = make_double2(ar[r], ai[r]);
     }
     __syncthreads();
     if (!use1 && !use2) {
@@ -591,8 +590,44 @@ __device__ double window_snr_t(const double2 *w, int fft_len_rt, const double2 *
     double noise = tot - sig;
     return 10.0 * log10(sig / noise);
 }
+// 16-point window (the reference's case: fft_len = 2^floor(log2(148/8)), FCCH_coarse_position.m:17): radix-4 x radix-4
+// FFT in registers, X[k1+4*k2] = sum_{n2} W16^{n2*k1} W4^{n2*k2} sum_{n1} x[4*n1+n2] W4^{n1*k1}.
+__device__ __forceinline__ void radix4(double2 a0, double2 a1, double2 a2, double2 a3, double2 &y0, double2 &y1, double2 &y2, double2 &y3) {
+    const double2 s02 = make_double2(a0.x + a2.x, a0.y + a2.y), d02 = make_double2(a0.x - a2.x, a0.y - a2.y);
+    const double2 s13 = make_double2(a1.x + a3.x, a1.y + a3.y), d13 = make_double2(a1.x - a3.x, a1.y - a3.y);
+    y0 = make_double2(s02.x + s13.x, s02.y + s13.y);
+    y2 = make_double2(s02.x - s13.x, s02.y - s13.y);
+    y1 = make_double2(d02.x + d13.y, d02.y - d13.x);            // d02 - i*d13
+    y3 = make_double2(d02.x - d13.y, d02.y + d13.x);            // d02 + i*d13
+}
+__device__ double window_snr16(const double2 *w) {
+    const double C1 = 0.92387953251128673848, S1 = 0.38268343236508978178, R2 = 0.70710678118654752440;
+    double2 A[4][4];
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) radix4(w[n2], w[4 + n2], w[8 + n2], w[12 + n2], A[n2][0], A[n2][1], A[n2][2], A[n2][3]);
+    // twiddles W16^{n2*k1} = (cos, -sin)(2*pi*n2*k1/16)
+    A[1][1] = cmul(A[1][1], make_double2(C1, -S1)); A[1][2] = cmul(A[1][2], make_double2(R2, -R2)); A[1][3] = cmul(A[1][3], make_double2(S1, -C1));
+    A[2][1] = cmul(A[2][1], make_double2(R2, -R2)); A[2][2] = make_double2(A[2][2].y, -A[2][2].x); A[2][3] = cmul(A[2][3], make_double2(-R2, -R2));
+    A[3][1] = cmul(A[3][1], make_double2(S1, -C1)); A[3][2] = cmul(A[3][2], make_double2(-R2, -R2)); A[3][3] = cmul(A[3][3], make_double2(-C1, S1));
+    double p[16];
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+        double2 y0, y1, y2, y3;
+        radix4(A[0][k1], A[1][k1], A[2][k1], A[3][k1], y0, y1, y2, y3);
+        p[k1] = fma(y0.x, y0.x, y0.y * y0.y); p[k1 + 4] = fma(y1.x, y1.x, y1.y * y1.y);
+        p[k1 + 8] = fma(y2.x, y2.x, y2.y * y2.y); p[k1 + 12] = fma(y3.x, y3.x, y3.y * y3.y);
+    }
+    double tot = 0.0, best = -1.0; int kbest = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { tot += p[k]; if (p[k] > best) { best = p[k]; kbest = k; } }   // first maximum
+    double pm = 0.0, pp = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { if (k == ((kbest + 15) & 15)) pm = p[k]; if (k == ((kbest + 1) & 15)) pp = p[k]; }
+    const double sig = pm + best + pp;
+    return 10.0 * log10(sig / (tot - sig));
+}
 __device__ __forceinline__ double window_snr(const double2 *w, int fft_len, const double2 *tw) {
-    return (fft_len == 16) ? window_snr_t<16>(w, 16, tw) : window_snr_t<0>(w, fft_len, tw);
+    return (fft_len == 16) ? window_snr16(w) : window_snr_t<0>(w, fft_len, tw);
 }
 
 // SNR of windows [w0, w0+n_win) (0-based window starts) of each stream -> snr[stream][0..n_win)
@@ -713,6 +748,20 @@ __global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src,
         if (nextA > limit) break;                                // run out of sampled signal (:49-51)
         const bool b_ok = nextB <= limit;                        // (:67-69)
         __syncthreads();
+        if (src.lazy) {
+            // L2 prefetch of what the FOLLOWING step can touch (its position depends on this step's hit by at most +-5):
+            // 10- and 11-frame successors of a group-A hit and the 10-frame successor of a group-B hit
+            const i64 centers[3] = {nextA + step10, nextA + step11, nextB + step10};
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                i64 lo = (centers[q] - 2 * max_offset - 2) * (i64)dec - nt1, hi = (centers[q] + 2 * max_offset + fft_len + 1) * (i64)dec;
+                if (lo < 0) lo = 0;
+                if (hi > src.n_iq) hi = src.n_iq;
+                const uintptr_t p0 = ((uintptr_t)(raw + 2 * lo)) & ~(uintptr_t)127, p1 = (uintptr_t)(raw + 2 * hi);
+                for (uintptr_t pa = p0 + 128 * (uintptr_t)tid; pa < p1; pa += 128 * CHAIN_THREADS)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+            }
+        }
         // the aligned words must stay inside this stream's row (the first samples of a capture use the scalar path)
         const i64 lo_raw = (nextA - max_offset - 1) * (i64)dec - nt1, hi_raw = (nextB + max_offset + fft_len) * (i64)dec;
         const bool staged = can_stage && lo_raw >= 4 && hi_raw + 4 < src.n_iq;
@@ -909,11 +958,12 @@ __global__ void __launch_bounds__(320) fine_peak_full_kernel(WinSrc src, StreamC
 #define FB_CERT 16
 __global__ void __launch_bounds__(FB_THREADS, 4) fine_peak_band_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ base_pos, int cap,
                                                                    int osr, i64 len_s_ov, const double2 *__restrict__ tw, double *__restrict__ fine_raw,
-                                                                   int *__restrict__ need_full) {
+                                                                   const int *__restrict__ need_band, int *__restrict__ need_full) {
     extern __shared__ double2 sm[];
     __shared__ double red_v[8];
     __shared__ int red_i[8];
     __shared__ double part[2 * (8 * 128 / FB_CERT + 2)];
+    if (need_band && !need_band[(i64)blockIdx.y * cap + blockIdx.x]) return;     // tier 1 already proved this burst
     const int burst = blockIdx.x, stream = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const StreamCtl c = ctl[stream];
     if (c.n_coarse < 5 || burst >= c.n_coarse) return;
@@ -1051,6 +1101,157 @@ __global__ void __launch_bounds__(FB_THREADS, 4) fine_peak_band_kernel(WinSrc sr
     if (tid == 0) {
         *o = (double)(sp + bestm);
         need_full[(i64)stream * cap + burst] = ok ? 0 : 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K5, tier 1: the same search tracking only FC_BINS = 8 bins around the tone, 32 window segments per burst.
+// Chunk sums (absolute phase) over 69 chunks of 4*osr samples + a prefix over chunks give every segment-start
+// spectrum as a difference of two prefix entries; each thread then slides 4*osr windows.  The Parseval/triangle
+// certificate (see fine_peak_band_kernel) is evaluated against these 8 bins; it holds for ~85-90 % of bursts
+// (it fails when the tone sits between two bins and the +-64-symbol edge windows hold 43 % GMSK data), the rest
+// go to the 64-bin band kernel and, if that cannot prove it either, to the all-bin kernel.
+#define FC_BINS 8
+#define FC_LO 3
+#define FC_THREADS 256
+__global__ void __launch_bounds__(FC_THREADS, 4) fine_peak_core_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ base_pos, int cap,
+                                                                      int osr, i64 len_s_ov, const double2 *__restrict__ tw, double *__restrict__ fine_raw,
+                                                                      int *__restrict__ need_band) {
+    extern __shared__ double2 sm[];
+    __shared__ double red_v[8];
+    __shared__ int red_i[8];
+    __shared__ double part[8 * 128 / FB_CERT + 2];
+    const int burst = blockIdx.x, stream = blockIdx.y, tid = threadIdx.x;
+    const StreamCtl c = ctl[stream];
+    if (c.n_coarse < 5 || burst >= c.n_coarse) return;
+    const int N = 148 * osr;
+    const int max_offset = 64;
+    const int n_win = 2 * max_offset * osr + 1;
+    const int n_smp = n_win + N - 1;
+    const i64 len_s = len_s_ov / osr;
+    const i64 position = (i64)base_pos[(i64)stream * cap + burst];
+    double *o = fine_raw + (i64)stream * cap + burst;
+    if (position + max_offset > len_s - 148 + 1) {            // run out of sampled signal (:35-38)
+        if (tid == 0) *o = INFINITY;
+        return;
+    }
+    const i64 sp = (position - max_offset - 1) * osr + 1;
+    double2 *win = sm;
+    double2 *X = win + n_smp;
+    {
+        const int part_n = (n_smp + 2) / 3;
+        for (int off = 0; off < n_smp; off += part_n)
+            load_window(src, c, stream, sp - 1 + off, (n_smp - off < part_n) ? n_smp - off : part_n, win + off, X, X);
+    }
+    const int CH = 4 * osr;                                     // chunk = segment length; n_smp = 69*CH, N = 37*CH, n_win-1 = 32*CH
+    const int n_ch = n_smp / CH, n_seg = (n_win - 1) / CH, wch = N / CH;
+    double2 *CS = X;                                             // [n_ch + 1][FC_BINS] prefix of chunk sums
+    const int n_chunk = n_smp / FB_CERT;
+    double *pe16 = reinterpret_cast<double *>(X + (n_ch + 1) * FC_BINS), *pa16 = pe16 + n_chunk + 2, *pa15 = pa16 + n_chunk + 2;
+    if (tid < n_chunk) {
+        double se = 0.0, sa = 0.0, sa15 = 0.0;
+        for (int i = 0; i < FB_CERT; ++i) {
+            const double2 v = win[tid * FB_CERT + i];
+            const double e = v.x * v.x + v.y * v.y;
+            se += e;
+            const double a = sqrt(e);
+            sa += a; if (i < FB_CERT - 1) sa15 += a;
+        }
+        pe16[tid + 1] = se; pa16[tid + 1] = sa; pa15[tid] = sa15;
+    }
+    // band centre from the phase slope of the centre window
+    const int mc = (n_win - 1) / 2;
+    double pr = 0.0, pi_ = 0.0;
+    for (int n = mc + tid; n < mc + N - 1; n += FC_THREADS) {
+        const double2 q2 = cmulc(win[n + 1], win[n]);
+        pr += q2.x; pi_ += q2.y;
+    }
+    pr = block_sum(pr, red_v);
+    pi_ = block_sum(pi_, red_v);
+    const int k0 = (int)floor(atan2(pi_, pr) * (double)N / (2.0 * GSMCAL_PI) + 0.5);
+    if (tid == 0) {
+        pe16[0] = 0.0; pa16[0] = 0.0;
+        for (int i = 1; i <= n_chunk; ++i) { pe16[i] += pe16[i - 1]; pa16[i] += pa16[i - 1]; }
+        for (int i = 0; i < n_chunk; ++i) pa15[i] += pa16[i];
+    }
+    // chunk sums sum_{n in chunk} s[n] W^{n*k}: (chunk, bin) pairs over the block, 4 accumulators per twiddle
+    for (int p = tid; p < n_ch * FC_BINS; p += FC_THREADS) {
+        const int cidx = p / FC_BINS, j = p % FC_BINS;
+        int k = (k0 - FC_LO + j) % N; if (k < 0) k += N;
+        const double2 wk = tw[k], wk2 = tw[(2 * k) % N], wk3 = tw[(3 * k) % N], wk4 = tw[(4 * k) % N];
+        const int a = cidx * CH;
+        double2 t = tw[(int)(((i64)a * k) % N)];
+        double a0r = 0.0, a0i = 0.0, a1r = 0.0, a1i = 0.0, a2r = 0.0, a2i = 0.0, a3r = 0.0, a3i = 0.0;
+        for (int n = a; n < a + CH; n += 4) {
+            const double2 s0 = win[n], s1 = win[n + 1], s2 = win[n + 2], s3 = win[n + 3];
+            a0r = fma(s0.x, t.x, fma(-s0.y, t.y, a0r)); a0i = fma(s0.x, t.y, fma(s0.y, t.x, a0i));
+            a1r = fma(s1.x, t.x, fma(-s1.y, t.y, a1r)); a1i = fma(s1.x, t.y, fma(s1.y, t.x, a1i));
+            a2r = fma(s2.x, t.x, fma(-s2.y, t.y, a2r)); a2i = fma(s2.x, t.y, fma(s2.y, t.x, a2i));
+            a3r = fma(s3.x, t.x, fma(-s3.y, t.y, a3r)); a3i = fma(s3.x, t.y, fma(s3.y, t.x, a3i));
+            t = cmul(t, wk4);
+        }
+        const double2 c1 = cmul(make_double2(a1r, a1i), wk), c2 = cmul(make_double2(a2r, a2i), wk2), c3 = cmul(make_double2(a3r, a3i), wk3);
+        CS[(cidx + 1) * FC_BINS + j] = make_double2((a0r + c1.x) + (c2.x + c3.x), (a0i + c1.y) + (c2.y + c3.y));
+    }
+    __syncthreads();
+    if (tid < FC_BINS) {                                         // prefix over chunks, one thread per bin
+        double yr = 0.0, yi = 0.0;
+        CS[tid] = make_double2(0.0, 0.0);
+        for (int cidx = 1; cidx <= n_ch; ++cidx) { const double2 v = CS[cidx * FC_BINS + tid]; yr += v.x; yi += v.y; CS[cidx * FC_BINS + tid] = make_double2(yr, yi); }
+    }
+    __syncthreads();
+    const int g = tid / FC_BINS, j = tid % FC_BINS;
+    const bool active = g < n_seg;
+    int k = (k0 - FC_LO + j) % N; if (k < 0) k += N;
+    const double2 wk = tw[k];
+    const int m0 = g * CH, m_end = (g == n_seg - 1) ? n_win : m0 + CH;
+    double xr = 0.0, xi = 0.0;
+    if (active) {
+        const double2 hi = CS[(g + wch) * FC_BINS + j], lo = CS[g * FC_BINS + j];
+        const double yr = hi.x - lo.x, yi = hi.y - lo.y;
+        const double2 t = tw[(int)(((i64)m0 * k) % N)];          // X_{m0}[k] = Y_{m0}[k] * exp(+2*pi*i*m0*k/N)
+        xr = yr * t.x + yi * t.y;
+        xi = yi * t.x - yr * t.y;
+    }
+    for (int m = tid; m < n_win - 1; m += FC_THREADS) {          // d[m] = s[m+N] - s[m] in place
+        const double2 s_old = win[m], s_new = win[m + N];
+        win[m] = make_double2(s_new.x - s_old.x, s_new.y - s_old.y);
+    }
+    __syncthreads();
+    const double wr = wk.x, wi = -wk.y;
+    double best = -1.0; int bestm = 0x7fffffff;
+    if (active) {
+        for (int m = m0; m < m_end; ++m) {
+            const double p = fma(xr, xr, xi * xi);
+            if (p > best) { best = p; bestm = m; }
+            if ((m % FB_CERT) == 0) {                             // the 8 bins of a segment are 8 adjacent lanes
+                double s2 = p;
+                const unsigned gm = 0xffu << (tid & 24);          // only this segment's 8 lanes (the last segment runs one window longer)
+                s2 += __shfl_xor_sync(gm, s2, 1); s2 += __shfl_xor_sync(gm, s2, 2); s2 += __shfl_xor_sync(gm, s2, 4);
+                if (j == 0) part[m / FB_CERT] = s2;
+            }
+            if (m + 1 < m_end) {
+                const double2 d = win[m];
+                const double tr = xr + d.x, ti = xi + d.y;
+                xr = fma(tr, wr, -(ti * wi));
+                xi = fma(tr, wi, ti * wr);
+            }
+        }
+    }
+    block_argmax(best, bestm, red_v, red_i);
+    const int n_cert = (n_win - 1) / FB_CERT + 1;
+    int ok = 1;
+    if (tid < n_cert) {
+        const int ci = tid, nc = N / FB_CERT;
+        const double R = (double)N * (pe16[ci + nc] - pe16[ci]) - part[ci];
+        const double A = (ci == n_cert - 1) ? 0.0 : (pa15[ci] - pa16[ci]) + (pa15[ci + nc] - pa16[ci + nc]);
+        const double bound = sqrt(R > 0.0 ? R : 0.0) + A;
+        ok = (bound * bound < best * (1.0 - 1e-6)) ? 1 : 0;
+    }
+    ok = __syncthreads_and(ok);
+    if (tid == 0) {
+        *o = (double)(sp + bestm);
+        need_band[(i64)stream * cap + burst] = ok ? 0 : 1;
     }
 }
 
@@ -1257,7 +1458,7 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
 #define SCH_THREADS 256
 #define SCH_LPG 12      // lags per warp
 #define SCH_NSL 16      // template samples per lane
-__global__ void __launch_bounds__(SCH_THREADS) sch_corr_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ fcch_pos, int cap,
+__global__ void __launch_bounds__(SCH_THREADS, 2) sch_corr_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ fcch_pos, int cap,
                                                               int osr, const double2 *__restrict__ tpl, double *__restrict__ sch_raw, int *__restrict__ sch_edge) {
     extern __shared__ double2 sm[];
     __shared__ double red_v[8];
