@@ -24,6 +24,7 @@ thread_local std::string g_err;
 thread_local int g_device = 0;
 std::atomic<long long> g_launches{0};
 int *g_last_need_full = nullptr, *g_last_need_band = nullptr; long long g_last_need_full_n = 0;
+int g_debug_groups = 4;           // stream groups per batch (1 = strictly sequential stages, enables per-stage timing)
 int g_debug_force_full = 0;       // tests: run the all-bin fine search for every burst
 
 int fail(int code, const char *fmt, ...) {
@@ -64,6 +65,7 @@ struct Ctx {
     bool attrs = false;
     DevBuf in, out, work, tplbuf;
     std::map<int, double2 *> tw;     // N -> exp(-2*pi*i*j/N)
+    std::vector<cudaStream_t> side;  // extra streams: stream groups of a batch overlap their latency-bound stages
 };
 std::map<int, Ctx> g_ctx;
 
@@ -177,6 +179,15 @@ int make_work(Ctx &c, i64 D, int cap, i64 snr_len, int tpl_len, Work *w) {
     return GSMCAL_OK;
 }
 
+Work sub_work(const Work &w, i64 d0, int cap) {
+    Work s = w;
+    s.ctl += d0; s.res += d0; s.power += d0;
+    s.coarse_pos += d0 * cap; s.coarse_snr += d0 * cap; s.fine_raw += d0 * cap; s.fcch_pos += d0 * cap; s.fo += d0 * cap; s.gate += d0 * cap;
+    s.sch_raw += d0 * cap; s.sch_pos += d0 * cap; s.post_pos += d0 * cap; s.pos_info += d0 * cap * 12; s.snr_map += d0 * w.snr_stride;
+    s.sch_edge += d0 * cap; s.need_full += d0 * cap; s.need_band += d0 * cap; s.kind += d0 * cap;
+    return s;
+}
+
 WinSrc mat_src(const double2 *base, i64 len, i64 stride, int interp) {
     WinSrc s; memset(&s, 0, sizeof s);
     s.lazy = 0; s.base = base; s.base_len = len; s.base_stride = stride; s.mat_interp = interp; s.dec = 1;
@@ -231,7 +242,6 @@ int run_fine_peak(Ctx &c, WinSrc src_peak, i64 n_iq, int osr, i64 D, int cap, Wo
         return GSMCAL_OK;
     }
     CU(cudaMemsetAsync(w.need_full, 0, sizeof(int) * D * cap, st));
-    g_last_need_full = w.need_full; g_last_need_band = w.need_band; g_last_need_full_n = (long long)D * cap;
     CU(cudaMemsetAsync(w.need_band, 0, sizeof(int) * D * cap, st));
     LAUNCH(fine_peak_core_kernel, dim3((unsigned)cap, (unsigned)D), FC_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, w.need_band);
     LAUNCH(fine_peak_band_kernel, dim3((unsigned)cap, (unsigned)D), FB_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, (const int *)w.need_band, w.need_full);
@@ -343,6 +353,7 @@ int64_t gsmcal_debug_get(int key) {
 }
 int gsmcal_debug_set(int key, int value) {
     if (key == 0) { g_debug_force_full = value; return GSMCAL_OK; }
+    if (key == 3) { g_debug_groups = value < 1 ? 1 : (value > 16 ? 16 : value); return GSMCAL_OK; }
     return fail(GSMCAL_ERR_ARG, "debug_set: unknown key");
 }
 int64_t gsmcal_launch_count(int reset) { long long v = g_launches.load(); if (reset) g_launches = 0; return v; }
@@ -755,45 +766,66 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
         draw = (const uint8_t *)din;
     }
     CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * D, st));
+    CU(cudaMemsetAsync(w.need_full, 0, sizeof(int) * D * cap, st));
+    CU(cudaMemsetAsync(w.need_band, 0, sizeof(int) * D * cap, st));
     CU(cudaMemcpyAsync(w.tpl, tpl, sizeof(double2) * 64 * osr, cudaMemcpyHostToDevice, st));
+    { const double2 *twp; TRY(get_twiddle(*c, 148 * osr, st, &twp)); }        // built on `st` before the groups fork
+    g_last_need_full = w.need_full; g_last_need_band = w.need_band; g_last_need_full_n = (long long)D * cap;
     g_stage_n = 0;
-    TRY(stage_mark(st));
-    if (raw_mem == GSMCAL_MEM_HOST) {
-        // copy and reduce in slices of streams so the column sums overlap the PCIe transfer of the next slice
-        const size_t per = (size_t)2 * n_iq;
-        i64 slice = (i64)((256u << 20) / per); if (slice < 1) slice = 1;
-        cudaStream_t cp; CU(cudaStreamCreateWithFlags(&cp, cudaStreamNonBlocking));
-        cudaEvent_t ev0; CU(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
-        CU(cudaEventRecord(ev0, st)); CU(cudaStreamWaitEvent(cp, ev0, 0));
-        for (i64 d0 = 0; d0 < D; d0 += slice) {
-            const i64 nd = (D - d0 < slice) ? D - d0 : slice;
-            CU(cudaMemcpyAsync((void *)(draw + d0 * per), raw + d0 * per, per * nd, cudaMemcpyHostToDevice, cp));
+    // Streams are independent, so the batch is cut into groups that run the stage sequence on their own CUDA
+    // streams: the latency-bound stages of one group (burst chain, per-stream solves) overlap the FP64-bound
+    // stages of the others, and with host input the H2D copy of group g+1 overlaps the compute of group g.
+    int n_groups = g_debug_groups;
+    if (raw_mem == GSMCAL_MEM_HOST && n_groups > 1) n_groups *= 2;
+    if (D < 2 * n_groups) n_groups = 1;
+    const bool timing = (n_groups == 1);
+    while ((int)c->side.size() < n_groups + 1) { cudaStream_t s2; CU(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking)); c->side.push_back(s2); }
+    cudaStream_t cp = c->side[n_groups];                                         // H2D copies
+    cudaEvent_t ev_fork; CU(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev_fork, st));
+    if (raw_mem == GSMCAL_MEM_HOST) CU(cudaStreamWaitEvent(cp, ev_fork, 0));
+    std::vector<cudaEvent_t> ev_done;
+    const size_t per = (size_t)2 * n_iq;
+    if (timing) TRY(stage_mark(st));
+    for (int g = 0; g < n_groups; ++g) {
+        const i64 d0 = D * g / n_groups, d1 = D * (g + 1) / n_groups, nd = d1 - d0;
+        cudaStream_t sg = (n_groups == 1) ? st : c->side[g];
+        if (sg != st) CU(cudaStreamWaitEvent(sg, ev_fork, 0));
+        Work ws = sub_work(w, d0, cap);
+        const uint8_t *graw = draw + d0 * per;
+        if (raw_mem == GSMCAL_MEM_HOST) {
+            CU(cudaMemcpyAsync((void *)graw, raw + d0 * per, per * nd, cudaMemcpyHostToDevice, cp));
             cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-            CU(cudaEventRecord(ev, cp)); CU(cudaStreamWaitEvent(st, ev, 0)); CU(cudaEventDestroy(ev));
-            TRY(run_colsum_u8(draw + d0 * per, n_iq, nd, w.ctl + d0, st));
+            CU(cudaEventRecord(ev, cp)); CU(cudaStreamWaitEvent(sg, ev, 0)); CU(cudaEventDestroy(ev));
         }
-        CU(cudaEventDestroy(ev0)); CU(cudaStreamDestroy(cp));
-    } else {
-        TRY(run_colsum_u8(draw, n_iq, D, w.ctl, st));
+        TRY(run_colsum_u8(graw, n_iq, nd, ws.ctl, sg));
+        if (timing) TRY(stage_mark(sg));
+        TRY(run_coarse(lazy_src(graw, n_iq, n_taps, 0, dec), len_dec, p, nd, cap, ws, sg));
+        if (timing) TRY(stage_mark(sg));
+        TRY(run_fine_peak(*c, lazy_src(graw, n_iq, n_taps, 0, 1), n_iq, osr, nd, cap, ws, sg));
+        if (timing) TRY(stage_mark(sg));
+        TRY(run_fine_rest(*c, lazy_src(graw, n_iq, n_taps, 1, 1), n_iq, osr, carrier_freq, nd, cap, ws, sg));
+        if (timing) TRY(stage_mark(sg));
+        TRY(run_sch(lazy_src(graw, n_iq, n_taps, 2, 1), osr, nd, cap, ws, sg));
+        if (timing) TRY(stage_mark(sg));
+        TRY(run_post(*c, lazy_src(graw, n_iq, n_taps, 3, 1), osr, carrier_freq, nd, cap, ws, true, sg));
+        if (timing) TRY(stage_mark(sg));
+        if (sg != st) {
+            cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            CU(cudaEventRecord(ev, sg)); CU(cudaStreamWaitEvent(st, ev, 0));
+            ev_done.push_back(ev);
+        }
     }
-    TRY(stage_mark(st));
-    TRY(run_coarse(lazy_src(draw, n_iq, n_taps, 0, dec), len_dec, p, D, cap, w, st));
-    TRY(stage_mark(st));
-    TRY(run_fine_peak(*c, lazy_src(draw, n_iq, n_taps, 0, 1), n_iq, osr, D, cap, w, st));
-    TRY(stage_mark(st));
-    TRY(run_fine_rest(*c, lazy_src(draw, n_iq, n_taps, 1, 1), n_iq, osr, carrier_freq, D, cap, w, st));
-    TRY(stage_mark(st));
-    TRY(run_sch(lazy_src(draw, n_iq, n_taps, 2, 1), osr, D, cap, w, st));
-    TRY(stage_mark(st));
-    TRY(run_post(*c, lazy_src(draw, n_iq, n_taps, 3, 1), osr, carrier_freq, D, cap, w, true, st));
-    TRY(stage_mark(st));
+    for (cudaEvent_t ev : ev_done) CU(cudaEventDestroy(ev));
+    CU(cudaEventDestroy(ev_fork));
     CU(cudaMemcpyAsync(results, w.res, sizeof(StreamResultDev) * D, cudaMemcpyDeviceToHost, st));
     if (coarse_pos) CU(cudaMemcpyAsync(coarse_pos, w.coarse_pos, sizeof(double) * D * cap, cudaMemcpyDeviceToHost, st));
     if (coarse_snr) CU(cudaMemcpyAsync(coarse_snr, w.coarse_snr, sizeof(double) * D * cap, cudaMemcpyDeviceToHost, st));
     if (fcch_pos) CU(cudaMemcpyAsync(fcch_pos, w.fcch_pos, sizeof(double) * D * cap, cudaMemcpyDeviceToHost, st));
     if (pos_info) CU(cudaMemcpyAsync(pos_info, w.pos_info, sizeof(double) * D * cap * 12, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    for (int i = 0; i + 1 < g_stage_n; ++i) CU(cudaEventElapsedTime(&g_stage_ms[i], g_stage_ev[i], g_stage_ev[i + 1]));
+    if (timing) for (int i = 0; i + 1 < g_stage_n; ++i) CU(cudaEventElapsedTime(&g_stage_ms[i], g_stage_ev[i], g_stage_ev[i + 1]));
+    if (!timing) g_stage_n = 0;
     return GSMCAL_OK;
 }
 
