@@ -216,12 +216,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)       # samples every 100 ms from the warm-up on: the timed region is only ~0.1 s long
+    sampler.start()
     for _ in range(args.warmup):
         res = step_device()
     barrier()
     gsmcal.launch_count(reset=True)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_acc = {}
     barrier()

@@ -345,3 +345,90 @@ def test_band_limited_fine_search_equals_all_bin_search(gpu, captures, coef47, t
         assert a["sampling_ppm"] == b["sampling_ppm"]
         n_fallback += 1 if (a["flags"] & 32) else 0
     assert n_fallback <= 1, "the band certificate should hold for clean captures"
+
+
+# ---- BASELINE full-size streams (10 s, 21 666 667 IQ) and size-independent properties ----------------------------
+N_10S = 21666667
+
+
+@pytest.fixture(scope="module")
+def captures_10s():
+    torch = pytest.importorskip("torch")
+    specs = [synth.random_spec(seed, N_10S) for seed in (101, 102)]
+    raw = synth.generate_batch(specs, device="cuda")
+    torch.cuda.synchronize()
+    return specs, raw
+
+
+def test_full_size_streams_match_oracle(gpu, captures_10s, coef47, tpl):
+    specs, raw = captures_10s
+    got = gpu.calibrate_batch(None, CARRIER, tpl, coef47, device_ptr=raw.data_ptr(), n_iq=N_10S, n_streams=raw.shape[0])
+    host = raw.cpu().numpy()
+    for d in range(raw.shape[0]):
+        ref = oracle.calibrate_stream(host[d], CARRIER, tpl, coef47)
+        _check_stream(got[d], ref)
+        assert len(got[d]["fcch_pos"]) > 200 and got[d]["pos_info"].shape[0] > 550
+        # sanity against the injected impairments (not parity): 10 s gives 0.05 ppm resolution on the sampling clock
+        assert abs(got[d]["total_sampling_ppm"] - specs[d].sampling_ppm) < 0.2
+        assert abs(got[d]["total_carrier_ppm"] - specs[d].carrier_ppm) < 1.6
+
+
+def test_full_size_structural_properties(gpu, captures_10s, coef47, tpl):
+    specs, raw = captures_10s
+    got = gpu.calibrate_batch(None, CARRIER, tpl, coef47, device_ptr=raw.data_ptr(), n_iq=N_10S, n_streams=raw.shape[0])
+    again = gpu.calibrate_batch(None, CARRIER, tpl, coef47, device_ptr=raw.data_ptr(), n_iq=N_10S, n_streams=raw.shape[0])
+    for a, b in zip(got, again):                                  # deterministic: integer atomics only
+        assert np.array_equal(a["pos_info"], b["pos_info"]) and a["carrier_ppm"] == b["carrier_ppm"]
+    for r in got:
+        d = np.diff(r["fcch_pos"])
+        assert set(d.tolist()) <= {100000.0, 110000.0}            # FCCH_pos is rebuilt on the ideal 10/11-frame grid
+        assert np.all(np.diff(r["coarse_pos"]) > 0)
+        p = r["pos_info"]
+        assert np.all(np.diff(p[:, 0]) > 0)                       # bursts in time order
+        assert set(p[:, 1].tolist()) == {0.0, 1.0, 2.0}
+        f = p[p[:, 1] == 0, 0]
+        s = p[p[:, 1] == 1, 0]
+        assert np.all(s[:len(f)] - f[:len(s)] == 10000)           # SCH one frame after its FCCH (SCH_corr_rate_correction.m:146-151)
+        b = p[p[:, 1] == 2, 0]
+        assert len(b) % 4 == 0 or len(b) >= 4
+
+
+def test_batch_is_stream_independent(gpu, captures, coef47, tpl):
+    """Permuting / duplicating streams permutes / duplicates the results: no cross-stream state."""
+    _, raw = captures
+    base = gpu.calibrate_batch(raw, CARRIER, tpl, coef47)
+    perm = [3, 0, 0, 4, 1, 2, 2]
+    got = gpu.calibrate_batch(raw[perm], CARRIER, tpl, coef47)
+    for i, src in enumerate(perm):
+        assert np.array_equal(got[i]["pos_info"], base[src]["pos_info"])
+        assert got[i]["sampling_ppm"] == base[src]["sampling_ppm"] and got[i]["carrier_ppm"] == base[src]["carrier_ppm"]
+    one = gpu.calibrate_batch(raw[2:3], CARRIER, tpl, coef47)     # D = 1
+    assert np.array_equal(one[0]["pos_info"], base[2]["pos_info"])
+
+
+@pytest.mark.parametrize("n_iq", [230016, 230017, 400001])
+def test_short_and_odd_length_captures(gpu, coef47, tpl, n_iq):
+    """23 frames is the minimum FCCH_coarse_position accepts (s(1:3594)); such captures end on the '<5 hits' sentinels."""
+    specs = [synth.random_spec(7, n_iq), synth.random_spec(8, n_iq)]
+    raw = synth.generate_batch(specs).numpy()
+    got = gpu.calibrate_batch(raw, CARRIER, tpl, coef47)
+    for d in range(2):
+        _check_stream(got[d], oracle.calibrate_stream(raw[d], CARRIER, tpl, coef47))
+
+
+def test_capture_shorter_than_23_frames_is_a_range_error(gpu, coef47, tpl):
+    raw = np.zeros((1, 2 * 200000), dtype=np.uint8)
+    with pytest.raises(gpu.GsmcalError) as e:
+        gpu.calibrate_batch(raw, CARRIER, tpl, coef47)
+    assert e.value.code == -4
+    with pytest.raises(IndexError):
+        oracle.calibrate_stream(raw[0] + 1, CARRIER, tpl, coef47)
+
+
+def test_other_filter_lengths_through_the_batch(gpu, captures, tpl):
+    _, raw = captures
+    for order in (30, 63):
+        coef = oracle.fir1(order, 200e3 / FS)
+        got = gpu.calibrate_batch(raw[:2], CARRIER, tpl, coef)
+        for d in range(2):
+            _check_stream(got[d], oracle.calibrate_stream(raw[d], CARRIER, tpl, coef))
