@@ -308,7 +308,9 @@ def main():
     # ---- optional: materialising per-stage kernels (the drop-in functions' device work) ------------
     stages = None
     if args.stages and rank == 0:
+        torch.cuda.profiler.start()
         stages = stage_rooflines(torch, gsmcal, lib(), raw, n_iq, coef, stream, hbm_peak)
+        torch.cuda.profiler.stop()
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only): the oracle on ONE of the streams ---
     cpu_baseline = None

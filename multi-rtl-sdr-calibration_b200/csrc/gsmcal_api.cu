@@ -287,6 +287,11 @@ int run_fir(const void *in, i64 n, i64 in_stride, const StreamCtl *ctl, int n_ta
         else                   LAUNCH((fir_full_kernel<128, U8>), dim3(gx, (unsigned)D), FIR_THREADS, smem(128), st, in, n, in_stride, ctl, out, n_out);
         return GSMCAL_OK;
     }
+    if (U8 && decim >= n_taps && (decim % 4) == 0 && n_taps <= 64) {
+        unsigned gx = (unsigned)((n_out + FDD_THREADS - 1) / FDD_THREADS);
+        LAUNCH(fir_decim_direct_u8_kernel<17>, dim3(gx, (unsigned)D), FDD_THREADS, 0, st, (const uint8_t *)in, n, ctl, n_taps, decim, out, n_out, power);
+        return GSMCAL_OK;
+    }
     int opb = 2048 / decim; if (opb < 1) opb = 1; if (opb > 1024) opb = 1024;
     int n_in = (opb - 1) * decim + n_taps;
     size_t smem = sizeof(double2) * (size_t)(n_in + n_in / 8 + 2);

@@ -398,18 +398,29 @@ __global__ void __launch_bounds__(FIR_THREADS) fir_full_kernel(const void *__res
     const int n_in = FIR_TILE + NT - 1;
     double mur = 0.0, mui = 0.0;
     if (FROM_U8) { mur = stream_mean(ctl[stream].sum_i, n); mui = stream_mean(ctl[stream].sum_q, n); }
-    for (int i = threadIdx.x; i < n_in; i += FIR_THREADS) {
-        i64 j = t0 - (NT - 1) + i;
-        double2 v = make_double2(0.0, 0.0);
-        if (j >= 0 && j < n) {
-            if (FROM_U8) {
-                uchar2 u = reinterpret_cast<const uchar2 *>(static_cast<const uint8_t *>(in_) + (i64)stream * in_stride)[j];
-                v = make_double2((double)u.x - mur, (double)u.y - mui);
-            } else {
-                v = __ldcs(static_cast<const double2 *>(in_) + (i64)stream * in_stride + j);
+    {   // all of a thread's loads are issued before the first is consumed (one memory latency per tile, not per element)
+        constexpr int NLD = (FIR_TILE + NT - 1 + FIR_THREADS - 1) / FIR_THREADS;
+        double2 v[NLD];
+        uchar2 u[NLD];
+#pragma unroll
+        for (int q = 0; q < NLD; ++q) {
+            const int i = threadIdx.x + q * FIR_THREADS;
+            const i64 j = t0 - (NT - 1) + i;
+            v[q] = make_double2(0.0, 0.0); u[q] = make_uchar2(0, 0);
+            if (i < n_in && j >= 0 && j < n) {
+                if (FROM_U8) u[q] = reinterpret_cast<const uchar2 *>(static_cast<const uint8_t *>(in_) + (i64)stream * in_stride)[j];
+                else v[q] = __ldcs(static_cast<const double2 *>(in_) + (i64)stream * in_stride + j);
             }
         }
-        sm[fir_pad(i)] = v;
+#pragma unroll
+        for (int q = 0; q < NLD; ++q) {
+            const int i = threadIdx.x + q * FIR_THREADS;
+            const i64 j = t0 - (NT - 1) + i;
+            if (i < n_in) {
+                if (FROM_U8) v[q] = (j >= 0 && j < n) ? make_double2((double)u[q].x - mur, (double)u[q].y - mui) : make_double2(0.0, 0.0);
+                sm[fir_pad(i)] = v[q];
+            }
+        }
     }
     __syncthreads();
     double ar[FIR_R], ai[FIR_R];
@@ -484,6 +495,61 @@ __global__ void __launch_bounds__(FIRD_THREADS) fir_decim_kernel(const void *__r
     if (power_acc) {
         __shared__ double red[8];
         double t = block_sum(pw, red);
+        if (threadIdx.x == 0) atomicAdd(&power_acc[stream], t);
+    }
+}
+
+// Decimating FIR straight from the uint8 capture when the windows do not overlap (decim >= n_taps: the /64 coarse
+// stream, multi_rtl_sdr_gsm_FCCH_scanner.m:133-135).  One thread per kept output; its 2*n_taps bytes are fetched as
+// 8-byte aligned words that are ALL in flight before the first use (the per-sample loop of the staged kernel paid a
+// memory latency per iteration), then unpacked and filtered in registers.  The byte phase of a row is the same for
+// every output of a stream (2*decim*m is a multiple of 8 for decim % 4 == 0), so tap indices stay warp-uniform.
+#define FDD_THREADS 128
+template <int MAXW>
+__global__ void __launch_bounds__(FDD_THREADS) fir_decim_direct_u8_kernel(const uint8_t *__restrict__ in, i64 n, const StreamCtl *__restrict__ ctl, int n_taps, int decim,
+                                                                         double2 *__restrict__ out, i64 n_out, double *__restrict__ power_acc) {
+    const int stream = blockIdx.y;
+    const uint8_t *raw = in + (i64)stream * 2 * n;
+    const double mur = stream_mean(ctl[stream].sum_i, n), mui = stream_mean(ctl[stream].sum_q, n);
+    const i64 m = (i64)blockIdx.x * FDD_THREADS + threadIdx.x;
+    const int nt1 = n_taps - 1;
+    double ar = 0.0, ai = 0.0;
+    bool valid = m < n_out;
+    if (valid) {
+        const i64 j0 = m * decim - nt1;                           // oldest sample of this output's window
+        const uintptr_t a = (uintptr_t)(raw + 2 * j0);
+        const int off = (int)((a & 7) >> 1);                      // samples between the aligned word and j0 (warp-uniform)
+        const int nw = (n_taps + off + 3) >> 2;
+        const i64 jw0 = j0 - off;                                 // sample index of the first aligned word
+        if (jw0 >= 0 && jw0 + 4 * (i64)nw <= n) {
+            const uint2 *wp = reinterpret_cast<const uint2 *>(a & ~(uintptr_t)7);
+            uint2 w[MAXW];
+#pragma unroll
+            for (int q = 0; q < MAXW; ++q) w[q] = (q < nw) ? __ldg(wp + q) : make_uint2(0u, 0u);
+#pragma unroll
+            for (int q = 0; q < MAXW; ++q) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int t = 4 * q + e - off;                // 0 = oldest sample -> tap nt1 - t
+                    if (q < nw && t >= 0 && t <= nt1) {
+                        const unsigned pr2 = ((e < 2) ? w[q].x : w[q].y) >> (16 * (e & 1));
+                        const double h = c_taps[nt1 - t];
+                        ar = fma(h, (double)(pr2 & 0xffu) - mur, ar);
+                        ai = fma(h, (double)((pr2 >> 8) & 0xffu) - mui, ai);
+                    }
+                }
+            }
+        } else {                                                  // first / last outputs of a row: scalar, zero initial state
+            const double2 v = fir_from_raw(raw, m * decim, n_taps, mur, mui);
+            ar = v.x; ai = v.y;
+        }
+        if (out) out[(i64)stream * n_out + m] = make_double2(ar, ai);
+    }
+    if (power_acc) {
+        __shared__ double red[8];
+        double pw = 0.0;
+        if (valid) { const double h = hypot(ar, ai); pw = h * h; }
+        const double t = block_sum(pw, red);
         if (threadIdx.x == 0) atomicAdd(&power_acc[stream], t);
     }
 }
