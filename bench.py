@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--n-iq", type=int, default=N_IQ_10S)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--groups", type=int, default=4, help="stream groups per batch inside the library (1 = no overlap; for profiling)")
     ap.add_argument("--stages", action="store_true", help="also time the materialising per-stage kernels (raw2iq, FIR, resample, derotate)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -199,6 +200,7 @@ def main():
     torch.cuda.synchronize()
     coef = gsmcal.fir1(46, 200e3 / FS)
     tpl = gsmcal.gsm_SCH_training_sequence_gen(8)
+    lib().gsmcal_debug_set(3, args.groups)
     stream = torch.cuda.current_stream()
     rec_bytes = C.sizeof(StreamResult)
     gathered = torch.empty((world * D * rec_bytes,), dtype=torch.uint8, device=dev) if world > 1 else None
@@ -253,7 +255,7 @@ def main():
         step_device()
         for k, v in gsmcal.api.last_batch_stage_ms().items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v
-    lib().gsmcal_debug_set(3, 4)
+    lib().gsmcal_debug_set(3, args.groups)
     stage_ms = {k: v / n_prof for k, v in stage_acc.items()}
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------
