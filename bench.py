@@ -170,7 +170,7 @@ def main():
     ap.add_argument("--n-iq", type=int, default=N_IQ_10S)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--groups", type=int, default=4, help="stream groups per batch inside the library (1 = no overlap; for profiling)")
+    ap.add_argument("--groups", type=int, default=8, help="stream groups per batch inside the library (1 = no overlap; for profiling)")
     ap.add_argument("--stages", action="store_true", help="also time the materialising per-stage kernels (raw2iq, FIR, resample, derotate)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

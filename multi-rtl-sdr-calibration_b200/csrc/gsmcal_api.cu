@@ -24,7 +24,8 @@ thread_local std::string g_err;
 thread_local int g_device = 0;
 std::atomic<long long> g_launches{0};
 int *g_last_need_full = nullptr, *g_last_need_band = nullptr; long long g_last_need_full_n = 0;
-int g_debug_groups = 4;           // stream groups per batch (1 = strictly sequential stages, enables per-stage timing)
+int g_debug_groups = 8;           // stream groups per batch (1 = strictly sequential stages, enables per-stage timing)
+int g_debug_fail_tier2 = 0;       // tests: pretend the 64-bin certificate failed
 int g_debug_force_full = 0;       // tests: run the all-bin fine search for every burst
 
 int fail(int code, const char *fmt, ...) {
@@ -154,10 +155,11 @@ int set_taps(const double *coef, int n_taps, cudaStream_t st) {
 struct Work {
     StreamCtl *ctl; StreamResultDev *res;
     double *coarse_pos, *coarse_snr, *fine_raw, *fcch_pos, *fo, *gate, *sch_raw, *sch_pos, *post_pos, *pos_info, *snr_map, *power;
-    int *sch_edge, *need_full, *need_band; unsigned char *kind; double2 *tpl;
+    int *sch_edge, *need_full, *need_band, *fall_list, *fall_count, *fall_m; double *fall_best; unsigned char *kind; double2 *tpl;
     i64 snr_stride;
 };
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+constexpr int kMaxGroups = 32;     // stream groups per batch (tier-3 scratch is per group); ceil(148*8/64) = 19 <= 24 bands
 
 int make_work(Ctx &c, i64 D, int cap, i64 snr_len, int tpl_len, Work *w) {
     size_t off = 0;
@@ -166,7 +168,7 @@ int make_work(Ctx &c, i64 D, int cap, i64 snr_len, int tpl_len, Work *w) {
     size_t per = sizeof(double) * D * cap;
     size_t o_cp = take(per), o_cs = take(per), o_fr = take(per), o_fp = take(per), o_fo = take(per), o_g = take(per), o_sr = take(per), o_sp = take(per), o_pp = take(per);
     size_t o_pi = take(per * 12), o_snr = take(sizeof(double) * D * snr_len), o_pw = take(sizeof(double) * D);
-    size_t o_se = take(sizeof(int) * D * cap), o_nf = take(sizeof(int) * D * cap), o_nb = take(sizeof(int) * D * cap), o_k = take(D * cap), o_tpl = take(sizeof(double2) * (tpl_len > 0 ? tpl_len : 1));
+    size_t o_se = take(sizeof(int) * D * cap), o_nf = take(sizeof(int) * D * cap), o_nb = take(sizeof(int) * D * cap), o_fl = take(sizeof(int) * D * cap), o_fc = take(sizeof(int) * D), o_fm = take(sizeof(int) * (size_t)FALL_GRID * 24 * kMaxGroups), o_fb = take(sizeof(double) * (size_t)FALL_GRID * 24 * kMaxGroups), o_k = take(D * cap), o_tpl = take(sizeof(double2) * (tpl_len > 0 ? tpl_len : 1));
     void *base;
     TRY(c.work.get(off, &base));
     char *b = static_cast<char *>(base);
@@ -174,17 +176,19 @@ int make_work(Ctx &c, i64 D, int cap, i64 snr_len, int tpl_len, Work *w) {
     w->coarse_pos = (double *)(b + o_cp); w->coarse_snr = (double *)(b + o_cs); w->fine_raw = (double *)(b + o_fr); w->fcch_pos = (double *)(b + o_fp);
     w->fo = (double *)(b + o_fo); w->gate = (double *)(b + o_g); w->sch_raw = (double *)(b + o_sr); w->sch_pos = (double *)(b + o_sp); w->post_pos = (double *)(b + o_pp);
     w->pos_info = (double *)(b + o_pi); w->snr_map = (double *)(b + o_snr); w->power = (double *)(b + o_pw);
-    w->sch_edge = (int *)(b + o_se); w->need_full = (int *)(b + o_nf); w->need_band = (int *)(b + o_nb); w->kind = (unsigned char *)(b + o_k); w->tpl = (double2 *)(b + o_tpl);
+    w->sch_edge = (int *)(b + o_se); w->need_full = (int *)(b + o_nf); w->need_band = (int *)(b + o_nb); w->fall_list = (int *)(b + o_fl); w->fall_count = (int *)(b + o_fc); w->fall_m = (int *)(b + o_fm); w->fall_best = (double *)(b + o_fb); w->kind = (unsigned char *)(b + o_k); w->tpl = (double2 *)(b + o_tpl);
     w->snr_stride = snr_len;
     return GSMCAL_OK;
 }
 
-Work sub_work(const Work &w, i64 d0, int cap) {
+Work sub_work(const Work &w, i64 d0, int cap, int group) {
     Work s = w;
     s.ctl += d0; s.res += d0; s.power += d0;
     s.coarse_pos += d0 * cap; s.coarse_snr += d0 * cap; s.fine_raw += d0 * cap; s.fcch_pos += d0 * cap; s.fo += d0 * cap; s.gate += d0 * cap;
     s.sch_raw += d0 * cap; s.sch_pos += d0 * cap; s.post_pos += d0 * cap; s.pos_info += d0 * cap * 12; s.snr_map += d0 * w.snr_stride;
     s.sch_edge += d0 * cap; s.need_full += d0 * cap; s.need_band += d0 * cap; s.kind += d0 * cap;
+    s.fall_list += d0 * cap; s.fall_count += d0;
+    s.fall_m += (size_t)group * FALL_GRID * 24; s.fall_best += (size_t)group * FALL_GRID * 24;
     return s;
 }
 
@@ -238,14 +242,21 @@ int run_coarse(WinSrc src, i64 len, const CoarseParams &p, i64 D, int cap, Work 
 int run_fine_peak(Ctx &c, WinSrc src_peak, i64 n_iq, int osr, i64 D, int cap, Work &w, cudaStream_t st) {
     const double2 *tw; TRY(get_twiddle(c, 148 * osr, st, &tw));
     if (g_debug_force_full || (osr % 4) != 0) {      // the band kernel's 16-sample certificate grid needs osr % 4 == 0
-        LAUNCH(fine_peak_full_kernel, dim3((unsigned)cap, (unsigned)D), kFineThreads, fine_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, (const int *)nullptr);
+        LAUNCH(fine_peak_full_kernel, dim3((unsigned)cap, (unsigned)D), kFineThreads, fine_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, (const int *)nullptr, (const int *)nullptr);
         return GSMCAL_OK;
     }
     CU(cudaMemsetAsync(w.need_full, 0, sizeof(int) * D * cap, st));
     CU(cudaMemsetAsync(w.need_band, 0, sizeof(int) * D * cap, st));
     LAUNCH(fine_peak_core_kernel, dim3((unsigned)cap, (unsigned)D), FC_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, w.need_band);
-    LAUNCH(fine_peak_band_kernel, dim3((unsigned)cap, (unsigned)D), FB_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, (const int *)w.need_band, w.need_full);
-    LAUNCH(fine_peak_full_kernel, dim3((unsigned)cap, (unsigned)D), kFineThreads, fine_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, (const int *)w.need_full);
+    CU(cudaMemsetAsync(w.fall_count, 0, sizeof(int), st));
+    LAUNCH(fine_peak_band_kernel, dim3((unsigned)cap, (unsigned)D), FB_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw,
+           (const int *)w.need_band, w.need_full, 0, w.fall_list, w.fall_count, w.fall_best, w.fall_m, g_debug_fail_tier2);
+    const int nb3 = (148 * osr + FB_BINS - 1) / FB_BINS;
+    LAUNCH(fine_peak_band_kernel, dim3((unsigned)nb3, (unsigned)FALL_GRID), FB_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw,
+           (const int *)nullptr, (int *)nullptr, 1, w.fall_list, w.fall_count, w.fall_best, w.fall_m, 0);
+    LAUNCH(fine_fall_combine_kernel, FALL_GRID / 128, 128, 0, st, w.fall_list, w.fall_count, w.fall_best, w.fall_m, nb3, w.coarse_pos, cap, osr, w.fine_raw, w.ctl);
+    LAUNCH(fine_peak_full_kernel, dim3((unsigned)cap, (unsigned)D), kFineThreads, fine_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw,
+           (const int *)w.need_full, (const int *)w.fall_count);
     return GSMCAL_OK;
 }
 int run_fine_rest(Ctx &c, WinSrc src_tone, i64 n_iq, int osr, double carrier_freq, i64 D, int cap, Work &w, cudaStream_t st) {
@@ -358,7 +369,8 @@ int64_t gsmcal_debug_get(int key) {
 }
 int gsmcal_debug_set(int key, int value) {
     if (key == 0) { g_debug_force_full = value; return GSMCAL_OK; }
-    if (key == 3) { g_debug_groups = value < 1 ? 1 : (value > 16 ? 16 : value); return GSMCAL_OK; }
+    if (key == 4) { g_debug_fail_tier2 = value; return GSMCAL_OK; }
+    if (key == 3) { g_debug_groups = value < 1 ? 1 : (value > kMaxGroups / 2 ? kMaxGroups / 2 : value); return GSMCAL_OK; }
     return fail(GSMCAL_ERR_ARG, "debug_set: unknown key");
 }
 int64_t gsmcal_launch_count(int reset) { long long v = g_launches.load(); if (reset) g_launches = 0; return v; }
@@ -796,14 +808,22 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
         const i64 d0 = D * g / n_groups, d1 = D * (g + 1) / n_groups, nd = d1 - d0;
         cudaStream_t sg = (n_groups == 1) ? st : c->side[g];
         if (sg != st) CU(cudaStreamWaitEvent(sg, ev_fork, 0));
-        Work ws = sub_work(w, d0, cap);
+        Work ws = sub_work(w, d0, cap, g);
         const uint8_t *graw = draw + d0 * per;
         if (raw_mem == GSMCAL_MEM_HOST) {
             CU(cudaMemcpyAsync((void *)graw, raw + d0 * per, per * nd, cudaMemcpyHostToDevice, cp));
             cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             CU(cudaEventRecord(ev, cp)); CU(cudaStreamWaitEvent(sg, ev, 0)); CU(cudaEventDestroy(ev));
+            TRY(run_colsum_u8(graw, n_iq, nd, ws.ctl, sg));
+        } else if (sg == st) {
+            TRY(run_colsum_u8(graw, n_iq, nd, ws.ctl, sg));
+        } else {
+            // device input: the HBM-bound column sums of all groups run back to back on the caller's stream, so group 0
+            // gets the whole bandwidth first and its latency-bound burst chain starts while the others are still summing
+            TRY(run_colsum_u8(graw, n_iq, nd, ws.ctl, st));
+            cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            CU(cudaEventRecord(ev, st)); CU(cudaStreamWaitEvent(sg, ev, 0)); CU(cudaEventDestroy(ev));
         }
-        TRY(run_colsum_u8(graw, n_iq, nd, ws.ctl, sg));
         if (timing) TRY(stage_mark(sg));
         TRY(run_coarse(lazy_src(graw, n_iq, n_taps, 0, dec), len_dec, p, nd, cap, ws, sg));
         if (timing) TRY(stage_mark(sg));
@@ -817,11 +837,11 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
         if (timing) TRY(stage_mark(sg));
         if (sg != st) {
             cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-            CU(cudaEventRecord(ev, sg)); CU(cudaStreamWaitEvent(st, ev, 0));
+            CU(cudaEventRecord(ev, sg));
             ev_done.push_back(ev);
         }
     }
-    for (cudaEvent_t ev : ev_done) CU(cudaEventDestroy(ev));
+    for (cudaEvent_t ev : ev_done) { CU(cudaStreamWaitEvent(st, ev, 0)); CU(cudaEventDestroy(ev)); }   // join (after ALL groups are enqueued)
     CU(cudaEventDestroy(ev_fork));
     CU(cudaMemcpyAsync(results, w.res, sizeof(StreamResultDev) * D, cudaMemcpyDeviceToHost, st));
     if (coarse_pos) CU(cudaMemcpyAsync(coarse_pos, w.coarse_pos, sizeof(double) * D * cap, cudaMemcpyDeviceToHost, st));

@@ -286,6 +286,36 @@ __device__ double block_sum(double v, double *sv) {
     return r;
 }
 
+// several block sums with one pair of barriers
+template <int K>
+__device__ void block_sum_n(double (&v)[K], double *sv /* >= 8*K */) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) sv[k * 8 + w] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double t = 0.0;
+        for (int i = 0; i < nw; ++i) t += sv[k * 8 + i];
+        v[k] = t;
+    }
+    __syncthreads();
+}
+// inclusive prefix sum of a[0..n) in shared memory, executed by ONE full warp
+__device__ void warp_scan_smem(double *a, int n, int lane) {
+    const int per = (n + 31) >> 5, b = lane * per;
+    double loc = 0.0;
+    for (int i = 0; i < per; ++i) if (b + i < n) loc += a[b + i];
+    double inc = loc;
+    for (int d = 1; d < 32; d <<= 1) { const double t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    double run = inc - loc;
+    for (int i = 0; i < per; ++i) if (b + i < n) { run += a[b + i]; a[b + i] = run; }
+}
+
 // ===================================================================================================
 // K1  raw2iq.m:5-8
 // ===================================================================================================
@@ -922,9 +952,11 @@ __global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src,
 // then takes the first-maximum over bins.  (max_m max_k == max_k max_m, and the first window attaining the
 // global maximum is the same either way, so no per-window reduction is needed.)
 #define FP_BPT 4
+#define FALL_GRID 256     // bursts tier 3 (multi-block band search) handles per launch; beyond that this single-block kernel takes over
 __global__ void __launch_bounds__(320) fine_peak_full_kernel(WinSrc src, StreamCtl *__restrict__ ctl, const double *__restrict__ base_pos, int cap,
                                                              int osr, i64 len_s_ov, const double2 *__restrict__ tw /* exp(-2*pi*i*j/N) */,
-                                                             double *__restrict__ fine_raw, const int *__restrict__ need_full) {
+                                                             double *__restrict__ fine_raw, const int *__restrict__ need_full,
+                                                             const int *__restrict__ fall_count) {
     extern __shared__ double2 sm[];
     __shared__ double red_v[16];
     __shared__ int red_i[16];
@@ -943,6 +975,7 @@ __global__ void __launch_bounds__(320) fine_peak_full_kernel(WinSrc src, StreamC
         return;
     }
     if (need_full && !need_full[(i64)stream * cap + burst]) return;   // the band-limited search already certified this burst
+    if (fall_count && *fall_count <= FALL_GRID) return;               // tier 3 (multi-block band search) covers the list
     if (need_full && threadIdx.x == 0) atomicOr(&ctl[stream].flags, 32);
     const i64 sp = (position - max_offset - 1) * osr + 1;     // 1-based
     double2 *win = sm;
@@ -1024,13 +1057,26 @@ __global__ void __launch_bounds__(320) fine_peak_full_kernel(WinSrc src, StreamC
 #define FB_CERT 16
 __global__ void __launch_bounds__(FB_THREADS, 4) fine_peak_band_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ base_pos, int cap,
                                                                    int osr, i64 len_s_ov, const double2 *__restrict__ tw, double *__restrict__ fine_raw,
-                                                                   const int *__restrict__ need_band, int *__restrict__ need_full) {
+                                                                   const int *__restrict__ need_band, int *__restrict__ need_full,
+                                                                   int mode, int *__restrict__ fall_list, int *__restrict__ fall_count,
+                                                                   double *__restrict__ fall_best, int *__restrict__ fall_m, int force_fail) {
+    // mode 0 (tier 2): grid (cap, streams); the band sits around the tone and must pass the certificate, otherwise the
+    //                  burst is appended to fall_list.
+    // mode 1 (tier 3): grid (ceil(N/64), FALL_GRID); block (z, y) searches bins [64z, 64z+64) of the y-th listed burst, no
+    //                  certificate needed because the blocks of a burst cover every bin; fine_fall_combine_kernel merges them.
     extern __shared__ double2 sm[];
     __shared__ double red_v[8];
     __shared__ int red_i[8];
     __shared__ double part[2 * (8 * 128 / FB_CERT + 2)];
-    if (need_band && !need_band[(i64)blockIdx.y * cap + blockIdx.x]) return;     // tier 1 already proved this burst
-    const int burst = blockIdx.x, stream = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double scan_sv[16];
+    int burst = blockIdx.x, stream = blockIdx.y;
+    if (mode == 1) {
+        const int cnt = *fall_count;
+        if ((int)blockIdx.y >= cnt || cnt > FALL_GRID) return;
+        const int id = fall_list[blockIdx.y];
+        stream = id / cap; burst = id % cap;
+    } else if (need_band && !need_band[(i64)blockIdx.y * cap + blockIdx.x]) return;   // tier 1 already proved this burst
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const StreamCtl c = ctl[stream];
     if (c.n_coarse < 5 || burst >= c.n_coarse) return;
     const int N = 148 * osr;
@@ -1066,26 +1112,24 @@ __global__ void __launch_bounds__(FB_THREADS, 4) fine_peak_band_kernel(WinSrc sr
         }
         pe16[tid + 1] = se; pa16[tid + 1] = sa; pa15[tid] = sa15;
     }
+    if (tid == 0) { pe16[0] = 0.0; pa16[0] = 0.0; }
     __syncthreads();
-    if (tid == 0) {                                             // pe16[i] = sum_{n<16i}|s|^2, pa16 likewise, pa15[i] = sum_{n<16i+15}|s|
-        pe16[0] = 0.0; pa16[0] = 0.0;
-        for (int i = 1; i <= n_chunk; ++i) { pe16[i] += pe16[i - 1]; pa16[i] += pa16[i - 1]; }
-        for (int i = 0; i < n_chunk; ++i) pa15[i] += pa16[i];
-    }
+    // pe16[i] = sum_{n<16i}|s|^2, pa16 likewise (two warps scan in parallel), pa15[i] = sum_{n<16i+15}|s|
+    if (warp == 0) warp_scan_smem(pe16, n_chunk + 1, lane);
+    if (warp == 1) { warp_scan_smem(pa16, n_chunk + 1, lane); __syncwarp(); for (int i = lane; i < n_chunk; i += 32) pa15[i] += pa16[i]; }
     // ---- band centre from the phase slope of the centre window ----
     const int mc = (n_win - 1) / 2;
-    double pr = 0.0, pi_ = 0.0;
+    double pq[2] = {0.0, 0.0};
     for (int n = mc + tid; n < mc + N - 1; n += FB_THREADS) {
         const double2 q2 = cmulc(win[n + 1], win[n]);
-        pr += q2.x; pi_ += q2.y;
+        pq[0] += q2.x; pq[1] += q2.y;
     }
-    pr = block_sum(pr, red_v);
-    pi_ = block_sum(pi_, red_v);
-    const int k0 = (int)floor(atan2(pi_, pr) * (double)N / (2.0 * GSMCAL_PI) + 0.5);
+    block_sum_n<2>(pq, scan_sv);
+    const int k0 = (int)floor(atan2(pq[1], pq[0]) * (double)N / (2.0 * GSMCAL_PI) + 0.5);
     // ---- thread = (segment g of windows, bin j).  Segment-start spectra from shared piece sums (absolute phase):
     //      pieces [0,q) [q,2q) [2q,3q) [3q,4q) [4q,N) [N,N+q) [N+q,N+2q) [N+2q,N+3q); window g*q = pieces g..g+4 ----
     const int g = tid / FB_BINS, j = tid % FB_BINS;
-    int k = (k0 - FB_LO + j) % N; if (k < 0) k += N;
+    int k = ((mode == 1 ? FB_BINS * (int)blockIdx.x : k0 - FB_LO) + j) % N; if (k < 0) k += N;
     const int q = (n_win - 1) / FB_SEGS;
     const double2 wk = tw[k];                                    // exp(-2*pi*i*k/N)
     double2 *PS = X;                                             // [8][FB_BINS]
@@ -1165,9 +1209,33 @@ __global__ void __launch_bounds__(FB_THREADS, 4) fine_peak_band_kernel(WinSrc sr
     }
     ok = __syncthreads_and(ok);
     if (tid == 0) {
-        *o = (double)(sp + bestm);
-        need_full[(i64)stream * cap + burst] = ok ? 0 : 1;
+        if (mode == 1) {
+            const int nb3 = (N + FB_BINS - 1) / FB_BINS;
+            fall_best[(i64)blockIdx.y * nb3 + blockIdx.x] = best;
+            fall_m[(i64)blockIdx.y * nb3 + blockIdx.x] = bestm;
+        } else {
+            *o = (double)(sp + bestm);
+            if (force_fail) ok = 0;                               // test hook: exercise tier 3 on every burst that reaches tier 2
+            need_full[(i64)stream * cap + burst] = ok ? 0 : 1;
+            if (!ok) fall_list[atomicAdd(fall_count, 1)] = stream * cap + burst;
+        }
     }
+}
+
+// merges the per-band results of tier 3: first maximum over all bins = larger power, then earlier window
+__global__ void fine_fall_combine_kernel(const int *__restrict__ fall_list, const int *__restrict__ fall_count, const double *__restrict__ fall_best,
+                                         const int *__restrict__ fall_m, int nb3, const double *__restrict__ base_pos, int cap, int osr,
+                                         double *__restrict__ fine_raw, StreamCtl *ctl) {
+    const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cnt = *fall_count;
+    if (wi >= cnt || cnt > FALL_GRID) return;
+    const int id = fall_list[wi];
+    double v = -1.0; int m = 0x7fffffff;
+    for (int z = 0; z < nb3; ++z) argmax_combine(v, m, fall_best[(i64)wi * nb3 + z], fall_m[(i64)wi * nb3 + z]);
+    const i64 position = (i64)base_pos[id];
+    const i64 sp = (position - 64 - 1) * osr + 1;
+    fine_raw[id] = (double)(sp + m);
+    atomicOr(&ctl[id / cap].flags, 32);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1187,6 +1255,7 @@ __global__ void __launch_bounds__(FC_THREADS, 4) fine_peak_core_kernel(WinSrc sr
     __shared__ double red_v[8];
     __shared__ int red_i[8];
     __shared__ double part[8 * 128 / FB_CERT + 2];
+    __shared__ double scan_sv[16];
     const int burst = blockIdx.x, stream = blockIdx.y, tid = threadIdx.x;
     const StreamCtl c = ctl[stream];
     if (c.n_coarse < 5 || burst >= c.n_coarse) return;
@@ -1225,20 +1294,20 @@ __global__ void __launch_bounds__(FC_THREADS, 4) fine_peak_core_kernel(WinSrc sr
         }
         pe16[tid + 1] = se; pa16[tid + 1] = sa; pa15[tid] = sa15;
     }
+    if (tid == 0) { pe16[0] = 0.0; pa16[0] = 0.0; }
     // band centre from the phase slope of the centre window
     const int mc = (n_win - 1) / 2;
-    double pr = 0.0, pi_ = 0.0;
+    double pq[2] = {0.0, 0.0};
     for (int n = mc + tid; n < mc + N - 1; n += FC_THREADS) {
         const double2 q2 = cmulc(win[n + 1], win[n]);
-        pr += q2.x; pi_ += q2.y;
+        pq[0] += q2.x; pq[1] += q2.y;
     }
-    pr = block_sum(pr, red_v);
-    pi_ = block_sum(pi_, red_v);
-    const int k0 = (int)floor(atan2(pi_, pr) * (double)N / (2.0 * GSMCAL_PI) + 0.5);
-    if (tid == 0) {
-        pe16[0] = 0.0; pa16[0] = 0.0;
-        for (int i = 1; i <= n_chunk; ++i) { pe16[i] += pe16[i - 1]; pa16[i] += pa16[i - 1]; }
-        for (int i = 0; i < n_chunk; ++i) pa15[i] += pa16[i];
+    block_sum_n<2>(pq, scan_sv);
+    const int k0 = (int)floor(atan2(pq[1], pq[0]) * (double)N / (2.0 * GSMCAL_PI) + 0.5);
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        if (warp == 0) warp_scan_smem(pe16, n_chunk + 1, lane);
+        if (warp == 1) { warp_scan_smem(pa16, n_chunk + 1, lane); __syncwarp(); for (int i = lane; i < n_chunk; i += 32) pa15[i] += pa16[i]; }
     }
     // chunk sums sum_{n in chunk} s[n] W^{n*k}: (chunk, bin) pairs over the block, 4 accumulators per twiddle
     for (int p = tid; p < n_ch * FC_BINS; p += FC_THREADS) {
@@ -1260,10 +1329,21 @@ __global__ void __launch_bounds__(FC_THREADS, 4) fine_peak_core_kernel(WinSrc sr
         CS[(cidx + 1) * FC_BINS + j] = make_double2((a0r + c1.x) + (c2.x + c3.x), (a0i + c1.y) + (c2.y + c3.y));
     }
     __syncthreads();
-    if (tid < FC_BINS) {                                         // prefix over chunks, one thread per bin
-        double yr = 0.0, yi = 0.0;
-        CS[tid] = make_double2(0.0, 0.0);
-        for (int cidx = 1; cidx <= n_ch; ++cidx) { const double2 v = CS[cidx * FC_BINS + tid]; yr += v.x; yi += v.y; CS[cidx * FC_BINS + tid] = make_double2(yr, yi); }
+    {   // prefix over chunks: warp b scans bin b (lanes own ceil(n_ch/32) consecutive chunks)
+        const int lane = tid & 31, bin = tid >> 5;
+        if (bin < FC_BINS) {
+            const int per = (n_ch + 31) >> 5, b0 = 1 + lane * per;
+            double lr = 0.0, li = 0.0;
+            for (int i = 0; i < per; ++i) if (b0 + i <= n_ch) { const double2 v = CS[(b0 + i) * FC_BINS + bin]; lr += v.x; li += v.y; }
+            double ir = lr, ii = li;
+            for (int d = 1; d < 32; d <<= 1) {
+                const double tr = __shfl_up_sync(0xffffffffu, ir, d), ti = __shfl_up_sync(0xffffffffu, ii, d);
+                if (lane >= d) { ir += tr; ii += ti; }
+            }
+            double rr = ir - lr, ri = ii - li;
+            for (int i = 0; i < per; ++i) if (b0 + i <= n_ch) { const double2 v = CS[(b0 + i) * FC_BINS + bin]; rr += v.x; ri += v.y; CS[(b0 + i) * FC_BINS + bin] = make_double2(rr, ri); }
+            if (lane == 0) CS[bin] = make_double2(0.0, 0.0);
+        }
     }
     __syncthreads();
     const int g = tid / FC_BINS, j = tid % FC_BINS;
@@ -1368,14 +1448,16 @@ __device__ double2 *fft_rows(const double2 *in, double2 *a, double2 *b, int N, c
     double2 *src = a, *dst = b;
     if ((M & (M - 1)) == 0) {
         const int lm = 31 - __clz(M), half = M / 2;
+        __shared__ double2 twm[64];                              // exp(-2*pi*i*j/M), j < M/2 (M <= 128)
+        for (int i = tid; i < half; i += T) twm[i] = tw[i * 37];
         for (int i = tid; i < N; i += T) { const int n2 = i >> lm, n1 = i & (M - 1); src[i] = in[37 * n1 + n2]; }
         __syncthreads();
-        int tstep = N / 2;
-        for (int Ns = 1; Ns < M; Ns <<= 1, tstep >>= 1) {
+        int tsh = lm - 1;                                        // twiddle index k * (M / (2*Ns)) = k << tsh
+        for (int Ns = 1; Ns < M; Ns <<= 1, --tsh) {
             for (int i = tid; i < 37 * half; i += T) {
                 const int row = i >> (lm - 1), j = i & (half - 1), k = j & (Ns - 1);
                 const double2 x0 = src[row * M + j];
-                const double2 x1 = cmul(src[row * M + j + half], tw[k * tstep]);
+                const double2 x1 = cmul(src[row * M + j + half], twm[k << tsh]);
                 const int o = row * M + ((j - k) << 1) + k;
                 dst[o] = make_double2(x0.x + x1.x, x0.y + x1.y);
                 dst[o + Ns] = make_double2(x0.x - x1.x, x0.y - x1.y);
@@ -1432,6 +1514,7 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
     __shared__ double red_v[8];
     __shared__ int red_i[8];
     __shared__ double2 step_sh;
+    __shared__ double red_n[24];
     const int burst = blockIdx.x, stream = blockIdx.y, tid = threadIdx.x;
     const StreamCtl c = ctl[stream];
     const int nb = (which == 1) ? (c.tone1_enable ? c.n_fcch : 0) : (c.post_enable ? c.n_post_fcch : 0);
@@ -1443,14 +1526,15 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
     const i64 sp = (i64)pos[(i64)stream * cap + burst];
     load_window(src, c, stream, sp - 1, N, u, X, Y);
     // energy and phase slope -> band centre
-    double e = 0.0, pr = 0.0, pi_ = 0.0;
+    double epq[3] = {0.0, 0.0, 0.0};
     for (int n = tid; n < N; n += TONE_THREADS) {
         const double2 v = u[n];
-        e = fma(v.x, v.x, fma(v.y, v.y, e));
-        if (n + 1 < N) { const double2 q = cmulc(u[n + 1], v); pr += q.x; pi_ += q.y; }
+        epq[0] = fma(v.x, v.x, fma(v.y, v.y, epq[0]));
+        if (n + 1 < N) { const double2 q = cmulc(u[n + 1], v); epq[1] += q.x; epq[2] += q.y; }
     }
-    e = block_sum(e, red_v); pr = block_sum(pr, red_v); pi_ = block_sum(pi_, red_v);
-    const int k0 = (int)floor(atan2(pi_, pr) * (double)N / (2.0 * GSMCAL_PI) + 0.5);
+    block_sum_n<3>(epq, red_n);
+    const double e = epq[0];
+    const int k0 = (int)floor(atan2(epq[2], epq[1]) * (double)N / (2.0 * GSMCAL_PI) + 0.5);
     const double2 *Tm = fft_rows(u, A, F, N, tw);
     // band search, shifted index j <-> bin (j + N/2) mod N; first maximum in j order (:149-150)
     double v = -1.0; int j_best = 0x7fffffff; double band_sum = 0.0;
@@ -1482,16 +1566,15 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
         A[n] = (h > 0.0) ? make_double2(w.x / h, w.y / h) : make_double2(1.0, 0.0);
     }
     __syncthreads();
-    double rr = 0.0, ri = 0.0;
+    double rri[2] = {0.0, 0.0};
     for (int n = tid; n < N - 1; n += TONE_THREADS) {
         const double2 a = A[n + 1], b = A[n];
         const double den = b.x * b.x + b.y * b.y;
-        rr += (a.x * b.x + a.y * b.y) / den;
-        ri += (a.y * b.x - a.x * b.y) / den;
+        rri[0] += (a.x * b.x + a.y * b.y) / den;
+        rri[1] += (a.y * b.x - a.x * b.y) / den;
     }
-    rr = block_sum(rr, red_v);
-    ri = block_sum(ri, red_v);
-    const double phase_rotate = atan2(ri / (double)(N - 1), rr / (double)(N - 1));
+    block_sum_n<2>(rri, red_n);
+    const double phase_rotate = atan2(rri[1] / (double)(N - 1), rri[0] / (double)(N - 1));
     const double fo = sampling_rate * (int_phase_rotate + phase_rotate) / (2 * GSMCAL_PI);
     if (tid == 0) fo_out[(i64)stream * cap + burst] = fo;
     if (which != 1) return;
@@ -1507,15 +1590,14 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
     __syncthreads();
     Tm = fft_rows(u, A, F, N, tw);
     const int hnl = (int)ceil(((double)N * 200e3 / sampling_rate) / 2.0);
-    double sig = 0.0, noise = 0.0;
+    double sn2[2] = {0.0, 0.0};
     for (int i = tid; i < 2 * hnl; i += TONE_THREADS) {
         const int k = (i < hnl) ? i : N - 2 * hnl + i;           // 0..hnl-1 and N-hnl..N-1
         const double p = abs2_ref(dft_col(Tm, k, N, tw));
-        if (k < 3 || k >= N - 2) sig += p; else noise += p;
+        if (k < 3 || k >= N - 2) sn2[0] += p; else sn2[1] += p;
     }
-    sig = block_sum(sig, red_v);
-    noise = block_sum(noise, red_v);
-    if (tid == 0) gate_out[(i64)stream * cap + burst] = 10.0 * log10(sig / noise);
+    block_sum_n<2>(sn2, red_n);
+    if (tid == 0) gate_out[(i64)stream * cap + burst] = 10.0 * log10(sn2[0] / sn2[1]);
 }
 
 // ===================================================================================================

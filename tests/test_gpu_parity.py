@@ -432,3 +432,27 @@ def test_other_filter_lengths_through_the_batch(gpu, captures, tpl):
         got = gpu.calibrate_batch(raw[:2], CARRIER, tpl, coef)
         for d in range(2):
             _check_stream(got[d], oracle.calibrate_stream(raw[d], CARRIER, tpl, coef))
+
+
+def test_tier3_multiblock_search_equals_all_bin_search(gpu, captures, coef47, tpl):
+    """Force every burst that reaches tier 2 to fail its certificate: tier 3 (19 band blocks per burst + combine, and the
+    single-block all-bin kernel once more than FALL_GRID bursts are listed) must reproduce the all-bin result."""
+    from gsmcal._lib import lib
+    _, raw = captures
+    lib().gsmcal_debug_set(0, 1)
+    try:
+        full = gpu.calibrate_batch(raw, CARRIER, tpl, coef47)
+    finally:
+        lib().gsmcal_debug_set(0, 0)
+    lib().gsmcal_debug_set(4, 1)
+    try:
+        for groups in (1, 2):
+            lib().gsmcal_debug_set(3, groups)
+            t3 = gpu.calibrate_batch(raw, CARRIER, tpl, coef47)
+            assert lib().gsmcal_debug_get(1) > 0
+            for a, b in zip(t3, full):
+                assert np.array_equal(a["fcch_pos"], b["fcch_pos"]) and np.array_equal(a["pos_info"], b["pos_info"])
+                assert a["sampling_ppm"] == b["sampling_ppm"] and a["carrier_ppm"] == b["carrier_ppm"]
+    finally:
+        lib().gsmcal_debug_set(4, 0)
+        lib().gsmcal_debug_set(3, 8)
