@@ -170,7 +170,7 @@ def main():
     ap.add_argument("--n-iq", type=int, default=N_IQ_10S)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--groups", type=int, default=8, help="stream groups per batch inside the library (1 = no overlap; for profiling)")
+    ap.add_argument("--groups", type=int, default=4, help="stream groups per batch inside the library (1 = no overlap; for profiling)")
     ap.add_argument("--stages", action="store_true", help="also time the materialising per-stage kernels (raw2iq, FIR, resample, derotate)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -258,6 +258,14 @@ def main():
     lib().gsmcal_debug_set(3, args.groups)
     stage_ms = {k: v / n_prof for k, v in stage_acc.items()}
 
+    # ---- FP64 pipe peak (microbenchmark) for the burst stages, which are FP64/latency bound, not HBM bound ----
+    fp64 = C.c_double(0.0)
+    lib().gsmcal_fp64_peak(C.byref(fp64), C.c_void_p(stream.cuda_stream))
+    n_bursts = sum(max(r.n_coarse, 0) for r in res)
+    # fp64 operations tier 1 of the fine search executes per burst: FIR 2208*47*2, chunk sums
+    # 2208*8*5, slide 1025*8*8 -> 361.5 k; tiers 2/3 and everything else are not counted (lower bound of the work done)
+    fine_tflops = 2.0 * n_bursts * 361.5e3 / (stage_ms.get("fine_peak", float("nan")) * 1e-3) / 1e12
+
     # ---- roofline of the dominant kernel -----------------------------------------------------------
     hbm_peak, peak_src = measured_peaks()
     colsum_gbs = (D * 2 * n_iq) / (stage_ms.get("colsum_u8", float("nan")) * 1e-3) / 1e9
@@ -265,7 +273,12 @@ def main():
     roofline = {"kernel": "colsum_u8_kernel", "bound": "hbm", "achieved": colsum_gbs, "peak": hbm_peak, "unit": "GB/s",
                 "frac": colsum_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": D * 2 * n_iq,
-                "note": "the only whole-stream pass of the fused pipeline (2 B per IQ sample); dominant stage by time this run: " + dominant}
+                "note": "the only whole-stream (HBM-proportional) pass of the fused pipeline, 2 B per IQ sample; the step time is "
+                        "dominated by the FP64/latency-bound per-burst stages, see fp64_stages"}
+    fp64_stages = {"dominant_stage": dominant, "dominant_stage_ms": stage_ms.get(dominant), "bound": "fp64 pipe / latency",
+                   "fp64_peak_tflops_measured": fp64.value, "fine_peak_tflops_lower_bound": fine_tflops,
+                   "fine_peak_frac_of_fp64_peak": fine_tflops / fp64.value if fp64.value else None, "bursts_rank0": n_bursts,
+                   "note": "fp64 pipe utilisation per kernel from ncu: profiles/r1*_pipeline_kernels.txt"}
 
     # ---- e2e: same call with host (pinned) buffers ---------------------------------------------------
     e2e = None
@@ -333,7 +346,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "stage_ms": stage_ms,
+                "roofline": roofline, "fp64_stages": fp64_stages, "cpu_baseline": cpu_baseline, "stage_ms": stage_ms,
                 "streams_fully_calibrated": f"{n_ok}/{D} on rank 0",
                 "fine_search_allbin_fallback_bursts": n_fallback, "fine_search_64bin_tier2_bursts": n_tier2}
         if stages is not None:

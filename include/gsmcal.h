@@ -176,6 +176,10 @@ int64_t gsmcal_debug_get(int key);
 /* kernel-launch counter (all launches since the last reset, this process) - for bench.py's gpu_launches */
 int64_t gsmcal_launch_count(int reset);
 
+/* measured FP64 FMA throughput of the current device in TFLOP/s (register-only DFMA kernel, CUDA events): the
+ * roofline denominator of the FP64-bound burst stages */
+int gsmcal_fp64_peak(double *tflops, void *cuda_stream);
+
 /* measurement helpers used by bench.py for per-stage rooflines on device-resident buffers.
  * stage: 0 colsum_u8, 1 raw2iq, 2 fir c128->c128, 3 fused u8->fir c128, 4 resample, 5 derotate,
  *        6 fused u8->fir->decimate(64).  Buffers are DEVICE pointers sized by the caller. */

@@ -24,7 +24,7 @@ thread_local std::string g_err;
 thread_local int g_device = 0;
 std::atomic<long long> g_launches{0};
 int *g_last_need_full = nullptr, *g_last_need_band = nullptr; long long g_last_need_full_n = 0;
-int g_debug_groups = 8;           // stream groups per batch (1 = strictly sequential stages, enables per-stage timing)
+int g_debug_groups = 4;           // stream groups per batch (1 = strictly sequential stages, enables per-stage timing)
 int g_debug_fail_tier2 = 0;       // tests: pretend the 64-bin certificate failed
 int g_debug_force_full = 0;       // tests: run the all-bin fine search for every burst
 
@@ -892,6 +892,30 @@ int gsmcal_fcch_scan(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t n_ch
     if (n_position) { h.resize(n_chan); CU(cudaMemcpyAsync(h.data(), w.ctl, sizeof(StreamCtl) * n_chan, cudaMemcpyDeviceToHost, st)); }
     CU(cudaStreamSynchronize(st));
     if (n_position) for (int64_t i = 0; i < n_chan; ++i) n_position[i] = h[i].n_coarse;
+    return GSMCAL_OK;
+}
+
+int gsmcal_fp64_peak(double *tflops, void *cuda_stream) {
+    // measured DFMA throughput of this GPU (2 flop per DFMA), CUDA events around a register-only FMA kernel
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!tflops) return fail(GSMCAL_ERR_ARG, "fp64_peak: null output");
+    Ctx *c; TRY(get_ctx(&c));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, g_device));
+    const int blocks = prop.multiProcessorCount * 8, iters = 1 << 14;
+    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(cudaEventRecord(e0, st));
+        LAUNCH(fp64_peak_kernel, blocks, 256, 0, st, (double *)nullptr, iters, 0.999999, 1e-9);
+        CU(cudaEventRecord(e1, st));
+        CU(cudaEventSynchronize(e1));
+        float ms; CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 8.0 * iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    CU(cudaEventDestroy(e0)); CU(cudaEventDestroy(e1));
+    *tflops = best;
     return GSMCAL_OK;
 }
 

@@ -1961,3 +1961,14 @@ __global__ void twiddle_init_kernel(double2 *tw, int N) {
         tw[j] = make_double2(cs, sn);
     }
 }
+
+// FP64 pipe microbenchmark (8 independent DFMA chains per thread): the denominator for the FP64-bound burst stages,
+// which MEASURED_PEAKS.json (HBM copy + bf16 GEMM) does not provide.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    if (a == 123.456) out[blockIdx.x * 256 + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}

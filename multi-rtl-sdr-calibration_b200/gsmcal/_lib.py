@@ -55,6 +55,7 @@ SIGNATURES = {
     "gsmcal_debug_set": (C.c_int, [C.c_int, C.c_int]),
     "gsmcal_debug_get": (c_i64, [C.c_int]),
     "gsmcal_launch_count": (c_i64, [C.c_int]),
+    "gsmcal_fp64_peak": (C.c_int, [c_dp, C.c_void_p]),
     "gsmcal_stage_launch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, c_i64, c_i64, C.c_void_p, C.c_int, C.c_void_p]),
 }
 

@@ -455,4 +455,4 @@ def test_tier3_multiblock_search_equals_all_bin_search(gpu, captures, coef47, tp
                 assert a["sampling_ppm"] == b["sampling_ppm"] and a["carrier_ppm"] == b["carrier_ppm"]
     finally:
         lib().gsmcal_debug_set(4, 0)
-        lib().gsmcal_debug_set(3, 8)
+        lib().gsmcal_debug_set(3, 4)
