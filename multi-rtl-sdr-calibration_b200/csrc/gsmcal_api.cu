@@ -96,8 +96,13 @@ int ensure_device() {
 constexpr int kFineThreads = 320;
 size_t fine_smem(int osr) { int N = 148 * osr, ns = 2 * 64 * osr + 1 + N - 1; return (size_t)(2 * ns + 8 + GSMCAL_XCAP(ns)) * sizeof(double2); }
 size_t fine_band_smem(int osr) {
-    int N = 148 * osr, ns = 2 * 64 * osr + 1 + N - 1, x = GSMCAL_XCAP((ns + 2) / 3);
-    if (x < 8 * FB_BINS) x = 8 * FB_BINS;                     // the piece sums reuse the staging scratch
+    // window + scratch; the scratch holds the loader's staging for one third of the window, later the piece / chunk sums
+    // and the three 16-sample prefix arrays of the certificate
+    const int N = 148 * osr, ns = 2 * 64 * osr + 1 + N - 1, n_chunk = ns / 16, pre = (3 * (n_chunk + 2) + 1) / 2 + 2;
+    int x = GSMCAL_XCAP((ns + 2) / 3);
+    const int need_band = 8 * FB_BINS + pre, need_core = (ns / (4 * osr) + 1) * FC_BINS + pre;
+    if (x < need_band) x = need_band;
+    if (x < need_core) x = need_core;
     return (size_t)(ns + x) * sizeof(double2);
 }
 size_t tone_smem(int osr) {

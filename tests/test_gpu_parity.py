@@ -456,3 +456,31 @@ def test_tier3_multiblock_search_equals_all_bin_search(gpu, captures, coef47, tp
     finally:
         lib().gsmcal_debug_set(4, 0)
         lib().gsmcal_debug_set(3, 4)
+
+
+def test_drop_in_chain_at_4x_oversampling(gpu, captures, tpl):
+    """The reference functions take oversampling_ratio as an argument; run the per-function chain at 4 samples/symbol on
+    the stream chn_filter_8x_4x produces (chn_filter_8x_4x.m: 60-tap equiripple filter, keep every 2nd sample)."""
+    _, raw = captures
+    with open(os.path.join(GOLDEN, "chn_filter_taps.json")) as f:
+        num8 = np.array([float.fromhex(h) for h in json.load(f)["Num_8x"]["hex"]])
+    b = oracle.raw2iq(raw[3])[:, 0]
+    s4_ref = oracle.chn_filter_8x_4x(b, num8)
+    s4 = gpu.chn_filter_8x_4x(gpu.raw2iq(raw[3])[:, 0])
+    assert rel_err(s4, s4_ref) < 1e-14
+    coarse_ref = oracle.FCCH_coarse_position(s4_ref[::32], 8)
+    coarse = gpu.FCCH_coarse_position(s4_ref[::32], 8)
+    assert np.array_equal(coarse[0], coarse_ref[0]) and len(coarse[0]) >= 5
+    ref = oracle.FCCH_fine_correction(s4_ref, coarse_ref[0], 4, CARRIER)
+    got = gpu.FCCH_fine_correction(s4_ref, coarse_ref[0], 4, CARRIER)
+    assert np.array_equal(got[0], ref[0]) and got[2] == ref[2] and abs(got[3] - ref[3]) < 1e-3
+    assert rel_err(got[1], ref[1]) < 1e-8
+    tpl4 = oracle.gsm_SCH_training_sequence_gen(4)
+    ref_s = oracle.SCH_corr_rate_correction(ref[1], ref[0], tpl4, 4)
+    got_s = gpu.SCH_corr_rate_correction(ref[1], ref[0], tpl4, 4)
+    assert np.array_equal(got_s[0], ref_s[0]) and got_s[2] == ref_s[2]
+    if ref_s[1] is not None:
+        ref_c = oracle.carrier_correct_post_SCH(ref_s[1], ref_s[0], 4, CARRIER)
+        got_c = gpu.carrier_correct_post_SCH(ref_s[1], ref_s[0], 4, CARRIER)
+        assert (ref_c[0] is None) == (got_c[0] is None)
+        assert (got_c[1] == ref_c[1]) if math.isinf(ref_c[1]) else abs(got_c[1] - ref_c[1]) < 1e-3
