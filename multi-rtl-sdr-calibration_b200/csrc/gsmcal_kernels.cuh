@@ -803,6 +803,8 @@ __global__ void specific_hit_kernel(const double *__restrict__ snr, i64 n, doubl
 // K4  burst chain  FCCH_coarse_position.m:32-91 - one warp per stream, 11 candidate windows per step
 // ===================================================================================================
 #define CHAIN_THREADS 64
+#define PF_BYTES 5632              // raw bytes one prefetched candidate range may hold ((2*5+2*5+16+3)*64+46 samples at dec 64)
+#define PF_STRIDE (PF_BYTES + PF_BYTES / 8 + 32)   // with one 16-byte pad per 128 bytes (bank spreading for the 128-byte window stride)
 #define CHAIN_MAXSTAGE 2200        // staged DC-removed samples per candidate group (lazy path, dec*(2*5+fft_len-1)+n_taps <= this)
 __global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src, StreamCtl *ctl, i64 len, int fft_len, double th, int step10, int step11,
                                                                     int dr, int cap, double *__restrict__ position, double *__restrict__ snr_out) {
@@ -814,7 +816,11 @@ __global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src,
     __shared__ double2 tw[128];
     __shared__ double2 buf[2][128 + 16];
     __shared__ int sh_hit; __shared__ double sh_snr;
+    __shared__ __align__(16) unsigned char pf_buf[2 * 3 * PF_STRIDE];
+    __shared__ i64 pf_lo[2][3], pf_hi[2][3];
     const int stream = blockIdx.x, tid = threadIdx.x;
+    if (tid < 6) { pf_lo[tid / 3][tid % 3] = 0; pf_hi[tid / 3][tid % 3] = 0; }
+    int step_no = 0;
     StreamCtl c = ctl[stream];
     double *pos_o = position + (i64)stream * cap;
     double *snr_o = snr_out + (i64)stream * cap;
@@ -844,20 +850,61 @@ __global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src,
         if (nextA > limit) break;                                // run out of sampled signal (:49-51)
         const bool b_ok = nextB <= limit;                        // (:67-69)
         __syncthreads();
+        // ---- shared-memory prefetch (cp.async) of what the FOLLOWING step can touch: its windows sit within +-5 of the 10-/11-frame
+        //      successors of a group-A hit and the 10-frame successor of a group-B hit.  Double buffered: this step reads what the
+        //      previous step requested, so no global-memory latency is left on the per-step critical path. ----
+        const int cur = step_no & 1, nxt = cur ^ 1;
         if (src.lazy) {
-            // L2 prefetch of what the FOLLOWING step can touch (its position depends on this step's hit by at most +-5):
-            // 10- and 11-frame successors of a group-A hit and the 10-frame successor of a group-B hit
             const i64 centers[3] = {nextA + step10, nextA + step11, nextB + step10};
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
                 i64 lo = (centers[q] - 2 * max_offset - 2) * (i64)dec - nt1, hi = (centers[q] + 2 * max_offset + fft_len + 1) * (i64)dec;
-                if (lo < 0) lo = 0;
-                if (hi > src.n_iq) hi = src.n_iq;
-                const uintptr_t p0 = ((uintptr_t)(raw + 2 * lo)) & ~(uintptr_t)127, p1 = (uintptr_t)(raw + 2 * hi);
-                for (uintptr_t pa = p0 + 128 * (uintptr_t)tid; pa < p1; pa += 128 * CHAIN_THREADS)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+                bool okr = lo >= 8 && hi + 8 < src.n_iq && (hi - lo) * 2 + 32 <= PF_BYTES;
+                const uintptr_t a0 = ((uintptr_t)(raw + 2 * lo)) & ~(uintptr_t)15;
+                const int nchunk = okr ? (int)(((uintptr_t)(raw + 2 * hi) - a0 + 15) >> 4) : 0;
+                unsigned char *dstb = pf_buf + (nxt * 3 + q) * PF_STRIDE;
+                for (int ch = tid; ch < nchunk; ch += CHAIN_THREADS) {
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(dstb + 16 * ch + 16 * (ch >> 3));
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(a0 + 16 * (uintptr_t)ch));
+                }
+                if (tid == 0) {
+                    pf_lo[nxt][q] = okr ? (i64)(((const uint8_t *)a0 - raw) / 2) : 0;     // sample index of byte 0 (a0 >= raw, even offset)
+                    pf_hi[nxt][q] = okr ? pf_lo[nxt][q] + 8 * (i64)nchunk : 0;            // exclusive
+                }
             }
         }
+        asm volatile("cp.async.commit_group;");
+        asm volatile("cp.async.wait_group 1;");                  // everything except the group just committed has landed
+        __syncthreads();
+        // which prefetched range serves this step's groups?
+        int srcA = -1, srcB = -1;
+        if (src.lazy && step_no > 0) {
+            const i64 needA0 = (nextA - max_offset - 1) * (i64)dec - nt1, needA1 = (nextA + max_offset + fft_len - 1) * (i64)dec;
+            const i64 needB0 = (nextB - max_offset - 1) * (i64)dec - nt1, needB1 = (nextB + max_offset + fft_len - 1) * (i64)dec;
+            for (int q = 0; q < 3; ++q) {
+                if (srcA < 0 && pf_hi[cur][q] > 0 && needA0 >= pf_lo[cur][q] && needA1 <= pf_hi[cur][q]) srcA = q;
+                if (srcB < 0 && pf_hi[cur][q] > 0 && needB0 >= pf_lo[cur][q] && needB1 <= pf_hi[cur][q]) srcB = q;
+            }
+        }
+        const bool fast = src.lazy && srcA >= 0 && (srcB >= 0 || !b_ok);
+        ++step_no;
+        if (fast) {
+            for (int i = tid; i < 2 * ns; i += CHAIN_THREADS) {
+                const int g = i / ns, r = i % ns;
+                if (g == 1 && !b_ok) continue;
+                const int q = g == 0 ? srcA : srcB;
+                const unsigned char *pb = pf_buf + (cur * 3 + q) * PF_STRIDE;
+                const i64 s0 = ((g == 0 ? nextA : nextB) - max_offset - 1 + r) * (i64)dec - nt1;   // oldest raw sample of this decimated sample
+                int bo = (int)(2 * (s0 - pf_lo[cur][q]));                                            // byte offset (unpadded)
+                double ar = 0.0, ai = 0.0;
+                for (int k = nt1; k >= 0; --k, bo += 2) {        // oldest tap first
+                    const uchar2 u = *reinterpret_cast<const uchar2 *>(pb + bo + 16 * (bo >> 7));
+                    ar = fma(c_taps[k], (double)u.x - mur, ar);
+                    ai = fma(c_taps[k], (double)u.y - mui, ai);
+                }
+                buf[g][r] = make_double2(ar, ai);
+            }
+        } else {
         // the aligned words must stay inside this stream's row (the first samples of a capture use the scalar path)
         const i64 lo_raw = (nextA - max_offset - 1) * (i64)dec - nt1, hi_raw = (nextB + max_offset + fft_len) * (i64)dec;
         const bool staged = can_stage && lo_raw >= 4 && hi_raw + 4 < src.n_iq;
@@ -920,6 +967,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src,
                 const int g = i / ns, r = i % ns;
                 if (g == 0 || b_ok) buf[g][r] = coarse_sample(src, c, stream, (g == 0 ? nextA : nextB) - max_offset - 1 + r);
             }
+        }
         }
         __syncthreads();
         if (tid < 32) {
