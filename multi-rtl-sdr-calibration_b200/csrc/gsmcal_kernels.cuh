@@ -1302,7 +1302,6 @@ __global__ void __launch_bounds__(FC_THREADS, 4) fine_peak_core_kernel(WinSrc sr
     extern __shared__ double2 sm[];
     __shared__ double red_v[8];
     __shared__ int red_i[8];
-    __shared__ double part[8 * 128 / FB_CERT + 2];
     __shared__ double scan_sv[16];
     const int burst = blockIdx.x, stream = blockIdx.y, tid = threadIdx.x;
     const StreamCtl c = ctl[stream];
@@ -1418,12 +1417,6 @@ __global__ void __launch_bounds__(FC_THREADS, 4) fine_peak_core_kernel(WinSrc sr
         for (int m = m0; m < m_end; ++m) {
             const double p = fma(xr, xr, xi * xi);
             if (p > best) { best = p; bestm = m; }
-            if ((m % FB_CERT) == 0) {                             // the 8 bins of a segment are 8 adjacent lanes
-                double s2 = p;
-                const unsigned gm = 0xffu << (tid & 24);          // only this segment's 8 lanes (the last segment runs one window longer)
-                s2 += __shfl_xor_sync(gm, s2, 1); s2 += __shfl_xor_sync(gm, s2, 2); s2 += __shfl_xor_sync(gm, s2, 4);
-                if (j == 0) part[m / FB_CERT] = s2;
-            }
             if (m + 1 < m_end) {
                 const double2 d = win[m];
                 const double tr = xr + d.x, ti = xi + d.y;
@@ -1433,13 +1426,50 @@ __global__ void __launch_bounds__(FC_THREADS, 4) fine_peak_core_kernel(WinSrc sr
         }
     }
     block_argmax(best, bestm, red_v, red_i);
-    const int n_cert = (n_win - 1) / FB_CERT + 1;
+    // ---- certificate at every segment-start window c = CH*g (g = 0..n_seg), straight from the chunk prefix table.
+    // For any split of the window into a part P1 of d samples and the rest P2, every untracked bin obeys
+    //   |X_c[k]| <= |P1[k]| + |P2[k]| <= sqrt(d*E_P1) + sqrt(N*E_P2 - sum_tracked |P2[k']|^2)
+    // (Cauchy-Schwarz on P1, Parseval on the zero-padded P2).  Putting the non-FCCH samples of an edge window into P1
+    // (d ~ |m* - c|, a few chunk-aligned candidates) is much tighter than Parseval on the whole window, whose bound
+    // charges all of the GMSK data energy to a single bin.  d = 0 is the plain Parseval bound. ----
     int ok = 1;
-    if (tid < n_cert) {
-        const int ci = tid, nc = N / FB_CERT;
-        const double R = (double)N * (pe16[ci + nc] - pe16[ci]) - part[ci];
-        const double A = (ci == n_cert - 1) ? 0.0 : (pa15[ci] - pa16[ci]) + (pa15[ci + nc] - pa16[ci + nc]);
-        const double bound = sqrt(R > 0.0 ? R : 0.0) + A;
+    if (tid <= n_seg) {
+        const int gq = tid, cw = gq * CH, per16 = CH / FB_CERT;      // chunk index of the window start; 16-sample units per chunk
+        const double e_all = pe16[(gq + wch) * per16] - pe16[gq * per16];
+        double t_all = 0.0;
+#pragma unroll
+        for (int jj = 0; jj < FC_BINS; ++jj) {
+            const double2 hi = CS[(gq + wch) * FC_BINS + jj], lo = CS[gq * FC_BINS + jj];
+            const double yr = hi.x - lo.x, yi = hi.y - lo.y;
+            t_all += yr * yr + yi * yi;
+        }
+        double r0 = (double)N * e_all - t_all;
+        double bmin = sqrt(r0 > 0.0 ? r0 : 0.0);
+        if (cw != bestm) {
+            const bool lead = cw < bestm;
+            const int dist = lead ? bestm - cw : cw - bestm;
+            const int d0 = (dist + CH - 1) / CH;
+            for (int dch = (d0 - 2 > 1 ? d0 - 2 : 1); dch <= d0 + 3 && dch < wch; ++dch) {
+                // P1 = first dch chunks (window starts before the burst) or last dch chunks (window runs past it)
+                const int p1a = lead ? gq : gq + wch - dch, p1b = p1a + dch;
+                const int p2a = lead ? gq + dch : gq, p2b = lead ? gq + wch : gq + wch - dch;
+                const double e1 = pe16[p1b * per16] - pe16[p1a * per16], e2 = pe16[p2b * per16] - pe16[p2a * per16];
+                double t2 = 0.0;
+#pragma unroll
+                for (int jj = 0; jj < FC_BINS; ++jj) {
+                    const double2 hi = CS[p2b * FC_BINS + jj], lo = CS[p2a * FC_BINS + jj];
+                    const double yr = hi.x - lo.x, yi = hi.y - lo.y;
+                    t2 += yr * yr + yi * yi;
+                }
+                const double r2 = (double)N * e2 - t2;
+                const double bnd = sqrt((double)(dch * CH) * (e1 > 0.0 ? e1 : 0.0)) + sqrt(r2 > 0.0 ? r2 : 0.0);
+                if (bnd < bmin) bmin = bnd;
+            }
+        }
+        // windows cw .. cw+CH-1 (only cw itself for the last one): slack = sum_{i=cw}^{cw+CH-2} (|s[i]| + |s[i+N]|)
+        const int i16 = gq * per16 + per16 - 1, j16 = (gq + wch) * per16 + per16 - 1;     // pa15[i16] = sum_{n < cw+CH-1} |s|
+        const double A = (gq == n_seg) ? 0.0 : (pa15[i16] - pa16[gq * per16]) + (pa15[j16] - pa16[(gq + wch) * per16]);
+        const double bound = bmin + A;
         ok = (bound * bound < best * (1.0 - 1e-6)) ? 1 : 0;
     }
     ok = __syncthreads_and(ok);
