@@ -1327,7 +1327,9 @@ __global__ void __launch_bounds__(FC_THREADS, 4) fine_peak_core_kernel(WinSrc sr
     }
     const int CH = 4 * osr;                                     // chunk = segment length; n_smp = 69*CH, N = 37*CH, n_win-1 = 32*CH
     const int n_ch = n_smp / CH, n_seg = (n_win - 1) / CH, wch = N / CH;
-    double2 *CS = X;                                             // [n_ch + 1][FC_BINS] prefix of chunk sums
+    double2 *CS = X;                                             // [FC_BINS][n_ch + 1] prefix of chunk sums (bin-major: the scans read contiguously)
+    const int csl = n_ch + 1;
+#define CSI(cc, jj) ((jj) * csl + (cc))
     const int n_chunk = n_smp / FB_CERT;
     double *pe16 = reinterpret_cast<double *>(X + (n_ch + 1) * FC_BINS), *pa16 = pe16 + n_chunk + 2, *pa15 = pa16 + n_chunk + 2;
     if (tid < n_chunk) {
@@ -1373,7 +1375,7 @@ __global__ void __launch_bounds__(FC_THREADS, 4) fine_peak_core_kernel(WinSrc sr
             t = cmul(t, wk4);
         }
         const double2 c1 = cmul(make_double2(a1r, a1i), wk), c2 = cmul(make_double2(a2r, a2i), wk2), c3 = cmul(make_double2(a3r, a3i), wk3);
-        CS[(cidx + 1) * FC_BINS + j] = make_double2((a0r + c1.x) + (c2.x + c3.x), (a0i + c1.y) + (c2.y + c3.y));
+        CS[CSI(cidx + 1, j)] = make_double2((a0r + c1.x) + (c2.x + c3.x), (a0i + c1.y) + (c2.y + c3.y));
     }
     __syncthreads();
     {   // prefix over chunks: warp b scans bin b (lanes own ceil(n_ch/32) consecutive chunks)
@@ -1381,15 +1383,15 @@ __global__ void __launch_bounds__(FC_THREADS, 4) fine_peak_core_kernel(WinSrc sr
         if (bin < FC_BINS) {
             const int per = (n_ch + 31) >> 5, b0 = 1 + lane * per;
             double lr = 0.0, li = 0.0;
-            for (int i = 0; i < per; ++i) if (b0 + i <= n_ch) { const double2 v = CS[(b0 + i) * FC_BINS + bin]; lr += v.x; li += v.y; }
+            for (int i = 0; i < per; ++i) if (b0 + i <= n_ch) { const double2 v = CS[CSI(b0 + i, bin)]; lr += v.x; li += v.y; }
             double ir = lr, ii = li;
             for (int d = 1; d < 32; d <<= 1) {
                 const double tr = __shfl_up_sync(0xffffffffu, ir, d), ti = __shfl_up_sync(0xffffffffu, ii, d);
                 if (lane >= d) { ir += tr; ii += ti; }
             }
             double rr = ir - lr, ri = ii - li;
-            for (int i = 0; i < per; ++i) if (b0 + i <= n_ch) { const double2 v = CS[(b0 + i) * FC_BINS + bin]; rr += v.x; ri += v.y; CS[(b0 + i) * FC_BINS + bin] = make_double2(rr, ri); }
-            if (lane == 0) CS[bin] = make_double2(0.0, 0.0);
+            for (int i = 0; i < per; ++i) if (b0 + i <= n_ch) { const double2 v = CS[CSI(b0 + i, bin)]; rr += v.x; ri += v.y; CS[CSI(b0 + i, bin)] = make_double2(rr, ri); }
+            if (lane == 0) CS[CSI(0, bin)] = make_double2(0.0, 0.0);
         }
     }
     __syncthreads();
@@ -1400,7 +1402,7 @@ __global__ void __launch_bounds__(FC_THREADS, 4) fine_peak_core_kernel(WinSrc sr
     const int m0 = g * CH, m_end = (g == n_seg - 1) ? n_win : m0 + CH;
     double xr = 0.0, xi = 0.0;
     if (active) {
-        const double2 hi = CS[(g + wch) * FC_BINS + j], lo = CS[g * FC_BINS + j];
+        const double2 hi = CS[CSI(g + wch, j)], lo = CS[CSI(g, j)];
         const double yr = hi.x - lo.x, yi = hi.y - lo.y;
         const double2 t = tw[(int)(((i64)m0 * k) % N)];          // X_{m0}[k] = Y_{m0}[k] * exp(+2*pi*i*m0*k/N)
         xr = yr * t.x + yi * t.y;
@@ -1432,24 +1434,17 @@ __global__ void __launch_bounds__(FC_THREADS, 4) fine_peak_core_kernel(WinSrc sr
     // (Cauchy-Schwarz on P1, Parseval on the zero-padded P2).  Putting the non-FCCH samples of an edge window into P1
     // (d ~ |m* - c|, a few chunk-aligned candidates) is much tighter than Parseval on the whole window, whose bound
     // charges all of the GMSK data energy to a single bin.  d = 0 is the plain Parseval bound. ----
+    // threads = (window, candidate split): 8 lanes per window, candidate 0 = plain Parseval, 1..6 = d0-2 .. d0+3 chunks
     int ok = 1;
-    if (tid <= n_seg) {
-        const int gq = tid, cw = gq * CH, per16 = CH / FB_CERT;      // chunk index of the window start; 16-sample units per chunk
-        const double e_all = pe16[(gq + wch) * per16] - pe16[gq * per16];
-        double t_all = 0.0;
-#pragma unroll
-        for (int jj = 0; jj < FC_BINS; ++jj) {
-            const double2 hi = CS[(gq + wch) * FC_BINS + jj], lo = CS[gq * FC_BINS + jj];
-            const double yr = hi.x - lo.x, yi = hi.y - lo.y;
-            t_all += yr * yr + yi * yi;
-        }
-        double r0 = (double)N * e_all - t_all;
-        double bmin = sqrt(r0 > 0.0 ? r0 : 0.0);
-        if (cw != bestm) {
+    for (int w0 = 0; w0 <= n_seg; w0 += FC_THREADS / 8) {
+        const int gq = w0 + (tid >> 3), cand = tid & 7;
+        double bnd = INFINITY;
+        if (gq <= n_seg && cand < 7) {
+            const int cw = gq * CH, per16 = CH / FB_CERT;
             const bool lead = cw < bestm;
             const int dist = lead ? bestm - cw : cw - bestm;
-            const int d0 = (dist + CH - 1) / CH;
-            for (int dch = (d0 - 2 > 1 ? d0 - 2 : 1); dch <= d0 + 3 && dch < wch; ++dch) {
+            const int dch = (cand == 0) ? 0 : (dist + CH - 1) / CH - 3 + cand;
+            if (dch == 0 || (cw != bestm && dch >= 1 && dch < wch)) {
                 // P1 = first dch chunks (window starts before the burst) or last dch chunks (window runs past it)
                 const int p1a = lead ? gq : gq + wch - dch, p1b = p1a + dch;
                 const int p2a = lead ? gq + dch : gq, p2b = lead ? gq + wch : gq + wch - dch;
@@ -1457,26 +1452,32 @@ __global__ void __launch_bounds__(FC_THREADS, 4) fine_peak_core_kernel(WinSrc sr
                 double t2 = 0.0;
 #pragma unroll
                 for (int jj = 0; jj < FC_BINS; ++jj) {
-                    const double2 hi = CS[p2b * FC_BINS + jj], lo = CS[p2a * FC_BINS + jj];
+                    const double2 hi = CS[CSI(p2b, jj)], lo = CS[CSI(p2a, jj)];
                     const double yr = hi.x - lo.x, yi = hi.y - lo.y;
                     t2 += yr * yr + yi * yi;
                 }
                 const double r2 = (double)N * e2 - t2;
-                const double bnd = sqrt((double)(dch * CH) * (e1 > 0.0 ? e1 : 0.0)) + sqrt(r2 > 0.0 ? r2 : 0.0);
-                if (bnd < bmin) bmin = bnd;
+                bnd = sqrt((double)(dch * CH) * (e1 > 0.0 ? e1 : 0.0)) + sqrt(r2 > 0.0 ? r2 : 0.0);
             }
         }
-        // windows cw .. cw+CH-1 (only cw itself for the last one): slack = sum_{i=cw}^{cw+CH-2} (|s[i]| + |s[i+N]|)
-        const int i16 = gq * per16 + per16 - 1, j16 = (gq + wch) * per16 + per16 - 1;     // pa15[i16] = sum_{n < cw+CH-1} |s|
-        const double A = (gq == n_seg) ? 0.0 : (pa15[i16] - pa16[gq * per16]) + (pa15[j16] - pa16[(gq + wch) * per16]);
-        const double bound = bmin + A;
-        ok = (bound * bound < best * (1.0 - 1e-6)) ? 1 : 0;
+        bnd = fmin(bnd, __shfl_xor_sync(0xffffffffu, bnd, 1));
+        bnd = fmin(bnd, __shfl_xor_sync(0xffffffffu, bnd, 2));
+        bnd = fmin(bnd, __shfl_xor_sync(0xffffffffu, bnd, 4));
+        if (gq <= n_seg && cand == 0) {
+            const int per16 = CH / FB_CERT;
+            // windows cw .. cw+CH-1 (only cw itself for the last one): slack = sum_{i=cw}^{cw+CH-2} (|s[i]| + |s[i+N]|)
+            const int i16 = gq * per16 + per16 - 1, j16 = (gq + wch) * per16 + per16 - 1;     // pa15[i16] = sum_{n < cw+CH-1} |s|
+            const double A = (gq == n_seg) ? 0.0 : (pa15[i16] - pa16[gq * per16]) + (pa15[j16] - pa16[(gq + wch) * per16]);
+            const double bound = bnd + A;
+            if (!(bound * bound < best * (1.0 - 1e-6))) ok = 0;
+        }
     }
     ok = __syncthreads_and(ok);
     if (tid == 0) {
         *o = (double)(sp + bestm);
         need_band[(i64)stream * cap + burst] = ok ? 0 : 1;
     }
+#undef CSI
 }
 
 // ===================================================================================================
