@@ -1614,17 +1614,43 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
     block_sum_n<3>(epq, red_n);
     const double e = epq[0];
     const int k0 = (int)floor(atan2(epq[2], epq[1]) * (double)N / (2.0 * GSMCAL_PI) + 0.5);
-    const double2 *Tm = fft_rows(u, A, F, N, tw);
-    // band search, shifted index j <-> bin (j + N/2) mod N; first maximum in j order (:149-150)
+    // band search without an FFT: 16 bins x 16 sample segments, absolute-phase partial DFTs (4 accumulators per twiddle,
+    // as in the fine search), summed over the segments through shared memory.
+    // shifted index j <-> bin (j + N/2) mod N; first maximum in j order (:149-150)
     double v = -1.0; int j_best = 0x7fffffff; double band_sum = 0.0;
-    if (tid < TONE_BAND) {
-        int k = (k0 - TONE_BAND / 2 + tid) % N; if (k < 0) k += N;
-        int j = k - N / 2; if (j < 0) j += N;
-        v = abs2_ref(dft_col(Tm, k, N, tw)); j_best = j; band_sum = v;
+    {
+        const int bin = tid & (TONE_BAND - 1), seg = tid / TONE_BAND, n_segs = TONE_THREADS / TONE_BAND;
+        int k = (k0 - TONE_BAND / 2 + bin) % N; if (k < 0) k += N;
+        const int per = (N + n_segs - 1) / n_segs, na = seg * per, nb2 = (na + per < N) ? na + per : N;
+        const double2 wk = tw[k], wk2 = tw[(2 * k) % N], wk3 = tw[(3 * k) % N], wk4 = tw[(4 * k) % N];
+        double2 t = tw[(int)(((i64)na * k) % N)];
+        double a0r = 0.0, a0i = 0.0, a1r = 0.0, a1i = 0.0, a2r = 0.0, a2i = 0.0, a3r = 0.0, a3i = 0.0;
+        int n = na;
+        for (; n + 3 < nb2; n += 4) {
+            const double2 s0 = u[n], s1 = u[n + 1], s2 = u[n + 2], s3 = u[n + 3];
+            a0r = fma(s0.x, t.x, fma(-s0.y, t.y, a0r)); a0i = fma(s0.x, t.y, fma(s0.y, t.x, a0i));
+            a1r = fma(s1.x, t.x, fma(-s1.y, t.y, a1r)); a1i = fma(s1.x, t.y, fma(s1.y, t.x, a1i));
+            a2r = fma(s2.x, t.x, fma(-s2.y, t.y, a2r)); a2i = fma(s2.x, t.y, fma(s2.y, t.x, a2i));
+            a3r = fma(s3.x, t.x, fma(-s3.y, t.y, a3r)); a3i = fma(s3.x, t.y, fma(s3.y, t.x, a3i));
+            t = cmul(t, wk4);
+        }
+        if (n < nb2)     { const double2 s0 = u[n];     a0r = fma(s0.x, t.x, fma(-s0.y, t.y, a0r)); a0i = fma(s0.x, t.y, fma(s0.y, t.x, a0i)); }
+        if (n + 1 < nb2) { const double2 s1 = u[n + 1]; a1r = fma(s1.x, t.x, fma(-s1.y, t.y, a1r)); a1i = fma(s1.x, t.y, fma(s1.y, t.x, a1i)); }
+        if (n + 2 < nb2) { const double2 s2 = u[n + 2]; a2r = fma(s2.x, t.x, fma(-s2.y, t.y, a2r)); a2i = fma(s2.x, t.y, fma(s2.y, t.x, a2i)); }
+        const double2 c1 = cmul(make_double2(a1r, a1i), wk), c2 = cmul(make_double2(a2r, a2i), wk2), c3 = cmul(make_double2(a3r, a3i), wk3);
+        A[seg * TONE_BAND + bin] = make_double2((a0r + c1.x) + (c2.x + c3.x), (a0i + c1.y) + (c2.y + c3.y));
+        __syncthreads();
+        if (tid < TONE_BAND) {
+            double xr = 0.0, xi = 0.0;
+            for (int sgi = 0; sgi < n_segs; ++sgi) { const double2 q = A[sgi * TONE_BAND + tid]; xr += q.x; xi += q.y; }
+            int j = k - N / 2; if (j < 0) j += N;                // here k is the bin of thread (seg 0, bin tid)
+            v = abs2_ref(make_double2(xr, xi)); j_best = j; band_sum = v;
+        }
     }
     band_sum = block_sum(band_sum, red_v);
     block_argmax(v, j_best, red_v, red_i);
-    if (!((double)N * e - band_sum < v * (1.0 - 1e-9))) {     // not certified: every bin (uniform branch)
+    if (!((double)N * e - band_sum < v * (1.0 - 1e-9))) {     // not certified: every bin through the row FFT (uniform branch)
+        const double2 *Tm = fft_rows(u, A, F, N, tw);
         v = -1.0; j_best = 0x7fffffff;
         for (int j = tid; j < N; j += TONE_THREADS) {
             int k = j + N / 2; if (k >= N) k -= N;
@@ -1667,7 +1693,7 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
         for (int n = tid; n < N; n += TONE_THREADS) { u[n] = cmul(u[n], ph); ph = cmul(ph, st); }
     }
     __syncthreads();
-    Tm = fft_rows(u, A, F, N, tw);
+    const double2 *Tm = fft_rows(u, A, F, N, tw);
     const int hnl = (int)ceil(((double)N * 200e3 / sampling_rate) / 2.0);
     double sn2[2] = {0.0, 0.0};
     for (int i = tid; i < 2 * hnl; i += TONE_THREADS) {
