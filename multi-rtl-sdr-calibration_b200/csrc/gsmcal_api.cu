@@ -829,6 +829,7 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
             cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             CU(cudaEventRecord(ev, st)); CU(cudaStreamWaitEvent(sg, ev, 0)); CU(cudaEventDestroy(ev));
         }
+        LAUNCH(mean_kernel, (unsigned)((nd + 127) / 128), 128, 0, sg, ws.ctl, (int)nd, n_iq);
         if (timing) TRY(stage_mark(sg));
         TRY(run_coarse(lazy_src(graw, n_iq, n_taps, 0, dec), len_dec, p, nd, cap, ws, sg));
         if (timing) TRY(stage_mark(sg));
@@ -888,6 +889,7 @@ int gsmcal_fcch_scan(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t n_ch
     }
     CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * n_chan, st));
     TRY(run_colsum_u8(draw, n_iq, n_chan, w.ctl, st));
+    LAUNCH(mean_kernel, (unsigned)((n_chan + 127) / 128), 128, 0, st, w.ctl, (int)n_chan, n_iq);
     TRY(run_coarse(lazy_src(draw, n_iq, n_taps, 0, dec), len_dec, p, n_chan, cap, w, st));
     LAUNCH(scan_accept_kernel, (unsigned)((n_chan + 63) / 64), 64, 0, st, w.ctl, (int)n_chan, cap, w.coarse_pos, w.coarse_snr, w.fo, w.gate);
     CU(cudaMemcpyAsync(snr, w.fo, sizeof(double) * n_chan, cudaMemcpyDeviceToHost, st));

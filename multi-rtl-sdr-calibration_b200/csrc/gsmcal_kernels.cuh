@@ -22,6 +22,7 @@ __constant__ double c_taps[GSMCAL_MAX_TAPS];      // FIR numerator of the curren
 // ---------------------------------------------------------------------------------------------------
 struct StreamCtl {
     u64    sum_i, sum_q;          // exact integer column sums of raw2iq.m:8
+    double mu_re, mu_im;          // sum / N, written once per stream by mean_kernel (saves two fp64 divisions per thread per window load)
     // coarse
     int    n_coarse;              // -1: no FCCH found (FCCH_coarse_position.m:27-30)
     int    first_hit;             // 1-based window index of the first hit, -1 none
@@ -128,7 +129,7 @@ __device__ void load_window(const WinSrc &src, const StreamCtl &c, int stream, i
     }
     const uint8_t *raw = src.raw + (i64)stream * 2 * src.n_iq;
     const i64 n0 = src.n_iq;
-    const double mur = stream_mean(c.sum_i, n0), mui = stream_mean(c.sum_q, n0);
+    const double mur = c.mu_re, mui = c.mu_im;
     const bool use2 = (src.level == 3) && c.interp2_on;
     const bool use1 = (src.level >= 1) && c.interp1_on;
     const bool derot = (src.level >= 2) && c.derot1_on;
@@ -238,7 +239,7 @@ __device__ void load_window(const WinSrc &src, const StreamCtl &c, int stream, i
 __device__ __forceinline__ double2 coarse_sample(const WinSrc &src, const StreamCtl &c, int stream, i64 idx0) {
     if (!src.lazy) return src.base[(i64)stream * src.base_stride + idx0];
     const uint8_t *raw = src.raw + (i64)stream * 2 * src.n_iq;
-    return fir_from_raw(raw, idx0 * src.dec, src.n_taps, stream_mean(c.sum_i, src.n_iq), stream_mean(c.sum_q, src.n_iq));
+    return fir_from_raw(raw, idx0 * src.dec, src.n_taps, c.mu_re, c.mu_im);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -841,7 +842,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src,
     const bool can_stage = src.lazy && n_stage <= CHAIN_MAXSTAGE;
     const int stage_cap = CHAIN_MAXSTAGE + CHAIN_MAXSTAGE / 32 + 4;
     const uint8_t *raw = src.raw + (i64)stream * 2 * src.n_iq;
-    const double mur = stream_mean(c.sum_i, src.n_iq), mui = stream_mean(c.sum_q, src.n_iq);
+    const double mur = c.mu_re, mui = c.mu_im;
     i64 pos = c.first_hit;
     int count = 1;
     if (tid == 0) { pos_o[0] = (double)((pos - 1) * dr + 1); snr_o[0] = c.hit_snr; }
@@ -1716,7 +1717,7 @@ __global__ void __launch_bounds__(SCH_THREADS, 2) sch_corr_kernel(WinSrc src, co
     extern __shared__ double2 sm[];
     __shared__ double red_v[8];
     __shared__ int red_i[8];
-    __shared__ double corr[160];
+    __shared__ double corr[160], corr_i[160];
     const int burst = blockIdx.x, stream = blockIdx.y;
     const StreamCtl c = ctl[stream];
     if (!c.sch_enable || burst >= c.n_fcch) return;
@@ -1769,7 +1770,7 @@ __global__ void __launch_bounds__(SCH_THREADS, 2) sch_corr_kernel(WinSrc src, co
 #pragma unroll
         for (int l = 0; l < SCH_LPG; ++l) {
             const double sr_ = warp_sum(ar[l]), si_ = warp_sum(ai[l]);
-            if (lane == 0 && l0 + l < n_lag) corr[l0 + l] = abs2_ref(make_double2(sr_, si_));
+            if (lane == 0 && l0 + l < n_lag) { corr[l0 + l] = sr_; corr_i[l0 + l] = si_; }
         }
     } else {
         for (int lag = w; lag < n_lag; lag += nw) {              // generic shapes: one warp per lag
@@ -1779,9 +1780,11 @@ __global__ void __launch_bounds__(SCH_THREADS, 2) sch_corr_kernel(WinSrc src, co
                 ar += p.x; ai += p.y;
             }
             ar = warp_sum(ar); ai = warp_sum(ai);
-            if (lane == 0) corr[lag] = abs2_ref(make_double2(ar, ai));
+            if (lane == 0) { corr[lag] = ar; corr_i[lag] = ai; }
         }
     }
+    __syncthreads();
+    if (threadIdx.x < n_lag) corr[threadIdx.x] = abs2_ref(make_double2(corr[threadIdx.x], corr_i[threadIdx.x]));   // abs(.)^2, one lag per thread
     __syncthreads();
     double v = -1.0; int bi = 0x7fffffff;
     for (int lag = threadIdx.x; lag < n_lag; lag += SCH_THREADS) argmax_combine(v, bi, corr[lag], lag);
@@ -2057,6 +2060,11 @@ __global__ void scan_accept_kernel(const StreamCtl *ctl, int n_chan, int cap, co
         }
     }
     snr_out[ch] = s; num_hit[ch] = h;
+}
+
+__global__ void mean_kernel(StreamCtl *ctl, int n_streams, i64 n_iq) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < n_streams) { ctl[d].mu_re = stream_mean(ctl[d].sum_i, n_iq); ctl[d].mu_im = stream_mean(ctl[d].sum_q, n_iq); }
 }
 
 __global__ void twiddle_init_kernel(double2 *tw, int N) {
