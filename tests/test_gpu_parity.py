@@ -484,3 +484,41 @@ def test_drop_in_chain_at_4x_oversampling(gpu, captures, tpl):
         got_c = gpu.carrier_correct_post_SCH(ref_s[1], ref_s[0], 4, CARRIER)
         assert (ref_c[0] is None) == (got_c[0] is None)
         assert (got_c[1] == ref_c[1]) if math.isinf(ref_c[1]) else abs(got_c[1] - ref_c[1]) < 1e-3
+
+
+# ---- BASELINE configs 2 and 4 at the reference's own sizes -----------------------------------------------------------
+def test_config2_fcch_scanner_all_126_frequencies(gpu):
+    """multi_rtl_sdr_gsm_FCCH_scanner.m: 935:0.2:960 MHz = 126 points, 640 000 IQ each, fir1(30), /64, coarse + acceptance."""
+    torch = pytest.importorskip("torch")
+    n, n_freq = 640000, 126
+    coef = oracle.fir1(30, 200e3 / FS)
+    carriers = {5: 11.0, 17: -23.0, 40: 3.5, 41: 30.0, 77: -8.0, 90: 0.0, 101: 19.0, 102: -31.0, 120: 7.0, 125: -2.0, 60: 14.0, 33: -17.0}
+    specs = []
+    for c in range(n_freq):
+        if c in carriers:
+            specs.append(synth.StreamSpec(seed=500 + c, n_samples=n, sampling_ppm=carriers[c], carrier_ppm=-carriers[c] / 2,
+                                          snr_db=12.0 + (c % 10), start_offset=float((c * 7919) % synth.MULTIFRAME)))
+        else:
+            specs.append(synth.StreamSpec(seed=500 + c, n_samples=n, noise_only=True))
+    raw = synth.generate_batch(specs, device="cuda").cpu().numpy()
+    snr, num_hit, positions = gpu.fcch_scan(raw, coef)
+    n_found = 0
+    for c in range(n_freq):
+        rs, rn, rp, _ = oracle.fcch_scan_channel(raw[c], coef)
+        assert np.array_equal(positions[c], rp), f"channel {c}"
+        assert num_hit[c] == rn and abs(snr[c] - rs) < 1e-9
+        n_found += rn > 0
+    assert n_found >= 10 and all(num_hit[c] == 0 for c in range(n_freq) if c not in carriers)
+
+
+def test_config4_band_power_scans_at_reference_sizes(gpu):
+    rng = np.random.default_rng(44)
+    # scan_band_power_spectrum.m:14-20,48: 251 frequencies x 2 dongles x 3 datagrams of 8192 bytes (12 288 IQ)
+    a = np.clip(np.round(rng.standard_normal((2 * 12288, 502)) * rng.uniform(3, 40, size=502) + 127.5), 0, 255).astype(np.uint8)
+    got, ref = gpu.band_power(a), oracle.band_power(a)
+    assert rel_err(got, ref) < 1e-12
+    assert np.max(np.abs(10 * np.log10(got) - 10 * np.log10(ref))) < 1e-10
+    # multi_rtl_sdr_split_scanner.m:40-57,71,154-156: 204 800 IQ per frequency at 2.048 MS/s, fir1(63, RBW/fs), /20 (64 of the 501 points)
+    a = np.clip(np.round(rng.standard_normal((2 * 204800, 64)) * rng.uniform(3, 40, size=64) + 127.5), 0, 255).astype(np.uint8)
+    coef = oracle.fir1(63, 0.05 / 2.048)
+    assert rel_err(gpu.band_power(a, coef, 20), oracle.band_power(a, coef, 20)) < 1e-12
