@@ -148,10 +148,10 @@ int get_twiddle(Ctx &c, int N, cudaStream_t st, const double2 **out) {
 
 int set_taps(const double *coef, int n_taps, cudaStream_t st) {
     if (n_taps < 1 || n_taps > GSMCAL_MAX_TAPS) return fail(GSMCAL_ERR_ARG, "n_taps must be 1..%d", GSMCAL_MAX_TAPS);
-    double tmp[GSMCAL_MAX_TAPS];
-    memset(tmp, 0, sizeof tmp);                          // zero padding on the old side adds exact zeros
-    memcpy(tmp, coef, sizeof(double) * n_taps);
-    CU(cudaMemcpyToSymbolAsync(c_taps, tmp, sizeof tmp, 0, cudaMemcpyHostToDevice, st));
+    double tmp[GSMCAL_MAX_TAPS + 8];
+    memset(tmp, 0, sizeof tmp);                          // zero padding (4 before, the rest after) adds exact zeros
+    memcpy(tmp + 4, coef, sizeof(double) * n_taps);
+    CU(cudaMemcpyToSymbolAsync(c_tapsp, tmp, sizeof tmp, 0, cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));                       // tmp lives on this stack frame
     return GSMCAL_OK;
 }

@@ -14,7 +14,10 @@ typedef unsigned long long u64;
 #define GSMCAL_MAX_TAPS 128
 #define GSMCAL_PI 3.14159265358979323846
 
-__constant__ double c_taps[GSMCAL_MAX_TAPS];      // FIR numerator of the current call (the analogue of `persistent coef`)
+// FIR numerator of the current call (the analogue of `persistent coef`), zero-padded on both sides so that the unrolled
+// kernels can index taps -4 .. MAX_TAPS+3 without a range check
+__constant__ double c_tapsp[GSMCAL_MAX_TAPS + 8];
+#define c_taps (c_tapsp + 4)
 
 // ---------------------------------------------------------------------------------------------------
 // per-stream control block: everything the tiny sequential stages decide, kept on the device so the
@@ -97,6 +100,36 @@ __device__ __forceinline__ double2 fir_from_raw(const uint8_t *__restrict__ raw,
     return make_double2(ar, ai);
 }
 
+// FIR over the staged (DC-removed) capture, 3 consecutive outputs per thread, fully unrolled for a compile-time tap count
+// NT (shorter filters are zero-padded on the OLD side, which adds exact zeros first): taps become constant-bank operands
+// of the DFMAs and every staged sample is loaded once per 3 outputs - about 7 instructions per 6 DFMA instead of ~20.
+template <int NT>
+__device__ __forceinline__ void fir_groups(const double2 *__restrict__ X, double2 *__restrict__ l0, int n_l0, int tid, int nt) {
+    constexpr int U = (NT == 48) ? 5 : 6;                        // (NT + 2) % U == 0
+    static_assert((NT + 2) % U == 0, "unroll factor");
+    const int n_grp = (n_l0 + 2) / 3;
+    for (int gi = tid; gi < n_grp; gi += nt) {
+        double ar[3] = {0.0, 0.0, 0.0}, ai[3] = {0.0, 0.0, 0.0};
+        const double2 *xb = X + 3 * gi;
+#pragma unroll 1
+        for (int k0 = 0; k0 < NT + 2; k0 += U) {                 // rolled by U: few live registers, no tap shifting, no range checks
+            const double *hp = c_taps + (NT - 1 - k0);           // tap of output r at input k0+j: hp[r - j] (zeros outside 0..NT-1)
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const double2 x = xb[k0 + j];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {                    // oldest input first, as direct-form-II-transposed nests the sum
+                    const double h = hp[r - j];
+                    ar[r] = fma(h, x.x, ar[r]); ai[r] = fma(h, x.y, ai[r]);
+                }
+            }
+        }
+        const int base = 3 * gi;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) if (base + r < n_l0) l0[base + r] = make_double2(ar[r], ai[r]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // block-cooperative window loader: dst[0..count) = samples [start, start+count) (0-based) of the stream
 // the stage works on.  X, Y: scratch of GSMCAL_XCAP(count) and (count + 8) double2.
@@ -151,7 +184,8 @@ __device__ void load_window(const WinSrc &src, const StreamCtl &c, int stream, i
     }
     if (a0 < 0) a0 = 0;
     if (b0 > n0 - 1) b0 = n0 - 1;
-    const int nt1 = src.n_taps - 1;
+    const int nt_sel = (src.n_taps <= 48) ? 48 : (src.n_taps <= 64 ? 64 : 0);      // unrolled FIR variants (taps zero-padded on the old side)
+    const int nt1 = (nt_sel ? nt_sel : src.n_taps) - 1;
     const int n_l0 = (int)(b0 - a0 + 1);
     const int n_raw = n_l0 + nt1;
     // stage the DC-removed capture once (zero before the first sample: zero initial filter state)
@@ -164,25 +198,29 @@ __device__ void load_window(const WinSrc &src, const StreamCtl &c, int stream, i
         }
         X[xpad(i)] = v;
     }
+    if (tid < 4) X[n_raw + tid] = make_double2(0.0, 0.0);        // the last output group reads up to 2 samples past the window
     __syncthreads();
-    // FIR, 3 consecutive outputs per thread from a sliding register window of taps (oldest input first, as
-    // direct-form-II-transposed nests the sum); every staged sample is read once per 3 outputs
     double2 *l0 = (use1 || use2) ? Y : dst;
-    const int n_grp = (n_l0 + 2) / 3;
-    for (int gi = tid; gi < n_grp; gi += nt) {
-        double ar[3] = {0.0, 0.0, 0.0}, ai[3] = {0.0, 0.0, 0.0};
-        double hw[3] = {c_taps[nt1], 0.0, 0.0};
-        const int base = 3 * gi;
-        for (int kk = 0; kk <= nt1 + 2; ++kk) {
-            const int ii = base + kk;
-            const double2 x = (ii < n_raw) ? X[xpad(ii)] : make_double2(0.0, 0.0);
+    if (nt_sel == 48) fir_groups<48>(X, l0, n_l0, tid, nt);
+    else if (nt_sel == 64) fir_groups<64>(X, l0, n_l0, tid, nt);
+    else {
+        // generic tap count: 3 consecutive outputs per thread from a sliding register window of taps
+        const int n_grp = (n_l0 + 2) / 3;
+        for (int gi = tid; gi < n_grp; gi += nt) {
+            double ar[3] = {0.0, 0.0, 0.0}, ai[3] = {0.0, 0.0, 0.0};
+            double hw[3] = {c_taps[nt1], 0.0, 0.0};
+            const int base = 3 * gi;
+            for (int kk = 0; kk <= nt1 + 2; ++kk) {
+                const int ii = base + kk;
+                const double2 x = (ii < n_raw) ? X[xpad(ii)] : make_double2(0.0, 0.0);
 #pragma unroll
-            for (int r = 0; r < 3; ++r) { ar[r] = fma(hw[r], x.x, ar[r]); ai[r] = fma(hw[r], x.y, ai[r]); }
-            hw[2] = hw[1]; hw[1] = hw[0];
-            hw[0] = (nt1 - kk - 1 >= 0) ? c_taps[nt1 - kk - 1] : 0.0;
+                for (int r = 0; r < 3; ++r) { ar[r] = fma(hw[r], x.x, ar[r]); ai[r] = fma(hw[r], x.y, ai[r]); }
+                hw[2] = hw[1]; hw[1] = hw[0];
+                hw[0] = (nt1 - kk - 1 >= 0) ? c_taps[nt1 - kk - 1] : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) if (base + r < n_l0) l0[base + r] = make_double2(ar[r], ai[r]);
         }
-#pragma unroll
-        for (int r = 0; r < 3; ++r) if (base + r < n_l0) l0[base + r] = make_double2(ar[r], ai[r]);
     }
     __syncthreads();
     if (!use1 && !use2) {
