@@ -188,15 +188,47 @@ __device__ void load_window(const WinSrc &src, const StreamCtl &c, int stream, i
     const int nt1 = (nt_sel ? nt_sel : src.n_taps) - 1;
     const int n_l0 = (int)(b0 - a0 + 1);
     const int n_raw = n_l0 + nt1;
-    // stage the DC-removed capture once (zero before the first sample: zero initial filter state)
-    for (int i = tid; i < n_raw; i += nt) {
-        i64 j = a0 - nt1 + i;
-        double2 v = make_double2(0.0, 0.0);
-        if (j >= 0) {
-            uchar2 u = *reinterpret_cast<const uchar2 *>(raw + 2 * j);
-            v = make_double2((double)u.x - mur, (double)u.y - mui);
+    // stage the DC-removed capture once (zero before the first sample: zero initial filter state).  8-byte aligned words
+    // (4 IQ pairs), every thread's loads issued before the first is consumed: one memory latency per call.
+    {
+        const i64 j00 = a0 - nt1;                                // sample staged at X[0]
+        const uintptr_t abase = (uintptr_t)(raw + 2 * j00);
+        const int off = (int)((abase & 7) >> 1);                 // samples between the aligned word and j00
+        const int nwords = (n_raw + off + 3) >> 2;
+        const bool words_ok = (j00 - off >= 0) && (j00 - off + 4 * (i64)nwords <= n0);   // aligned words stay inside this stream's row
+        if (words_ok) {
+            const uint2 *wp = reinterpret_cast<const uint2 *>(abase & ~(uintptr_t)7);
+            constexpr int MAXQ = 4;
+            for (int w0 = 0; w0 < nwords; w0 += MAXQ * nt) {
+                uint2 wv[MAXQ];
+#pragma unroll
+                for (int q = 0; q < MAXQ; ++q) { const int wi = w0 + tid + q * nt; wv[q] = (wi < nwords) ? __ldg(wp + wi) : make_uint2(0u, 0u); }
+#pragma unroll
+                for (int q = 0; q < MAXQ; ++q) {
+                    const int wi = w0 + tid + q * nt;
+                    if (wi < nwords) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int i = 4 * wi + e - off;
+                            if (i >= 0 && i < n_raw) {
+                                const unsigned pr2 = ((e < 2) ? wv[q].x : wv[q].y) >> (16 * (e & 1));
+                                X[xpad(i)] = make_double2((double)(pr2 & 0xffu) - mur, (double)((pr2 >> 8) & 0xffu) - mui);
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int i = tid; i < n_raw; i += nt) {
+                const i64 j = j00 + i;
+                double2 v = make_double2(0.0, 0.0);
+                if (j >= 0) {
+                    const uchar2 u = *reinterpret_cast<const uchar2 *>(raw + 2 * j);
+                    v = make_double2((double)u.x - mur, (double)u.y - mui);
+                }
+                X[xpad(i)] = v;
+            }
         }
-        X[xpad(i)] = v;
     }
     if (tid < 4) X[n_raw + tid] = make_double2(0.0, 0.0);        // the last output group reads up to 2 samples past the window
     __syncthreads();
