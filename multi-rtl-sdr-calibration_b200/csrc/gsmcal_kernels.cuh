@@ -1244,7 +1244,10 @@ __global__ void __launch_bounds__(FB_THREADS, 4) fine_peak_band_kernel(WinSrc sr
         pq[0] += q2.x; pq[1] += q2.y;
     }
     block_sum_n<2>(pq, scan_sv);
-    const int k0 = (int)floor(atan2(pq[1], pq[0]) * (double)N / (2.0 * GSMCAL_PI) + 0.5);
+    if (tid == 0) red_i[0] = (int)floor(atan2(pq[1], pq[0]) * (double)N / (2.0 * GSMCAL_PI) + 0.5);     // one atan2 per block
+    __syncthreads();
+    const int k0 = red_i[0];
+    __syncthreads();
     // ---- thread = (segment g of windows, bin j).  Segment-start spectra from shared piece sums (absolute phase):
     //      pieces [0,q) [q,2q) [2q,3q) [3q,4q) [4q,N) [N,N+q) [N+q,N+2q) [N+2q,N+3q); window g*q = pieces g..g+4 ----
     const int g = tid / FB_BINS, j = tid % FB_BINS;
@@ -1423,7 +1426,10 @@ __global__ void __launch_bounds__(FC_THREADS, 4) fine_peak_core_kernel(WinSrc sr
         pq[0] += q2.x; pq[1] += q2.y;
     }
     block_sum_n<2>(pq, scan_sv);
-    const int k0 = (int)floor(atan2(pq[1], pq[0]) * (double)N / (2.0 * GSMCAL_PI) + 0.5);
+    if (tid == 0) red_i[0] = (int)floor(atan2(pq[1], pq[0]) * (double)N / (2.0 * GSMCAL_PI) + 0.5);     // one atan2 per block
+    __syncthreads();
+    const int k0 = red_i[0];
+    __syncthreads();
     {
         const int lane = tid & 31, warp = tid >> 5;
         if (warp == 0) warp_scan_smem(pe16, n_chunk + 1, lane);
@@ -1665,6 +1671,8 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
     __shared__ int red_i[8];
     __shared__ double2 step_sh;
     __shared__ double red_n[24];
+    __shared__ int sh_k0;
+    __shared__ double sh_pr;
     const int burst = blockIdx.x, stream = blockIdx.y, tid = threadIdx.x;
     const StreamCtl c = ctl[stream];
     const int nb = (which == 1) ? (c.tone1_enable ? c.n_fcch : 0) : (c.post_enable ? c.n_post_fcch : 0);
@@ -1684,7 +1692,9 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
     }
     block_sum_n<3>(epq, red_n);
     const double e = epq[0];
-    const int k0 = (int)floor(atan2(epq[2], epq[1]) * (double)N / (2.0 * GSMCAL_PI) + 0.5);
+    if (tid == 0) sh_k0 = (int)floor(atan2(epq[2], epq[1]) * (double)N / (2.0 * GSMCAL_PI) + 0.5);     // one atan2 per block, not per thread
+    __syncthreads();
+    const int k0 = sh_k0;
     // band search without an FFT: 16 bins x 16 sample segments, absolute-phase partial DFTs (4 accumulators per twiddle,
     // as in the fine search), summed over the segments through shared memory.
     // shifted index j <-> bin (j + N/2) mod N; first maximum in j order (:149-150)
@@ -1738,19 +1748,22 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
     for (int n = tid; n < N; n += TONE_THREADS, tidx = (tidx + tinc >= N) ? tidx + tinc - N : tidx + tinc) {
         const double2 w = cmul(u[n], tw[tidx]);
         u[n] = w;
-        const double h = hypot(w.x, w.y);
-        A[n] = (h > 0.0) ? make_double2(w.x / h, w.y / h) : make_double2(1.0, 0.0);
+        const double h2 = fma(w.x, w.x, w.y * w.y);
+        const double inv = rsqrt(h2);                            // exp(1i*angle(w)) = w/|w| (samples are O(1..100): no over/underflow)
+        A[n] = (h2 > 0.0) ? make_double2(w.x * inv, w.y * inv) : make_double2(1.0, 0.0);
     }
     __syncthreads();
     double rri[2] = {0.0, 0.0};
     for (int n = tid; n < N - 1; n += TONE_THREADS) {
         const double2 a = A[n + 1], b = A[n];
-        const double den = b.x * b.x + b.y * b.y;
-        rri[0] += (a.x * b.x + a.y * b.y) / den;
-        rri[1] += (a.y * b.x - a.x * b.y) / den;
+        const double inv_den = 1.0 / (b.x * b.x + b.y * b.y);      // complex division by a (nearly) unit phasor
+        rri[0] += (a.x * b.x + a.y * b.y) * inv_den;
+        rri[1] += (a.y * b.x - a.x * b.y) * inv_den;
     }
     block_sum_n<2>(rri, red_n);
-    const double phase_rotate = atan2(rri[1] / (double)(N - 1), rri[0] / (double)(N - 1));
+    if (tid == 0) sh_pr = atan2(rri[1] / (double)(N - 1), rri[0] / (double)(N - 1));
+    __syncthreads();
+    const double phase_rotate = sh_pr;
     const double fo = sampling_rate * (int_phase_rotate + phase_rotate) / (2 * GSMCAL_PI);
     if (tid == 0) fo_out[(i64)stream * cap + burst] = fo;
     if (which != 1) return;
