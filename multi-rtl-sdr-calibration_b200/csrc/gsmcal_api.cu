@@ -25,6 +25,7 @@ thread_local int g_device = 0;
 std::atomic<long long> g_launches{0};
 int *g_last_need_full = nullptr, *g_last_need_band = nullptr; long long g_last_need_full_n = 0;
 int g_debug_groups = 4;           // stream groups per batch (1 = strictly sequential stages, enables per-stage timing)
+int g_debug_fall_limit = FALL_GRID;  // tier 3 handles work lists up to this length (tests set 0 to exercise the single-block list mode)
 int g_debug_fail_tier2 = 0;       // tests: pretend the 64-bin certificate failed
 int g_debug_force_full = 0;       // tests: run the all-bin fine search for every burst
 
@@ -247,7 +248,7 @@ int run_coarse(WinSrc src, i64 len, const CoarseParams &p, i64 D, int cap, Work 
 int run_fine_peak(Ctx &c, WinSrc src_peak, i64 n_iq, int osr, i64 D, int cap, Work &w, cudaStream_t st) {
     const double2 *tw; TRY(get_twiddle(c, 148 * osr, st, &tw));
     if (g_debug_force_full || (osr % 4) != 0) {      // the band kernel's 16-sample certificate grid needs osr % 4 == 0
-        LAUNCH(fine_peak_full_kernel, dim3((unsigned)cap, (unsigned)D), kFineThreads, fine_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, (const int *)nullptr, (const int *)nullptr);
+        LAUNCH(fine_peak_full_kernel, dim3((unsigned)cap, (unsigned)D), kFineThreads, fine_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, (const int *)nullptr, (const int *)nullptr, 0);
         return GSMCAL_OK;
     }
     CU(cudaMemsetAsync(w.need_full, 0, sizeof(int) * D * cap, st));
@@ -258,10 +259,10 @@ int run_fine_peak(Ctx &c, WinSrc src_peak, i64 n_iq, int osr, i64 D, int cap, Wo
            (const int *)w.need_band, w.need_full, 0, w.fall_list, w.fall_count, w.fall_best, w.fall_m, g_debug_fail_tier2);
     const int nb3 = (148 * osr + FB_BINS - 1) / FB_BINS;
     LAUNCH(fine_peak_band_kernel, dim3((unsigned)nb3, (unsigned)FALL_GRID), FB_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw,
-           (const int *)nullptr, (int *)nullptr, 1, w.fall_list, w.fall_count, w.fall_best, w.fall_m, 0);
-    LAUNCH(fine_fall_combine_kernel, FALL_GRID / 128, 128, 0, st, w.fall_list, w.fall_count, w.fall_best, w.fall_m, nb3, w.coarse_pos, cap, osr, w.fine_raw, w.ctl);
-    LAUNCH(fine_peak_full_kernel, dim3((unsigned)cap, (unsigned)D), kFineThreads, fine_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw,
-           (const int *)w.need_full, (const int *)w.fall_count);
+           (const int *)nullptr, (int *)nullptr, 1, w.fall_list, w.fall_count, w.fall_best, w.fall_m, g_debug_fall_limit);
+    LAUNCH(fine_fall_combine_kernel, FALL_GRID / 128, 128, 0, st, w.fall_list, w.fall_count, w.fall_best, w.fall_m, nb3, w.coarse_pos, cap, osr, w.fine_raw, w.ctl, g_debug_fall_limit);
+    LAUNCH(fine_peak_full_kernel, 296, kFineThreads, fine_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw,
+           (const int *)w.fall_list, (const int *)w.fall_count, g_debug_fall_limit);
     return GSMCAL_OK;
 }
 int run_fine_rest(Ctx &c, WinSrc src_tone, i64 n_iq, int osr, double carrier_freq, i64 D, int cap, Work &w, cudaStream_t st) {
@@ -375,6 +376,7 @@ int64_t gsmcal_debug_get(int key) {
 int gsmcal_debug_set(int key, int value) {
     if (key == 0) { g_debug_force_full = value; return GSMCAL_OK; }
     if (key == 4) { g_debug_fail_tier2 = value; return GSMCAL_OK; }
+    if (key == 5) { g_debug_fall_limit = value < 0 ? 0 : (value > FALL_GRID ? FALL_GRID : value); return GSMCAL_OK; }
     if (key == 3) { g_debug_groups = value < 1 ? 1 : (value > kMaxGroups / 2 ? kMaxGroups / 2 : value); return GSMCAL_OK; }
     return fail(GSMCAL_ERR_ARG, "debug_set: unknown key");
 }

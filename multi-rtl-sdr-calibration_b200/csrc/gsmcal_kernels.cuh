@@ -1072,14 +1072,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src,
 // global maximum is the same either way, so no per-window reduction is needed.)
 #define FP_BPT 4
 #define FALL_GRID 256     // bursts tier 3 (multi-block band search) handles per launch; beyond that this single-block kernel takes over
-__global__ void __launch_bounds__(320) fine_peak_full_kernel(WinSrc src, StreamCtl *__restrict__ ctl, const double *__restrict__ base_pos, int cap,
-                                                             int osr, i64 len_s_ov, const double2 *__restrict__ tw /* exp(-2*pi*i*j/N) */,
-                                                             double *__restrict__ fine_raw, const int *__restrict__ need_full,
-                                                             const int *__restrict__ fall_count) {
-    extern __shared__ double2 sm[];
-    __shared__ double red_v[16];
-    __shared__ int red_i[16];
-    const int burst = blockIdx.x, stream = blockIdx.y;
+__device__ void fine_peak_full_body(const WinSrc &src, StreamCtl *__restrict__ ctl, const double *__restrict__ base_pos, int cap,
+                                    int osr, i64 len_s_ov, const double2 *__restrict__ tw /* exp(-2*pi*i*j/N) */,
+                                    double *__restrict__ fine_raw, bool listed, int burst, int stream, double2 *sm, double *red_v, int *red_i) {
     const StreamCtl c = ctl[stream];
     if (c.n_coarse < 5 || burst >= c.n_coarse) return;
     const int N = 148 * osr;
@@ -1093,9 +1088,7 @@ __global__ void __launch_bounds__(320) fine_peak_full_kernel(WinSrc src, StreamC
         if (threadIdx.x == 0) *o = INFINITY;
         return;
     }
-    if (need_full && !need_full[(i64)stream * cap + burst]) return;   // the band-limited search already certified this burst
-    if (fall_count && *fall_count <= FALL_GRID) return;               // tier 3 (multi-block band search) covers the list
-    if (need_full && threadIdx.x == 0) atomicOr(&ctl[stream].flags, 32);
+    if (listed && threadIdx.x == 0) atomicOr(&ctl[stream].flags, 32);
     const i64 sp = (position - max_offset - 1) * osr + 1;     // 1-based
     double2 *win = sm;
     double2 *X = win + n_smp;
@@ -1158,6 +1151,28 @@ __global__ void __launch_bounds__(320) fine_peak_full_kernel(WinSrc src, StreamC
     if (threadIdx.x == 0) *o = (double)(sp + mi);              // sp + max_idx - 1, max_idx = mi + 1
 }
 
+// direct mode (fall_list == nullptr): grid (cap, streams), every burst - the drop-in / forced path and the tiers' test oracle.
+// list mode: a small grid walks the tier-3 work list, and only when it is longer than the multi-block tier handles.
+__global__ void __launch_bounds__(320) fine_peak_full_kernel(WinSrc src, StreamCtl *__restrict__ ctl, const double *__restrict__ base_pos, int cap,
+                                                             int osr, i64 len_s_ov, const double2 *__restrict__ tw,
+                                                             double *__restrict__ fine_raw, const int *__restrict__ fall_list,
+                                                             const int *__restrict__ fall_count, int fall_limit) {
+    extern __shared__ double2 sm[];
+    __shared__ double red_v[16];
+    __shared__ int red_i[16];
+    if (!fall_list) {
+        fine_peak_full_body(src, ctl, base_pos, cap, osr, len_s_ov, tw, fine_raw, false, blockIdx.x, blockIdx.y, sm, red_v, red_i);
+        return;
+    }
+    const int cnt = *fall_count;
+    if (cnt <= fall_limit) return;
+    for (int wi = blockIdx.x; wi < cnt; wi += gridDim.x) {
+        const int id = fall_list[wi];
+        __syncthreads();
+        fine_peak_full_body(src, ctl, base_pos, cap, osr, len_s_ov, tw, fine_raw, true, id % cap, id / cap, sm, red_v, red_i);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K5, fast path: the same argmax from a 64-bin band around the FCCH tone, with a proof that no other bin
 // can matter.  For every window m the reference takes max_k |X_m[k]|^2 over ALL N bins; here
@@ -1191,7 +1206,7 @@ __global__ void __launch_bounds__(FB_THREADS, 4) fine_peak_band_kernel(WinSrc sr
     int burst = blockIdx.x, stream = blockIdx.y;
     if (mode == 1) {
         const int cnt = *fall_count;
-        if ((int)blockIdx.y >= cnt || cnt > FALL_GRID) return;
+        if ((int)blockIdx.y >= cnt || cnt > force_fail) return;    // in mode 1 `force_fail` carries the list-length limit of this tier
         const int id = fall_list[blockIdx.y];
         stream = id / cap; burst = id % cap;
     } else if (need_band && !need_band[(i64)blockIdx.y * cap + blockIdx.x]) return;   // tier 1 already proved this burst
@@ -1347,10 +1362,10 @@ __global__ void __launch_bounds__(FB_THREADS, 4) fine_peak_band_kernel(WinSrc sr
 // merges the per-band results of tier 3: first maximum over all bins = larger power, then earlier window
 __global__ void fine_fall_combine_kernel(const int *__restrict__ fall_list, const int *__restrict__ fall_count, const double *__restrict__ fall_best,
                                          const int *__restrict__ fall_m, int nb3, const double *__restrict__ base_pos, int cap, int osr,
-                                         double *__restrict__ fine_raw, StreamCtl *ctl) {
+                                         double *__restrict__ fine_raw, StreamCtl *ctl, int fall_limit) {
     const int wi = blockIdx.x * blockDim.x + threadIdx.x;
     const int cnt = *fall_count;
-    if (wi >= cnt || cnt > FALL_GRID) return;
+    if (wi >= cnt || cnt > fall_limit) return;
     const int id = fall_list[wi];
     double v = -1.0; int m = 0x7fffffff;
     for (int z = 0; z < nb3; ++z) argmax_combine(v, m, fall_best[(i64)wi * nb3 + z], fall_m[(i64)wi * nb3 + z]);

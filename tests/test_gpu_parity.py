@@ -446,8 +446,9 @@ def test_tier3_multiblock_search_equals_all_bin_search(gpu, captures, coef47, tp
         lib().gsmcal_debug_set(0, 0)
     lib().gsmcal_debug_set(4, 1)
     try:
-        for groups in (1, 2):
+        for groups, limit in ((1, 256), (2, 256), (1, 0)):       # limit 0: the work list goes to the single-block all-bin kernel
             lib().gsmcal_debug_set(3, groups)
+            lib().gsmcal_debug_set(5, limit)
             t3 = gpu.calibrate_batch(raw, CARRIER, tpl, coef47)
             assert lib().gsmcal_debug_get(1) > 0
             for a, b in zip(t3, full):
@@ -455,6 +456,7 @@ def test_tier3_multiblock_search_equals_all_bin_search(gpu, captures, coef47, tp
                 assert a["sampling_ppm"] == b["sampling_ppm"] and a["carrier_ppm"] == b["carrier_ppm"]
     finally:
         lib().gsmcal_debug_set(4, 0)
+        lib().gsmcal_debug_set(5, 256)
         lib().gsmcal_debug_set(3, 4)
 
 
