@@ -524,3 +524,20 @@ def test_config4_band_power_scans_at_reference_sizes(gpu):
     a = np.clip(np.round(rng.standard_normal((2 * 204800, 64)) * rng.uniform(3, 40, size=64) + 127.5), 0, 255).astype(np.uint8)
     coef = oracle.fir1(63, 0.05 / 2.048)
     assert rel_err(gpu.band_power(a, coef, 20), oracle.band_power(a, coef, 20)) < 1e-12
+
+
+def test_randomised_impairment_sweep(gpu, coef47, tpl):
+    """32 streams with wide random impairments (SNR 4-25 dB, amplitude 8-60 LSB, +-45 ppm clock, +-28 ppm carrier): every
+    outcome - full lock, SNR-gate failure, short chains, no FCCH - must equal the oracle's (tests/stress_parity.py is the long form)."""
+    rng = np.random.default_rng(7)
+    specs = [synth.StreamSpec(seed=3000 + i, n_samples=N_SYNC, sampling_ppm=float(rng.uniform(-45, 45)), carrier_ppm=float(rng.uniform(-28, 28)),
+                              snr_db=float(rng.uniform(4, 25)), phase0=float(rng.uniform(0, 6.28)),
+                              start_offset=float(rng.integers(0, synth.MULTIFRAME)), amplitude=float(rng.uniform(8, 60))) for i in range(32)]
+    raw = synth.generate_batch(specs, device="cuda").cpu().numpy()
+    got = gpu.calibrate_batch(raw, CARRIER, tpl, coef47)
+    outcomes = set()
+    for d in range(len(specs)):
+        ref = oracle.calibrate_stream(raw[d], CARRIER, tpl, coef47)
+        _check_stream(got[d], ref)
+        outcomes.add((ref["fcch_pos"][0] == -1, ref["pos_info"].shape[0] > 1))
+    assert len(outcomes) >= 2
