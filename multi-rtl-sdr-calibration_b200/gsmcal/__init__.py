@@ -5,6 +5,6 @@ this package is the Python stand-in for the MATLAB call sites, used by the tests
 """
 from .api import (FCCH_coarse_position, FCCH_fine_correction, GsmcalError, SCH_corr_rate_correction,  # noqa: F401
                   band_power, calibrate_batch, carrier_correct_post_SCH, chn_filter_4x, chn_filter_8x_4x,
-                  chn_filter_taps, device_count, fcch_scan, fir1, fir_filter, gsm_SCH_training_sequence_gen,
+                  chn_filter_taps, device_count, diversity_power_spectrum, fcch_scan, fir1, fir_filter, gsm_SCH_training_sequence_gen,
                   launch_count, max_bursts, move_fft_snr_runtime_avg, move_fft_snr_trace, raw2iq, raw2iq_fir,
                   set_device, specific_fft_snr_fix_avg, total_ppm_calculation)

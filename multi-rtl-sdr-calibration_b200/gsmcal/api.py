@@ -305,3 +305,13 @@ def fcch_scan(raw, coef, osr: int = 8, coarse_dr: int = 8):
                                  _ptr(snr), _ptr(num_hit), _ptr(pos), _ptr(npos), None))
     positions = [np.array([-1.0]) if npos[i] < 0 else pos[i, :npos[i]].copy() for i in range(n_chan)]
     return snr, num_hit, positions
+
+
+def diversity_power_spectrum(s_all_u8, coef, decim: int):
+    """multi_rtl_sdr_diversity_scanner.m:150-176: every dongle scans the same band; per-dongle mean power after
+    raw2iq -> filter -> r(1:decim:end), then the incoherent mean across dongles.  s_all_u8: [2N, n_freq, n_dongle] uint8.
+    Returns (power_spectrum [n_dongle, n_freq], power_spectrum_combine [n_freq]), linear units."""
+    s_all_u8 = np.asarray(s_all_u8, dtype=np.uint8)
+    per = np.stack([band_power(s_all_u8[:, :, i], coef, decim) for i in range(s_all_u8.shape[2])], axis=0)
+    combine = per.sum(axis=0) / per.shape[0]                      # mean(power_spectrum, 1)
+    return per, combine

@@ -541,3 +541,13 @@ def test_randomised_impairment_sweep(gpu, coef47, tpl):
         _check_stream(got[d], ref)
         outcomes.add((ref["fcch_pos"][0] == -1, ref["pos_info"].shape[0] > 1))
     assert len(outcomes) >= 2
+
+
+def test_diversity_scanner_combine(gpu):
+    """multi_rtl_sdr_diversity_scanner.m:150-176: per-dongle power spectra and their incoherent mean."""
+    rng = np.random.default_rng(5)
+    s_all = np.clip(np.round(rng.standard_normal((2 * 20480, 12, 3)) * rng.uniform(3, 40, size=(1, 12, 3)) + 127.5), 0, 255).astype(np.uint8)
+    coef = oracle.fir1(63, 0.05 / 2.048)
+    per, comb = gpu.diversity_power_spectrum(s_all, coef, 20)
+    ref = np.stack([oracle.band_power(s_all[:, :, i], coef, 20) for i in range(3)], axis=0)
+    assert rel_err(per, ref) < 1e-12 and rel_err(comb, ref.mean(axis=0)) < 1e-12
