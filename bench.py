@@ -270,8 +270,12 @@ def main():
     hbm_peak, peak_src = measured_peaks()
     colsum_gbs = (D * 2 * n_iq) / (stage_ms.get("colsum_u8", float("nan")) * 1e-3) / 1e9
     dominant = max(stage_ms, key=stage_ms.get) if stage_ms else "colsum_u8"
+    # dram__bytes_read+write of this kernel in the ncu --set full capture (profiles/r1a_colsum_u8.txt, 16 streams): 701,975,808 B for
+    # 693,333,344 algorithmic bytes -> ratio 1.01246, scaled to this launch
+    traffic = int(D * 2 * n_iq * 1.01246)
     roofline = {"kernel": "colsum_u8_kernel", "bound": "hbm", "achieved": colsum_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": colsum_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": colsum_gbs / hbm_peak, "traffic": traffic, "traffic_source": "ncu dram bytes of a 16-stream capture scaled by launch size (ratio 1.0125 to algorithmic)",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": D * 2 * n_iq,
                 "note": "the only whole-stream (HBM-proportional) pass of the fused pipeline, 2 B per IQ sample; the step time is "
                         "dominated by the FP64/latency-bound per-burst stages, see fp64_stages"}
@@ -317,6 +321,8 @@ def main():
             ems = float(t.item())
         e2e = {"value": total_iq / (ems / e_steps * 1e-3) / 1e6, "unit": "MS/s", "h2d_bytes_per_step": D * 2 * n_iq,
                "d2h_bytes_per_step": D * rec_bytes, "steps": e_steps, "ms_per_step": ems / e_steps,
+               "h2d_gbs_achieved": D * 2 * n_iq / (ems / e_steps * 1e-3) / 1e9,
+               "bound": "host-to-device transfer (uint8 IQ is already the wire format; PCIe Gen5 x16 ~ 55 GB/s from pinned memory)",
                "api": "gsmcal_calibrate_batch(raw_mem=HOST) from pinned host memory"}
         del host
 
