@@ -1834,8 +1834,34 @@ __global__ void __launch_bounds__(SCH_THREADS, 2) sch_corr_kernel(WinSrc src, co
     const int n_lag = 2 * max_offset - 5 * osr + 1;            // 89 at osr 8
     const int n_smp = n_lag + L - 1;
     double2 *win = sm, *t = win + n_smp, *X = t + L, *Y = X + GSMCAL_XCAP(n_smp);
-    for (int i = threadIdx.x; i < L; i += SCH_THREADS) t[i] = tpl[i];
+    // the 64*osr-sample template (8 KB at osr 8) is staged by ONE TMA bulk copy (cp.async.bulk -> UBLKCP) that completes on an
+    // mbarrier while all threads evaluate the burst window; it is consumed only after the wait below
+    __shared__ __align__(8) unsigned long long tpl_bar;
+    const unsigned bar_a = (unsigned)__cvta_generic_to_shared(&tpl_bar);
+    const bool tma_ok = (((uintptr_t)tpl & 15) == 0) && (((uintptr_t)t & 15) == 0);
+    if (tma_ok) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+            asm volatile("fence.mbarrier_init.release.cluster;");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned bytes = (unsigned)(L * sizeof(double2));
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes));
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((unsigned)__cvta_generic_to_shared(t)), "l"(tpl), "r"(bytes), "r"(bar_a) : "memory");
+        }
+    } else {
+        for (int i = threadIdx.x; i < L; i += SCH_THREADS) t[i] = tpl[i];
+    }
     load_window(src, c, stream, sp - 1, n_smp, win, X, Y);
+    if (tma_ok) {                                                // phase 0 of the barrier: spin until the bulk copy has landed
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar_a), "r"(0u) : "memory");
+        }
+    }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = SCH_THREADS >> 5;
     if (L == 32 * SCH_NSL && n_lag <= nw * SCH_LPG) {
         // register-tiled correlation: warp w owns lags [12w, 12w+12), lane owns template samples [16*lane, 16*lane+16);
