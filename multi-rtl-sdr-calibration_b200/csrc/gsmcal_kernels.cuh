@@ -1685,7 +1685,7 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
     __shared__ double red_v[8];
     __shared__ int red_i[8];
     __shared__ double2 step_sh;
-    __shared__ double red_n[24];
+    __shared__ double red_n[80];
     __shared__ int sh_k0;
     __shared__ double sh_pr;
     const int burst = blockIdx.x, stream = blockIdx.y, tid = threadIdx.x;
@@ -1785,13 +1785,37 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
     // SNR gate (:185-189): fine derotation, then only the bins the gate reads: [1:3,end-1:end] vs [4:hnl, end-hnl+1:end-2]
     if (tid == 0) { double sn, cs; sincos((double)TONE_THREADS * phase_rotate, &sn, &cs); step_sh = make_double2(cs, -sn); }
     __syncthreads();
+    double sg[10] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};   // bins 0, +1, -1, +2, -2 of the derotated burst (re, im)
     {
         double sn, cs; sincos((double)tid * phase_rotate, &sn, &cs);
         double2 ph = make_double2(cs, -sn);
         const double2 st = step_sh;
-        for (int n = tid; n < N; n += TONE_THREADS) { u[n] = cmul(u[n], ph); ph = cmul(ph, st); }
+        for (int n = tid; n < N; n += TONE_THREADS) {
+            const double2 w = cmul(u[n], ph);
+            u[n] = w;
+            ph = cmul(ph, st);
+            const double2 t1 = tw[n], t2 = tw[(2 * n) % N];
+            sg[0] += w.x; sg[1] += w.y;
+            sg[2] += w.x * t1.x - w.y * t1.y; sg[3] += w.x * t1.y + w.y * t1.x;      // * W^{n}
+            sg[4] += w.x * t1.x + w.y * t1.y; sg[5] += w.y * t1.x - w.x * t1.y;      // * conj(W^{n})
+            sg[6] += w.x * t2.x - w.y * t2.y; sg[7] += w.x * t2.y + w.y * t2.x;
+            sg[8] += w.x * t2.x + w.y * t2.y; sg[9] += w.y * t2.x - w.x * t2.y;
+        }
     }
-    __syncthreads();
+    block_sum_n<10>(sg, red_n);                                  // also orders the u[] writes before the FFT below
+    // Only the DECISION "SNR >= 5 dB" leaves this stage (:192-196).  The five signal bins [1:3, end-1:end] are computed
+    // directly; every noise bin is among the other N-5, whose total power is N*E - sig by Parseval (derotation keeps the
+    // energy E).  So sig >= 10^0.5 * (N*E - sig) proves the burst passes the gate without any FFT; bursts that cannot be
+    // proven this way evaluate the 110 bins exactly.
+    {
+        double sig5 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) sig5 += sg[2 * q] * sg[2 * q] + sg[2 * q + 1] * sg[2 * q + 1];
+        if (sig5 >= 3.16227766016838 * (1.0 + 1e-9) * ((double)N * e - sig5)) {
+            if (tid == 0) gate_out[(i64)stream * cap + burst] = 99.0;      // "certified above the 5 dB gate"
+            return;
+        }
+    }
     const double2 *Tm = fft_rows(u, A, F, N, tw);
     const int hnl = (int)ceil(((double)N * 200e3 / sampling_rate) / 2.0);
     double sn2[2] = {0.0, 0.0};
