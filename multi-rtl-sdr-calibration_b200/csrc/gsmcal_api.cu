@@ -122,6 +122,8 @@ int get_ctx(Ctx **out) {
         CU(cudaFuncSetAttribute(fine_peak_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(tone_est_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(sch_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CU(cudaFuncSetAttribute(fir_full_tma_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CU(cudaFuncSetAttribute(fir_full_tma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CU(cudaFuncSetAttribute(coarse_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CU(cudaFuncSetAttribute(fine_ppm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CU(cudaFuncSetAttribute(fine_carrier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -295,6 +297,14 @@ template <bool U8>
 int run_fir(const void *in, i64 n, i64 in_stride, const StreamCtl *ctl, int n_taps, int decim, i64 D, double2 *out, i64 n_out, double *power, cudaStream_t st) {
     if (decim < 1) return fail(GSMCAL_ERR_ARG, "decim must be >= 1");
     if (n <= 0) return GSMCAL_OK;
+    if (decim == 1 && !power && !U8 && n_taps <= 64 && in_stride == n && n_out == n && (((uintptr_t)in & 15) == 0)) {
+        // complex128 in/out: persistent TMA-pipelined kernel
+        const i64 n_tiles = ((n + FT_TILE - 1) / FT_TILE) * D;
+        i64 gx = 148 * 4; if (gx > n_tiles) gx = n_tiles;        // 4 resident blocks per SM (122 registers, 38 KB)
+        if (n_taps <= 48) LAUNCH((fir_full_tma_kernel<48>), (unsigned)gx, FT_THREADS, sizeof(double2) * 2 * (FT_TILE + 47), st, (const double2 *)in, n, D, out);
+        else              LAUNCH((fir_full_tma_kernel<64>), (unsigned)gx, FT_THREADS, sizeof(double2) * 2 * (FT_TILE + 63), st, (const double2 *)in, n, D, out);
+        return GSMCAL_OK;
+    }
     if (decim == 1 && !power) {
         unsigned gx = (unsigned)((n + FIR_TILE - 1) / FIR_TILE);
         auto smem = [](int NT) { int n_in = FIR_TILE + NT - 1; return sizeof(double2) * (size_t)(n_in + n_in / 8 + 2); };

@@ -548,6 +548,82 @@ __global__ void __launch_bounds__(FIR_THREADS) fir_full_kernel(const void *__res
     }
 }
 
+// Full-rate complex128 FIR, persistent + TMA double buffering.  Each block loops over tiles of FT_TILE outputs; the
+// (FT_TILE + NT - 1)-sample input tile (18.7 KB, contiguous, 16-byte aligned) is fetched by ONE cp.async.bulk (UBLKCP)
+// per tile that completes on an mbarrier, two tiles in flight, so the FP64 pipe never waits for global memory.  Each
+// thread produces 9 consecutive outputs from a register sliding window; 9*16 B = 144 B lane stride is bank-conflict
+// free on the dense layout the bulk copy writes, so no re-layout pass is needed.
+#define FT_R 9
+#define FT_THREADS 128
+#define FT_TILE (FT_R * FT_THREADS)
+template <int NT>
+__global__ void __launch_bounds__(FT_THREADS) fir_full_tma_kernel(const double2 *__restrict__ in, i64 n, i64 n_col, double2 *__restrict__ out) {
+    extern __shared__ __align__(16) double2 sm[];                // [2][FT_TILE + NT - 1]
+    __shared__ __align__(8) unsigned long long full_bar[2];
+    constexpr int TILE_IN = FT_TILE + NT - 1;
+    const i64 tiles_per_col = (n + FT_TILE - 1) / FT_TILE, n_tiles = tiles_per_col * n_col;
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&full_bar[0]);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    __syncthreads();
+    auto issue = [&](i64 tile, int stage) {                      // thread 0 only
+        const i64 col = tile / tiles_per_col, t0 = (tile % tiles_per_col) * FT_TILE;
+        const i64 j0 = (t0 - (NT - 1) > 0) ? t0 - (NT - 1) : 0;                       // first valid input sample
+        i64 j1 = t0 + FT_TILE; if (j1 > n) j1 = n;
+        const unsigned bytes = (unsigned)((j1 - j0) * sizeof(double2));
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(sm + (size_t)stage * TILE_IN + (j0 - (t0 - (NT - 1))));
+        const unsigned bar = bar0 + 8 * stage;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes));
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(in + col * n + j0), "r"(bytes), "r"(bar) : "memory");
+    };
+    i64 tile = blockIdx.x;
+    if (threadIdx.x == 0) {
+        if (tile < n_tiles) issue(tile, 0);
+        if (tile + gridDim.x < n_tiles) issue(tile + gridDim.x, 1);
+    }
+    unsigned phase[2] = {0u, 0u};
+    for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int stage = it & 1;
+        const i64 col = tile / tiles_per_col, t0 = (tile % tiles_per_col) * FT_TILE;
+        double2 *buf = sm + (size_t)stage * TILE_IN;
+        {
+            unsigned done = 0;
+            const unsigned bar = bar0 + 8 * stage;
+            while (!done)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(bar), "r"(phase[stage]) : "memory");
+            phase[stage] ^= 1u;
+        }
+        if (t0 == 0) {                                           // zero initial filter state: the halo before the first sample
+            for (int i = threadIdx.x; i < NT - 1; i += FT_THREADS) buf[i] = make_double2(0.0, 0.0);
+            __syncthreads();
+        }
+        double ar[FT_R], ai[FT_R];
+#pragma unroll
+        for (int r = 0; r < FT_R; ++r) { ar[r] = 0.0; ai[r] = 0.0; }
+        const double2 *xb = buf + threadIdx.x * FT_R;
+#pragma unroll
+        for (int k = 0; k < NT - 1 + FT_R; ++k) {
+            const double2 x = xb[k];
+#pragma unroll
+            for (int r = 0; r < FT_R; ++r) {
+                const int tap = (NT - 1) + r - k;                // oldest input first: h[NT-1] ... h[0]
+                if (tap >= 0 && tap < NT) { ar[r] = fma(c_taps[tap], x.x, ar[r]); ai[r] = fma(c_taps[tap], x.y, ai[r]); }
+            }
+        }
+        double2 *o = out + col * n + t0 + threadIdx.x * FT_R;
+#pragma unroll
+        for (int r = 0; r < FT_R; ++r)
+            if (t0 + threadIdx.x * FT_R + r < n) __stcs(o + r, make_double2(ar[r], ai[r]));
+        __syncthreads();                                         // every thread is done reading this stage
+        if (threadIdx.x == 0 && tile + 2 * (i64)gridDim.x < n_tiles) issue(tile + 2 * (i64)gridDim.x, stage);
+    }
+}
+
 // Decimating FIR: one thread per kept output r(1+m*decim); input tile staged contiguously (coalesced) in
 // shared memory.  Used for decim > 1 (2: chn_filter_8x_4x, 20: split scanner, 64: coarse stream).
 #define FIRD_THREADS 128
