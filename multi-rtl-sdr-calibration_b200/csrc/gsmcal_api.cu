@@ -367,6 +367,8 @@ void gsmcal_release(void) {
         kv.second.in.release(); kv.second.out.release(); kv.second.work.release(); kv.second.tplbuf.release();
         for (auto &t : kv.second.tw) cudaFree(t.second);
         kv.second.tw.clear();
+        for (cudaStream_t s2 : kv.second.side) cudaStreamDestroy(s2);
+        kv.second.side.clear();
     }
 }
 int64_t gsmcal_debug_get(int key) {
