@@ -307,11 +307,11 @@ def main():
     hbm_peak, peak_src = measured_peaks()
     colsum_gbs = (D * 2 * n_iq) / (stage_ms.get("colsum_u8", float("nan")) * 1e-3) / 1e9
     dominant = max(stage_ms, key=stage_ms.get) if stage_ms else "colsum_u8"
-    # dram__bytes_read+write of this kernel in the ncu --set full capture (profiles/r1a_colsum_u8.txt, 16 streams): 701,975,808 B for
-    # 693,333,344 algorithmic bytes -> ratio 1.01246, scaled to this launch
-    traffic = int(D * 2 * n_iq * 1.01246)
+    # dram__bytes_read+write of this kernel in the ncu --set full capture of this command (profiles/r1_final_colsum_u8.txt, one
+    # 32-stream group launch): 1,391,976,000 + 5,536,512 B for 1,386,666,688 algorithmic bytes -> ratio 1.0078, scaled to this launch
+    traffic = int(D * 2 * n_iq * 1.0078)
     roofline = {"kernel": "colsum_u8_kernel", "bound": "hbm", "achieved": colsum_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": colsum_gbs / hbm_peak, "traffic": traffic, "traffic_source": "ncu dram bytes of a 16-stream capture scaled by launch size (ratio 1.0125 to algorithmic)",
+                "frac": colsum_gbs / hbm_peak, "traffic": traffic, "traffic_source": "ncu --set full dram bytes of a 32-stream launch of this command scaled by launch size (ratio 1.0078 to algorithmic)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": D * 2 * n_iq,
                 "note": "the only whole-stream (HBM-proportional) pass of the fused pipeline, 2 B per IQ sample; the step time is "
