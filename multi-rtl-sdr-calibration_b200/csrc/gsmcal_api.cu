@@ -101,7 +101,7 @@ size_t fine_band_smem(int osr) {
     // and the three 16-sample prefix arrays of the certificate
     const int N = 148 * osr, ns = 2 * 64 * osr + 1 + N - 1, n_chunk = ns / 16, pre = (3 * (n_chunk + 2) + 1) / 2 + 2;
     int x = GSMCAL_XCAP((ns + 2) / 3);
-    const int need_band = 8 * FB_BINS + pre, need_core = (ns / (4 * osr) + 1) * FC_BINS + pre;
+    const int need_band = 8 * FB_BINS + pre, need_core = (ns / (4 * osr) + 1) * FC_BINS + pre + 4 + (2 * 64 * osr / (4 * osr) + 2) * 4;   // + pass-0 tracked powers [n_seg+1][8] doubles
     if (x < need_band) x = need_band;
     if (x < need_core) x = need_core;
     return (size_t)(ns + x) * sizeof(double2);
@@ -255,7 +255,7 @@ int run_fine_peak(Ctx &c, WinSrc src_peak, i64 n_iq, int osr, i64 D, int cap, Wo
     }
     CU(cudaMemsetAsync(w.need_full, 0, sizeof(int) * D * cap, st));
     CU(cudaMemsetAsync(w.need_band, 0, sizeof(int) * D * cap, st));
-    LAUNCH(fine_peak_core_kernel, dim3((unsigned)cap, (unsigned)D), FC_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, w.need_band);
+    LAUNCH(fine_peak_core_kernel, dim3((unsigned)cap, (unsigned)D), FC_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, w.need_band, g_debug_fail_tier2);
     CU(cudaMemsetAsync(w.fall_count, 0, sizeof(int), st));
     LAUNCH(fine_peak_band_kernel, dim3((unsigned)cap, (unsigned)D), FB_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw,
            (const int *)w.need_band, w.need_full, 0, w.fall_list, w.fall_count, w.fall_best, w.fall_m, g_debug_fail_tier2);

@@ -1463,7 +1463,7 @@ __global__ void fine_fall_combine_kernel(const int *__restrict__ fall_list, cons
 #define FC_THREADS 256
 __global__ void __launch_bounds__(FC_THREADS, 4) fine_peak_core_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ base_pos, int cap,
                                                                       int osr, i64 len_s_ov, const double2 *__restrict__ tw, double *__restrict__ fine_raw,
-                                                                      int *__restrict__ need_band) {
+                                                                      int *__restrict__ need_band, int force_fail) {
     extern __shared__ double2 sm[];
     __shared__ double red_v[8];
     __shared__ int red_i[8];
@@ -1526,124 +1526,143 @@ __global__ void __launch_bounds__(FC_THREADS, 4) fine_peak_core_kernel(WinSrc sr
         if (warp == 0) warp_scan_smem(pe16, n_chunk + 1, lane);
         if (warp == 1) { warp_scan_smem(pa16, n_chunk + 1, lane); __syncwarp(); for (int i = lane; i < n_chunk; i += 32) pa15[i] += pa16[i]; }
     }
-    // chunk sums sum_{n in chunk} s[n] W^{n*k}: (chunk, bin) pairs over the block, 4 accumulators per twiddle
-    for (int p = tid; p < n_ch * FC_BINS; p += FC_THREADS) {
-        const int cidx = p / FC_BINS, j = p % FC_BINS;
-        int k = (k0 - FC_LO + j) % N; if (k < 0) k += N;
-        const double2 wk = tw[k], wk2 = tw[(2 * k) % N], wk3 = tw[(3 * k) % N], wk4 = tw[(4 * k) % N];
-        const int a = cidx * CH;
-        double2 t = tw[(int)(((i64)a * k) % N)];
-        double a0r = 0.0, a0i = 0.0, a1r = 0.0, a1i = 0.0, a2r = 0.0, a2i = 0.0, a3r = 0.0, a3i = 0.0;
-        for (int n = a; n < a + CH; n += 4) {
-            const double2 s0 = win[n], s1 = win[n + 1], s2 = win[n + 2], s3 = win[n + 3];
-            a0r = fma(s0.x, t.x, fma(-s0.y, t.y, a0r)); a0i = fma(s0.x, t.y, fma(s0.y, t.x, a0i));
-            a1r = fma(s1.x, t.x, fma(-s1.y, t.y, a1r)); a1i = fma(s1.x, t.y, fma(s1.y, t.x, a1i));
-            a2r = fma(s2.x, t.x, fma(-s2.y, t.y, a2r)); a2i = fma(s2.x, t.y, fma(s2.y, t.x, a2i));
-            a3r = fma(s3.x, t.x, fma(-s3.y, t.y, a3r)); a3i = fma(s3.x, t.y, fma(s3.y, t.x, a3i));
-            t = cmul(t, wk4);
-        }
-        const double2 c1 = cmul(make_double2(a1r, a1i), wk), c2 = cmul(make_double2(a2r, a2i), wk2), c3 = cmul(make_double2(a3r, a3i), wk3);
-        CS[CSI(cidx + 1, j)] = make_double2((a0r + c1.x) + (c2.x + c3.x), (a0i + c1.y) + (c2.y + c3.y));
-    }
-    __syncthreads();
-    {   // prefix over chunks: warp b scans bin b (lanes own ceil(n_ch/32) consecutive chunks)
-        const int lane = tid & 31, bin = tid >> 5;
-        if (bin < FC_BINS) {
-            const int per = (n_ch + 31) >> 5, b0 = 1 + lane * per;
-            double lr = 0.0, li = 0.0;
-            for (int i = 0; i < per; ++i) if (b0 + i <= n_ch) { const double2 v = CS[CSI(b0 + i, bin)]; lr += v.x; li += v.y; }
-            double ir = lr, ii = li;
-            for (int d = 1; d < 32; d <<= 1) {
-                const double tr = __shfl_up_sync(0xffffffffu, ir, d), ti = __shfl_up_sync(0xffffffffu, ii, d);
-                if (lane >= d) { ir += tr; ii += ti; }
+    // Two passes at most.  Pass 0 tracks the 8 bins k0-3 .. k0+4.  If its certificate fails, pass 1 adds k0-7 .. k0-4 and
+    // k0+5 .. k0+8 (16 tracked bins in total: their tracked power only tightens every bound) and re-checks; the samples
+    // are restored from the in-place differences first.  Whatever still cannot be proven goes to the 64-bin band kernel.
+    double *T2 = pa15 + n_chunk + 2 + ((n_chunk & 1) ? 1 : 0);                      // [n_seg+1][8] tracked power of pass 0 per (window, split), behind the prefix arrays
+    double g_best = -1.0; int g_bestm = 0x7fffffff;
+    int ok = 0;
+    for (int pass = 0; pass < 2 && !ok; ++pass) {
+        if (pass == 1) {                                         // s[m] = s[m+N] - d[m] for m < n_win-1 (d was stored in place)
+            for (int m = tid; m < n_win - 1; m += FC_THREADS) {
+                const double2 dd = win[m], s_new = win[m + N];
+                win[m] = make_double2(s_new.x - dd.x, s_new.y - dd.y);
             }
-            double rr = ir - lr, ri = ii - li;
-            for (int i = 0; i < per; ++i) if (b0 + i <= n_ch) { const double2 v = CS[CSI(b0 + i, bin)]; rr += v.x; ri += v.y; CS[CSI(b0 + i, bin)] = make_double2(rr, ri); }
-            if (lane == 0) CS[CSI(0, bin)] = make_double2(0.0, 0.0);
+            __syncthreads();
         }
-    }
-    __syncthreads();
-    const int g = tid / FC_BINS, j = tid % FC_BINS;
-    const bool active = g < n_seg;
-    int k = (k0 - FC_LO + j) % N; if (k < 0) k += N;
-    const double2 wk = tw[k];
-    const int m0 = g * CH, m_end = (g == n_seg - 1) ? n_win : m0 + CH;
-    double xr = 0.0, xi = 0.0;
-    if (active) {
-        const double2 hi = CS[CSI(g + wch, j)], lo = CS[CSI(g, j)];
-        const double yr = hi.x - lo.x, yi = hi.y - lo.y;
-        const double2 t = tw[(int)(((i64)m0 * k) % N)];          // X_{m0}[k] = Y_{m0}[k] * exp(+2*pi*i*m0*k/N)
-        xr = yr * t.x + yi * t.y;
-        xi = yi * t.x - yr * t.y;
-    }
-    for (int m = tid; m < n_win - 1; m += FC_THREADS) {          // d[m] = s[m+N] - s[m] in place
-        const double2 s_old = win[m], s_new = win[m + N];
-        win[m] = make_double2(s_new.x - s_old.x, s_new.y - s_old.y);
-    }
-    __syncthreads();
-    const double wr = wk.x, wi = -wk.y;
-    double best = -1.0; int bestm = 0x7fffffff;
-    if (active) {
-        for (int m = m0; m < m_end; ++m) {
-            const double p = fma(xr, xr, xi * xi);
-            if (p > best) { best = p; bestm = m; }
-            if (m + 1 < m_end) {
-                const double2 d = win[m];
-                const double tr = xr + d.x, ti = xi + d.y;
-                xr = fma(tr, wr, -(ti * wi));
-                xi = fma(tr, wi, ti * wr);
+        // chunk sums sum_{n in chunk} s[n] W^{n*k}: (chunk, bin) pairs over the block, 4 accumulators per twiddle
+        for (int p = tid; p < n_ch * FC_BINS; p += FC_THREADS) {
+            const int cidx = p / FC_BINS, j = p % FC_BINS;
+            int k = (k0 + ((pass == 0) ? j - FC_LO : (j < 4 ? j - 7 : j + 1))) % N; if (k < 0) k += N;
+            const double2 wk = tw[k], wk2 = tw[(2 * k) % N], wk3 = tw[(3 * k) % N], wk4 = tw[(4 * k) % N];
+            const int a = cidx * CH;
+            double2 t = tw[(int)(((i64)a * k) % N)];
+            double a0r = 0.0, a0i = 0.0, a1r = 0.0, a1i = 0.0, a2r = 0.0, a2i = 0.0, a3r = 0.0, a3i = 0.0;
+            for (int n = a; n < a + CH; n += 4) {
+                const double2 s0 = win[n], s1 = win[n + 1], s2 = win[n + 2], s3 = win[n + 3];
+                a0r = fma(s0.x, t.x, fma(-s0.y, t.y, a0r)); a0i = fma(s0.x, t.y, fma(s0.y, t.x, a0i));
+                a1r = fma(s1.x, t.x, fma(-s1.y, t.y, a1r)); a1i = fma(s1.x, t.y, fma(s1.y, t.x, a1i));
+                a2r = fma(s2.x, t.x, fma(-s2.y, t.y, a2r)); a2i = fma(s2.x, t.y, fma(s2.y, t.x, a2i));
+                a3r = fma(s3.x, t.x, fma(-s3.y, t.y, a3r)); a3i = fma(s3.x, t.y, fma(s3.y, t.x, a3i));
+                t = cmul(t, wk4);
             }
+            const double2 c1 = cmul(make_double2(a1r, a1i), wk), c2 = cmul(make_double2(a2r, a2i), wk2), c3 = cmul(make_double2(a3r, a3i), wk3);
+            CS[CSI(cidx + 1, j)] = make_double2((a0r + c1.x) + (c2.x + c3.x), (a0i + c1.y) + (c2.y + c3.y));
         }
-    }
-    block_argmax(best, bestm, red_v, red_i);
-    // ---- certificate at every segment-start window c = CH*g (g = 0..n_seg), straight from the chunk prefix table.
-    // For any split of the window into a part P1 of d samples and the rest P2, every untracked bin obeys
-    //   |X_c[k]| <= |P1[k]| + |P2[k]| <= sqrt(d*E_P1) + sqrt(N*E_P2 - sum_tracked |P2[k']|^2)
-    // (Cauchy-Schwarz on P1, Parseval on the zero-padded P2).  Putting the non-FCCH samples of an edge window into P1
-    // (d ~ |m* - c|, a few chunk-aligned candidates) is much tighter than Parseval on the whole window, whose bound
-    // charges all of the GMSK data energy to a single bin.  d = 0 is the plain Parseval bound. ----
-    // threads = (window, candidate split): 8 lanes per window, candidate 0 = plain Parseval, 1..6 = d0-2 .. d0+3 chunks
-    int ok = 1;
-    for (int w0 = 0; w0 <= n_seg; w0 += FC_THREADS / 8) {
-        const int gq = w0 + (tid >> 3), cand = tid & 7;
-        double bnd = INFINITY;
-        if (gq <= n_seg && cand < 7) {
-            const int cw = gq * CH, per16 = CH / FB_CERT;
-            const bool lead = cw < bestm;
-            const int dist = lead ? bestm - cw : cw - bestm;
-            const int dch = (cand == 0) ? 0 : (dist + CH - 1) / CH - 3 + cand;
-            if (dch == 0 || (cw != bestm && dch >= 1 && dch < wch)) {
-                // P1 = first dch chunks (window starts before the burst) or last dch chunks (window runs past it)
-                const int p1a = lead ? gq : gq + wch - dch, p1b = p1a + dch;
-                const int p2a = lead ? gq + dch : gq, p2b = lead ? gq + wch : gq + wch - dch;
-                const double e1 = pe16[p1b * per16] - pe16[p1a * per16], e2 = pe16[p2b * per16] - pe16[p2a * per16];
-                double t2 = 0.0;
-#pragma unroll
-                for (int jj = 0; jj < FC_BINS; ++jj) {
-                    const double2 hi = CS[CSI(p2b, jj)], lo = CS[CSI(p2a, jj)];
-                    const double yr = hi.x - lo.x, yi = hi.y - lo.y;
-                    t2 += yr * yr + yi * yi;
+        __syncthreads();
+        {   // prefix over chunks: warp b scans bin b (lanes own ceil(n_ch/32) consecutive chunks)
+            const int lane = tid & 31, bin = tid >> 5;
+            if (bin < FC_BINS) {
+                const int per = (n_ch + 31) >> 5, b0 = 1 + lane * per;
+                double lr = 0.0, li = 0.0;
+                for (int i = 0; i < per; ++i) if (b0 + i <= n_ch) { const double2 v = CS[CSI(b0 + i, bin)]; lr += v.x; li += v.y; }
+                double ir = lr, ii = li;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const double tr = __shfl_up_sync(0xffffffffu, ir, d), ti = __shfl_up_sync(0xffffffffu, ii, d);
+                    if (lane >= d) { ir += tr; ii += ti; }
                 }
-                const double r2 = (double)N * e2 - t2;
-                bnd = sqrt((double)(dch * CH) * (e1 > 0.0 ? e1 : 0.0)) + sqrt(r2 > 0.0 ? r2 : 0.0);
+                double rr = ir - lr, ri = ii - li;
+                for (int i = 0; i < per; ++i) if (b0 + i <= n_ch) { const double2 v = CS[CSI(b0 + i, bin)]; rr += v.x; ri += v.y; CS[CSI(b0 + i, bin)] = make_double2(rr, ri); }
+                if (lane == 0) CS[CSI(0, bin)] = make_double2(0.0, 0.0);
             }
         }
-        bnd = fmin(bnd, __shfl_xor_sync(0xffffffffu, bnd, 1));
-        bnd = fmin(bnd, __shfl_xor_sync(0xffffffffu, bnd, 2));
-        bnd = fmin(bnd, __shfl_xor_sync(0xffffffffu, bnd, 4));
-        if (gq <= n_seg && cand == 0) {
-            const int per16 = CH / FB_CERT;
-            // windows cw .. cw+CH-1 (only cw itself for the last one): slack = sum_{i=cw}^{cw+CH-2} (|s[i]| + |s[i+N]|)
-            const int i16 = gq * per16 + per16 - 1, j16 = (gq + wch) * per16 + per16 - 1;     // pa15[i16] = sum_{n < cw+CH-1} |s|
-            const double A = (gq == n_seg) ? 0.0 : (pa15[i16] - pa16[gq * per16]) + (pa15[j16] - pa16[(gq + wch) * per16]);
-            const double bound = bnd + A;
-            if (!(bound * bound < best * (1.0 - 1e-6))) ok = 0;
+        __syncthreads();
+        const int g = tid / FC_BINS, j = tid % FC_BINS;
+        const bool active = g < n_seg;
+        int k = (k0 + ((pass == 0) ? j - FC_LO : (j < 4 ? j - 7 : j + 1))) % N; if (k < 0) k += N;
+        const double2 wk = tw[k];
+        const int m0 = g * CH, m_end = (g == n_seg - 1) ? n_win : m0 + CH;
+        double xr = 0.0, xi = 0.0;
+        if (active) {
+            const double2 hi = CS[CSI(g + wch, j)], lo = CS[CSI(g, j)];
+            const double yr = hi.x - lo.x, yi = hi.y - lo.y;
+            const double2 t = tw[(int)(((i64)m0 * k) % N)];      // X_{m0}[k] = Y_{m0}[k] * exp(+2*pi*i*m0*k/N)
+            xr = yr * t.x + yi * t.y;
+            xi = yi * t.x - yr * t.y;
         }
+        for (int m = tid; m < n_win - 1; m += FC_THREADS) {      // d[m] = s[m+N] - s[m] in place
+            const double2 s_old = win[m], s_new = win[m + N];
+            win[m] = make_double2(s_new.x - s_old.x, s_new.y - s_old.y);
+        }
+        __syncthreads();
+        const double wr = wk.x, wi = -wk.y;
+        double best = -1.0; int bestm = 0x7fffffff;
+        if (active) {
+            for (int m = m0; m < m_end; ++m) {
+                const double p = fma(xr, xr, xi * xi);
+                if (p > best) { best = p; bestm = m; }
+                if (m + 1 < m_end) {
+                    const double2 d = win[m];
+                    const double tr = xr + d.x, ti = xi + d.y;
+                    xr = fma(tr, wr, -(ti * wi));
+                    xi = fma(tr, wi, ti * wr);
+                }
+            }
+        }
+        block_argmax(best, bestm, red_v, red_i);
+        if (pass == 0) { g_best = best; g_bestm = bestm; }
+        else if (best > g_best || (best == g_best && bestm < g_bestm)) break;   // the extra bins would move the argmax: leave it to tier 2
+        // ---- certificate at every segment-start window c = CH*g (g = 0..n_seg), straight from the chunk prefix table.
+        // For any split of the window into a part P1 of d samples and the rest P2, every untracked bin obeys
+        //   |X_c[k]| <= |P1[k]| + |P2[k]| <= sqrt(d*E_P1) + sqrt(N*E_P2 - sum_tracked |P2[k']|^2)
+        // (Cauchy-Schwarz on P1, Parseval on the zero-padded P2).  Putting the non-FCCH samples of an edge window into P1
+        // (d ~ |m* - c|, a few chunk-aligned candidates) is much tighter than Parseval on the whole window, whose bound
+        // charges all of the GMSK data energy to a single bin.  d = 0 is the plain Parseval bound. ----
+        // threads = (window, candidate split): 8 lanes per window, candidate 0 = plain Parseval, 1..6 = d0-2 .. d0+3 chunks
+        ok = 1;
+        for (int w0 = 0; w0 <= n_seg; w0 += FC_THREADS / 8) {
+            const int gq = w0 + (tid >> 3), cand = tid & 7;
+            double bnd = INFINITY;
+            if (gq <= n_seg && cand < 7) {
+                const int cw = gq * CH, per16 = CH / FB_CERT;
+                const bool lead = cw < g_bestm;
+                const int dist = lead ? g_bestm - cw : cw - g_bestm;
+                const int dch = (cand == 0) ? 0 : (dist + CH - 1) / CH - 3 + cand;
+                if (dch == 0 || (cw != g_bestm && dch >= 1 && dch < wch)) {
+                    // P1 = first dch chunks (window starts before the burst) or last dch chunks (window runs past it)
+                    const int p1a = lead ? gq : gq + wch - dch, p1b = p1a + dch;
+                    const int p2a = lead ? gq + dch : gq, p2b = lead ? gq + wch : gq + wch - dch;
+                    const double e1 = pe16[p1b * per16] - pe16[p1a * per16], e2 = pe16[p2b * per16] - pe16[p2a * per16];
+                    double t2 = (pass == 0) ? 0.0 : T2[gq * 8 + cand];
+#pragma unroll
+                    for (int jj = 0; jj < FC_BINS; ++jj) {
+                        const double2 hi = CS[CSI(p2b, jj)], lo = CS[CSI(p2a, jj)];
+                        const double yr = hi.x - lo.x, yi = hi.y - lo.y;
+                        t2 += yr * yr + yi * yi;
+                    }
+                    if (pass == 0) T2[gq * 8 + cand] = t2;
+                    const double r2 = (double)N * e2 - t2;
+                    bnd = sqrt((double)(dch * CH) * (e1 > 0.0 ? e1 : 0.0)) + sqrt(r2 > 0.0 ? r2 : 0.0);
+                }
+            }
+            bnd = fmin(bnd, __shfl_xor_sync(0xffffffffu, bnd, 1));
+            bnd = fmin(bnd, __shfl_xor_sync(0xffffffffu, bnd, 2));
+            bnd = fmin(bnd, __shfl_xor_sync(0xffffffffu, bnd, 4));
+            if (gq <= n_seg && cand == 0) {
+                const int per16 = CH / FB_CERT;
+                // windows cw .. cw+CH-1 (only cw itself for the last one): slack = sum_{i=cw}^{cw+CH-2} (|s[i]| + |s[i+N]|)
+                const int i16 = gq * per16 + per16 - 1, j16 = (gq + wch) * per16 + per16 - 1;     // pa15[i16] = sum_{n < cw+CH-1} |s|
+                const double A = (gq == n_seg) ? 0.0 : (pa15[i16] - pa16[gq * per16]) + (pa15[j16] - pa16[(gq + wch) * per16]);
+                const double bound = bnd + A;
+                if (!(bound * bound < g_best * (1.0 - 1e-6))) ok = 0;
+            }
+        }
+        ok = __syncthreads_and(ok);
     }
-    ok = __syncthreads_and(ok);
+    const int bestm = g_bestm;
     if (tid == 0) {
         *o = (double)(sp + bestm);
-        need_band[(i64)stream * cap + burst] = ok ? 0 : 1;
+        need_band[(i64)stream * cap + burst] = (ok && !force_fail) ? 0 : 1;       // force_fail: test hook, sends every burst to tier 2
     }
 #undef CSI
 }
