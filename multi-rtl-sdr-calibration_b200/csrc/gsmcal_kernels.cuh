@@ -268,6 +268,14 @@ __device__ void load_window(const WinSrc &src, const StreamCtl &c, int stream, i
     if (use1) {
         double2 *l1 = use2 ? X : dst;
         const int n_l1 = (int)(b1 - a1 + 1);
+        // derotation phasor exp(1i*j*dphi1): exact sincos of the (rounded) product for the thread's first sample - the
+        // argument reaches 1e6 rad, which is the slow Payne-Hanek path - then a fixed complex step of nt samples
+        double2 ph = make_double2(1.0, 0.0), st = make_double2(1.0, 0.0);
+        if (derot) {
+            double sn, cs;
+            sincos((double)(a1 + tid) * c.dphi1, &sn, &cs); ph = make_double2(cs, sn);
+            sincos((double)nt * c.dphi1, &sn, &cs); st = make_double2(cs, sn);
+        }
         for (int i = tid; i < n_l1; i += nt) {
             i64 j = a1 + i;
             double xq = (double)j * s1;
@@ -275,10 +283,7 @@ __device__ void load_window(const WinSrc &src, const StreamCtl &c, int stream, i
             if (i0 > n0 - 1) i0 = n0 - 1;
             i64 i1 = (i0 + 1 > n0 - 1) ? n0 - 1 : i0 + 1;
             double2 v = lerp_ref(Y[i0 - a0], Y[i1 - a0], xq - (double)i0);
-            if (derot) {
-                double sn, cs; sincos((double)j * c.dphi1, &sn, &cs);
-                v = cmul(v, make_double2(cs, sn));
-            }
+            if (derot) { v = cmul(v, ph); ph = cmul(ph, st); }
             l1[i] = v;
         }
         __syncthreads();
