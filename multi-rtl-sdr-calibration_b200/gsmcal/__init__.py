@@ -8,3 +8,4 @@ from .api import (FCCH_coarse_position, FCCH_fine_correction, GsmcalError, SCH_c
                   chn_filter_taps, device_count, diversity_power_spectrum, fcch_scan, fir1, fir_filter, gsm_SCH_training_sequence_gen,
                   launch_count, max_bursts, move_fft_snr_runtime_avg, move_fft_snr_trace, raw2iq, raw2iq_fir,
                   set_device, specific_fft_snr_fix_avg, total_ppm_calculation)
+from . import ingest  # noqa: F401,E402  (rtl_tcp capture side: set_*_tcp, DongleIngest, calibrate_from_dongles)
