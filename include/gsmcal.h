@@ -116,6 +116,39 @@ int gsmcal_carrier_correct_post_SCH(const double *s, int64_t n, const double *po
 /* ---- K11  ppm_out = total_ppm_calculation(ppm_in)   total_ppm_calculation.m:5-21 ---- */
 int gsmcal_total_ppm_calculation(const double *ppm_in, int64_t n, double *ppm_out);
 
+/* ---- the consumers of r_correct / pos_info (gsm_sync_demod.m:143-146) -------------
+ * The reference functions have no outputs (they disp / plot); these entry points return the quantities they compute.
+ *
+ * s = gsm_normal_training_sequence_gen(oversampling_ratio)   gsm_normal_training_sequence_gen.m:5-59
+ *   s: (26*osr) x 8 complex128, column q = GMSK of training sequence code q (same modulator caveat as T1). */
+int gsmcal_normal_training_sequence_gen(int oversampling_ratio, double *s);
+
+/* FCCH_demod(s, pos_info, oversampling_ratio, carrier_freq)   FCCH_demod.m:5-66
+ *   per FCCH row of pos_info: freq (:41), snr (:57-63), max_idx - (fft_len/2+1) (:66); mean_freq (:43), carrier_ppm (:47).
+ *   *n_fcch = -1 on the `pos_info==-1` path (:7-10), else the number of FCCH rows (<= cap). */
+int gsmcal_FCCH_demod(const double *s, int64_t n, const double *pos_info, int64_t n_rows, int oversampling_ratio,
+                      double carrier_freq, double *freq, double *snr, double *max_idx, int64_t cap,
+                      int64_t *n_fcch, double *mean_freq, double *carrier_ppm);
+
+/* BCCH_demod(s, pos_info, training_sequence, oversampling_ratio)   BCCH_demod.m:5-106
+ *   The reference reads `carrier_freq` and `normal_training_sequence` without defining them (:68,:91); here they are
+ *   arguments (nts = the (26*osr) x 8 matrix above).  carrier_ppm (:68); nts_idx = 1..8 when the first four BCCH bursts
+ *   agree on the best-correlating normal training sequence (:91-97), -1 otherwise (:99-102); both -1 on the early
+ *   returns (:6-16).  corr_abs (optional): abs(corr_val), 8 x 4 column-major (:91-93). */
+int gsmcal_BCCH_demod(const double *s, int64_t n, const double *pos_info, int64_t n_rows, const double *nts,
+                      int oversampling_ratio, double carrier_freq, double *carrier_ppm, int *nts_idx, double *corr_abs);
+
+/* SCH_demod(s, pos_info, training_sequence, oversampling_ratio)   SCH_demod.m:5-121
+ *   per SCH row of pos_info: frequency-domain equalisation on the 64-symbol training sequence (:79-90), GMSK MLSE
+ *   demodulation (comm.GMSKDemodulator, TracebackDepth 30 - closed source, restated as a 32-state Viterbi over the
+ *   modulator of T1: parity unpinned), the 148 burst bits (:94-95), their differential decoding (:97) and the
+ *   +-1 correlation with the training bits over 85 lags (:103-110).
+ *   demod_bits, bits_to_decoder: 148 x cap uint8 (column per burst); corr_val: 85 x cap double.
+ *   *n_sch = -1 on the `pos_info==-1` path (:8-11).  GSMCAL_ERR_RANGE where `x = s(sp:ep)` (:81) would fail. */
+int gsmcal_SCH_demod(const double *s, int64_t n, const double *pos_info, int64_t n_rows, const double *sch_training_sequence,
+                     int oversampling_ratio, int64_t cap, int64_t *n_sch, uint8_t *demod_bits, uint8_t *bits_to_decoder,
+                     double *corr_val);
+
 /* ---- batched pipeline: gsm_sync_demod.m:107-124 for many dongle streams in one call ------------------
  * raw: n_streams rows of 2*n_iq uint8 (row d == column d of the reference's 2N x D matrix `s`).
  * Returns exactly what the function-by-function chain returns per stream (positions, pos_info, ppm),

@@ -2,6 +2,7 @@
 // No torch types, no CPU fallback: every compute entry point fails with GSMCAL_ERR_CUDA without a device.
 #include "../../include/gsmcal.h"
 #include "gsmcal_kernels.cuh"
+#include "gsmcal_demod.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -981,18 +982,23 @@ double gmsk_q(double tau) {
     const double g0 = gq_big_g(-2.0), g1 = gq_big_g(2.0);
     return (gq_big_g(tau - 2.0) - g0) / (g1 - g0);
 }
-void gmsk_template(int osr, double *out) {
-    static const int bits[64] = {1, 0, 1, 1, 1, 0, 0, 1, 0, 1, 1, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0,
-                                 0, 0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 1, 0, 1, 1, 0, 1, 0, 1, 0, 0, 0,
-                                 1, 0, 1, 0, 1, 1, 1, 0, 1, 1, 0, 0, 0, 0, 1, 1, 0, 1, 1};
-    double a[64];
+void gmsk_bits(const int *bits, int nb, int osr, double *out) {      // differential encoding against a leading 0, bit 1 -> +1, then GMSK
+    std::vector<double> a((size_t)nb);
     int prev = 0;
-    for (int k = 0; k < 64; ++k) { a[k] = (bits[k] == prev) ? 1.0 : -1.0; prev = bits[k]; }   // ~abs(diff([0;data])), bit 1 -> +1
-    for (int n = 0; n < 64 * osr; ++n) {
+    for (int k = 0; k < nb; ++k) { a[k] = (bits[k] == prev) ? 1.0 : -1.0; prev = bits[k]; }   // ~abs(diff([0;data]))
+    for (int n = 0; n < nb * osr; ++n) {
         double phase = 0.0;
-        for (int k = 0; k < 64; ++k) phase += a[k] * gmsk_q(((double)n - (double)k * osr) / osr);
+        for (int k = 0; k < nb; ++k) phase += a[k] * gmsk_q(((double)n - (double)k * osr) / osr);
         out[2 * n] = cos((M_PI / 2.0) * phase);
         out[2 * n + 1] = sin((M_PI / 2.0) * phase);
     }
 }
+void gmsk_template(int osr, double *out) {
+    static const int bits[64] = {1, 0, 1, 1, 1, 0, 0, 1, 0, 1, 1, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0,
+                                 0, 0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 1, 0, 1, 1, 0, 1, 0, 1, 0, 0, 0,
+                                 1, 0, 1, 0, 1, 1, 1, 0, 1, 1, 0, 0, 0, 0, 1, 1, 0, 1, 1};
+    gmsk_bits(bits, 64, osr, out);
+}
 }  // namespace
+
+#include "gsmcal_demod_api.inc"

@@ -47,6 +47,13 @@ SIGNATURES = {
                                                   C.c_void_p, c_i64, c_i64p, c_dp]),
     "gsmcal_carrier_correct_post_SCH": (C.c_int, [C.c_void_p, c_i64, C.c_void_p, c_i64, C.c_int, C.c_double, C.c_void_p, c_i64, c_i64p, c_dp]),
     "gsmcal_total_ppm_calculation": (C.c_int, [C.c_void_p, c_i64, c_dp]),
+    "gsmcal_normal_training_sequence_gen": (C.c_int, [C.c_int, C.c_void_p]),
+    "gsmcal_FCCH_demod": (C.c_int, [C.c_void_p, c_i64, C.c_void_p, c_i64, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, c_i64,
+                                    C.POINTER(c_i64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "gsmcal_BCCH_demod": (C.c_int, [C.c_void_p, c_i64, C.c_void_p, c_i64, C.c_void_p, C.c_int, C.c_double,
+                                    C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p]),
+    "gsmcal_SCH_demod": (C.c_int, [C.c_void_p, c_i64, C.c_void_p, c_i64, C.c_void_p, C.c_int, c_i64, C.POINTER(c_i64),
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsmcal_calibrate_batch": (C.c_int, [C.c_void_p, C.c_int, c_i64, c_i64, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsmcal_last_batch_stage_ms": (C.c_int, [C.c_void_p, C.c_int]),

@@ -227,6 +227,62 @@ def total_ppm_calculation(ppm_in) -> float:
     return out.value
 
 
+# ---- FCCH_demod.m, BCCH_demod.m, SCH_demod.m, gsm_normal_training_sequence_gen.m -------------
+def _pinfo(pos_info):
+    pinfo = np.asarray(pos_info, dtype=np.float64).reshape(-1, 2)
+    return pinfo, np.ascontiguousarray(np.concatenate([pinfo[:, 0], pinfo[:, 1]]))
+
+
+def gsm_normal_training_sequence_gen(oversampling_ratio: int) -> np.ndarray:
+    """(26*osr) x 8 complex128, one normal training sequence per column."""
+    out = np.empty((8, 26 * int(oversampling_ratio)), dtype=np.complex128)
+    check(lib().gsmcal_normal_training_sequence_gen(int(oversampling_ratio), _ptr(out)))
+    return out.T
+
+
+def FCCH_demod(s, pos_info, oversampling_ratio: int, carrier_freq: float):
+    """What FCCH_demod.m displays: dict(freq, mean_freq, carrier_ppm, snr, max_idx); None on the `pos_info==-1` path."""
+    pinfo, flat = _pinfo(pos_info)
+    s = _stream(s if s is not None else [-1.0])
+    cap = max(1, pinfo.shape[0])
+    freq, snr, idx = np.empty(cap), np.empty(cap), np.empty(cap)
+    n, mf, cp = C.c_int64(0), C.c_double(), C.c_double()
+    check(lib().gsmcal_FCCH_demod(_ptr(s), len(s), _ptr(flat), pinfo.shape[0], int(oversampling_ratio), float(carrier_freq),
+                                  _ptr(freq), _ptr(snr), _ptr(idx), cap, C.byref(n), C.byref(mf), C.byref(cp)))
+    if n.value < 0:
+        return None
+    k = n.value
+    return dict(freq=freq[:k], mean_freq=mf.value, carrier_ppm=cp.value, snr=snr[:k], max_idx=idx[:k])
+
+
+def BCCH_demod(s, pos_info, normal_training_sequence, oversampling_ratio: int, carrier_freq: float):
+    """(carrier_ppm, normal_training_sequence_idx, |corr_val| 8 x 4 or None); (-1, -1, None) on the early returns."""
+    pinfo, flat = _pinfo(pos_info)
+    s = _stream(s if s is not None else [-1.0])
+    nts = np.ascontiguousarray(np.asarray(normal_training_sequence, dtype=np.complex128).T)     # column-major (26*osr) x 8
+    mag = np.full((4, 8), np.nan)
+    cp, idx = C.c_double(), C.c_int()
+    check(lib().gsmcal_BCCH_demod(_ptr(s), len(s), _ptr(flat), pinfo.shape[0], _ptr(nts), int(oversampling_ratio), float(carrier_freq),
+                                  C.byref(cp), C.byref(idx), _ptr(mag)))
+    return cp.value, idx.value, (None if np.isnan(mag).all() else mag.T.copy())
+
+
+def SCH_demod(s, pos_info, training_sequence, oversampling_ratio: int):
+    """dict(demod_bits [H x 148], bits_to_decoder [H x 148], corr_val [H x 85]); None on the `pos_info==-1` path."""
+    pinfo, flat = _pinfo(pos_info)
+    s = _stream(s if s is not None else [-1.0])
+    tpl = _stream(training_sequence)
+    cap = max(1, pinfo.shape[0])
+    bits, dec, corr = np.zeros((cap, 148), dtype=np.uint8), np.zeros((cap, 148), dtype=np.uint8), np.zeros((cap, 85))
+    n = C.c_int64(0)
+    check(lib().gsmcal_SCH_demod(_ptr(s), len(s), _ptr(flat), pinfo.shape[0], _ptr(tpl), int(oversampling_ratio), cap, C.byref(n),
+                                 _ptr(bits), _ptr(dec), _ptr(corr)))
+    if n.value < 0:
+        return None
+    k = n.value
+    return dict(demod_bits=bits[:k].astype(np.int64), bits_to_decoder=dec[:k].astype(np.int64), corr_val=corr[:k])
+
+
 # ---- batched pipeline ---------------------------------------------------------------------------------
 def max_bursts(n_iq: int, osr: int = 8, coarse_dr: int = 8) -> int:
     dec = osr * coarse_dr

@@ -62,6 +62,7 @@ class StreamSpec:
     dc: complex = 127.4 + 127.6j
     drop_fcch: tuple = field(default_factory=tuple)   # indices (0-based, in order of appearance) of FCCH bursts to replace by data
     noise_only: bool = False
+    tsc: int | None = None          # normal training sequence code (0..7) put at bits 61..86 of every normal burst; None = random bits
 
 
 def random_spec(seed: int, n_samples: int, carrier_freq: float = 957.4e6) -> StreamSpec:
@@ -76,12 +77,25 @@ def random_spec(seed: int, n_samples: int, carrier_freq: float = 957.4e6) -> Str
                       start_offset=float(rng.integers(0, MULTIFRAME)))
 
 
-def _slot_bits(n_slots: int, gen: torch.Generator, device, drop_fcch=()) -> torch.Tensor:
+NORMAL_TRAINING_BITS = (      # gsm_normal_training_sequence_gen.m:17-24
+    (0, 0, 1, 0, 0, 1, 0, 1, 1, 1, 0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 1, 0, 1, 1, 1),
+    (0, 0, 1, 0, 1, 1, 0, 1, 1, 1, 0, 1, 1, 1, 1, 0, 0, 0, 1, 0, 1, 1, 0, 1, 1, 1),
+    (0, 1, 0, 0, 0, 0, 1, 1, 1, 0, 1, 1, 1, 0, 1, 0, 0, 1, 0, 0, 0, 0, 1, 1, 1, 0),
+    (0, 1, 0, 0, 0, 1, 1, 1, 1, 0, 1, 1, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1, 1, 1, 1, 0),
+    (0, 0, 0, 1, 1, 0, 1, 0, 1, 1, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1, 1, 0, 1, 0, 1, 1),
+    (0, 1, 0, 0, 1, 1, 1, 0, 1, 0, 1, 1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 1, 1, 0, 1, 0),
+    (1, 0, 1, 0, 0, 1, 1, 1, 1, 1, 0, 1, 1, 0, 0, 0, 1, 0, 1, 0, 0, 1, 1, 1, 1, 1),
+    (1, 1, 1, 0, 1, 1, 1, 1, 0, 0, 0, 1, 0, 0, 1, 0, 1, 1, 1, 0, 1, 1, 1, 1, 0, 0))
+
+
+def _slot_bits(n_slots: int, gen: torch.Generator, device, drop_fcch=(), tsc=None) -> torch.Tensor:
     """[n_slots, 156] bits: TS0 of frames 0/10/20/30/40 (mod 51) FCCH, 1/11/21/31/41 SCH, else random."""
     bits = torch.randint(0, 2, (n_slots, SYM_PER_SLOT), generator=gen, device=device, dtype=torch.int64)
     bits[:, 0:3] = 0
     bits[:, 145:148] = 0
     bits[:, 148:156] = 1
+    if tsc is not None:
+        bits[:, 61:87] = torch.tensor(NORMAL_TRAINING_BITS[int(tsc)], device=device, dtype=torch.int64)
     slot = torch.arange(n_slots, device=device)
     frame = (slot // 8) % 51
     ts0 = (slot % 8) == 0
@@ -110,7 +124,7 @@ def generate_stream(spec: StreamSpec, device="cpu", out: torch.Tensor | None = N
     inv = 1.0 / (1.0 + spec.sampling_ppm * 1e-6)
     t_end = spec.start_offset + n * inv
     n_slots = int(t_end // SLOT) + 3
-    bits = _slot_bits(n_slots, gen, dev, spec.drop_fcch).flatten()
+    bits = _slot_bits(n_slots, gen, dev, spec.drop_fcch, spec.tsc).flatten()
     prev = torch.cat([torch.ones(1, dtype=torch.int64, device=dev), bits[:-1]])
     a = (1 - 2 * (bits ^ prev)).to(torch.int64)                 # +1 where a bit equals its predecessor
     psum = torch.cumsum(a, 0)                                   # P[m] = sum_{i<=m} a_i

@@ -298,6 +298,98 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     mxFree(res); mxFree(pi); if (own) mxFree((void *)tpl);
 }
 
+#elif defined(GSMCAL_MEX_gsm_normal_training_sequence_gen)
+/* s = gsm_normal_training_sequence_gen(oversampling_ratio)                 gsm_normal_training_sequence_gen.m:5 */
+void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
+    (void)nlhs; need(nrhs, 1, "s = gsm_normal_training_sequence_gen(oversampling_ratio)");
+    int osr = (int)mxGetScalar(prhs[0]);
+    double *buf = (double *)mxMalloc(2 * 8 * 26 * (size_t)(osr > 0 ? osr : 1) * sizeof(double));
+    fail_on(gsmcal_normal_training_sequence_gen(osr, buf), "gsm_normal_training_sequence_gen");
+    plhs[0] = put_c128(buf, 26 * (size_t)osr, 8);
+    mxFree(buf);
+}
+
+#elif defined(GSMCAL_MEX_FCCH_demod)
+/* FCCH_demod(s, pos_info, oversampling_ratio, carrier_freq)                                     FCCH_demod.m:5
+ * The reference only displays; optional outputs here: [freq, snr, carrier_ppm, max_idx]. */
+void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
+    init_once(); need(nrhs, 4, "FCCH_demod(s,pos_info,oversampling_ratio,carrier_freq)");
+    int own; const double *s = get_c128(prhs[0], &own);
+    int64_t n = (int64_t)mxGetNumberOfElements(prhs[0]);
+    if (!mxIsDouble(prhs[1]) || mxIsComplex(prhs[1]) || mxGetN(prhs[1]) != 2) mexErrMsgIdAndTxt("gsmcal:size", "pos_info must be R x 2");
+    size_t rows = mxGetM(prhs[1]), cap = rows ? rows : 1;
+    double *freq = (double *)mxMalloc(3 * cap * sizeof(double)), *snr = freq + cap, *idx = snr + cap, mean_freq, cppm;
+    int64_t h = 0;
+    fail_on(gsmcal_FCCH_demod(s, n, mxGetPr(prhs[1]), (int64_t)rows, (int)mxGetScalar(prhs[2]), mxGetScalar(prhs[3]),
+                              freq, snr, idx, (int64_t)cap, &h, &mean_freq, &cppm), "FCCH_demod");
+    mexPrintf(" \n");
+    if (h < 0) mexPrintf("FCCH demod: Warning! No valid position information!\n");                   /* :8 */
+    else {
+        mexPrintf("FCCH demod: FCCH freq");  for (int64_t i = 0; i < h; ++i) mexPrintf(" %.5g", freq[i]); mexPrintf("\n");      /* :42 */
+        mexPrintf("FCCH demod: mean FCCH freq %.5g\nFCCH demod: carrier error ppm %.5g\n", mean_freq, cppm);                   /* :44,48 */
+        mexPrintf("FCCH demod: SNR");        for (int64_t i = 0; i < h; ++i) mexPrintf(" %.5g", snr[i]);  mexPrintf("\n");      /* :65 */
+        mexPrintf("FCCH demod: max idx");    for (int64_t i = 0; i < h; ++i) mexPrintf(" %g", idx[i]);    mexPrintf("\n");      /* :66 */
+    }
+    size_t k = h < 0 ? 0 : (size_t)h;
+    if (nlhs > 0) plhs[0] = row_vector(freq, k);
+    if (nlhs > 1) plhs[1] = row_vector(snr, k);
+    if (nlhs > 2) plhs[2] = scalar(cppm);
+    if (nlhs > 3) plhs[3] = row_vector(idx, k);
+    mxFree(freq); if (own) mxFree((void *)s);
+}
+
+#elif defined(GSMCAL_MEX_BCCH_demod)
+/* BCCH_demod(s, pos_info, normal_training_sequence, oversampling_ratio [, carrier_freq])       BCCH_demod.m:5
+ * (the reference reads carrier_freq without defining it; default 957.4e6, gsm_sync_demod.m:14).
+ * Optional outputs: [carrier_ppm, normal_training_sequence_idx, abs(corr_val)]. */
+void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
+    init_once(); need(nrhs, 4, "BCCH_demod(s,pos_info,normal_training_sequence,oversampling_ratio[,carrier_freq])");
+    int own, own_t; const double *s = get_c128(prhs[0], &own);
+    int64_t n = (int64_t)mxGetNumberOfElements(prhs[0]);
+    if (!mxIsDouble(prhs[1]) || mxIsComplex(prhs[1]) || mxGetN(prhs[1]) != 2) mexErrMsgIdAndTxt("gsmcal:size", "pos_info must be R x 2");
+    const double *nts = get_c128(prhs[2], &own_t);
+    int osr = (int)mxGetScalar(prhs[3]);
+    if (mxGetM(prhs[2]) != (size_t)(26 * osr) || mxGetN(prhs[2]) != 8) mexErrMsgIdAndTxt("gsmcal:size", "normal_training_sequence must be (26*oversampling_ratio) x 8");
+    double carrier_freq = nrhs > 4 ? mxGetScalar(prhs[4]) : 957.4e6, cppm, mag[32];
+    int idx;
+    for (int i = 0; i < 32; ++i) mag[i] = 0.0;
+    fail_on(gsmcal_BCCH_demod(s, n, mxGetPr(prhs[1]), (int64_t)mxGetM(prhs[1]), nts, osr, carrier_freq, &cppm, &idx, mag), "BCCH_demod");
+    if (idx > 0) mexPrintf("Normal training sequence idx (BCCH) %d\n", idx);                       /* :95 */
+    else if (cppm != -1.0) mexPrintf("Fail to identity normal training sequence idx (BCCH).\n");   /* :98 */
+    if (nlhs > 0) plhs[0] = scalar(cppm);
+    if (nlhs > 1) plhs[1] = scalar((double)idx);
+    if (nlhs > 2) { plhs[2] = mxCreateDoubleMatrix(8, 4, mxREAL); memcpy(mxGetPr(plhs[2]), mag, sizeof mag); }
+    if (own) mxFree((void *)s); if (own_t) mxFree((void *)nts);
+}
+
+#elif defined(GSMCAL_MEX_SCH_demod)
+/* SCH_demod(s, pos_info, training_sequence, oversampling_ratio)                                 SCH_demod.m:5
+ * Optional outputs: [demod_bits (148 x H), bits_to_decoder (148 x H), corr_val (85 x H)]. */
+void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
+    init_once(); need(nrhs, 4, "SCH_demod(s,pos_info,training_sequence,oversampling_ratio)");
+    int own, own_t; const double *s = get_c128(prhs[0], &own);
+    int64_t n = (int64_t)mxGetNumberOfElements(prhs[0]);
+    if (!mxIsDouble(prhs[1]) || mxIsComplex(prhs[1]) || mxGetN(prhs[1]) != 2) mexErrMsgIdAndTxt("gsmcal:size", "pos_info must be R x 2");
+    const double *tpl = get_c128(prhs[2], &own_t);
+    int osr = (int)mxGetScalar(prhs[3]);
+    if (mxGetNumberOfElements(prhs[2]) != (size_t)(64 * osr)) mexErrMsgIdAndTxt("gsmcal:size", "training_sequence must have 64*oversampling_ratio samples");
+    size_t rows = mxGetM(prhs[1]), cap = rows ? rows : 1;
+    uint8_t *bits = (uint8_t *)mxMalloc(2 * 148 * cap), *dec = bits + 148 * cap;
+    double *corr = (double *)mxMalloc(85 * cap * sizeof(double));
+    int64_t h = 0;
+    fail_on(gsmcal_SCH_demod(s, n, mxGetPr(prhs[1]), (int64_t)rows, tpl, osr, (int64_t)cap, &h, bits, dec, corr), "SCH_demod");
+    mexPrintf(" \n");
+    if (h < 0) mexPrintf("SCH demod: Warning! No valid position information!\n");                    /* :9 */
+    size_t k = h < 0 ? 0 : (size_t)h;
+    for (int o = 0; o < 2 && o < nlhs; ++o) {
+        plhs[o] = mxCreateDoubleMatrix(148, k, mxREAL);
+        const uint8_t *src = o ? dec : bits;
+        for (size_t i = 0; i < 148 * k; ++i) mxGetPr(plhs[o])[i] = (double)src[i];
+    }
+    if (nlhs > 2) { plhs[2] = mxCreateDoubleMatrix(85, k, mxREAL); memcpy(mxGetPr(plhs[2]), corr, 85 * k * sizeof(double)); }
+    mxFree(bits); mxFree(corr); if (own) mxFree((void *)s); if (own_t) mxFree((void *)tpl);
+}
+
 #else
 #error "define GSMCAL_MEX_<function> (see the header of this file)"
 #endif

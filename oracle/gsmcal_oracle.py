@@ -510,6 +510,175 @@ def total_ppm_calculation(ppm_in) -> float:
 
 
 # ----------------------------------------------------------------------------------------------------
+# the consumers of r_correct / pos_info (gsm_sync_demod.m:143-146).  The reference
+# functions return nothing (they disp / plot); the restatements return the quantities they compute.
+# ----------------------------------------------------------------------------------------------------
+NORMAL_TRAINING_BITS = np.array([                      # gsm_normal_training_sequence_gen.m:17-24 (TSC 0..7)
+    [0, 0, 1, 0, 0, 1, 0, 1, 1, 1, 0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 1, 0, 1, 1, 1],
+    [0, 0, 1, 0, 1, 1, 0, 1, 1, 1, 0, 1, 1, 1, 1, 0, 0, 0, 1, 0, 1, 1, 0, 1, 1, 1],
+    [0, 1, 0, 0, 0, 0, 1, 1, 1, 0, 1, 1, 1, 0, 1, 0, 0, 1, 0, 0, 0, 0, 1, 1, 1, 0],
+    [0, 1, 0, 0, 0, 1, 1, 1, 1, 0, 1, 1, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1, 1, 1, 1, 0],
+    [0, 0, 0, 1, 1, 0, 1, 0, 1, 1, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1, 1, 0, 1, 0, 1, 1],
+    [0, 1, 0, 0, 1, 1, 1, 0, 1, 0, 1, 1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 1, 1, 0, 1, 0],
+    [1, 0, 1, 0, 0, 1, 1, 1, 1, 1, 0, 1, 1, 0, 0, 0, 1, 0, 1, 0, 0, 1, 1, 1, 1, 1],
+    [1, 1, 1, 0, 1, 1, 1, 1, 0, 0, 0, 1, 0, 0, 1, 0, 1, 1, 1, 0, 1, 1, 1, 1, 0, 0]], dtype=np.int64)
+
+
+def gsm_normal_training_sequence_gen(oversampling_ratio: int) -> np.ndarray:
+    """gsm_normal_training_sequence_gen.m:5-59 -> (26*osr) x 8, one GMSK-modulated normal training sequence per column
+    (each column differentially encoded against a leading 0, :38; modulator reset per column, :51)."""
+    return np.stack([gmsk_modulate(differential_encode(b), oversampling_ratio) for b in NORMAL_TRAINING_BITS], axis=1)
+
+
+def _all_minus_one(pos_info: np.ndarray) -> bool:
+    return pos_info.size > 0 and bool(np.all(pos_info == -1))
+
+
+def FCCH_demod(s, pos_info, oversampling_ratio: int, carrier_freq: float):
+    """FCCH_demod.m:5-66.  Returns None on the `pos_info==-1` path (:7-10), else a dict with what the function
+    displays: freq per burst (:41-42), mean_freq (:43), carrier_ppm (:47), snr per burst (:57-63) and
+    max_idx - (fft_len/2+1) (:66)."""
+    pos_info = np.asarray(pos_info, dtype=np.float64).reshape(-1, 2)
+    if _all_minus_one(pos_info):
+        return None
+    s = np.asarray(s).reshape(-1)
+    osr = oversampling_ratio
+    fft_len = LEN_FCCH_CW * osr
+    sampling_rate = SYMBOL_RATE * osr
+    fcch_pos = [int(p) for p in pos_info[pos_info[:, 1] == 0, 0]]
+    fcch_mat = np.stack([s[p - 1:p - 1 + fft_len] for p in fcch_pos], axis=1)
+    fd = abs2(np.fft.fft(fcch_mat, fft_len, axis=0))
+    fd = np.concatenate([fd[fft_len // 2:, :], fd[:fft_len // 2, :]], axis=0)
+    max_idx = np.argmax(fd, axis=0) + 1
+    freq, _, _ = tone_freq_estimate(s, fcch_pos, fft_len, sampling_rate)            # :36-41 (same statements)
+    mean_freq = matlab_mean(freq)
+    carrier_ppm = 1e6 * (mean_freq - SYMBOL_RATE / 4) / carrier_freq
+    half_noise_len = math.ceil((fft_len * 200e3 / sampling_rate) / 2)
+    sp = (fft_len // 2 + 1) - half_noise_len
+    ep = (fft_len // 2 + 1) + half_noise_len - 1
+    snr = np.zeros(len(fcch_pos))
+    for i in range(len(fcch_pos)):
+        sset = (np.arange(max_idx[i] - 2, max_idx[i] + 3) - 1) % fft_len            # 0-based after the mod (:59-60)
+        signal_power = float(np.sum(fd[sset, i]))
+        noise_power = float(np.sum(fd[sp - 1:ep, i])) - signal_power
+        snr[i] = 10.0 * math.log10(signal_power / noise_power) if signal_power / noise_power > 0 else float("nan")
+    return dict(freq=freq, mean_freq=mean_freq, carrier_ppm=carrier_ppm, snr=snr,
+                max_idx=(max_idx - (fft_len // 2 + 1)).astype(np.float64))
+
+
+def BCCH_demod(s, pos_info, normal_training_sequence, oversampling_ratio: int, carrier_freq: float):
+    """BCCH_demod.m:5-106 (the reference reads `carrier_freq` and `normal_training_sequence` without defining
+    them - :68,:91 - so they are arguments here).  Returns (carrier_ppm, normal_training_sequence_idx, |corr_val| 8x4);
+    (-1, -1, None) on the early returns (:6-16), idx = -1 when the four bursts disagree (:99-102)."""
+    pos_info = np.asarray(pos_info, dtype=np.float64).reshape(-1, 2)
+    if _all_minus_one(pos_info) or int(np.sum(pos_info[:, 1] == 2)) < 4:
+        return -1.0, -1, None
+    osr = oversampling_ratio
+    r, carrier_ppm = carrier_correct_post_SCH(s, pos_info, osr, carrier_freq)       # :47-73 are the same statements
+    nts = np.asarray(normal_training_sequence)
+    bcch_pos = [int(p) for p in pos_info[pos_info[:, 1] == 2, 0]]
+    L = 26 * osr
+    corr_mat = np.stack([r[p + 61 * osr - 1:p + 61 * osr - 1 + L] for p in bcch_pos[:4]], axis=1)     # :85-89
+    corr_val = nts.conj().T @ corr_mat                                               # :91, 8 x 4
+    mag = np.abs(corr_val)
+    max_idx = np.argmax(mag, axis=0) + 1
+    idx = int(max_idx[0]) if np.all(max_idx == max_idx[0]) else -1                   # :94-102
+    return carrier_ppm, idx, mag
+
+
+def gmsk_branch_table(osr: int) -> np.ndarray:
+    """Reference waveforms of one symbol interval for the 16 (a_m, a_m-1, a_m-2, a_m-3) combinations (bit 1 -> +1),
+    zero accumulated phase: exp(i*pi/2*(a_m q(t) + a_m-1 q(t+1) + a_m-2 q(t+2) + a_m-3 q(t+3))), t = j/osr."""
+    tau = np.arange(osr, dtype=np.float64) / osr
+    q = [gmsk_q(tau + d) for d in range(4)]
+    W = np.zeros((16, osr), dtype=np.complex128)
+    for combo in range(16):
+        a = [2.0 * ((combo >> (3 - d)) & 1) - 1.0 for d in range(4)]
+        W[combo] = np.exp(1j * (math.pi / 2.0) * (a[0] * q[0] + a[1] * q[1] + a[2] * q[2] + a[3] * q[3]))
+    return W
+
+
+def gmsk_viterbi_demod(x, osr: int, traceback: int) -> np.ndarray:
+    """MLSE demodulator for the GMSK of gmsk_modulate (BT 0.3, L = 4, h = 1/2, zero phase offset), standing in for
+    comm.GMSKDemodulator('BitOutput',true,...,'TracebackDepth',D) of SCH_demod.m:63 (closed source: PARITY UNPINNED).
+
+    32 states (4 accumulated phases x 3 previous symbols), all start metrics 0; per symbol the 16 branch correlations
+    sum_j x[m*osr+j]*conj(W[combo][j]) are rotated by the state phase; first maximum wins every comparison; output
+    bit m is the decision for symbol m-D traced from the best state after symbol m (0 while m < D)."""
+    x = np.asarray(x).reshape(-1)
+    nsym = len(x) // osr
+    W = gmsk_branch_table(osr).conj()
+    D = traceback
+    metric = np.zeros(32)
+    hist = np.zeros(32, dtype=np.uint64)
+    out = np.zeros(nsym, dtype=np.int64)
+    for m in range(nsym):
+        seg = x[m * osr:(m + 1) * osr]
+        c = np.zeros(16, dtype=np.complex128)
+        for j in range(osr):                                   # ascending-sample accumulation (the order the kernel uses)
+            c = c + seg[j] * W[:, j]
+        new_metric = np.empty(32)
+        new_hist = np.empty(32, dtype=np.uint64)
+        for sn in range(32):
+            pn, c1, c2, c3 = sn >> 3, (sn >> 2) & 1, (sn >> 1) & 1, sn & 1
+            best, bh = None, None
+            for b3 in (0, 1):
+                p = (pn - (1 if b3 else -1)) % 4
+                pred = p * 8 + (c2 << 2) + (c3 << 1) + b3
+                cv = c[(c1 << 3) + (c2 << 2) + (c3 << 1) + b3]
+                bm = (cv.real, cv.imag, -cv.real, -cv.imag)[p]
+                cand = metric[pred] + bm
+                if best is None or cand > best:
+                    best, bh = cand, hist[pred]
+            new_metric[sn] = best
+            new_hist[sn] = ((int(bh) << 1) | c1) & 0xFFFFFFFFFFFFFFFF
+        metric, hist = new_metric, new_hist
+        if m >= D:
+            out[m] = (int(hist[int(np.argmax(metric))]) >> D) & 1
+    return out
+
+
+def SCH_demod(s, pos_info, training_sequence, oversampling_ratio: int):
+    """SCH_demod.m:5-121.  Returns None on the `pos_info==-1` path, else a dict of per-SCH-burst arrays:
+    demod_bits [H x 148] (:93-94), bits_to_decoder [H x 148] (:97), corr_val [H x 85] (:110)."""
+    pos_info = np.asarray(pos_info, dtype=np.float64).reshape(-1, 2)
+    if _all_minus_one(pos_info):
+        return None
+    s = np.asarray(s).reshape(-1)
+    ts = np.asarray(training_sequence).reshape(-1)
+    osr = oversampling_ratio
+    sch_pos = [int(p) for p in pos_info[pos_info[:, 1] == 1, 0]]
+    num_ef = int(mround(625 / 4 - 8.25))                                              # 148 (:22)
+    L_ts, L_pre, D, ex_len = 64, 42, 30, 8                                           # :25-28,:45,:53
+    data = 2 * differential_encode(SCH_TRAINING_BITS) - 1                            # :47-51
+    len_fde_ov = (num_ef + 2 * ex_len + D) * osr                                     # :54-55
+    sp_tr = (ex_len + L_pre) * osr                                                    # 0-based start of the training part (:56)
+    td = np.zeros(len_fde_ov, dtype=np.complex128)
+    td[sp_tr:sp_tr + L_ts * osr] = ts
+    fd_training = np.fft.fft(td)                                                      # :57-59
+    n_lag = num_ef - L_ts + 1                                                         # 85 (:103-105)
+    bits_all, dec_all, corr_all = [], [], []
+    for p in sch_pos:
+        sp = p - ex_len * osr                                                         # :79-81
+        if sp < 1 or sp + len_fde_ov - 1 > len(s):
+            raise IndexError("SCH_demod: burst window outside the stream (MATLAB: index exceeds matrix dimensions)")
+        x = s[sp - 1:sp - 1 + len_fde_ov]
+        rt = np.zeros(len_fde_ov, dtype=np.complex128)
+        rt[sp_tr:sp_tr + L_ts * osr] = x[sp_tr:sp_tr + L_ts * osr]                    # :83-84
+        fd_chn = np.fft.fft(rt) / fd_training                                         # :85-86
+        x = np.fft.ifft(np.fft.fft(x) / fd_chn)                                       # :88-90
+        bits = gmsk_viterbi_demod(x, osr, D)                                          # :92-93
+        bits = bits[D + ex_len:][:num_ef]                                             # :94-95
+        nb = 1 - bits
+        dec = np.abs(np.diff(np.concatenate([[0], nb])))                              # :97
+        pm = 2 * bits - 1
+        corr = np.array([int(np.dot(data, pm[k:k + L_ts])) for k in range(n_lag)])    # :103-110
+        bits_all.append(bits); dec_all.append(dec); corr_all.append(corr)
+    return dict(demod_bits=np.array(bits_all).reshape(-1, num_ef), bits_to_decoder=np.array(dec_all).reshape(-1, num_ef),
+                corr_val=np.array(corr_all, dtype=np.float64).reshape(-1, n_lag))
+
+
+# ----------------------------------------------------------------------------------------------------
 # driver restatement: gsm_sync_demod.m:107-124 for one stream; scanners' per-column processing
 # ----------------------------------------------------------------------------------------------------
 def calibrate_stream(raw_u8: np.ndarray, carrier_freq: float, template: np.ndarray, coef: np.ndarray,

@@ -13,7 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MEX = os.path.join(ROOT, "multi-rtl-sdr-calibration_b200", "mex")
 FUNCS = ["raw2iq", "fir_filter", "chn_filter_8x_4x", "chn_filter_4x", "move_fft_snr_runtime_avg", "specific_fft_snr_fix_avg",
          "FCCH_coarse_position", "FCCH_fine_correction", "gsm_SCH_training_sequence_gen", "SCH_corr_rate_correction",
-         "carrier_correct_post_SCH", "total_ppm_calculation", "gsm_calibrate_batch"]
+         "carrier_correct_post_SCH", "total_ppm_calculation", "gsm_calibrate_batch",
+         "gsm_normal_training_sequence_gen", "FCCH_demod", "BCCH_demod", "SCH_demod"]
 
 
 @pytest.mark.parametrize("fn", FUNCS)
@@ -80,3 +81,35 @@ def test_sentinel_shapes_through_the_gateway(built_lib, tmp_path):
             return 0;
         }""", built_lib, tmp_path).split()
     assert out == ["-1", "1", "-1", "1", "inf", "inf"]
+
+
+def test_normal_training_sequence_gateway(built_lib, tmp_path):
+    out = _run_harness("gsm_normal_training_sequence_gen", """
+        int main(void) {
+            mxArray *in = mxCreateDoubleScalar(4.0);
+            mxArray *out[1]; const mxArray *rhs[1] = {in};
+            mexFunction(1, out, 1, rhs);
+            printf("%zu %zu %d\\n", mxGetM(out[0]), mxGetN(out[0]), mxIsComplex(out[0]));
+            for (int i = 0; i < 104 * 8; ++i) printf("%.17g %.17g\\n", mxGetPr(out[0])[i], mxGetPi(out[0])[i]);
+            return 0;
+        }""", built_lib, tmp_path).split("\n")
+    assert out[0] == "104 8 1"
+    got = np.array([[float(x) for x in ln.split()] for ln in out[1:104 * 8 + 1]])
+    ref = oracle.gsm_normal_training_sequence_gen(4)
+    assert np.max(np.abs((got[:, 0] + 1j * got[:, 1]).reshape(8, 104).T - ref)) < 1e-12
+
+
+def test_demod_gateways_warn_on_invalid_pos_info(built_lib, tmp_path):
+    """pos_info == -1: SCH_demod / FCCH_demod print the reference's warning and return (SCH_demod.m:8-11, FCCH_demod.m:7-10)."""
+    for fn, extra, msg in (("SCH_demod", "mxCreateDoubleMatrix(512, 1, mxCOMPLEX), mxCreateDoubleScalar(8.0)", "SCH demod: Warning! No valid position information!"),
+                           ("FCCH_demod", "mxCreateDoubleScalar(8.0), mxCreateDoubleScalar(957.4e6)", "FCCH demod: Warning! No valid position information!")):
+        out = _run_harness(fn, """
+            int main(void) {
+                mxArray *s = mxCreateDoubleMatrix(100, 1, mxCOMPLEX), *pi = mxCreateDoubleMatrix(1, 2, mxREAL);
+                mxGetPr(pi)[0] = -1; mxGetPr(pi)[1] = -1;
+                mxArray *out[3]; const mxArray *rhs[4] = {s, pi, %s};
+                mexFunction(1, out, 4, rhs);
+                printf("n=%%zu\\n", mxGetNumberOfElements(out[0]));
+                return 0;
+            }""" % extra, built_lib, tmp_path)
+        assert msg in out and "n=0" in out

@@ -176,3 +176,70 @@ def test_oracle_sentinel_paths():
     assert c == (None, math.inf)
     with pytest.raises(IndexError):
         oracle.FCCH_coarse_position(noise[:3000], 8)          # s(1:3594) would raise in MATLAB
+
+
+# ---- demodulator family -------------------------------------------------------------------
+def test_normal_training_sequences_follow_the_reference_table():
+    nts = oracle.gsm_normal_training_sequence_gen(8)
+    assert nts.shape == (208, 8) and np.allclose(np.abs(nts), 1.0)
+    assert oracle.NORMAL_TRAINING_BITS.shape == (8, 26)
+    assert oracle.NORMAL_TRAINING_BITS[0].tolist() == [0, 0, 1, 0, 0, 1, 0, 1, 1, 1, 0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 1, 0, 1, 1, 1]
+    for q in range(8):                                # column q: differential encoding against a leading 0, own modulator state
+        ref = oracle.gmsk_modulate(oracle.differential_encode(oracle.NORMAL_TRAINING_BITS[q]), 8)
+        assert np.array_equal(nts[:, q], ref)
+    gram = np.abs(nts.conj().T @ nts) / 208           # the eight sequences are mutually distinguishable
+    assert np.all(gram[~np.eye(8, dtype=bool)] < 0.8)
+
+
+@pytest.mark.parametrize("osr,noise", [(8, 0.0), (8, 0.25), (4, 0.2), (1, 0.1)])
+def test_gmsk_viterbi_inverts_the_modulator(osr, noise):
+    rng = np.random.default_rng(osr)
+    bits = rng.integers(0, 2, 160)
+    x = oracle.gmsk_modulate(bits, osr)
+    x = x + noise * (rng.standard_normal(len(x)) + 1j * rng.standard_normal(len(x)))
+    out = oracle.gmsk_viterbi_demod(x, osr, 30)
+    assert out[:30].tolist() == [0] * 30              # TracebackDepth delay
+    assert np.array_equal(out[30:], bits[:130])
+
+
+def test_fcch_demod_on_a_pure_tone():
+    osr, n = 8, 6000
+    f = oracle.SYMBOL_RATE / 4 + 1234.5
+    s = np.exp(2j * np.pi * f * np.arange(n) / FS + 0.3j)
+    pinfo = np.array([[101.0, 0.0], [2001.0, 0.0], [3000.0, 1.0]])
+    d = oracle.FCCH_demod(s, pinfo, osr, 957.4e6)
+    assert len(d["freq"]) == 2 and np.max(np.abs(d["freq"] - f)) < 1e-6
+    assert abs(d["carrier_ppm"] - 1e6 * 1234.5 / 957.4e6) < 1e-9
+    assert d["max_idx"].tolist() == [round(f * 1184 / FS)] * 2 and np.all(d["snr"] > 5)
+    assert oracle.FCCH_demod(s, np.array([[-1.0, -1.0]]), osr, 957.4e6) is None
+
+
+def test_sch_demod_finds_the_training_sequence():
+    osr = 4
+    rng = np.random.default_rng(11)
+    bits = rng.integers(0, 2, 148 + 90)
+    b0 = 30
+    bits[b0 + 42:b0 + 42 + 64] = oracle.SCH_TRAINING_BITS
+    prev = np.concatenate([[1], bits[:-1]])
+    tx = oracle.gmsk_modulate((bits == prev).astype(np.int64), osr) * np.exp(0.7j)
+    tx = tx + 0.02 * (rng.standard_normal(len(tx)) + 1j * rng.standard_normal(len(tx)))
+    d = oracle.SCH_demod(tx, np.array([[b0 * osr + 1.0, 1.0]]), oracle.gsm_SCH_training_sequence_gen(osr), osr)
+    assert d["demod_bits"].shape == (1, 148) and d["corr_val"].shape == (1, 85)
+    assert d["corr_val"][0].argmax() == 42 and d["corr_val"][0].max() == 64
+    sent = (bits == prev).astype(np.int64)[b0:b0 + 148]
+    assert np.mean(d["demod_bits"][0] == sent) > 0.97
+    # bits_to_decoder = abs(diff([0 ~demod_bits])) (:97): its running XOR gives ~demod_bits back
+    assert np.array_equal(np.cumsum(d["bits_to_decoder"][0]) % 2, 1 - d["demod_bits"][0])
+    with pytest.raises(IndexError):
+        oracle.SCH_demod(tx, np.array([[len(tx) - 100.0, 1.0]]), oracle.gsm_SCH_training_sequence_gen(osr), osr)
+
+
+def test_bcch_demod_identifies_the_training_sequence_code():
+    import dataclasses
+    spec = dataclasses.replace(synth.random_spec(2, 1020000), tsc=5)
+    raw = synth.generate_stream(spec).numpy()
+    res = oracle.calibrate_stream(raw, spec.carrier_freq, oracle.gsm_SCH_training_sequence_gen(8), oracle.fir1(46, 200e3 / FS))
+    nts = oracle.gsm_normal_training_sequence_gen(8)
+    ppm, idx, mag = oracle.BCCH_demod(res["r_final"], res["pos_info"], nts, 8, spec.carrier_freq)
+    assert idx == 6 and mag.shape == (8, 4) and abs(ppm) < 1e-6      # r_final is already carrier-corrected
+    assert oracle.BCCH_demod(res["r_final"], np.array([[-1.0, -1.0]]), nts, 8, spec.carrier_freq) == (-1.0, -1, None)
