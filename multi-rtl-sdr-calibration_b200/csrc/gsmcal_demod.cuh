@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(FD_THREADS) fcch_demod_kernel(const double2 *_
     double sn[2] = {0.0, 0.0};
     if (tid < 5) { int j = (j_best - 2 + tid) % N; if (j < 0) j += N; sn[0] = P[j]; }
     for (int j = N / 2 - hnl + tid; j <= N / 2 + hnl - 1; j += FD_THREADS) sn[1] += P[j];
-    block_sum_n<2>(sn, red_n);
+    block_sum_n<2, false>(sn, red_n);
     if (tid == 0) {
         const double noise = sn[1] - sn[0];
         snr_out[burst] = 10.0 * log10(sn[0] / noise);
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(FD_THREADS) fcch_demod_kernel(const double2 *_
         rri[0] += (a.x * b.x + a.y * b.y) / den;
         rri[1] += (a.y * b.x - a.x * b.y) / den;
     }
-    block_sum_n<2>(rri, red_n);
+    block_sum_n<2, false>(rri, red_n);
     if (tid == 0) sh_pr = atan2(rri[1] / (double)(N - 1), rri[0] / (double)(N - 1));
     __syncthreads();
     if (tid == 0) freq_out[burst] = sampling_rate * (int_phase_rotate + sh_pr) / (2 * GSMCAL_PI);

@@ -362,8 +362,10 @@ __device__ double block_sum(double v, double *sv) {
     return r;
 }
 
-// several block sums with one pair of barriers
-template <int K>
+// several block sums at once.  ALL = true: every thread receives the totals (thread k adds the per-warp partials of value k, a third
+// barrier publishes them - the earlier "every thread adds all 8*K partials" form cost more instructions than the FIR in the tone
+// estimator).  ALL = false: only thread 0 receives them (K <= 4): warp 0 adds the partials with a segmented shuffle tree.
+template <int K, bool ALL = true>
 __device__ void block_sum_n(double (&v)[K], double *sv /* >= 8*K */) {
 #pragma unroll
     for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
@@ -373,11 +375,25 @@ __device__ void block_sum_n(double (&v)[K], double *sv /* >= 8*K */) {
         for (int k = 0; k < K; ++k) sv[k * 8 + w] = v[k];
     }
     __syncthreads();
+    if (ALL) {
+        if (threadIdx.x < K) {
+            double t = 0.0;
+            for (int i = 0; i < nw; ++i) t += sv[threadIdx.x * 8 + i];
+            sv[threadIdx.x * 8] = t;                             // row k is only touched by thread k
+        }
+        __syncthreads();
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        double t = 0.0;
-        for (int i = 0; i < nw; ++i) t += sv[k * 8 + i];
-        v[k] = t;
+        for (int k = 0; k < K; ++k) v[k] = sv[k * 8];
+    } else {
+        static_assert(ALL || K <= 4, "thread-0 variant handles up to 4 values (32 partials)");
+        if (w == 0) {
+            double t = (lane < 8 * K && (lane & 7) < nw) ? sv[lane] : 0.0;
+            t += __shfl_down_sync(0xffffffffu, t, 4);
+            t += __shfl_down_sync(0xffffffffu, t, 2);
+            t += __shfl_down_sync(0xffffffffu, t, 1);
+#pragma unroll
+            for (int k = 0; k < K; ++k) v[k] = __shfl_sync(0xffffffffu, t, 8 * k);
+        }
     }
     __syncthreads();
 }
@@ -1339,7 +1355,7 @@ __global__ void __launch_bounds__(FB_THREADS, 4) fine_peak_band_kernel(WinSrc sr
         const double2 q2 = cmulc(win[n + 1], win[n]);
         pq[0] += q2.x; pq[1] += q2.y;
     }
-    block_sum_n<2>(pq, scan_sv);
+    block_sum_n<2, false>(pq, scan_sv);
     if (tid == 0) red_i[0] = (int)floor(atan2(pq[1], pq[0]) * (double)N / (2.0 * GSMCAL_PI) + 0.5);     // one atan2 per block
     __syncthreads();
     const int k0 = red_i[0];
@@ -1521,7 +1537,7 @@ __global__ void __launch_bounds__(FC_THREADS, 4) fine_peak_core_kernel(WinSrc sr
         const double2 q2 = cmulc(win[n + 1], win[n]);
         pq[0] += q2.x; pq[1] += q2.y;
     }
-    block_sum_n<2>(pq, scan_sv);
+    block_sum_n<2, false>(pq, scan_sv);
     if (tid == 0) red_i[0] = (int)floor(atan2(pq[1], pq[0]) * (double)N / (2.0 * GSMCAL_PI) + 0.5);     // one atan2 per block
     __syncthreads();
     const int k0 = red_i[0];
@@ -1670,41 +1686,6 @@ __global__ void __launch_bounds__(FC_THREADS, 4) fine_peak_core_kernel(WinSrc sr
         need_band[(i64)stream * cap + burst] = (ok && !force_fail) ? 0 : 1;       // force_fail: test hook, sends every burst to tier 2
     }
 #undef CSI
-}
-
-// ===================================================================================================
-// N = 37 * M point DFT of a shared-memory vector (M = 4*osr): two direct stages, exact twiddle table.
-//   X[k1 + 37*k2] = sum_{n2<M} W_N^{n2*k1} W_M^{n2*k2} sum_{n1<37} x[M*n1+n2] W_37^{n1*k1}
-// ===================================================================================================
-__device__ void dft_37xM(const double2 *in, double2 *tmp, double2 *out, int N, const double2 *__restrict__ tw) {
-    const int M = N / 37;
-    for (int idx = threadIdx.x; idx < N; idx += blockDim.x) {
-        const int n2 = idx % M, k1 = idx / M;
-        double ar = 0.0, ai = 0.0;
-        int t = 0; const int stp = (M * k1) % N;
-        for (int n1 = 0; n1 < 37; ++n1) {
-            const double2 x = in[M * n1 + n2], w = tw[t];
-            ar = fma(x.x, w.x, fma(-x.y, w.y, ar));
-            ai = fma(x.x, w.y, fma(x.y, w.x, ai));
-            t += stp; if (t >= N) t -= N;
-        }
-        tmp[idx] = cmul(make_double2(ar, ai), tw[(n2 * k1) % N]);
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < N; idx += blockDim.x) {
-        const int k1 = idx % 37, k2 = idx / 37;
-        double ar = 0.0, ai = 0.0;
-        int t = 0; const int stp = (37 * k2) % N;
-        const double2 *a = tmp + M * k1;
-        for (int n2 = 0; n2 < M; ++n2) {
-            const double2 x = a[n2], w = tw[t];
-            ar = fma(x.x, w.x, fma(-x.y, w.y, ar));
-            ai = fma(x.x, w.y, fma(x.y, w.x, ai));
-            t += stp; if (t >= N) t -= N;
-        }
-        out[k1 + 37 * k2] = make_double2(ar, ai);
-    }
-    __syncthreads();
 }
 
 // ===================================================================================================
@@ -1875,7 +1856,7 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
         rri[0] += (a.x * b.x + a.y * b.y) * inv_den;
         rri[1] += (a.y * b.x - a.x * b.y) * inv_den;
     }
-    block_sum_n<2>(rri, red_n);
+    block_sum_n<2, false>(rri, red_n);
     if (tid == 0) sh_pr = atan2(rri[1] / (double)(N - 1), rri[0] / (double)(N - 1));
     __syncthreads();
     const double phase_rotate = sh_pr;
@@ -1924,7 +1905,7 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
         const double p = abs2_ref(dft_col(Tm, k, N, tw));
         if (k < 3 || k >= N - 2) sn2[0] += p; else sn2[1] += p;
     }
-    block_sum_n<2>(sn2, red_n);
+    block_sum_n<2, false>(sn2, red_n);
     if (tid == 0) gate_out[(i64)stream * cap + burst] = 10.0 * log10(sn2[0] / sn2[1]);
 }
 

@@ -8,7 +8,6 @@ goes through libgsmcal.so and raises if the library or a CUDA device is missing.
 from __future__ import annotations
 
 import ctypes as C
-import math
 
 import numpy as np
 

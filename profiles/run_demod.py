@@ -4,7 +4,6 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "multi-rtl-sdr-calibration_b200"))
 import numpy as np
-import torch
 import gsmcal
 from gsmcal import synth
 
@@ -14,7 +13,7 @@ spec = synth.random_spec(7, N)
 spec.tsc = 3
 raw = synth.generate_batch([spec], device="cuda").cpu().numpy()
 coef, tpl = gsmcal.fir1(46, 200e3 / FS), gsmcal.gsm_SCH_training_sequence_gen(8)
-r = gsmcal.raw2iq_fir(raw[0][:, None] if raw[0].ndim == 1 else raw[0], coef)[:, 0] if False else gsmcal.fir_filter(coef, gsmcal.raw2iq(raw[0]))
+r = gsmcal.fir_filter(coef, gsmcal.raw2iq(raw[0]))
 r = np.ascontiguousarray(np.asarray(r).reshape(-1))
 pos, _ = gsmcal.FCCH_coarse_position(r[::64], 8)
 fpos, r1, _, _ = gsmcal.FCCH_fine_correction(r, pos, 8, 957.4e6)
