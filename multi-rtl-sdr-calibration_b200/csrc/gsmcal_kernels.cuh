@@ -73,6 +73,9 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
 __device__ __forceinline__ double2 cmulc(double2 a, double2 b) {   // a * conj(b)
     return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
 }
+// upper bound of sqrt(e) for the certificates (they only need |s| <= bound): both roundings go up, a handful of fp32 instructions
+// instead of the ~20-instruction fp64 sqrt; at most 2.4e-7 above the true value, far inside the certificates' 1e-6 margin
+__device__ __forceinline__ double sqrt_ub(double e) { return (double)__fsqrt_ru(__double2float_ru(e)); }
 __device__ __forceinline__ double abs2_ref(double2 a) {            // abs(z).^2: sqrt first, then square
     double h = hypot(a.x, a.y);
     return h * h;
@@ -1338,7 +1341,7 @@ __global__ void __launch_bounds__(FB_THREADS, 4) fine_peak_band_kernel(WinSrc sr
             const double2 v = win[tid * FB_CERT + i];
             const double e = v.x * v.x + v.y * v.y;
             se += e;
-            const double a = sqrt(e);
+            const double a = sqrt_ub(e);
             sa += a; if (i < FB_CERT - 1) sa15 += a;
         }
         pe16[tid + 1] = se; pa16[tid + 1] = sa; pa15[tid] = sa15;
@@ -1438,7 +1441,7 @@ __global__ void __launch_bounds__(FB_THREADS, 4) fine_peak_band_kernel(WinSrc sr
         const double R = (double)N * (pe16[ci + nc] - pe16[ci]) - sum_s;
         // windows c..c+15 (only c itself for the last one): slack = sum_{i=c}^{c+14} (|s[i]| + |s[i+N]|)
         const double A = (ci == n_cert - 1) ? 0.0 : (pa15[ci] - pa16[ci]) + (pa15[ci + nc] - pa16[ci + nc]);
-        const double bound = sqrt(R > 0.0 ? R : 0.0) + A;
+        const double bound = sqrt_ub(R > 0.0 ? R : 0.0) + A;
         ok = (bound * bound < best * (1.0 - 1e-6)) ? 1 : 0;
     }
     ok = __syncthreads_and(ok);
@@ -1524,7 +1527,7 @@ __global__ void __launch_bounds__(FC_THREADS, 4) fine_peak_core_kernel(WinSrc sr
             const double2 v = win[tid * FB_CERT + i];
             const double e = v.x * v.x + v.y * v.y;
             se += e;
-            const double a = sqrt(e);
+            const double a = sqrt_ub(e);
             sa += a; if (i < FB_CERT - 1) sa15 += a;
         }
         pe16[tid + 1] = se; pa16[tid + 1] = sa; pa15[tid] = sa15;
@@ -1663,7 +1666,7 @@ __global__ void __launch_bounds__(FC_THREADS, 4) fine_peak_core_kernel(WinSrc sr
                     }
                     if (pass == 0) T2[gq * 8 + cand] = t2;
                     const double r2 = (double)N * e2 - t2;
-                    bnd = sqrt((double)(dch * CH) * (e1 > 0.0 ? e1 : 0.0)) + sqrt(r2 > 0.0 ? r2 : 0.0);
+                    bnd = sqrt_ub((double)(dch * CH) * (e1 > 0.0 ? e1 : 0.0)) + sqrt_ub(r2 > 0.0 ? r2 : 0.0);
                 }
             }
             bnd = fmin(bnd, __shfl_xor_sync(0xffffffffu, bnd, 1));
@@ -1851,10 +1854,9 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
     __syncthreads();
     double rri[2] = {0.0, 0.0};
     for (int n = tid; n < N - 1; n += TONE_THREADS) {
-        const double2 a = A[n + 1], b = A[n];
-        const double inv_den = 1.0 / (b.x * b.x + b.y * b.y);      // complex division by a (nearly) unit phasor
-        rri[0] += (a.x * b.x + a.y * b.y) * inv_den;
-        rri[1] += (a.y * b.x - a.x * b.y) * inv_den;
+        const double2 a = A[n + 1], b = A[n];                      // a / b with |b| = 1 to 1 ulp: a * conj(b) (the division by |b|^2 changes
+        rri[0] += a.x * b.x + a.y * b.y;                           // the mean by < 2e-16 relative and cost a reciprocal per sample)
+        rri[1] += a.y * b.x - a.x * b.y;
     }
     block_sum_n<2, false>(rri, red_n);
     if (tid == 0) sh_pr = atan2(rri[1] / (double)(N - 1), rri[0] / (double)(N - 1));
