@@ -112,7 +112,15 @@ size_t tone_smem(int osr) {
     if (work < 2 * N) work = 2 * N;
     return (size_t)(N + work) * sizeof(double2);
 }
-size_t sch_smem(int osr) { int L = 64 * osr, ns = 16 * osr - 5 * osr + 1 + L - 1; return (size_t)(2 * ns + L + 8 + GSMCAL_XCAP(ns)) * sizeof(double2); }
+size_t sch_smem(int osr) {
+    int L = 64 * osr, ns = 16 * osr - 5 * osr + 1 + L - 1;
+    size_t slots = (size_t)(2 * ns + L + 8 + GSMCAL_XCAP(ns));
+    if (osr == 8) {     // register-tiled path: padded window + padded template + 192 partial-sum rows of 33 doubles behind X
+        size_t need = (size_t)(ns + L + 8) + (size_t)(ns + (ns >> 4) + 2) + (size_t)(L + (L >> 4) + 2) + (192 * 33 + 1) / 2 + 2;
+        if (slots < need) slots = need;
+    }
+    return slots * sizeof(double2);
+}
 
 int get_ctx(Ctx **out) {
     TRY(ensure_device());

@@ -187,6 +187,10 @@ __device__ void load_window(const WinSrc &src, const StreamCtl &c, int stream, i
     }
     if (a0 < 0) a0 = 0;
     if (b0 > n0 - 1) b0 = n0 - 1;
+    // derotation base phasor exp(1i*a1*dphi1): the argument reaches 1e5..1e6 rad (Payne-Hanek path of sincos, ~150 instructions), so ONE
+    // thread evaluates it while the others stage and filter; it is read after the barriers below
+    __shared__ double2 lw_base;
+    if (derot && use1 && tid == 0) { double sn, cs; sincos((double)a1 * c.dphi1, &sn, &cs); lw_base = make_double2(cs, sn); }
     const int nt_sel = (src.n_taps <= 48) ? 48 : (src.n_taps <= 64 ? 64 : 0);      // unrolled FIR variants (taps zero-padded on the old side)
     const int nt1 = (nt_sel ? nt_sel : src.n_taps) - 1;
     const int n_l0 = (int)(b0 - a0 + 1);
@@ -271,12 +275,12 @@ __device__ void load_window(const WinSrc &src, const StreamCtl &c, int stream, i
     if (use1) {
         double2 *l1 = use2 ? X : dst;
         const int n_l1 = (int)(b1 - a1 + 1);
-        // derotation phasor exp(1i*j*dphi1): exact sincos of the (rounded) product for the thread's first sample - the
-        // argument reaches 1e6 rad, which is the slow Payne-Hanek path - then a fixed complex step of nt samples
+        // derotation phasor exp(1i*j*dphi1) = base * exp(1i*tid*dphi1) for the thread's first sample (small arguments: the short
+        // sincos path), then a fixed complex step of nt samples
         double2 ph = make_double2(1.0, 0.0), st = make_double2(1.0, 0.0);
         if (derot) {
             double sn, cs;
-            sincos((double)(a1 + tid) * c.dphi1, &sn, &cs); ph = make_double2(cs, sn);
+            sincos((double)tid * c.dphi1, &sn, &cs); ph = cmul(lw_base, make_double2(cs, sn));
             sincos((double)nt * c.dphi1, &sn, &cs); st = make_double2(cs, sn);
         }
         for (int i = tid; i < n_l1; i += nt) {
@@ -1998,10 +2002,22 @@ __global__ void __launch_bounds__(SCH_THREADS, 2) sch_corr_kernel(WinSrc src, co
 #pragma unroll
             for (int l = 0; l < SCH_LPG - 1; ++l) wr_[l] = wr_[l + 1];
         }
+        // sum over the 32 lanes through shared memory (24 shuffle trees per warp cost half as many instructions as the MACs above):
+        // row (lag, re|im) of 33 doubles, lane-major, then one thread per row
+        double *part = reinterpret_cast<double *>(tp + (L + (L >> 4) + 2));
 #pragma unroll
         for (int l = 0; l < SCH_LPG; ++l) {
-            const double sr_ = warp_sum(ar[l]), si_ = warp_sum(ai[l]);
-            if (lane == 0 && l0 + l < n_lag) { corr[l0 + l] = sr_; corr_i[l0 + l] = si_; }
+            part[(2 * (l0 + l)) * 33 + lane] = ar[l];
+            part[(2 * (l0 + l) + 1) * 33 + lane] = ai[l];
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 * nw * SCH_LPG) {
+            const double *row = part + threadIdx.x * 33;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+            for (int i = 0; i < 32; i += 2) { s0 += row[i]; s1 += row[i + 1]; }
+            const int lag = threadIdx.x >> 1;
+            if (lag < n_lag) { if (threadIdx.x & 1) corr_i[lag] = s0 + s1; else corr[lag] = s0 + s1; }
         }
     } else {
         for (int lag = w; lag < n_lag; lag += nw) {              // generic shapes: one warp per lag
