@@ -187,6 +187,17 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
                            double *coarse_pos, double *coarse_snr, double *fcch_pos, double *pos_info,
                            void *cuda_stream);
 
+/* The same pipeline with several batches in flight (continuous captures): _submit enqueues batch `slot` (0..3) on the library's
+ * own streams once the caller's `cuda_stream` has produced the DEVICE-resident capture, and returns; _collect waits for that batch
+ * and fills the result pointers given to _submit (they must stay valid until then).  The latency-bound front of one batch
+ * (column sums, ~0.8 ms dependent burst chain) then runs underneath the FP64-bound kernels of the previous one.
+ * Results are identical to gsmcal_calibrate_batch.  The capture must not be overwritten before _collect returns. */
+int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq, int64_t n_streams, double carrier_freq,
+                                  const double *sch_training_sequence, const double *coef, int n_taps,
+                                  int oversampling_ratio, int coarse_decimation_ratio, gsmcal_stream_result *results,
+                                  double *coarse_pos, double *coarse_snr, double *fcch_pos, double *pos_info, void *cuda_stream);
+int gsmcal_calibrate_batch_collect(int slot);
+
 /* CUDA-event times (ms) of the stages of the last gsmcal_calibrate_batch call on this process:
  * [0] uint8 column sums (+ H2D when raw is on the host) [1] coarse FCCH [2] fine FCCH sliding-DFT peak search
  * [3] fine ppm + tone estimate + gate [4] SCH correlation + pos_info [5] post-SCH tone estimate + result records.

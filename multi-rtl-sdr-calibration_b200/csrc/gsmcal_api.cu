@@ -29,6 +29,7 @@ int g_debug_groups = 4;           // stream groups per batch (1 = strictly seque
 int g_debug_fall_limit = FALL_GRID;  // tier 3 handles work lists up to this length (tests set 0 to exercise the single-block list mode)
 int g_debug_fail_tier2 = 0;       // tests: pretend the 64-bin certificate failed
 int g_debug_force_full = 0;       // tests: run the all-bin fine search for every burst
+int g_debug_hi_prio = 1;          // burst chain of each stream group on a high-priority CUDA stream
 
 int fail(int code, const char *fmt, ...) {
     char buf[512];
@@ -64,11 +65,26 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// one in-flight batch of the submit/collect API: its own workspace, streams and pinned result staging, so that consecutive batches
+// overlap on the device (the ~1 ms latency-bound front of batch k+1 - column sums, burst chain - runs under the FP64 kernels of batch k)
+constexpr int kSlots = 4;
+struct Slot {
+    DevBuf work;
+    cudaStream_t front = nullptr;
+    std::vector<cudaStream_t> grp, hi;
+    cudaEvent_t done = nullptr;
+    bool busy = false;
+    char *stage = nullptr; size_t stage_cap = 0;               // pinned host staging of the results
+    gsmcal_stream_result *results = nullptr; double *coarse_pos = nullptr, *coarse_snr = nullptr, *fcch_pos = nullptr, *pos_info = nullptr;
+    size_t n_res = 0, n_per = 0;                                // bytes of the result records / of one D*cap double array
+};
 struct Ctx {
     bool attrs = false;
+    Slot slots[kSlots];
     DevBuf in, out, work, tplbuf;
     std::map<int, double2 *> tw;     // N -> exp(-2*pi*i*j/N)
     std::vector<cudaStream_t> side;  // extra streams: stream groups of a batch overlap their latency-bound stages
+    std::vector<cudaStream_t> side_hi; // one high-priority stream per group for the latency-bound burst chain (see gsmcal_calibrate_batch)
 };
 std::map<int, Ctx> g_ctx;
 
@@ -158,13 +174,21 @@ int get_twiddle(Ctx &c, int N, cudaStream_t st, const double2 **out) {
     return GSMCAL_OK;
 }
 
+double g_taps_host[GSMCAL_MAX_TAPS + 8]; int g_taps_n = -1; int g_taps_dev = -1;
+bool any_slot_busy() {
+    for (auto &kv : g_ctx) for (Slot &sl : kv.second.slots) if (sl.busy) return true;
+    return false;
+}
 int set_taps(const double *coef, int n_taps, cudaStream_t st) {
     if (n_taps < 1 || n_taps > GSMCAL_MAX_TAPS) return fail(GSMCAL_ERR_ARG, "n_taps must be 1..%d", GSMCAL_MAX_TAPS);
     double tmp[GSMCAL_MAX_TAPS + 8];
     memset(tmp, 0, sizeof tmp);                          // zero padding (4 before, the rest after) adds exact zeros
     memcpy(tmp + 4, coef, sizeof(double) * n_taps);
+    if (g_taps_n == n_taps && g_taps_dev == g_device && memcmp(tmp, g_taps_host, sizeof tmp) == 0) return GSMCAL_OK;   // the constant table already holds them
+    if (any_slot_busy()) CU(cudaDeviceSynchronize());    // submitted batches still read the old table
     CU(cudaMemcpyToSymbolAsync(c_tapsp, tmp, sizeof tmp, 0, cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));                       // tmp lives on this stack frame
+    memcpy(g_taps_host, tmp, sizeof tmp); g_taps_n = n_taps; g_taps_dev = g_device;
     return GSMCAL_OK;
 }
 
@@ -178,7 +202,7 @@ struct Work {
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 constexpr int kMaxGroups = 32;     // stream groups per batch (tier-3 scratch is per group); ceil(148*8/64) = 19 <= 24 bands
 
-int make_work(Ctx &c, i64 D, int cap, i64 snr_len, int tpl_len, Work *w) {
+int make_work(DevBuf &wb, i64 D, int cap, i64 snr_len, int tpl_len, Work *w) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
     size_t o_ctl = take(sizeof(StreamCtl) * D), o_res = take(sizeof(StreamResultDev) * D);
@@ -187,7 +211,7 @@ int make_work(Ctx &c, i64 D, int cap, i64 snr_len, int tpl_len, Work *w) {
     size_t o_pi = take(per * 12), o_snr = take(sizeof(double) * D * snr_len), o_pw = take(sizeof(double) * D);
     size_t o_se = take(sizeof(int) * D * cap), o_nf = take(sizeof(int) * D * cap), o_nb = take(sizeof(int) * D * cap), o_fl = take(sizeof(int) * D * cap), o_fc = take(sizeof(int) * D), o_fm = take(sizeof(int) * (size_t)FALL_GRID * 24 * kMaxGroups), o_fb = take(sizeof(double) * (size_t)FALL_GRID * 24 * kMaxGroups), o_k = take(D * cap), o_tpl = take(sizeof(double2) * (tpl_len > 0 ? tpl_len : 1));
     void *base;
-    TRY(c.work.get(off, &base));
+    TRY(wb.get(off, &base));
     char *b = static_cast<char *>(base);
     w->ctl = (StreamCtl *)(b + o_ctl); w->res = (StreamResultDev *)(b + o_res);
     w->coarse_pos = (double *)(b + o_cp); w->coarse_snr = (double *)(b + o_cs); w->fine_raw = (double *)(b + o_fr); w->fcch_pos = (double *)(b + o_fp);
@@ -378,6 +402,18 @@ void gsmcal_release(void) {
         kv.second.tw.clear();
         for (cudaStream_t s2 : kv.second.side) cudaStreamDestroy(s2);
         kv.second.side.clear();
+        for (cudaStream_t s2 : kv.second.side_hi) cudaStreamDestroy(s2);
+        kv.second.side_hi.clear();
+        for (Slot &sl : kv.second.slots) {
+            if (sl.done) { cudaEventSynchronize(sl.done); cudaEventDestroy(sl.done); sl.done = nullptr; }
+            for (cudaStream_t s2 : sl.grp) cudaStreamDestroy(s2);
+            for (cudaStream_t s2 : sl.hi) cudaStreamDestroy(s2);
+            if (sl.front) cudaStreamDestroy(sl.front);
+            sl.grp.clear(); sl.hi.clear(); sl.front = nullptr;
+            if (sl.stage) cudaFreeHost(sl.stage);
+            sl.stage = nullptr; sl.stage_cap = 0; sl.busy = false;
+            sl.work.release();
+        }
     }
 }
 int64_t gsmcal_debug_get(int key) {
@@ -398,6 +434,7 @@ int gsmcal_debug_set(int key, int value) {
     if (key == 0) { g_debug_force_full = value; return GSMCAL_OK; }
     if (key == 4) { g_debug_fail_tier2 = value; return GSMCAL_OK; }
     if (key == 5) { g_debug_fall_limit = value < 0 ? 0 : (value > FALL_GRID ? FALL_GRID : value); return GSMCAL_OK; }
+    if (key == 6) { g_debug_hi_prio = value ? 1 : 0; return GSMCAL_OK; }
     if (key == 3) { g_debug_groups = value < 1 ? 1 : (value > kMaxGroups / 2 ? kMaxGroups / 2 : value); return GSMCAL_OK; }
     return fail(GSMCAL_ERR_ARG, "debug_set: unknown key");
 }
@@ -418,7 +455,7 @@ int gsmcal_raw2iq_u8(const uint8_t *a, int64_t n_iq, int64_t n_col, double *b) {
     void *din, *dout; Work w;
     TRY(c->in.get((size_t)2 * n_iq * n_col, &din));
     TRY(c->out.get(sizeof(double2) * (size_t)n_iq * n_col, &dout));
-    TRY(make_work(*c, n_col, 1, 1, 0, &w));
+    TRY(make_work(c->work, n_col, 1, 1, 0, &w));
     CU(cudaMemcpyAsync(din, a, (size_t)2 * n_iq * n_col, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * n_col, st));
     TRY(run_colsum_u8((const uint8_t *)din, n_iq, n_col, w.ctl, st));
@@ -441,7 +478,7 @@ int gsmcal_raw2iq_f64(const double *a, int64_t n_iq, int64_t n_col, double *b) {
     void *din, *dout; Work w;
     TRY(c->in.get(sizeof(double) * (size_t)2 * n_iq * n_col, &din));
     TRY(c->out.get(sizeof(double2) * (size_t)n_iq * n_col, &dout));
-    TRY(make_work(*c, n_col, 1, 1, 0, &w));
+    TRY(make_work(c->work, n_col, 1, 1, 0, &w));
     CU(cudaMemcpyAsync(din, a, sizeof(double) * (size_t)2 * n_iq * n_col, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * n_col, st));
     i64 gx = (n_iq + 256 * 8 - 1) / (256 * 8); if (gx > 148 * 16) gx = 148 * 16; if (gx < 1) gx = 1;
@@ -499,7 +536,7 @@ int gsmcal_raw2iq_fir_u8(const uint8_t *a, int64_t n_iq, int64_t n_col, const do
     void *din, *dout; Work w;
     TRY(c->in.get((size_t)2 * n_iq * n_col, &din));
     TRY(c->out.get(sizeof(double2) * (size_t)n_out * n_col, &dout));
-    TRY(make_work(*c, n_col, 1, 1, 0, &w));
+    TRY(make_work(c->work, n_col, 1, 1, 0, &w));
     TRY(set_taps(coef, n_taps, st));
     CU(cudaMemcpyAsync(din, a, (size_t)2 * n_iq * n_col, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * n_col, st));
@@ -526,7 +563,7 @@ int gsmcal_band_power_u8(const uint8_t *a, int64_t n_iq, int64_t n_col, const do
     cudaStream_t st = 0;
     void *din; Work w;
     TRY(c->in.get((size_t)2 * n_iq * n_col, &din));
-    TRY(make_work(*c, n_col, 1, 1, 0, &w));
+    TRY(make_work(c->work, n_col, 1, 1, 0, &w));
     if (coef) TRY(set_taps(coef, n_taps, st));
     CU(cudaMemcpyAsync(din, a, (size_t)2 * n_iq * n_col, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * n_col, st));
@@ -551,7 +588,7 @@ static int snr_windows(const double *s, int64_t len, int fft_len, i64 w0, i64 n_
     Ctx *c; TRY(get_ctx(&c));
     void *din;
     TRY(c->in.get(sizeof(double2) * (size_t)len, &din));
-    TRY(make_work(*c, 1, 1, n_win > 0 ? n_win : 1, 0, w));
+    TRY(make_work(c->work, 1, 1, n_win > 0 ? n_win : 1, 0, w));
     CU(cudaMemcpyAsync(din, s, sizeof(double2) * (size_t)len, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(w->ctl, 0, sizeof(StreamCtl), st));
     if (n_win > 0) {
@@ -621,7 +658,7 @@ int gsmcal_FCCH_coarse_position(const double *s, int64_t len, int decimation_rat
     Ctx *c; TRY(get_ctx(&c));
     cudaStream_t st = 0; void *din; Work w;
     TRY(c->in.get(sizeof(double2) * (size_t)len, &din));
-    TRY(make_work(*c, 1, cap, p.n_first, 0, &w));
+    TRY(make_work(c->work, 1, cap, p.n_first, 0, &w));
     CU(cudaMemcpyAsync(din, s, sizeof(double2) * (size_t)len, cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl), st));
     TRY(run_coarse(mat_src((const double2 *)din, len, len, 0), len, p, 1, cap, w, st));
@@ -655,7 +692,7 @@ int gsmcal_FCCH_fine_correction(const double *s, int64_t n, const double *base_p
     cudaStream_t st = 0; void *din; Work w;
     const int cap = (int)n_base;
     TRY(c->in.get(sizeof(double2) * (size_t)n, &din));
-    TRY(make_work(*c, 1, cap, 1, 0, &w));
+    TRY(make_work(c->work, 1, cap, 1, 0, &w));
     CU(cudaMemcpyAsync(din, s, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, st));
     StreamCtl h; memset(&h, 0, sizeof h); h.n_coarse = cap;
     CU(cudaMemcpyAsync(w.ctl, &h, sizeof h, cudaMemcpyHostToDevice, st));
@@ -703,7 +740,7 @@ int gsmcal_SCH_corr_rate_correction(const double *s, int64_t n, const double *FC
     Ctx *c; TRY(get_ctx(&c));
     cudaStream_t st = 0; void *din; Work w;
     TRY(c->in.get(sizeof(double2) * (size_t)n, &din));
-    TRY(make_work(*c, 1, cap, 1, L, &w));
+    TRY(make_work(c->work, 1, cap, 1, L, &w));
     CU(cudaMemcpyAsync(din, s, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(w.tpl, tpl, sizeof(double2) * L, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(w.fcch_pos, FCCH_pos, sizeof(double) * cap, cudaMemcpyHostToDevice, st));
@@ -759,7 +796,7 @@ int gsmcal_carrier_correct_post_SCH(const double *s, int64_t n, const double *po
     const int cap = (int)fpos.size();
     TRY(c->in.get(sizeof(double2) * (size_t)n, &din));
     TRY(c->out.get(sizeof(double2) * (size_t)n, &dout));
-    TRY(make_work(*c, 1, cap, 1, 0, &w));
+    TRY(make_work(c->work, 1, cap, 1, 0, &w));
     CU(cudaMemcpyAsync(din, s, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(w.post_pos, fpos.data(), sizeof(double) * cap, cudaMemcpyHostToDevice, st));
     StreamCtl h; memset(&h, 0, sizeof h); h.post_enable = 1; h.n_post_fcch = cap; h.len2 = n;
@@ -803,7 +840,7 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
     Ctx *c; TRY(get_ctx(&c));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     Work w;
-    TRY(make_work(*c, D, cap, p.n_first, 64 * osr, &w));
+    TRY(make_work(c->work, D, cap, p.n_first, 64 * osr, &w));
     TRY(set_taps(coef, n_taps, st));
     const uint8_t *draw = raw;
     if (raw_mem == GSMCAL_MEM_HOST) {
@@ -825,6 +862,10 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
     if (D < 2 * n_groups) n_groups = 1;
     const bool timing = (n_groups == 1);
     while ((int)c->side.size() < n_groups + 1) { cudaStream_t s2; CU(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking)); c->side.push_back(s2); }
+    if (g_debug_hi_prio) {
+        int lo_p = 0, hi_p = 0; CU(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+        while ((int)c->side_hi.size() < n_groups) { cudaStream_t s2; CU(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, hi_p)); c->side_hi.push_back(s2); }
+    }
     cudaStream_t cp = c->side[n_groups];                                         // H2D copies
     cudaEvent_t ev_fork; CU(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     CU(cudaEventRecord(ev_fork, st));
@@ -854,6 +895,17 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
         }
         LAUNCH(mean_kernel, (unsigned)((nd + 127) / 128), 128, 0, sg, ws.ctl, (int)nd, n_iq);
         if (timing) TRY(stage_mark(sg));
+        if (sg != st && g_debug_hi_prio) {
+            // the coarse stage is a handful of small latency-bound kernels (a 0.8 ms dependent burst chain): on the group's own stream
+            // their blocks queue behind the thousands of pending blocks of the other groups' FP64 kernels.  A high-priority stream
+            // lets the block scheduler place them as soon as a slot frees, so the chain runs underneath the heavy kernels.
+            cudaStream_t sh = c->side_hi[g];
+            cudaEvent_t e1, e2; CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            CU(cudaEventRecord(e1, sg)); CU(cudaStreamWaitEvent(sh, e1, 0));
+            TRY(run_coarse(lazy_src(graw, n_iq, n_taps, 0, dec), len_dec, p, nd, cap, ws, sh));
+            CU(cudaEventRecord(e2, sh)); CU(cudaStreamWaitEvent(sg, e2, 0));
+            CU(cudaEventDestroy(e1)); CU(cudaEventDestroy(e2));
+        } else
         TRY(run_coarse(lazy_src(graw, n_iq, n_taps, 0, dec), len_dec, p, nd, cap, ws, sg));
         if (timing) TRY(stage_mark(sg));
         TRY(run_fine_peak(*c, lazy_src(graw, n_iq, n_taps, 0, 1), n_iq, osr, nd, cap, ws, sg));
@@ -883,6 +935,108 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
     return GSMCAL_OK;
 }
 
+// ---- submit / collect: the same pipeline, several batches in flight -----------------------------------------------------------
+int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq, int64_t D, double carrier_freq, const double *tpl,
+                                  const double *coef, int n_taps, int osr, int coarse_dr, gsmcal_stream_result *results,
+                                  double *coarse_pos, double *coarse_snr, double *fcch_pos, double *pos_info, void *cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (slot < 0 || slot >= kSlots) return fail(GSMCAL_ERR_ARG, "calibrate_batch_submit: slot must be 0..%d", kSlots - 1);
+    if (!raw_dev || !tpl || !coef || !results || n_iq < 1 || D < 1 || osr < 1 || osr > 8) return fail(GSMCAL_ERR_ARG, "calibrate_batch_submit: bad arguments (osr 1..8)");
+    CoarseParams p; TRY(coarse_params(coarse_dr, &p));
+    const int dec = osr * coarse_dr;
+    const i64 len_dec = (n_iq + dec - 1) / dec;
+    if (p.n_first > len_dec) return fail(GSMCAL_ERR_RANGE, "calibrate_batch_submit: capture shorter than 23 frames");
+    const int cap = (int)gsmcal_max_bursts(len_dec, coarse_dr);
+    Ctx *c; TRY(get_ctx(&c));
+    Slot &sl = c->slots[slot];
+    if (sl.busy) return fail(GSMCAL_ERR_ARG, "calibrate_batch_submit: slot %d still holds an uncollected batch", slot);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int n_groups = g_debug_groups;
+    if (D < 2 * n_groups) n_groups = 1;
+    if (!sl.front) { CU(cudaStreamCreateWithFlags(&sl.front, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)); }
+    int lo_p = 0, hi_p = 0; CU(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+    while ((int)sl.grp.size() < n_groups) { cudaStream_t s2; CU(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking)); sl.grp.push_back(s2); }
+    while ((int)sl.hi.size() < n_groups) { cudaStream_t s2; CU(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, hi_p)); sl.hi.push_back(s2); }
+    Work w;
+    TRY(make_work(sl.work, D, cap, p.n_first, 64 * osr, &w));
+    TRY(set_taps(coef, n_taps, st));
+    // pinned staging: records | coarse_pos | coarse_snr | fcch_pos | pos_info (x12)
+    sl.n_res = sizeof(StreamResultDev) * (size_t)D; sl.n_per = sizeof(double) * (size_t)D * cap;
+    const size_t need = align_up(sl.n_res) + 15 * sl.n_per + 64 * osr * sizeof(double2);
+    if (need > sl.stage_cap) {
+        if (sl.stage) cudaFreeHost(sl.stage);
+        sl.stage = nullptr; sl.stage_cap = 0;
+        CU(cudaMallocHost((void **)&sl.stage, need));
+        sl.stage_cap = need;
+    }
+    char *h_res = sl.stage, *h_arr = sl.stage + align_up(sl.n_res), *h_tpl = h_arr + 15 * sl.n_per;
+    memcpy(h_tpl, tpl, sizeof(double2) * 64 * osr);              // the caller's template may be pageable and short-lived
+    { const double2 *twp; TRY(get_twiddle(*c, 148 * osr, st, &twp)); }
+    cudaStream_t fr = sl.front;
+    cudaEvent_t ev_in; CU(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev_in, st)); CU(cudaStreamWaitEvent(fr, ev_in, 0)); CU(cudaEventDestroy(ev_in));     // the capture is ready on the caller's stream
+    CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * D, fr));
+    CU(cudaMemsetAsync(w.need_full, 0, sizeof(int) * D * cap, fr));
+    CU(cudaMemsetAsync(w.need_band, 0, sizeof(int) * D * cap, fr));
+    CU(cudaMemcpyAsync(w.tpl, h_tpl, sizeof(double2) * 64 * osr, cudaMemcpyHostToDevice, fr));
+    g_last_need_full = w.need_full; g_last_need_band = w.need_band; g_last_need_full_n = (long long)D * cap;
+    const size_t per = (size_t)2 * n_iq;
+    std::vector<cudaEvent_t> ev_done;
+    for (int g = 0; g < n_groups; ++g) {
+        const i64 d0 = D * g / n_groups, d1 = D * (g + 1) / n_groups, nd = d1 - d0;
+        cudaStream_t sg = sl.grp[g], sh = sl.hi[g];
+        Work ws = sub_work(w, d0, cap, g);
+        const uint8_t *graw = raw_dev + d0 * per;
+        TRY(run_colsum_u8(graw, n_iq, nd, ws.ctl, fr));         // HBM-bound sums back to back on the front stream (group 0 first)
+        cudaEvent_t e0, e1; CU(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+        CU(cudaEventRecord(e0, fr)); CU(cudaStreamWaitEvent(sh, e0, 0));
+        LAUNCH(mean_kernel, (unsigned)((nd + 127) / 128), 128, 0, sh, ws.ctl, (int)nd, n_iq);
+        TRY(run_coarse(lazy_src(graw, n_iq, n_taps, 0, dec), len_dec, p, nd, cap, ws, sh));      // latency-bound chain: high priority
+        CU(cudaEventRecord(e1, sh)); CU(cudaStreamWaitEvent(sg, e1, 0));
+        CU(cudaEventDestroy(e0)); CU(cudaEventDestroy(e1));
+        TRY(run_fine_peak(*c, lazy_src(graw, n_iq, n_taps, 0, 1), n_iq, osr, nd, cap, ws, sg));
+        TRY(run_fine_rest(*c, lazy_src(graw, n_iq, n_taps, 1, 1), n_iq, osr, carrier_freq, nd, cap, ws, sg));
+        TRY(run_sch(lazy_src(graw, n_iq, n_taps, 2, 1), osr, nd, cap, ws, sg));
+        TRY(run_post(*c, lazy_src(graw, n_iq, n_taps, 3, 1), osr, carrier_freq, nd, cap, ws, true, sg));
+        cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CU(cudaEventRecord(ev, sg));
+        ev_done.push_back(ev);
+    }
+    for (cudaEvent_t ev : ev_done) { CU(cudaStreamWaitEvent(fr, ev, 0)); CU(cudaEventDestroy(ev)); }
+    CU(cudaMemcpyAsync(h_res, w.res, sl.n_res, cudaMemcpyDeviceToHost, fr));
+    if (coarse_pos) CU(cudaMemcpyAsync(h_arr, w.coarse_pos, sl.n_per, cudaMemcpyDeviceToHost, fr));
+    if (coarse_snr) CU(cudaMemcpyAsync(h_arr + sl.n_per, w.coarse_snr, sl.n_per, cudaMemcpyDeviceToHost, fr));
+    if (fcch_pos) CU(cudaMemcpyAsync(h_arr + 2 * sl.n_per, w.fcch_pos, sl.n_per, cudaMemcpyDeviceToHost, fr));
+    if (pos_info) CU(cudaMemcpyAsync(h_arr + 3 * sl.n_per, w.pos_info, 12 * sl.n_per, cudaMemcpyDeviceToHost, fr));
+    CU(cudaEventRecord(sl.done, fr));
+    sl.results = results; sl.coarse_pos = coarse_pos; sl.coarse_snr = coarse_snr; sl.fcch_pos = fcch_pos; sl.pos_info = pos_info;
+    sl.busy = true;
+    return GSMCAL_OK;
+}
+
+int gsmcal_calibrate_batch_collect(int slot) {
+    cudaEvent_t done;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (slot < 0 || slot >= kSlots) return fail(GSMCAL_ERR_ARG, "calibrate_batch_collect: slot must be 0..%d", kSlots - 1);
+        Ctx *c; TRY(get_ctx(&c));
+        if (!c->slots[slot].busy) return fail(GSMCAL_ERR_ARG, "calibrate_batch_collect: nothing was submitted to slot %d", slot);
+        done = c->slots[slot].done;
+    }
+    CU(cudaEventSynchronize(done));                              // outside the lock: other slots can be submitted meanwhile
+    std::lock_guard<std::mutex> lk(g_mu);
+    Ctx *c; TRY(get_ctx(&c));
+    Slot &sl = c->slots[slot];
+    const char *h_res = sl.stage, *h_arr = sl.stage + align_up(sl.n_res);
+    memcpy(sl.results, h_res, sl.n_res);
+    if (sl.coarse_pos) memcpy(sl.coarse_pos, h_arr, sl.n_per);
+    if (sl.coarse_snr) memcpy(sl.coarse_snr, h_arr + sl.n_per, sl.n_per);
+    if (sl.fcch_pos) memcpy(sl.fcch_pos, h_arr + 2 * sl.n_per, sl.n_per);
+    if (sl.pos_info) memcpy(sl.pos_info, h_arr + 3 * sl.n_per, 12 * sl.n_per);
+    sl.busy = false;
+    return GSMCAL_OK;
+}
+
 int gsmcal_last_batch_stage_ms(double *ms, int cap_n) {
     // colsum(+H2D), coarse, fine_peak, fine ppm+tone+carrier, SCH, post-SCH - of the last gsmcal_calibrate_batch call
     int n = g_stage_n > 0 ? g_stage_n - 1 : 0;
@@ -902,7 +1056,7 @@ int gsmcal_fcch_scan(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t n_ch
     Ctx *c; TRY(get_ctx(&c));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     Work w;
-    TRY(make_work(*c, n_chan, cap, p.n_first, 0, &w));
+    TRY(make_work(c->work, n_chan, cap, p.n_first, 0, &w));
     TRY(set_taps(coef, n_taps, st));
     const uint8_t *draw = raw;
     if (raw_mem == GSMCAL_MEM_HOST) {
@@ -954,7 +1108,7 @@ int gsmcal_stage_launch(int stage, const void *in, void *out, int64_t n_iq, int6
     Ctx *c; TRY(get_ctx(&c));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     static Work w; static i64 w_cols = 0;
-    if (stage == 0 || w_cols != n_col) { TRY(make_work(*c, n_col, 1, 1, 0, &w)); w_cols = n_col; }
+    if (stage == 0 || w_cols != n_col) { TRY(make_work(c->work, n_col, 1, 1, 0, &w)); w_cols = n_col; }
     if (coef) TRY(set_taps(coef, n_taps, st));
     switch (stage) {
     case 0:

@@ -338,6 +338,38 @@ def calibrate_batch(raw, carrier_freq: float, sch_training_sequence, coef, osr: 
     return _unpack_results(res, D, cap, coarse_pos, coarse_snr, fcch_pos, pos_info)
 
 
+class PendingBatch:
+    """A batch submitted with calibrate_batch_submit: owns the output arrays until collect() fills them."""
+
+    def __init__(self, slot, D, cap, res, arrays, keep):
+        self.slot, self.D, self.cap, self.res, self.arrays, self._keep = slot, D, cap, res, arrays, keep
+
+    def collect(self, details: bool | None = None):
+        check(lib().gsmcal_calibrate_batch_collect(self.slot))
+        if self.arrays is None or details is False:
+            return self.res
+        return _unpack_results(self.res, self.D, self.cap, *self.arrays)
+
+
+def calibrate_batch_submit(slot: int, device_ptr: int, n_iq: int, n_streams: int, carrier_freq: float, sch_training_sequence, coef,
+                           osr: int = 8, coarse_dr: int = 8, cuda_stream: int = 0, details: bool = False) -> PendingBatch:
+    """Enqueue gsm_sync_demod.m:107-124 for a capture resident in HBM and return at once; `.collect()` waits for the results.
+    Up to 4 slots may be in flight: the front of batch k+1 overlaps the FP64-bound stages of batch k on the device."""
+    tpl = _stream(sch_training_sequence)
+    coef = np.ascontiguousarray(coef, dtype=np.float64)
+    D = int(n_streams)
+    cap = max_bursts(n_iq, osr, coarse_dr)
+    res = (StreamResult * D)()
+    if details:
+        arrays = (np.empty((D, cap)), np.empty((D, cap)), np.empty((D, cap)), np.empty((D, 6 * cap, 2)))
+        ptrs = [_ptr(a) for a in arrays]
+    else:
+        arrays, ptrs = None, [None] * 4
+    check(lib().gsmcal_calibrate_batch_submit(int(slot), C.c_void_p(int(device_ptr)), int(n_iq), D, float(carrier_freq), _ptr(tpl), _ptr(coef),
+                                              len(coef), int(osr), int(coarse_dr), C.cast(res, C.c_void_p), *ptrs, C.c_void_p(cuda_stream)))
+    return PendingBatch(int(slot), D, cap, res, arrays, (tpl, coef))
+
+
 STAGE_NAMES = ("colsum_u8", "coarse", "fine_peak", "fine_tone", "sch", "post")
 
 

@@ -551,3 +551,32 @@ def test_diversity_scanner_combine(gpu):
     per, comb = gpu.diversity_power_spectrum(s_all, coef, 20)
     ref = np.stack([oracle.band_power(s_all[:, :, i], coef, 20) for i in range(3)], axis=0)
     assert rel_err(per, ref) < 1e-12 and rel_err(comb, ref.mean(axis=0)) < 1e-12
+
+
+# ---- submit / collect: several batches in flight give the results of the synchronous call ---------------------------------------
+def test_submit_collect_matches_synchronous_call(gpu, captures, coef47, tpl):
+    import torch
+    _, raw = captures
+    a = torch.from_numpy(raw[:3].copy()).cuda()
+    b = torch.from_numpy(raw[2:5].copy()).cuda()
+    torch.cuda.synchronize()
+    st = torch.cuda.current_stream().cuda_stream
+    ref_a = gpu.calibrate_batch(None, CARRIER, tpl, coef47, device_ptr=a.data_ptr(), n_iq=N_SYNC, n_streams=3, cuda_stream=st)
+    ref_b = gpu.calibrate_batch(None, CARRIER, tpl, coef47, device_ptr=b.data_ptr(), n_iq=N_SYNC, n_streams=3, cuda_stream=st)
+    pend = [gpu.calibrate_batch_submit(0, a.data_ptr(), N_SYNC, 3, CARRIER, tpl, coef47, cuda_stream=st, details=True),
+            gpu.calibrate_batch_submit(1, b.data_ptr(), N_SYNC, 3, CARRIER, tpl, coef47, cuda_stream=st, details=True),
+            gpu.calibrate_batch_submit(2, a.data_ptr(), N_SYNC, 3, CARRIER, tpl, coef47, cuda_stream=st, details=True)]
+    from gsmcal._lib import GsmcalError
+    with pytest.raises(GsmcalError):                       # a slot holds one batch at a time
+        gpu.calibrate_batch_submit(1, b.data_ptr(), N_SYNC, 3, CARRIER, tpl, coef47, cuda_stream=st)
+    got = [p.collect() for p in pend]
+    for g, ref in zip(got, (ref_a, ref_b, ref_a)):
+        for x, y in zip(g, ref):
+            for k in ("coarse_pos", "coarse_snr", "fcch_pos", "pos_info"):
+                np.testing.assert_array_equal(x[k], y[k])
+            assert x["sampling_ppm"] == y["sampling_ppm"] and x["carrier_ppm"] == y["carrier_ppm"] and x["flags"] == y["flags"]
+    with pytest.raises(GsmcalError):
+        pend[0].collect()                                  # nothing pending in the slot any more
+    # slots are reusable, and the synchronous call still works in between
+    again = gpu.calibrate_batch_submit(0, b.data_ptr(), N_SYNC, 3, CARRIER, tpl, coef47, cuda_stream=st, details=True).collect()
+    assert [x["pos_info"].tolist() for x in again] == [y["pos_info"].tolist() for y in ref_b]
