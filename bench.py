@@ -242,6 +242,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--groups", type=int, default=4, help="stream groups per batch inside the library (1 = no overlap; for profiling)")
     ap.add_argument("--pipeline", type=int, default=2, help="batches in flight through gsmcal_calibrate_batch_submit/_collect (1 = the synchronous call)")
+    ap.add_argument("--submit-groups", type=int, default=1, help="stream groups inside each submitted batch (pipelined mode)")
+    ap.add_argument("--persist-colsum", type=int, default=None, help="blocks per SM of the persistent high-priority column-sum kernel in pipelined mode (0 = per-group launches)")
     ap.add_argument("--no-hi-prio", action="store_true", help="burst chain on the group stream instead of a high-priority stream (A/B)")
     ap.add_argument("--stages", action="store_true", help="also time the materialising per-stage kernels (raw2iq, FIR, resample, derotate)")
     ap.add_argument("--ingest", type=int, default=0, metavar="D",
@@ -278,6 +280,9 @@ def main():
     tpl = gsmcal.gsm_SCH_training_sequence_gen(8)
     lib().gsmcal_debug_set(3, args.groups)
     lib().gsmcal_debug_set(6, 0 if args.no_hi_prio else 1)
+    if args.persist_colsum is not None:
+        lib().gsmcal_debug_set(7, args.persist_colsum)
+    lib().gsmcal_debug_set(8, args.submit_groups)
     stream = torch.cuda.current_stream()
     rec_bytes = C.sizeof(StreamResult)
     gathered = torch.empty((world * D * rec_bytes,), dtype=torch.uint8, device=dev) if world > 1 else None

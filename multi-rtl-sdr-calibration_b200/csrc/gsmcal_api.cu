@@ -29,6 +29,8 @@ int g_debug_groups = 4;           // stream groups per batch (1 = strictly seque
 int g_debug_fall_limit = FALL_GRID;  // tier 3 handles work lists up to this length (tests set 0 to exercise the single-block list mode)
 int g_debug_fail_tier2 = 0;       // tests: pretend the 64-bin certificate failed
 int g_debug_force_full = 0;       // tests: run the all-bin fine search for every burst
+int g_debug_submit_groups = 1;    // stream groups inside a submitted batch
+int g_debug_persist_colsum = 0;   // submit/collect: blocks per SM of the persistent high-priority column-sum kernel (0 = per-group launches)
 int g_debug_hi_prio = 1;          // burst chain of each stream group on a high-priority CUDA stream
 
 int fail(int code, const char *fmt, ...) {
@@ -70,7 +72,7 @@ struct DevBuf {
 constexpr int kSlots = 4;
 struct Slot {
     DevBuf work;
-    cudaStream_t front = nullptr;
+    cudaStream_t front = nullptr, front_hi = nullptr;
     std::vector<cudaStream_t> grp, hi;
     cudaEvent_t done = nullptr;
     bool busy = false;
@@ -254,6 +256,14 @@ int run_colsum_u8(const uint8_t *raw, i64 n_iq, i64 D, StreamCtl *ctl, cudaStrea
     return GSMCAL_OK;
 }
 
+int run_colsum_u8_persist(const uint8_t *raw, i64 n_iq, i64 D, StreamCtl *ctl, int blocks, cudaStream_t st) {
+    if (((uintptr_t)raw & 1) != 0) return fail(GSMCAL_ERR_ARG, "uint8 capture must start on an even address");
+    const i64 chunk = 512 * 1024;
+    i64 chunks = (2 * n_iq + chunk - 1) / chunk; if (chunks < 1) chunks = 1;
+    LAUNCH(colsum_u8_persist_kernel, (unsigned)blocks, 256, 0, st, raw, n_iq, chunk, chunks, D, ctl);
+    return GSMCAL_OK;
+}
+
 struct CoarseParams { int fft_len, mv_len, step10, step11, dr; i64 n_first; double th; };
 double host_mround(double x) { return x >= 0 ? floor(x + 0.5) : -floor(-x + 0.5); }
 int coarse_params(int dr, CoarseParams *p) {
@@ -409,6 +419,8 @@ void gsmcal_release(void) {
             for (cudaStream_t s2 : sl.grp) cudaStreamDestroy(s2);
             for (cudaStream_t s2 : sl.hi) cudaStreamDestroy(s2);
             if (sl.front) cudaStreamDestroy(sl.front);
+            if (sl.front_hi) cudaStreamDestroy(sl.front_hi);
+            sl.front_hi = nullptr;
             sl.grp.clear(); sl.hi.clear(); sl.front = nullptr;
             if (sl.stage) cudaFreeHost(sl.stage);
             sl.stage = nullptr; sl.stage_cap = 0; sl.busy = false;
@@ -435,6 +447,8 @@ int gsmcal_debug_set(int key, int value) {
     if (key == 4) { g_debug_fail_tier2 = value; return GSMCAL_OK; }
     if (key == 5) { g_debug_fall_limit = value < 0 ? 0 : (value > FALL_GRID ? FALL_GRID : value); return GSMCAL_OK; }
     if (key == 6) { g_debug_hi_prio = value ? 1 : 0; return GSMCAL_OK; }
+    if (key == 8) { g_debug_submit_groups = value < 1 ? 1 : (value > kMaxGroups / 2 ? kMaxGroups / 2 : value); return GSMCAL_OK; }
+    if (key == 7) { g_debug_persist_colsum = value < 0 ? 0 : (value > 8 ? 8 : value); return GSMCAL_OK; }
     if (key == 3) { g_debug_groups = value < 1 ? 1 : (value > kMaxGroups / 2 ? kMaxGroups / 2 : value); return GSMCAL_OK; }
     return fail(GSMCAL_ERR_ARG, "debug_set: unknown key");
 }
@@ -951,10 +965,11 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
     Slot &sl = c->slots[slot];
     if (sl.busy) return fail(GSMCAL_ERR_ARG, "calibrate_batch_submit: slot %d still holds an uncollected batch", slot);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    int n_groups = g_debug_groups;
+    int n_groups = g_debug_submit_groups;                       // 1: with batches in flight the overlap comes from the next batch; groups only add grid tails
     if (D < 2 * n_groups) n_groups = 1;
     if (!sl.front) { CU(cudaStreamCreateWithFlags(&sl.front, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)); }
     int lo_p = 0, hi_p = 0; CU(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+    if (!sl.front_hi) CU(cudaStreamCreateWithPriority(&sl.front_hi, cudaStreamNonBlocking, hi_p));
     while ((int)sl.grp.size() < n_groups) { cudaStream_t s2; CU(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking)); sl.grp.push_back(s2); }
     while ((int)sl.hi.size() < n_groups) { cudaStream_t s2; CU(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, hi_p)); sl.hi.push_back(s2); }
     Work w;
@@ -982,14 +997,26 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
     g_last_need_full = w.need_full; g_last_need_band = w.need_band; g_last_need_full_n = (long long)D * cap;
     const size_t per = (size_t)2 * n_iq;
     std::vector<cudaEvent_t> ev_done;
+    cudaEvent_t e_sum = nullptr;
+    if (g_debug_persist_colsum > 0) {
+        // all column sums in ONE persistent launch of fixed footprint on the high-priority front stream (see colsum_u8_persist_kernel)
+        int n_sm = 148; CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, g_device));
+        cudaEvent_t e_in; CU(cudaEventCreateWithFlags(&e_in, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&e_sum, cudaEventDisableTiming));
+        CU(cudaEventRecord(e_in, fr)); CU(cudaStreamWaitEvent(sl.front_hi, e_in, 0)); CU(cudaEventDestroy(e_in));
+        TRY(run_colsum_u8_persist(raw_dev, n_iq, D, w.ctl, n_sm * g_debug_persist_colsum, sl.front_hi));
+        CU(cudaEventRecord(e_sum, sl.front_hi));
+    }
     for (int g = 0; g < n_groups; ++g) {
         const i64 d0 = D * g / n_groups, d1 = D * (g + 1) / n_groups, nd = d1 - d0;
         cudaStream_t sg = sl.grp[g], sh = sl.hi[g];
         Work ws = sub_work(w, d0, cap, g);
         const uint8_t *graw = raw_dev + d0 * per;
-        TRY(run_colsum_u8(graw, n_iq, nd, ws.ctl, fr));         // HBM-bound sums back to back on the front stream (group 0 first)
         cudaEvent_t e0, e1; CU(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
-        CU(cudaEventRecord(e0, fr)); CU(cudaStreamWaitEvent(sh, e0, 0));
+        if (e_sum) CU(cudaStreamWaitEvent(sh, e_sum, 0));
+        else {
+            TRY(run_colsum_u8(graw, n_iq, nd, ws.ctl, fr));     // HBM-bound sums back to back on the front stream (group 0 first)
+            CU(cudaEventRecord(e0, fr)); CU(cudaStreamWaitEvent(sh, e0, 0));
+        }
         LAUNCH(mean_kernel, (unsigned)((nd + 127) / 128), 128, 0, sh, ws.ctl, (int)nd, n_iq);
         TRY(run_coarse(lazy_src(graw, n_iq, n_taps, 0, dec), len_dec, p, nd, cap, ws, sh));      // latency-bound chain: high priority
         CU(cudaEventRecord(e1, sh)); CU(cudaStreamWaitEvent(sg, e1, 0));
@@ -1002,6 +1029,7 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
         CU(cudaEventRecord(ev, sg));
         ev_done.push_back(ev);
     }
+    if (e_sum) CU(cudaEventDestroy(e_sum));
     for (cudaEvent_t ev : ev_done) { CU(cudaStreamWaitEvent(fr, ev, 0)); CU(cudaEventDestroy(ev)); }
     CU(cudaMemcpyAsync(h_res, w.res, sl.n_res, cudaMemcpyDeviceToHost, fr));
     if (coarse_pos) CU(cudaMemcpyAsync(h_arr, w.coarse_pos, sl.n_per, cudaMemcpyDeviceToHost, fr));

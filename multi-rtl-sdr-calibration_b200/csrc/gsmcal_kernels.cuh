@@ -420,8 +420,7 @@ __device__ void warp_scan_smem(double *a, int n, int lane) {
 // ===================================================================================================
 // exact integer column sums: 16-byte loads, dp4a byte sums, one 64-bit atomic per warp.
 // grid (chunks, streams); each block owns `chunk_bytes` (multiple of 16) of one stream.
-__global__ void __launch_bounds__(256) colsum_u8_kernel(const uint8_t *__restrict__ raw, i64 n_iq, i64 chunk_bytes, StreamCtl *ctl) {
-    const int stream = blockIdx.y;
+__device__ __forceinline__ void colsum_u8_chunk(const uint8_t *__restrict__ raw, i64 n_iq, i64 chunk_bytes, StreamCtl *ctl, int stream, i64 chunk_id) {
     const uint8_t *p = raw + (i64)stream * 2 * n_iq;
     const i64 total = 2 * n_iq;
     const i64 head = (16 - ((uintptr_t)p & 15)) & 15;            // even, since every stream starts on an even byte
@@ -429,7 +428,7 @@ __global__ void __launch_bounds__(256) colsum_u8_kernel(const uint8_t *__restric
     unsigned si = 0, sq = 0;
     u64 li = 0, lq = 0;
     {
-        const i64 c0 = (i64)blockIdx.x * chunk_bytes;
+        const i64 c0 = chunk_id * chunk_bytes;
         i64 c1 = c0 + chunk_bytes; if (c1 > body) c1 = body;
         const uint4 *v = reinterpret_cast<const uint4 *>(p + head);
         const i64 i0 = c0 / 16, i1 = c1 / 16;
@@ -449,7 +448,7 @@ __global__ void __launch_bounds__(256) colsum_u8_kernel(const uint8_t *__restric
 #undef GSMCAL_ACC
     }
     li = si; lq = sq;
-    if (blockIdx.x == 0) {                                        // ragged head / tail bytes, scalar
+    if (chunk_id == 0) {                                          // ragged head / tail bytes, scalar
         const i64 hb = (head < total) ? head : total;
         for (i64 j = threadIdx.x; j < hb; j += 256) { if (j & 1) lq += p[j]; else li += p[j]; }
         for (i64 j = hb + body + threadIdx.x; j < total; j += 256) { if (j & 1) lq += p[j]; else li += p[j]; }
@@ -462,6 +461,16 @@ __global__ void __launch_bounds__(256) colsum_u8_kernel(const uint8_t *__restric
         if (li) atomicAdd(&ctl[stream].sum_i, li);
         if (lq) atomicAdd(&ctl[stream].sum_q, lq);
     }
+}
+
+__global__ void __launch_bounds__(256) colsum_u8_kernel(const uint8_t *__restrict__ raw, i64 n_iq, i64 chunk_bytes, StreamCtl *ctl) {
+    colsum_u8_chunk(raw, n_iq, chunk_bytes, ctl, blockIdx.y, blockIdx.x);
+}
+// persistent form for the submit/collect pipeline: a FIXED small footprint (2 blocks per SM) launched on a high-priority stream, so the
+// HBM-bound sums of batch k+1 share the SMs with the register-file-filling FP64 kernels of batch k instead of waiting behind them
+__global__ void __launch_bounds__(256) colsum_u8_persist_kernel(const uint8_t *__restrict__ raw, i64 n_iq, i64 chunk_bytes, i64 n_chunks, i64 n_streams, StreamCtl *ctl) {
+    const i64 total = n_chunks * n_streams;
+    for (i64 w = blockIdx.x; w < total; w += gridDim.x) colsum_u8_chunk(raw, n_iq, chunk_bytes, ctl, (int)(w / n_chunks), w % n_chunks);
 }
 
 // b = c - mean: one thread per IQ pair, 2-byte load, 16-byte store (warp stores 512 contiguous bytes)
