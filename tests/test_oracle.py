@@ -274,3 +274,50 @@ def test_online_reestimation_after_correction_is_zero():
     r3, _ = oracle.carrier_correct_post_SCH(r2, pinfo, 8, spec.carrier_freq)
     fo3, _, _ = oracle.tone_freq_estimate(r3, pinfo[pinfo[:, 1] == 0, 0], 1184, FS)
     assert abs(oracle.matlab_mean(fo3) - oracle.SYMBOL_RATE / 4) < 1e-6
+
+
+# ---- fixtures lifted from / generated with the reference tree (oracle/make_golden.py) ---------------------------------------------
+def test_training_bit_tables_match_the_reference_literals():
+    """tests/golden/training_bits.json is PARSED from gsm_SCH_training_sequence_gen.m:17-19 and
+    gsm_normal_training_sequence_gen.m:17-24; every hand-typed copy of the tables must equal it."""
+    with open(os.path.join(GOLDEN, "training_bits.json")) as f:
+        g = json.load(f)
+    sch, nts = g["sch_extended_training_sequence"]["bits"], g["normal_training_sequences"]["bits"]
+    assert oracle.SCH_TRAINING_BITS.tolist() == sch and list(synth.SCH_TRAINING_BITS) == sch
+    assert oracle.NORMAL_TRAINING_BITS.tolist() == nts and [list(r) for r in synth.NORMAL_TRAINING_BITS] == nts
+
+
+def test_library_training_sequences_use_the_reference_bits(built_lib):
+    """The two generators are host code (no GPU needed): their embedded bit tables must be the reference's."""
+    import gsmcal
+    with open(os.path.join(GOLDEN, "training_bits.json")) as f:
+        g = json.load(f)
+    sch = np.array(g["sch_extended_training_sequence"]["bits"])
+    ref = oracle.gmsk_modulate(oracle.differential_encode(sch), 8)
+    assert np.max(np.abs(gsmcal.gsm_SCH_training_sequence_gen(8) - ref)) < 1e-12
+    nts = gsmcal.gsm_normal_training_sequence_gen(8)
+    for q, bits in enumerate(g["normal_training_sequences"]["bits"]):
+        ref = oracle.gmsk_modulate(oracle.differential_encode(np.array(bits)), 8)
+        assert np.max(np.abs(nts[:, q] - ref)) < 1e-12
+
+
+def test_oracle_reproduces_committed_demod_fixture():
+    import dataclasses
+    with open(os.path.join(GOLDEN, "demod_golden.json")) as f:
+        g = json.load(f)
+    c = g["cases"]["2"]
+    spec = dataclasses.replace(synth.random_spec(2, g["n_samples"]), tsc=c["tsc"])
+    raw = synth.generate_stream(spec).numpy()
+    assert hashlib.sha256(raw.tobytes()).hexdigest() == c["raw_sha256"], "synthetic generator drifted"
+    tpl = oracle.gsm_SCH_training_sequence_gen(8)
+    res = oracle.calibrate_stream(raw, spec.carrier_freq, tpl, oracle.fir1(46, 200e3 / FS))
+    r3, pinfo = res["r_final"], res["pos_info"]
+    keep = np.array([not (t == 1 and p - 64 + 1552 - 1 > len(r3)) for p, t in pinfo])
+    sd = oracle.SCH_demod(r3, pinfo[keep], tpl, 8)
+    assert ["".join(str(int(b)) for b in row) for row in sd["demod_bits"]] == c["sch_demod_bits"]
+    assert sd["corr_val"].argmax(axis=1).tolist() == c["sch_corr_argmax"] and sd["corr_val"].max(axis=1).tolist() == c["sch_corr_peak"]
+    fd = oracle.FCCH_demod(r3, pinfo, 8, spec.carrier_freq)
+    assert fd["max_idx"].tolist() == c["fcch_max_idx"]
+    assert np.max(np.abs(fd["freq"] - np.array(c["fcch_freq"]))) < 1e-6 and np.max(np.abs(fd["snr"] - np.array(c["fcch_snr"]))) < 1e-9
+    ppm, idx, _ = oracle.BCCH_demod(r3, pinfo, oracle.gsm_normal_training_sequence_gen(8), 8, spec.carrier_freq)
+    assert idx == c["bcch_idx"] == c["tsc"] + 1 and abs(ppm - c["bcch_carrier_ppm"]) < 1e-9
