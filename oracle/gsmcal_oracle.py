@@ -29,6 +29,23 @@ from scipy.signal import firwin, lfilter
 
 SYMBOL_RATE = (1625.0 / 6.0) * 1e3          # gsm_sync_demod.m:16
 LEN_FCCH_CW = 148                           # FCCH_fine_correction.m:20
+# Algorithm constants of the reference (SURVEY 8a "must not drift"); tests/golden/reference_constants.json holds the same values
+# parsed from the .m files and tests/test_oracle.py compares them.
+CONSTANTS = dict(
+    coarse_th_db=10.0,            # FCCH_coarse_position.m:21
+    coarse_mv_len_factor=10,      # :22  mv_len = 10*fft_len
+    coarse_first_frames=23,       # :25
+    coarse_max_offset=5,          # :45
+    min_bursts=5,                 # FCCH_fine_correction.m:12, SCH_corr_rate_correction.m:11
+    fine_max_offset_sym=64,       # FCCH_fine_correction.m:30
+    fine_max_ppm=4000,            # :83
+    fine_snr_gate_db=5,           # :192
+    sch_training_sym=64,          # SCH_corr_rate_correction.m:22
+    sch_pre_training_sym=42,      # :24
+    sch_max_offset_sym=8,         # :36
+    sch_upper_trim_sym=5,         # :46
+    sch_max_ppm=400,              # :94
+)
 
 
 def mround(x: float) -> float:
@@ -146,9 +163,9 @@ def FCCH_coarse_position(s, decimation_ratio: int):
     num_sym_per_frame = (625.0 / 4.0) * 8
     fft_len = 2 ** int(math.floor(math.log2(LEN_FCCH_CW / decimation_ratio)))
     length = len(s)
-    th = 10.0
-    mv_len = 10 * fft_len
-    n_first = int(math.ceil(23 * num_sym_per_frame / decimation_ratio))
+    th = CONSTANTS["coarse_th_db"]
+    mv_len = CONSTANTS["coarse_mv_len_factor"] * fft_len
+    n_first = int(math.ceil(CONSTANTS["coarse_first_frames"] * num_sym_per_frame / decimation_ratio))
     if n_first > length:
         raise IndexError("FCCH_coarse_position: stream shorter than 23 frames (reference would error)")
     hit_flag, hit_idx, hit_avg_snr, hit_snr = move_fft_snr_runtime_avg(s[:n_first], mv_len, fft_len, th)
@@ -158,7 +175,7 @@ def FCCH_coarse_position(s, decimation_ratio: int):
     step11 = mround(11 * num_sym_per_frame / decimation_ratio)
     position = [hit_idx]
     snr = [hit_snr]
-    max_offset = 5
+    max_offset = CONSTANTS["coarse_max_offset"]
     limit = (length - (fft_len - 1)) - max_offset
     while True:
         nxt = position[-1] + step10
@@ -266,14 +283,14 @@ def FCCH_fine_correction(s, base_position, oversampling_ratio: int, carrier_freq
     r = None
     sampling_ppm = math.inf
     carrier_ppm = math.inf
-    if len(base_position) < 5:
+    if len(base_position) < CONSTANTS["min_bursts"]:
         return np.array([-1.0]), r, sampling_ppm, carrier_ppm
     osr = oversampling_ratio
     sampling_rate = SYMBOL_RATE * osr
     fft_len = LEN_FCCH_CW * osr
     half_noise_len = int(math.ceil((fft_len * 200e3 / sampling_rate) / 2))
     len_s = len(s) // osr
-    max_offset = 64
+    max_offset = CONSTANTS["fine_max_offset_sym"]
     pos_list = []
     margins = []
     for p in base_position:
@@ -297,7 +314,7 @@ def FCCH_fine_correction(s, base_position, oversampling_ratio: int, carrier_freq
     if last_idx >= 5:
         r = s
         first = FCCH_pos[0]
-        ok, a_l, b_l, expected, d10, d11 = classify_spacing(FCCH_pos, osr, 4000)
+        ok, a_l, b_l, expected, d10, d11 = classify_spacing(FCCH_pos, osr, CONSTANTS["fine_max_ppm"])
         if not ok:
             return np.array([-1.0]), r, sampling_ppm, carrier_ppm
         actual = FCCH_pos[-1] - FCCH_pos[0]
@@ -331,7 +348,7 @@ def FCCH_fine_correction(s, base_position, oversampling_ratio: int, carrier_freq
         if info is not None:
             info["fine_fo"] = fo
             info["fine_gate_snr"] = snr
-        if np.sum(snr < 5) > 0:
+        if np.sum(snr < CONSTANTS["fine_snr_gate_db"]) > 0:
             return np.array([-1.0]), r, sampling_ppm, carrier_ppm
     return FCCH_pos, r, sampling_ppm, carrier_ppm
 
@@ -390,20 +407,20 @@ def SCH_corr_rate_correction(s, FCCH_pos, sch_training_sequence, oversampling_ra
     FCCH_pos = np.asarray(FCCH_pos, dtype=np.float64).reshape(-1)
     r = None
     sampling_ppm = math.inf
-    if len(FCCH_pos) < 5:
+    if len(FCCH_pos) < CONSTANTS["min_bursts"]:
         return np.array([[-1.0, -1.0]]), r, sampling_ppm
     s = np.asarray(s).reshape(-1)
     ts = np.asarray(sch_training_sequence).reshape(-1)
     osr = oversampling_ratio
     slot_ov = int((625 * osr) // 4)                 # num_sym_per_slot_ov (1250 at osr 8)
     frame_ov = slot_ov * 8
-    len_ts_ov = 64 * osr
-    len_pre_ov = 42 * osr
+    len_ts_ov = CONSTANTS["sch_training_sym"] * osr
+    len_pre_ov = CONSTANTS["sch_pre_training_sym"] * osr
     fix_off_ov = frame_ov + len_pre_ov              # (1250+42)*osr
     num_hit = len(FCCH_pos)
     pos_info = -np.ones((3 * num_hit, 2))
     len_s_ov = len(s)
-    max_offset = 8 * osr
+    max_offset = CONSTANTS["sch_max_offset_sym"] * osr
     sch = []
     margins = []
     for p in FCCH_pos:
@@ -411,7 +428,7 @@ def SCH_corr_rate_correction(s, FCCH_pos, sch_training_sequence, oversampling_ra
         if (training_sp + max_offset) > (len_s_ov - len_ts_ov + 1):
             break
         sp = training_sp - max_offset
-        ep = training_sp + max_offset - 5 * osr
+        ep = training_sp + max_offset - CONSTANTS["sch_upper_trim_sym"] * osr
         length = ep - sp + 1
         win = np.lib.stride_tricks.sliding_window_view(s[sp - 1:sp - 1 + length + len_ts_ov - 1], len_ts_ov)
         corr_val = abs2(win @ np.conj(ts))
@@ -431,7 +448,7 @@ def SCH_corr_rate_correction(s, FCCH_pos, sch_training_sequence, oversampling_ra
         return pos_info, r, sampling_ppm
     r = s
     first = SCH_pos[0]
-    ok, a_l, b_l, expected, d10, d11 = classify_spacing(SCH_pos, osr, 400)
+    ok, a_l, b_l, expected, d10, d11 = classify_spacing(SCH_pos, osr, CONSTANTS["sch_max_ppm"])
     if not ok:
         return pos_info, r, sampling_ppm
     actual = SCH_pos[-1] - SCH_pos[0]

@@ -321,3 +321,12 @@ def test_oracle_reproduces_committed_demod_fixture():
     assert np.max(np.abs(fd["freq"] - np.array(c["fcch_freq"]))) < 1e-6 and np.max(np.abs(fd["snr"] - np.array(c["fcch_snr"]))) < 1e-9
     ppm, idx, _ = oracle.BCCH_demod(r3, pinfo, oracle.gsm_normal_training_sequence_gen(8), 8, spec.carrier_freq)
     assert idx == c["bcch_idx"] == c["tsc"] + 1 and abs(ppm - c["bcch_carrier_ppm"]) < 1e-9
+
+
+def test_algorithm_constants_match_the_reference_source():
+    """tests/golden/reference_constants.json is extracted by regular expressions from the defining lines of the .m files."""
+    with open(os.path.join(GOLDEN, "reference_constants.json")) as f:
+        g = json.load(f)
+    for k, v in oracle.CONSTANTS.items():
+        assert float(v) == g[k]["value"], (k, v, g[k])
+    assert g["min_bursts_sch"]["value"] == oracle.CONSTANTS["min_bursts"] and g["len_fcch_cw"]["value"] == oracle.LEN_FCCH_CW
