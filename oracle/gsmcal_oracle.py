@@ -9,6 +9,9 @@ PARITY UNPINNED.  The reference ships no tests, golden vectors or fixtures for t
 MATLAB nor Octave exists in this image, so the reference itself cannot be run.  What pins this oracle:
   * the two FIR numerators recovered from the reference's own gsm_chn_filter_{8x,4x}.fda sessions
     (tests/golden/chn_filter_taps.json, made by oracle/make_golden.py);
+  * the training-sequence bit patterns and the algorithm constants (thresholds, search ranges, ppm limits), both parsed from
+    the text of the .m files by oracle/make_golden.py (tests/golden/training_bits.json, reference_constants.json);
+  * the reference's own manual checks as assertions (test_diff_GMSK_mod_demod.m, CW_check.m, the "test on line" blocks);
   * hand-derived known answers for MATLAB semantics (round half away from zero, first-max, 1-based
     indices, toeplitz window ordering, pos_info row rules) in tests/test_oracle.py;
   * MATLAB built-ins are restated by their public definitions: fft -> numpy.fft.fft, filter ->
@@ -17,6 +20,7 @@ MATLAB nor Octave exists in this image, so the reference itself cannot be run.  
   * comm.GMSKModulator (gsm_SCH_training_sequence_gen.m:14,39) is closed source: the template generator
     here follows GSM 05.04 (BT 0.3, L=4, h=0.5, zero initial phase, no prehistory) and is NOT a bit match
     of MathWorks' output.  The template is an *input* at the boundary (SCH_corr_rate_correction.m:5).
+    comm.GMSKDemodulator (SCH_demod.m:63) likewise: restated as a 32-state MLSE over that modulator (gmsk_viterbi_demod).
 
 All positions and indices returned are 1-based doubles exactly as the reference returns them.
 """
