@@ -330,3 +330,51 @@ def test_algorithm_constants_match_the_reference_source():
     for k, v in oracle.CONSTANTS.items():
         assert float(v) == g[k]["value"], (k, v, g[k])
     assert g["min_bursts_sch"]["value"] == oracle.CONSTANTS["min_bursts"] and g["len_fcch_cw"]["value"] == oracle.LEN_FCCH_CW
+
+
+@pytest.mark.parametrize("gaps,flagged", [((10, 10, 10, 11, 10, 10), {5}), ((10, 10, 10, 10, 11, 10), {1, 6}), ((10, 10, 10, 10, 10), set())])
+def test_pos_info_rows_known_answer(gaps, flagged):
+    """K10 by hand (SCH_corr_rate_correction.m:138-181): templates planted exactly where the burst format puts them, so the peak is
+    the centre lag, e = 0, and every row of pos_info can be written down: per SCH i the FCCH row (SCH-10336, 0), the SCH row
+    (SCH-336, 1), and four BCCH rows (+k*10000, 2) after the SCH bursts flagged by the 11-frame gaps (b_idx+1 and b_idx-4)."""
+    osr, frame = 8, 10000
+    ts = oracle.gsm_SCH_training_sequence_gen(osr)
+    fcch = np.cumsum([2001] + [g * frame for g in gaps]).astype(np.float64)
+    n = int(fcch[-1]) + 10336 + 512 + 5 * frame
+    s = np.zeros(n, dtype=np.complex128)
+    for p in fcch:
+        t0 = int(p) + 10336                              # training_sp (1-based)
+        s[t0 - 1:t0 - 1 + 512] = ts
+    pos_info, r, ppm = oracle.SCH_corr_rate_correction(s, fcch, ts, osr)
+    assert ppm == 0.0 and np.array_equal(r, s)           # e == 0: no interp1 (:120)
+    rows = []
+    for i, p in enumerate(fcch, 1):
+        sch = p + 10336
+        rows.append([sch - 10336, 0.0])
+        rows.append([sch - 336, 1.0])
+        if i in flagged:
+            rows += [[sch - 336 + k * frame, 2.0] for k in (1, 2, 3, 4)]
+    assert pos_info.tolist() == rows
+
+
+def test_fine_correction_known_answer_on_planted_tones():
+    """K5-K8 by hand (FCCH_fine_correction.m:32-165): six 1184-sample tones planted 10/11 frames apart in weak noise.  The window
+    that covers a tone completely has the largest max-bin power, so FCCH_pos are the planted starts; the spacing is nominal, so
+    e = 0 and the regridded positions (:127-133) equal the found ones; the carrier error follows from the tone frequency."""
+    osr, frame, n_tone = 8, 10000, 1184
+    f_tone = oracle.SYMBOL_RATE / 4 + 2500.0
+    rng = np.random.default_rng(5)
+    starts = np.cumsum([30001] + [g * frame for g in (10, 10, 11, 10, 10)])
+    n = int(starts[-1]) + 3 * frame
+    s = 1e-3 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    for p in starts:
+        k = np.arange(n_tone)
+        s[p - 1:p - 1 + n_tone] += np.exp(2j * np.pi * f_tone * (p - 1 + k) / FS)
+    base = np.round((starts - 1) / osr) + 1 + np.array([3, -7, 0, 11, -20, 5])          # coarse guesses, within +-64 symbols
+    fpos, r, sppm, cppm = oracle.FCCH_fine_correction(s, base, osr, 957.4e6)
+    assert fpos.tolist() == starts.astype(float).tolist()
+    assert sppm == 0.0 and len(r) == n
+    assert abs(cppm - 1e6 * 2500.0 / 957.4e6) < 1e-3                                   # the 1e-3 noise floor moves the estimate by ~0.03 Hz
+    # r = s .* exp(1i*n*comp) (:163-165): the tone sits on fs_sym/4 afterwards
+    fo, _, _ = oracle.tone_freq_estimate(r, fpos, n_tone, FS)
+    assert np.max(np.abs(fo - oracle.SYMBOL_RATE / 4)) < 1e-4
