@@ -94,3 +94,24 @@ def test_bad_arguments_are_rejected(built_lib):
         gsmcal.chn_filter_taps(5)
     with pytest.raises(ValueError):
         gsmcal.SCH_corr_rate_correction(np.zeros(10, complex), np.arange(5.0), np.ones(100, complex), 8)
+
+
+def test_demod_family_sentinels_and_loud_failure(built_lib):
+    """the `pos_info==-1` returns are decided on the host; real work without a GPU is an error, not a fallback."""
+    import gsmcal
+    s = np.zeros(20000, dtype=np.complex128)
+    m1 = np.array([[-1.0, -1.0]])
+    assert gsmcal.FCCH_demod(s, m1, 8, 957.4e6) is None
+    assert gsmcal.SCH_demod(s, m1, np.ones(512, complex), 8) is None
+    assert gsmcal.BCCH_demod(s, m1, np.ones((208, 8), complex), 8, 957.4e6) == (-1.0, -1, None)
+    assert gsmcal.gsm_normal_training_sequence_gen(8).shape == (208, 8)
+    if gsmcal.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    rows = np.array([[1001.0, 0.0], [1001.0 + 10336 - 336, 1.0]] + [[3000.0 + k * 1250, 2.0] for k in range(4)])
+    for call in (lambda: gsmcal.FCCH_demod(s, rows, 8, 957.4e6),
+                 lambda: gsmcal.SCH_demod(s, rows, np.ones(512, complex), 8),
+                 lambda: gsmcal.BCCH_demod(s, rows, np.ones((208, 8), complex), 8, 957.4e6),
+                 lambda: gsmcal.calibrate_batch_submit(0, 0x1000, 300000, 1, 957.4e6, np.ones(512, complex), gsmcal.fir1(46, 0.09))):
+        with pytest.raises(gsmcal.GsmcalError) as e:
+            call()
+        assert e.value.code == -2
