@@ -215,7 +215,8 @@ int gsmcal_fcch_scan(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t n_ch
 /* test / tuning hooks: key 0, value 1 = run the all-bin fine FCCH search for every burst (no band-limited fast path);
  * 3 = stream groups of gsmcal_calibrate_batch; 4 = pretend the tier-1/2 certificates failed; 5 = tier-3 list limit;
  * 6 = burst chain on high-priority streams (default 1); 7 = blocks per SM of a persistent high-priority column-sum kernel in
- * _submit (default 0 = per-group launches); 8 = stream groups inside a submitted batch (default 1) */
+ * _submit (default 0 = per-group launches); 8 = stream groups inside a submitted batch (default 1); 9, value 1 = the generic tier-1 fine
+ * search without the osr-8 fast path and its filtered-window cache (A/B and tests) */
 int gsmcal_debug_set(int key, int value);
 /* key 1: number of bursts of the last fine FCCH search whose band certificate failed (all-bin fallback ran) */
 int64_t gsmcal_debug_get(int key);

@@ -2,6 +2,7 @@
 // No torch types, no CPU fallback: every compute entry point fails with GSMCAL_ERR_CUDA without a device.
 #include "../../include/gsmcal.h"
 #include "gsmcal_kernels.cuh"
+#include "gsmcal_burst8.cuh"
 #include "gsmcal_demod.cuh"
 
 #include <atomic>
@@ -32,6 +33,7 @@ int g_debug_force_full = 0;       // tests: run the all-bin fine search for ever
 int g_debug_submit_groups = 1;    // stream groups inside a submitted batch
 int g_debug_persist_colsum = 0;   // submit/collect: blocks per SM of the persistent high-priority column-sum kernel (0 = per-group launches)
 int g_debug_hi_prio = 1;          // burst chain of each stream group on a high-priority CUDA stream
+int g_debug_no_core8 = 0;         // tests / A-B: 1 = round-1 tier-1 kernel and no filtered-window cache
 
 int fail(int code, const char *fmt, ...) {
     char buf[512];
@@ -71,7 +73,7 @@ struct DevBuf {
 // overlap on the device (the ~1 ms latency-bound front of batch k+1 - column sums, burst chain - runs under the FP64 kernels of batch k)
 constexpr int kSlots = 4;
 struct Slot {
-    DevBuf work;
+    DevBuf work, wc;                                            // wc: filtered-window cache of the osr-8 fast path
     cudaStream_t front = nullptr, front_hi = nullptr;
     std::vector<cudaStream_t> grp, hi;
     cudaEvent_t done = nullptr;
@@ -83,7 +85,7 @@ struct Slot {
 struct Ctx {
     bool attrs = false;
     Slot slots[kSlots];
-    DevBuf in, out, work, tplbuf;
+    DevBuf in, out, work, tplbuf, wc;
     std::map<int, double2 *> tw;     // N -> exp(-2*pi*i*j/N)
     std::vector<cudaStream_t> side;  // extra streams: stream groups of a batch overlap their latency-bound stages
     std::vector<cudaStream_t> side_hi; // one high-priority stream per group for the latency-bound burst chain (see gsmcal_calibrate_batch)
@@ -147,6 +149,9 @@ int get_ctx(Ctx **out) {
         CU(cudaFuncSetAttribute(fine_peak_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(fine_peak_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(fine_peak_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        CU(cudaFuncSetAttribute(fine_core8_kernel<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, B8_SMEM));
+        CU(cudaFuncSetAttribute(fine_core8_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, B8_SMEM));
+        CU(cudaFuncSetAttribute(fine_core8_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, B8_SMEM));
         CU(cudaFuncSetAttribute(tone_est_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(sch_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CU(cudaFuncSetAttribute(fir_full_tma_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -200,6 +205,8 @@ struct Work {
     double *coarse_pos, *coarse_snr, *fine_raw, *fcch_pos, *fo, *gate, *sch_raw, *sch_pos, *post_pos, *pos_info, *snr_map, *power;
     int *sch_edge, *need_full, *need_band, *fall_list, *fall_count, *fall_m; double *fall_best; unsigned char *kind; double2 *tpl;
     i64 snr_stride;
+    double2 *wcache;              // [D][cap][B8_WLEN] or nullptr (set by attach_wcache)
+    bool wc_valid;                // the fine search of this call filled the cache
 };
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 constexpr int kMaxGroups = 32;     // stream groups per batch (tier-3 scratch is per group); ceil(148*8/64) = 19 <= 24 bands
@@ -221,6 +228,20 @@ int make_work(DevBuf &wb, i64 D, int cap, i64 snr_len, int tpl_len, Work *w) {
     w->pos_info = (double *)(b + o_pi); w->snr_map = (double *)(b + o_snr); w->power = (double *)(b + o_pw);
     w->sch_edge = (int *)(b + o_se); w->need_full = (int *)(b + o_nf); w->need_band = (int *)(b + o_nb); w->fall_list = (int *)(b + o_fl); w->fall_count = (int *)(b + o_fc); w->fall_m = (int *)(b + o_fm); w->fall_best = (double *)(b + o_fb); w->kind = (unsigned char *)(b + o_k); w->tpl = (double2 *)(b + o_tpl);
     w->snr_stride = snr_len;
+    w->wcache = nullptr; w->wc_valid = false;
+    return GSMCAL_OK;
+}
+
+// filtered-window cache of the osr-8 fast path: 36,432 bytes per (stream, burst); skipped (the stages re-filter) when it would not fit
+constexpr size_t kMaxWcacheBytes = (size_t)24 << 30;
+int attach_wcache(DevBuf &buf, i64 D, int cap, int osr, Work *w) {
+    w->wcache = nullptr;
+    if (osr != 8) return GSMCAL_OK;
+    const size_t bytes = (size_t)D * cap * B8_WLEN * sizeof(double2);
+    if (bytes > kMaxWcacheBytes) return GSMCAL_OK;
+    void *p;
+    if (buf.get(bytes, &p) != GSMCAL_OK) { cudaGetLastError(); return GSMCAL_OK; }   // no memory for it: run without
+    w->wcache = (double2 *)p;
     return GSMCAL_OK;
 }
 
@@ -232,6 +253,7 @@ Work sub_work(const Work &w, i64 d0, int cap, int group) {
     s.sch_edge += d0 * cap; s.need_full += d0 * cap; s.need_band += d0 * cap; s.kind += d0 * cap;
     s.fall_list += d0 * cap; s.fall_count += d0;
     s.fall_m += (size_t)group * FALL_GRID * 24; s.fall_best += (size_t)group * FALL_GRID * 24;
+    if (s.wcache) s.wcache += (size_t)d0 * cap * B8_WLEN;
     return s;
 }
 
@@ -243,6 +265,10 @@ WinSrc mat_src(const double2 *base, i64 len, i64 stride, int interp) {
 WinSrc lazy_src(const uint8_t *raw, i64 n_iq, int n_taps, int level, int dec) {
     WinSrc s; memset(&s, 0, sizeof s);
     s.lazy = 1; s.raw = raw; s.n_iq = n_iq; s.n_taps = n_taps; s.level = level; s.dec = dec;
+    return s;
+}
+WinSrc with_cache(WinSrc s, const Work &w, int cap) {            // level-0 samples of cached bursts come from the fine search's window cache
+    if (w.wcache && w.wc_valid) { s.wcache = w.wcache; s.wc_pos = w.coarse_pos; s.wc_cap = cap; }
     return s;
 }
 
@@ -285,7 +311,7 @@ int run_coarse(WinSrc src, i64 len, const CoarseParams &p, i64 D, int cap, Work 
     LAUNCH(snr_map_kernel, dim3((unsigned)((n_win + SNR_THREADS - 1) / SNR_THREADS), (unsigned)D), SNR_THREADS, smem, st,
            src, w.ctl, (i64)0, n_win, p.fft_len, w.snr_map, w.snr_stride);
     LAUNCH(first_hit_scan_kernel, (unsigned)((D + 3) / 4), 128, 0, st, w.snr_map, w.snr_stride, n_win, p.mv_len, p.th, w.ctl, (int)D);
-    size_t chain_smem = src.lazy ? sizeof(double2) * 2 * (CHAIN_MAXSTAGE + CHAIN_MAXSTAGE / 32 + 4) : 0;
+    const size_t chain_smem = sizeof(double2) * (size_t)(p.fft_len + 2 * (2 * 5 + p.fft_len));    // twiddles + the two candidate groups
     LAUNCH(coarse_chain_kernel, (unsigned)D, CHAIN_THREADS, chain_smem, st, src, w.ctl, len, p.fft_len, p.th, p.step10, p.step11, p.dr, cap, w.coarse_pos, w.coarse_snr);
     return GSMCAL_OK;
 }
@@ -298,6 +324,16 @@ int run_fine_peak(Ctx &c, WinSrc src_peak, i64 n_iq, int osr, i64 D, int cap, Wo
     }
     CU(cudaMemsetAsync(w.need_full, 0, sizeof(int) * D * cap, st));
     CU(cudaMemsetAsync(w.need_band, 0, sizeof(int) * D * cap, st));
+    w.wc_valid = false;
+    if (src_peak.lazy && osr == 8 && src_peak.n_taps <= 64 && !g_debug_no_core8) {
+        // osr-8 fast path: FIR once per burst, filtered window cached for tier 2 and the tone stages
+        const dim3 grid((unsigned)cap, (unsigned)D);
+        if (src_peak.n_taps == 47)      LAUNCH((fine_core8_kernel<47>), grid, B8_THREADS, B8_SMEM, st, src_peak.raw, n_iq, w.ctl, w.coarse_pos, cap, tw, w.fine_raw, w.need_band, g_debug_fail_tier2, w.wcache);
+        else if (src_peak.n_taps <= 48) LAUNCH((fine_core8_kernel<48>), grid, B8_THREADS, B8_SMEM, st, src_peak.raw, n_iq, w.ctl, w.coarse_pos, cap, tw, w.fine_raw, w.need_band, g_debug_fail_tier2, w.wcache);
+        else                            LAUNCH((fine_core8_kernel<64>), grid, B8_THREADS, B8_SMEM, st, src_peak.raw, n_iq, w.ctl, w.coarse_pos, cap, tw, w.fine_raw, w.need_band, g_debug_fail_tier2, w.wcache);
+        w.wc_valid = (w.wcache != nullptr);
+        src_peak = with_cache(src_peak, w, cap);
+    } else
     LAUNCH(fine_peak_core_kernel, dim3((unsigned)cap, (unsigned)D), FC_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, w.need_band, g_debug_fail_tier2);
     CU(cudaMemsetAsync(w.fall_count, 0, sizeof(int), st));
     LAUNCH(fine_peak_band_kernel, dim3((unsigned)cap, (unsigned)D), FB_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw,
@@ -407,7 +443,7 @@ void gsmcal_release(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto &kv : g_ctx) {
         cudaSetDevice(kv.first);
-        kv.second.in.release(); kv.second.out.release(); kv.second.work.release(); kv.second.tplbuf.release();
+        kv.second.in.release(); kv.second.out.release(); kv.second.work.release(); kv.second.tplbuf.release(); kv.second.wc.release();
         for (auto &t : kv.second.tw) cudaFree(t.second);
         kv.second.tw.clear();
         for (cudaStream_t s2 : kv.second.side) cudaStreamDestroy(s2);
@@ -424,7 +460,7 @@ void gsmcal_release(void) {
             sl.grp.clear(); sl.hi.clear(); sl.front = nullptr;
             if (sl.stage) cudaFreeHost(sl.stage);
             sl.stage = nullptr; sl.stage_cap = 0; sl.busy = false;
-            sl.work.release();
+            sl.work.release(); sl.wc.release();
         }
     }
 }
@@ -447,6 +483,7 @@ int gsmcal_debug_set(int key, int value) {
     if (key == 4) { g_debug_fail_tier2 = value; return GSMCAL_OK; }
     if (key == 5) { g_debug_fall_limit = value < 0 ? 0 : (value > FALL_GRID ? FALL_GRID : value); return GSMCAL_OK; }
     if (key == 6) { g_debug_hi_prio = value ? 1 : 0; return GSMCAL_OK; }
+    if (key == 9) { g_debug_no_core8 = value ? 1 : 0; return GSMCAL_OK; }
     if (key == 8) { g_debug_submit_groups = value < 1 ? 1 : (value > kMaxGroups / 2 ? kMaxGroups / 2 : value); return GSMCAL_OK; }
     if (key == 7) { g_debug_persist_colsum = value < 0 ? 0 : (value > 8 ? 8 : value); return GSMCAL_OK; }
     if (key == 3) { g_debug_groups = value < 1 ? 1 : (value > kMaxGroups / 2 ? kMaxGroups / 2 : value); return GSMCAL_OK; }
@@ -855,6 +892,7 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
     cudaStream_t st = (cudaStream_t)cuda_stream;
     Work w;
     TRY(make_work(c->work, D, cap, p.n_first, 64 * osr, &w));
+    TRY(attach_wcache(c->wc, D, cap, osr, &w));
     TRY(set_taps(coef, n_taps, st));
     const uint8_t *draw = raw;
     if (raw_mem == GSMCAL_MEM_HOST) {
@@ -924,11 +962,11 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
         if (timing) TRY(stage_mark(sg));
         TRY(run_fine_peak(*c, lazy_src(graw, n_iq, n_taps, 0, 1), n_iq, osr, nd, cap, ws, sg));
         if (timing) TRY(stage_mark(sg));
-        TRY(run_fine_rest(*c, lazy_src(graw, n_iq, n_taps, 1, 1), n_iq, osr, carrier_freq, nd, cap, ws, sg));
+        TRY(run_fine_rest(*c, with_cache(lazy_src(graw, n_iq, n_taps, 1, 1), ws, cap), n_iq, osr, carrier_freq, nd, cap, ws, sg));
         if (timing) TRY(stage_mark(sg));
         TRY(run_sch(lazy_src(graw, n_iq, n_taps, 2, 1), osr, nd, cap, ws, sg));
         if (timing) TRY(stage_mark(sg));
-        TRY(run_post(*c, lazy_src(graw, n_iq, n_taps, 3, 1), osr, carrier_freq, nd, cap, ws, true, sg));
+        TRY(run_post(*c, with_cache(lazy_src(graw, n_iq, n_taps, 3, 1), ws, cap), osr, carrier_freq, nd, cap, ws, true, sg));
         if (timing) TRY(stage_mark(sg));
         if (sg != st) {
             cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -974,6 +1012,7 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
     while ((int)sl.hi.size() < n_groups) { cudaStream_t s2; CU(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, hi_p)); sl.hi.push_back(s2); }
     Work w;
     TRY(make_work(sl.work, D, cap, p.n_first, 64 * osr, &w));
+    TRY(attach_wcache(sl.wc, D, cap, osr, &w));
     TRY(set_taps(coef, n_taps, st));
     // pinned staging: records | coarse_pos | coarse_snr | fcch_pos | pos_info (x12)
     sl.n_res = sizeof(StreamResultDev) * (size_t)D; sl.n_per = sizeof(double) * (size_t)D * cap;
@@ -1022,9 +1061,9 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
         CU(cudaEventRecord(e1, sh)); CU(cudaStreamWaitEvent(sg, e1, 0));
         CU(cudaEventDestroy(e0)); CU(cudaEventDestroy(e1));
         TRY(run_fine_peak(*c, lazy_src(graw, n_iq, n_taps, 0, 1), n_iq, osr, nd, cap, ws, sg));
-        TRY(run_fine_rest(*c, lazy_src(graw, n_iq, n_taps, 1, 1), n_iq, osr, carrier_freq, nd, cap, ws, sg));
+        TRY(run_fine_rest(*c, with_cache(lazy_src(graw, n_iq, n_taps, 1, 1), ws, cap), n_iq, osr, carrier_freq, nd, cap, ws, sg));
         TRY(run_sch(lazy_src(graw, n_iq, n_taps, 2, 1), osr, nd, cap, ws, sg));
-        TRY(run_post(*c, lazy_src(graw, n_iq, n_taps, 3, 1), osr, carrier_freq, nd, cap, ws, true, sg));
+        TRY(run_post(*c, with_cache(lazy_src(graw, n_iq, n_taps, 3, 1), ws, cap), osr, carrier_freq, nd, cap, ws, true, sg));
         cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CU(cudaEventRecord(ev, sg));
         ev_done.push_back(ev);

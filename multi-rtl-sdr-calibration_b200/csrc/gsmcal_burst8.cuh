@@ -1,0 +1,281 @@
+// gsmcal_burst8.cuh - the fine FCCH search specialised for the reference's oversampling ratio 8 on the lazy (uint8) source.
+//
+// Same arithmetic and the same certificates as fine_peak_core_kernel (gsmcal_kernels.cuh; FCCH_fine_correction.m:32-64), with
+// every size a compile-time constant (N = 1184 = 37*32, 1025 window starts, 2208 samples = 69 chunks of 32) and the phases
+// rebuilt around what bounds them on an SM:
+//   * the 47-tap FIR (56 % of the arithmetic) runs ONCE per burst, 9 outputs per thread from a register window with constant-bank
+//     taps (1 LDS.128 per 18 DFMA), in place: staged capture and filtered window share one buffer, so 4 blocks stay resident;
+//   * the filtered window goes to an L2/HBM cache with one TMA bulk store, so the two tone stages and the 64-bin tier never filter
+//     these samples again;
+//   * chunk sums by Horner's rule, 4 bins per thread sharing every sample load (4 DFMA per sample and bin instead of 5, 1 LDS per
+//     16 DFMA), on a window layout with one pad slot per chunk so the chunk starts of a quarter-warp fall into different banks;
+//   * the slack of the certificate from chunk energies (Cauchy-Schwarz) instead of a per-sample square root.
+#pragma once
+
+#define B8_N       1184
+#define B8_NWIN    1025
+#define B8_CH      32
+#define B8_NSEG    32
+#define B8_WCH     37
+#define B8_THREADS 256
+#define B8_R       9
+#define B8_BUF     2304                      // staged samples: 2208 + (NT-1 <= 63) + R-1, rounded up
+#define B8_CSL     71                        // row stride of the chunk prefix table (odd: bins fall into different banks)
+#define B8_SMEM    (B8_BUF * 16 + 8 * B8_CSL * 16 + 72 * 8 + 72 * 8 + 33 * 8 * 8)
+
+template <int NT>
+__global__ void __launch_bounds__(B8_THREADS, 4) fine_core8_kernel(const uint8_t *__restrict__ raw_all, i64 n_iq, const StreamCtl *__restrict__ ctl,
+                                                                  const double *__restrict__ base_pos, int cap, const double2 *__restrict__ tw,
+                                                                  double *__restrict__ fine_raw, int *__restrict__ need_band, int force_fail,
+                                                                  double2 *__restrict__ wcache) {
+    extern __shared__ __align__(128) unsigned char b8_sm[];
+    double2 *B = reinterpret_cast<double2 *>(b8_sm);             // staged capture, then the filtered window (padded layout)
+    double2 *CS = B + B8_BUF;                                    // [8][B8_CSL] prefix of chunk sums, bin-major
+    double *PE = reinterpret_cast<double *>(CS + 8 * B8_CSL);    // [70] prefix of chunk energies
+    double *E31 = PE + 72;                                       // [69] energy of the first 31 samples of every chunk
+    double *T2 = E31 + 72;                                       // [33][8] tracked power of pass 0 per (window, split)
+    __shared__ double red_v[8];
+    __shared__ int red_i[8];
+    __shared__ double scan_sv[16];
+    const int burst = blockIdx.x, stream = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const StreamCtl c = ctl[stream];
+    if (c.n_coarse < 5 || burst >= c.n_coarse) return;
+    const i64 len_s = n_iq / 8;
+    const i64 position = (i64)base_pos[(i64)stream * cap + burst];
+    double *o = fine_raw + (i64)stream * cap + burst;
+    if (position + 64 > len_s - 148 + 1) {                       // run out of sampled signal (:35-38)
+        if (tid == 0) *o = INFINITY;
+        return;
+    }
+    const i64 sp0 = (position - 65) * 8;                         // 0-based first sample of the first window (sp - 1)
+    // ---- stage the DC-removed capture: one 2-byte IQ pair per thread and load, all loads in flight ----
+    {
+        constexpr int NRAW = B8_NSMP + NT - 1;
+        constexpr int NLD = (NRAW + B8_THREADS - 1) / B8_THREADS;
+        const unsigned short *rp = reinterpret_cast<const unsigned short *>(raw_all + (i64)stream * 2 * n_iq);
+        const i64 j00 = sp0 - (NT - 1);
+        const double mur = c.mu_re, mui = c.mu_im;
+        unsigned wv[NLD];
+#pragma unroll
+        for (int q = 0; q < NLD; ++q) {
+            const int i = tid + q * B8_THREADS;
+            const i64 j = j00 + i;
+            wv[q] = (i < NRAW && j >= 0) ? (unsigned)__ldg(rp + j) : 0x10000u;     // zero initial filter state before the first sample
+        }
+#pragma unroll
+        for (int q = 0; q < NLD; ++q) {
+            const int i = tid + q * B8_THREADS;
+            if (i < NRAW)
+                B[i] = (wv[q] & 0x10000u) ? make_double2(0.0, 0.0)
+                                          : make_double2(u8_to_f64(wv[q] & 0xffu) - mur, u8_to_f64((wv[q] >> 8) & 0xffu) - mui);
+        }
+        if (tid < B8_R + 7) B[NRAW + tid] = make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    // ---- FIR, 9 outputs per thread, in place: all reads happen before the barrier, all writes after it ----
+    {
+        constexpr int NGRP = (B8_NSMP + B8_R - 1) / B8_R;        // 246 <= 256: one round
+        double ar[B8_R], ai[B8_R];
+        if (tid < NGRP) fir_taps_const<NT, B8_R>(B + B8_R * tid, ar, ai);
+        __syncthreads();
+        if (tid < NGRP) {
+#pragma unroll
+            for (int r = 0; r < B8_R; ++r) {
+                const int i = B8_R * tid + r;
+                if (i < B8_NSMP) B[B8_WPAD(i)] = make_double2(ar[r], ai[r]);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- the filtered window goes to the cache with ONE TMA bulk store (reads shared memory asynchronously: waited for below,
+    //      before the window is overwritten by differences) ----
+    if (wcache && tid == 0) {
+        double2 *dstp = wcache + ((i64)stream * cap + burst) * B8_WLEN;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(dstp), "r"((unsigned)__cvta_generic_to_shared(B)), "r"((unsigned)(B8_WLEN * sizeof(double2))) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    // ---- chunk energies: thread = (chunk, half), 16 samples each, the start rotated per lane so a quarter-warp reads 8 banks ----
+    {
+        double se = 0.0, se31 = 0.0;
+        const int cch = tid >> 1, h = tid & 1;
+        if (tid < 2 * B8_NCH) {
+            const double2 *bp = B + 33 * cch + 16 * h;
+            const int rot = (tid + 1) >> 1;
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const int idx = (i + rot) & 15;
+                const double2 v = bp[idx];
+                const double e = fma(v.x, v.x, v.y * v.y);
+                se += e;
+                if (!(h == 1 && idx == 15)) se31 += e;
+            }
+        }
+        if (warp < 5) {                                          // 138 tasks live in warps 0..4; the halves of a chunk are lane neighbours
+            const double se_o = __shfl_xor_sync(0xffffffffu, se, 1), se31_o = __shfl_xor_sync(0xffffffffu, se31, 1);
+            if (tid < 2 * B8_NCH && h == 0) { PE[cch + 1] = se + se_o; E31[cch] = se31 + se31_o; }
+        }
+        if (tid == 0) PE[0] = 0.0;
+    }
+    // ---- band centre from the phase slope of the centre window ----
+    {
+        double pq[2] = {0.0, 0.0};
+        for (int n = 512 + tid; n < 512 + B8_N - 1; n += B8_THREADS) {
+            const double2 q2 = cmulc(B[B8_WPAD(n + 1)], B[B8_WPAD(n)]);
+            pq[0] += q2.x; pq[1] += q2.y;
+        }
+        block_sum_n<2, false>(pq, scan_sv);                      // (its barriers also publish PE / E31)
+        if (tid == 0) red_i[0] = (int)floor(atan2(pq[1], pq[0]) * (double)B8_N / (2.0 * GSMCAL_PI) + 0.5);   // one atan2 per block
+    }
+    if (warp == 1) warp_scan_smem(PE, B8_NCH + 1, lane);         // PE[i] = sum_{n < 32 i} |s[n]|^2
+    __syncthreads();
+    const int k0 = red_i[0];
+    __syncthreads();
+    // Two passes at most (see fine_peak_core_kernel): pass 0 tracks k0-3 .. k0+4, pass 1 adds k0-7 .. k0-4 and k0+5 .. k0+8.
+    double g_best = -1.0; int g_bestm = 0x7fffffff;
+    int ok = 0;
+    for (int pass = 0; pass < 2 && !ok; ++pass) {
+        if (pass == 1) {                                         // s[m] = s[m+N] - d[m] for m < 1024 (d was stored in place)
+            for (int m = tid; m < B8_NWIN - 1; m += B8_THREADS) {
+                const int i0 = B8_WPAD(m);
+                const double2 dd = B[i0], s_new = B[i0 + 33 * B8_WCH];
+                B[i0] = make_double2(s_new.x - dd.x, s_new.y - dd.y);
+            }
+            __syncthreads();
+        }
+        // ---- chunk sums sum_{n in chunk} s[n] W^{n k} by Horner's rule from the last sample: thread = (chunk, 4 bins) ----
+        if (tid < 2 * B8_NCH) {
+            const int cch = tid >> 1, q = tid & 1;
+            int kk[4]; double2 z[4], acc[4];
+            const double2 *bp = B + 33 * cch;
+            const double2 s_last = bp[31];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                int k = (k0 + ((pass == 0) ? 4 * q + b - 3 : (q == 0 ? b - 7 : b + 5))) % B8_N; if (k < 0) k += B8_N;
+                kk[b] = k; z[b] = tw[k]; acc[b] = s_last;
+            }
+#pragma unroll 31
+            for (int i = 30; i >= 0; --i) {
+                const double2 s = bp[i];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const double nr = fma(acc[b].x, z[b].x, fma(-acc[b].y, z[b].y, s.x));
+                    const double ni = fma(acc[b].x, z[b].y, fma(acc[b].y, z[b].x, s.y));
+                    acc[b] = make_double2(nr, ni);
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                CS[(4 * q + b) * B8_CSL + cch + 1] = cmul(acc[b], tw[(32 * cch * kk[b]) % B8_N]);
+        }
+        __syncthreads();
+        {   // prefix over chunks: warp b scans bin b (lanes own 3 consecutive chunks)
+            double2 *row = CS + warp * B8_CSL;
+            constexpr int per = (B8_NCH + 31) / 32;
+            const int b0 = 1 + lane * per;
+            double lr = 0.0, li = 0.0;
+#pragma unroll
+            for (int i = 0; i < per; ++i) if (b0 + i <= B8_NCH) { const double2 v = row[b0 + i]; lr += v.x; li += v.y; }
+            double ir = lr, ii = li;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double tr = __shfl_up_sync(0xffffffffu, ir, d), ti = __shfl_up_sync(0xffffffffu, ii, d);
+                if (lane >= d) { ir += tr; ii += ti; }
+            }
+            double rr = ir - lr, ri = ii - li;
+#pragma unroll
+            for (int i = 0; i < per; ++i) if (b0 + i <= B8_NCH) { const double2 v = row[b0 + i]; rr += v.x; ri += v.y; row[b0 + i] = make_double2(rr, ri); }
+            if (lane == 0) row[0] = make_double2(0.0, 0.0);
+        }
+        if (pass == 0 && tid == 0 && wcache) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the bulk store has read the window
+        __syncthreads();
+        const int g = tid >> 3, j = tid & 7;
+        int k = (k0 + ((pass == 0) ? j - 3 : (j < 4 ? j - 7 : j + 1))) % B8_N; if (k < 0) k += B8_N;
+        const double2 wk = tw[k];
+        double xr, xi;
+        {
+            const double2 hi = CS[j * B8_CSL + g + B8_WCH], lo = CS[j * B8_CSL + g];
+            const double yr = hi.x - lo.x, yi = hi.y - lo.y;
+            const double2 t = tw[(32 * g * k) % B8_N];           // X_{m0}[k] = Y_{m0}[k] * exp(+2*pi*i*m0*k/N)
+            xr = yr * t.x + yi * t.y;
+            xi = yi * t.x - yr * t.y;
+        }
+        for (int m = tid; m < B8_NWIN - 1; m += B8_THREADS) {    // d[m] = s[m+N] - s[m] in place
+            const int i0 = B8_WPAD(m);
+            const double2 s_old = B[i0], s_new = B[i0 + 33 * B8_WCH];
+            B[i0] = make_double2(s_new.x - s_old.x, s_new.y - s_old.y);
+        }
+        __syncthreads();
+        const double wr = wk.x, wi = -wk.y;
+        double best = -1.0; int bestm = 0x7fffffff;
+        {
+            const double2 *dp = B + 33 * g;                      // d[32 g + i] sits at 33 g + i
+            const int m0 = 32 * g;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) {
+                const double p = fma(xr, xr, xi * xi);
+                if (p > best) { best = p; bestm = m0 + i; }
+                if (i < 31 || g == B8_NSEG - 1) {
+                    const double2 d = dp[i];
+                    const double tr = xr + d.x, ti = xi + d.y;
+                    xr = fma(tr, wr, -(ti * wi));
+                    xi = fma(tr, wi, ti * wr);
+                }
+            }
+            if (g == B8_NSEG - 1) {                              // the last segment also owns window 1024
+                const double p = fma(xr, xr, xi * xi);
+                if (p > best) { best = p; bestm = m0 + 32; }
+            }
+        }
+        block_argmax(best, bestm, red_v, red_i);
+        if (pass == 0) { g_best = best; g_bestm = bestm; }
+        else if (best > g_best || (best == g_best && bestm < g_bestm)) break;   // the extra bins would move the argmax: leave it to tier 2
+        // ---- certificate at every segment-start window c = 32 g (g = 0..32), straight from the chunk prefix tables: for any split of
+        // the window into a part P1 of d samples and the rest P2, every untracked bin obeys
+        //   |X_c[k]| <= sqrt(d*E_P1) + sqrt(N*E_P2 - sum_tracked |P2[k']|^2)
+        // and the triangle inequality carries the bound to the 31 windows in between with the slack
+        //   sum_{i=c}^{c+30} (|s[i]| + |s[i+N]|) <= sqrt(31*E31[g]) + sqrt(31*E31[g+37])        (Cauchy-Schwarz). ----
+        ok = 1;
+        for (int w0 = 0; w0 <= B8_NSEG; w0 += B8_THREADS / 8) {
+            const int gq = w0 + (tid >> 3), cand = tid & 7;
+            double bnd = INFINITY;
+            if (gq <= B8_NSEG && cand < 7) {
+                const int cw = gq * B8_CH;
+                const bool lead = cw < g_bestm;
+                const int dist = lead ? g_bestm - cw : cw - g_bestm;
+                const int dch = (cand == 0) ? 0 : (dist + B8_CH - 1) / B8_CH - 3 + cand;
+                if (dch == 0 || (cw != g_bestm && dch >= 1 && dch < B8_WCH)) {
+                    // P1 = first dch chunks (window starts before the burst) or last dch chunks (window runs past it)
+                    const int p1a = lead ? gq : gq + B8_WCH - dch, p1b = p1a + dch;
+                    const int p2a = lead ? gq + dch : gq, p2b = lead ? gq + B8_WCH : gq + B8_WCH - dch;
+                    const double e1 = PE[p1b] - PE[p1a], e2 = PE[p2b] - PE[p2a];
+                    double t2 = (pass == 0) ? 0.0 : T2[gq * 8 + cand];
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const double2 hi = CS[jj * B8_CSL + p2b], lo = CS[jj * B8_CSL + p2a];
+                        const double yr = hi.x - lo.x, yi = hi.y - lo.y;
+                        t2 += yr * yr + yi * yi;
+                    }
+                    if (pass == 0) T2[gq * 8 + cand] = t2;
+                    const double r2 = (double)B8_N * e2 - t2;
+                    bnd = sqrt_ub((double)(dch * B8_CH) * (e1 > 0.0 ? e1 : 0.0)) + sqrt_ub(r2 > 0.0 ? r2 : 0.0);
+                }
+            }
+            bnd = fmin(bnd, __shfl_xor_sync(0xffffffffu, bnd, 1));
+            bnd = fmin(bnd, __shfl_xor_sync(0xffffffffu, bnd, 2));
+            bnd = fmin(bnd, __shfl_xor_sync(0xffffffffu, bnd, 4));
+            if (gq <= B8_NSEG && cand == 0) {
+                const double A = (gq == B8_NSEG) ? 0.0 : sqrt_ub(31.0 * E31[gq]) + sqrt_ub(31.0 * E31[gq + B8_WCH]);
+                const double bound = (bnd + A) * (1.0 + 1e-9);   // the prefix differences and sums above round to nearest
+                if (!(bound * bound < g_best * (1.0 - 1e-6))) ok = 0;
+            }
+        }
+        ok = __syncthreads_and(ok);
+    }
+    if (tid == 0) {
+        if (wcache) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the bulk store is complete before the block retires
+        *o = (double)(sp0 + 1 + g_bestm);                        // sp + max_idx - 1
+        need_band[(i64)stream * cap + burst] = (ok && !force_fail) ? 0 : 1;       // force_fail: test hook, sends every burst to tier 2
+    }
+}

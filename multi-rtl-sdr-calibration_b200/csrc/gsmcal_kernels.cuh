@@ -61,7 +61,16 @@ struct WinSrc {
     i64            n_iq;
     int            n_taps;
     int            dec;         // decimation applied on top (coarse stage: osr*dr), else 1
+    // filtered-window cache (osr 8 fast path): the fine search stores every burst's filtered (level-0) search window
+    // [ (p-65)*8, +2208 ) so that the two tone stages re-use it instead of re-filtering the capture (see gsmcal_burst8.cuh)
+    const double2 *wcache;      // [n_streams][wc_cap][B8_WLEN] padded layout, nullptr = no cache
+    const double  *wc_pos;      // [n_streams][wc_cap] coarse positions the windows were cut at
+    int            wc_cap;
 };
+#define B8_NSMP 2208                        // samples of a fine-search window at osr 8 (1025 window starts + 1184 - 1)
+#define B8_NCH  69                          // 32-sample chunks per window
+#define B8_WPAD(i) ((i) + ((i) >> 5))       // one pad slot per chunk: chunk starts fall into different shared-memory banks
+#define B8_WLEN (B8_NSMP + B8_NCH)          // padded entries per cached window (36,432 bytes)
 
 // capacity (double2) of load_window's scratch X for a window of `count` samples
 #define GSMCAL_XCAP(count) ((count) + GSMCAL_MAX_TAPS + 8)
@@ -103,35 +112,39 @@ __device__ __forceinline__ double2 fir_from_raw(const uint8_t *__restrict__ raw,
     return make_double2(ar, ai);
 }
 
-// FIR over the staged (DC-removed) capture, 3 consecutive outputs per thread, fully unrolled for a compile-time tap count
-// NT (shorter filters are zero-padded on the OLD side, which adds exact zeros first): taps become constant-bank operands
-// of the DFMAs and every staged sample is loaded once per 3 outputs - about 7 instructions per 6 DFMA instead of ~20.
-template <int NT>
-__device__ __forceinline__ void fir_groups(const double2 *__restrict__ X, double2 *__restrict__ l0, int n_l0, int tid, int nt) {
-    constexpr int U = (NT == 48) ? 5 : 6;                        // (NT + 2) % U == 0
-    static_assert((NT + 2) % U == 0, "unroll factor");
-    const int n_grp = (n_l0 + 2) / 3;
-    for (int gi = tid; gi < n_grp; gi += nt) {
-        double ar[3] = {0.0, 0.0, 0.0}, ai[3] = {0.0, 0.0, 0.0};
-        const double2 *xb = X + 3 * gi;
-#pragma unroll 1
-        for (int k0 = 0; k0 < NT + 2; k0 += U) {                 // rolled by U: few live registers, no tap shifting, no range checks
-            const double *hp = c_taps + (NT - 1 - k0);           // tap of output r at input k0+j: hp[r - j] (zeros outside 0..NT-1)
+// R consecutive FIR outputs from a register sliding window, fully unrolled for a compile-time tap count: every tap is a
+// constant-bank operand of its DFMA and every staged sample is loaded once per R outputs (1 LDS.128 per 2R DFMA; a 128-bit
+// shared load costs 4 cycles of the 128 B/clk crossbar, so R >= 4 keeps the loop FP64-bound).  Odd R: the R*16-byte lane
+// stride is bank-conflict free.  Oldest input first, as direct-form-II-transposed nests the sum.
+template <int NT, int R, int FENCE = 0>
+__device__ __forceinline__ void fir_taps_const(const double2 *__restrict__ xb, double (&ar)[R], double (&ai)[R]) {
 #pragma unroll
-            for (int j = 0; j < U; ++j) {
-                const double2 x = xb[k0 + j];
+    for (int r = 0; r < R; ++r) { ar[r] = 0.0; ai[r] = 0.0; }
 #pragma unroll
-                for (int r = 0; r < 3; ++r) {                    // oldest input first, as direct-form-II-transposed nests the sum
-                    const double h = hp[r - j];
-                    ar[r] = fma(h, x.x, ar[r]); ai[r] = fma(h, x.y, ai[r]);
-                }
-            }
+    for (int k = 0; k < NT - 1 + R; ++k) {
+        if (FENCE > 0 && k > 0 && (k % FENCE) == 0) asm volatile("" ::: "memory");   // keeps the compiler from hoisting every load (register pressure)
+        const double2 x = xb[k];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int tap = (NT - 1) + r - k;
+            if (tap >= 0 && tap < NT) { ar[r] = fma(c_taps[tap], x.x, ar[r]); ai[r] = fma(c_taps[tap], x.y, ai[r]); }
         }
-        const int base = 3 * gi;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) if (base + r < n_l0) l0[base + r] = make_double2(ar[r], ai[r]);
     }
 }
+#define LW_R 5
+template <int NT>
+__device__ __forceinline__ void fir_groups_c(const double2 *__restrict__ X, double2 *__restrict__ l0, int n_l0, int tid, int nt) {
+    const int n_grp = (n_l0 + LW_R - 1) / LW_R;
+    for (int gi = tid; gi < n_grp; gi += nt) {
+        double ar[LW_R], ai[LW_R];
+        fir_taps_const<NT, LW_R, 6>(X + LW_R * gi, ar, ai);
+        const int base = LW_R * gi;
+#pragma unroll
+        for (int r = 0; r < LW_R; ++r) if (base + r < n_l0) l0[base + r] = make_double2(ar[r], ai[r]);
+    }
+}
+// exact uint8 -> double without the quarter-rate I2F: the integer sits in the low mantissa bits of 2^52
+__device__ __forceinline__ double u8_to_f64(unsigned v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
 
 // ---------------------------------------------------------------------------------------------------
 // block-cooperative window loader: dst[0..count) = samples [start, start+count) (0-based) of the stream
@@ -140,7 +153,7 @@ __device__ __forceinline__ void fir_groups(const double2 *__restrict__ X, double
 // SCH_corr_rate_correction.m:126-127 (second interp1) on top of raw2iq + filter.
 // ---------------------------------------------------------------------------------------------------
 __device__ void load_window(const WinSrc &src, const StreamCtl &c, int stream, i64 start, int count,
-                            double2 *dst, double2 *X, double2 *Y) {
+                            double2 *dst, double2 *X, double2 *Y, int burst = -1) {
     const int tid = threadIdx.x, nt = blockDim.x;
     if (!src.lazy) {
         const double2 *b = src.base + (i64)stream * src.base_stride;
@@ -191,57 +204,51 @@ __device__ void load_window(const WinSrc &src, const StreamCtl &c, int stream, i
     // thread evaluates it while the others stage and filter; it is read after the barriers below
     __shared__ double2 lw_base;
     if (derot && use1 && tid == 0) { double sn, cs; sincos((double)a1 * c.dphi1, &sn, &cs); lw_base = make_double2(cs, sn); }
-    const int nt_sel = (src.n_taps <= 48) ? 48 : (src.n_taps <= 64 ? 64 : 0);      // unrolled FIR variants (taps zero-padded on the old side)
+    const int nt_sel = (src.n_taps == 47) ? 47 : ((src.n_taps <= 48) ? 48 : (src.n_taps <= 64 ? 64 : 0));   // unrolled FIR variants (taps zero-padded on the old side)
     const int nt1 = (nt_sel ? nt_sel : src.n_taps) - 1;
     const int n_l0 = (int)(b0 - a0 + 1);
     const int n_raw = n_l0 + nt1;
-    // stage the DC-removed capture once (zero before the first sample: zero initial filter state).  8-byte aligned words
-    // (4 IQ pairs), every thread's loads issued before the first is consumed: one memory latency per call.
+    double2 *l0 = (use1 || use2) ? Y : dst;
+    // the fine search left this burst's filtered window in the cache: level 0 is a copy, no staging, no FIR
+    bool from_cache = false;
+    if (src.wcache && burst >= 0) {
+        const i64 wbase = ((i64)src.wc_pos[(i64)stream * src.wc_cap + burst] - 65) * 8;
+        if (a0 >= wbase && b0 < wbase + B8_NSMP) {
+            const double2 *wc = src.wcache + ((i64)stream * src.wc_cap + burst) * B8_WLEN;
+            const int o = (int)(a0 - wbase);
+            for (int i = tid; i < n_l0; i += nt) l0[i] = wc[B8_WPAD(o + i)];
+            from_cache = true;
+        }
+    }
+    if (!from_cache) {
+    // stage the DC-removed capture once (zero before the first sample: zero initial filter state).  One 2-byte IQ pair per
+    // thread and load, four loads in flight; consecutive threads write consecutive 16-byte slots (conflict free).
     {
         const i64 j00 = a0 - nt1;                                // sample staged at X[0]
-        const uintptr_t abase = (uintptr_t)(raw + 2 * j00);
-        const int off = (int)((abase & 7) >> 1);                 // samples between the aligned word and j00
-        const int nwords = (n_raw + off + 3) >> 2;
-        const bool words_ok = (j00 - off >= 0) && (j00 - off + 4 * (i64)nwords <= n0);   // aligned words stay inside this stream's row
-        if (words_ok) {
-            const uint2 *wp = reinterpret_cast<const uint2 *>(abase & ~(uintptr_t)7);
-            constexpr int MAXQ = 4;
-            for (int w0 = 0; w0 < nwords; w0 += MAXQ * nt) {
-                uint2 wv[MAXQ];
+        const unsigned short *rp = reinterpret_cast<const unsigned short *>(raw);
+        constexpr int MAXQ = 4;
+        for (int i0 = 0; i0 < n_raw; i0 += MAXQ * nt) {
+            unsigned wv[MAXQ];
 #pragma unroll
-                for (int q = 0; q < MAXQ; ++q) { const int wi = w0 + tid + q * nt; wv[q] = (wi < nwords) ? __ldg(wp + wi) : make_uint2(0u, 0u); }
-#pragma unroll
-                for (int q = 0; q < MAXQ; ++q) {
-                    const int wi = w0 + tid + q * nt;
-                    if (wi < nwords) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int i = 4 * wi + e - off;
-                            if (i >= 0 && i < n_raw) {
-                                const unsigned pr2 = ((e < 2) ? wv[q].x : wv[q].y) >> (16 * (e & 1));
-                                X[xpad(i)] = make_double2((double)(pr2 & 0xffu) - mur, (double)((pr2 >> 8) & 0xffu) - mui);
-                            }
-                        }
-                    }
-                }
-            }
-        } else {
-            for (int i = tid; i < n_raw; i += nt) {
+            for (int q = 0; q < MAXQ; ++q) {
+                const int i = i0 + tid + q * nt;
                 const i64 j = j00 + i;
-                double2 v = make_double2(0.0, 0.0);
-                if (j >= 0) {
-                    const uchar2 u = *reinterpret_cast<const uchar2 *>(raw + 2 * j);
-                    v = make_double2((double)u.x - mur, (double)u.y - mui);
-                }
-                X[xpad(i)] = v;
+                wv[q] = (i < n_raw && j >= 0 && j < n0) ? (unsigned)__ldg(rp + j) : 0x10000u;      // bit 16: no sample here
+            }
+#pragma unroll
+            for (int q = 0; q < MAXQ; ++q) {
+                const int i = i0 + tid + q * nt;
+                if (i < n_raw)
+                    X[xpad(i)] = (wv[q] & 0x10000u) ? make_double2(0.0, 0.0)
+                                                    : make_double2(u8_to_f64(wv[q] & 0xffu) - mur, u8_to_f64((wv[q] >> 8) & 0xffu) - mui);
             }
         }
     }
-    if (tid < 4) X[n_raw + tid] = make_double2(0.0, 0.0);        // the last output group reads up to 2 samples past the window
+    if (tid < 8) X[n_raw + tid] = make_double2(0.0, 0.0);        // the last output group reads up to LW_R-1 samples past the window
     __syncthreads();
-    double2 *l0 = (use1 || use2) ? Y : dst;
-    if (nt_sel == 48) fir_groups<48>(X, l0, n_l0, tid, nt);
-    else if (nt_sel == 64) fir_groups<64>(X, l0, n_l0, tid, nt);
+    if (nt_sel == 47) fir_groups_c<47>(X, l0, n_l0, tid, nt);
+    else if (nt_sel == 48) fir_groups_c<48>(X, l0, n_l0, tid, nt);
+    else if (nt_sel == 64) fir_groups_c<64>(X, l0, n_l0, tid, nt);
     else {
         // generic tap count: 3 consecutive outputs per thread from a sliding register window of taps
         const int n_grp = (n_l0 + 2) / 3;
@@ -260,6 +267,7 @@ __device__ void load_window(const WinSrc &src, const StreamCtl &c, int stream, i
 #pragma unroll
             for (int r = 0; r < 3; ++r) if (base + r < n_l0) l0[base + r] = make_double2(ar[r], ai[r]);
         }
+    }
     }
     __syncthreads();
     if (!use1 && !use2) {
@@ -989,21 +997,24 @@ __global__ void specific_hit_kernel(const double *__restrict__ snr, i64 n, doubl
 #define CHAIN_THREADS 64
 #define PF_BYTES 5632              // raw bytes one prefetched candidate range may hold ((2*5+2*5+16+3)*64+46 samples at dec 64)
 #define PF_STRIDE (PF_BYTES + PF_BYTES / 8 + 32)   // with one 16-byte pad per 128 bytes (bank spreading for the 128-byte window stride)
-#define CHAIN_MAXSTAGE 2200        // staged DC-removed samples per candidate group (lazy path, dec*(2*5+fft_len-1)+n_taps <= this)
+#define PF_RANGES 2                // candidate ranges per step: after a 10-frame step, after an 11-frame step
 __global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src, StreamCtl *ctl, i64 len, int fft_len, double th, int step10, int step11,
                                                                     int dr, int cap, double *__restrict__ position, double *__restrict__ snr_out) {
     // Each step evaluates the 11 windows around the 10-frame prediction (:47-58) AND the 11 around the 11-frame
     // prediction (:65-76) at once; the second set is only consulted when the first has no hit, as in the reference.
-    // Lazy source: the uint8 samples both groups need are staged with coalesced loads (one memory latency per step),
-    // then every decimated sample is a FIR over shared memory.
-    extern __shared__ double2 stage[];                           // [2][CHAIN_MAXSTAGE + pad] when src.lazy
-    __shared__ double2 tw[128];
-    __shared__ double2 buf[2][128 + 16];
+    // Lazy source: the raw bytes a step can touch are prefetched one step ahead into a double-buffered shared-memory ring with
+    // cp.async, then every decimated sample is a FIR over shared memory.  The footprint (26 KB, 64 threads) lets 7 blocks share an
+    // SM, so the dependent chains of 1024 streams run side by side instead of in waves.
+    extern __shared__ double2 chain_sm[];                        // tw[fft_len] | buf[2][2*5 + fft_len]
     __shared__ int sh_hit; __shared__ double sh_snr;
-    __shared__ __align__(16) unsigned char pf_buf[2 * 3 * PF_STRIDE];
-    __shared__ i64 pf_lo[2][3], pf_hi[2][3];
+    __shared__ __align__(16) unsigned char pf_buf[2 * PF_RANGES * PF_STRIDE];
+    __shared__ i64 pf_lo[2][PF_RANGES], pf_hi[2][PF_RANGES];
     const int stream = blockIdx.x, tid = threadIdx.x;
-    if (tid < 6) { pf_lo[tid / 3][tid % 3] = 0; pf_hi[tid / 3][tid % 3] = 0; }
+    const int max_offset = 5;
+    const int n_cand = 2 * max_offset + 1;
+    const int ns = 2 * max_offset + fft_len;
+    double2 *tw = chain_sm, *buf0 = chain_sm + fft_len, *buf1 = buf0 + ns;
+    if (tid < 2 * PF_RANGES) { pf_lo[tid / PF_RANGES][tid % PF_RANGES] = 0; pf_hi[tid / PF_RANGES][tid % PF_RANGES] = 0; }
     int step_no = 0;
     StreamCtl c = ctl[stream];
     double *pos_o = position + (i64)stream * cap;
@@ -1016,56 +1027,55 @@ __global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src,
         double sn, cs; sincospi(-2.0 * (double)j / (double)fft_len, &sn, &cs);
         tw[j] = make_double2(cs, sn);
     }
-    const int max_offset = 5;
-    const int n_cand = 2 * max_offset + 1;
     const i64 limit = (len - (fft_len - 1)) - max_offset;
-    const int ns = 2 * max_offset + fft_len;
     const int dec = src.dec, nt1 = src.n_taps - 1;
-    const int n_stage = (ns - 1) * dec + src.n_taps;             // raw samples one group touches
-    const bool can_stage = src.lazy && n_stage <= CHAIN_MAXSTAGE;
-    const int stage_cap = CHAIN_MAXSTAGE + CHAIN_MAXSTAGE / 32 + 4;
     const uint8_t *raw = src.raw + (i64)stream * 2 * src.n_iq;
     const double mur = c.mu_re, mui = c.mu_im;
+    // prefetch of the raw bytes around two window centres (decimated indices) into ring slot `slot`
+    auto prefetch = [&](int slot, i64 cen0, i64 cen1) {
+        const i64 centers[PF_RANGES] = {cen0, cen1};
+#pragma unroll
+        for (int q = 0; q < PF_RANGES; ++q) {
+            const i64 lo = (centers[q] - 2 * max_offset - 2) * (i64)dec - nt1, hi = (centers[q] + 2 * max_offset + fft_len + 1) * (i64)dec;
+            const bool okr = lo >= 8 && hi + 8 < src.n_iq && (hi - lo) * 2 + 32 <= PF_BYTES;
+            const uintptr_t a0 = ((uintptr_t)(raw + 2 * lo)) & ~(uintptr_t)15;
+            const int nchunk = okr ? (int)(((uintptr_t)(raw + 2 * hi) - a0 + 15) >> 4) : 0;
+            unsigned char *dstb = pf_buf + (slot * PF_RANGES + q) * PF_STRIDE;
+            for (int ch = tid; ch < nchunk; ch += CHAIN_THREADS) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(dstb + 16 * ch + 16 * (ch >> 3));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(a0 + 16 * (uintptr_t)ch));
+            }
+            if (tid == 0) {
+                pf_lo[slot][q] = okr ? (i64)(((const uint8_t *)a0 - raw) / 2) : 0;      // sample index of byte 0 (a0 >= raw, even offset)
+                pf_hi[slot][q] = okr ? pf_lo[slot][q] + 8 * (i64)nchunk : 0;            // exclusive
+            }
+        }
+        asm volatile("cp.async.commit_group;");
+    };
     i64 pos = c.first_hit;
     int count = 1;
     if (tid == 0) { pos_o[0] = (double)((pos - 1) * dr + 1); snr_o[0] = c.hit_snr; }
+    __syncthreads();
+    if (src.lazy) prefetch(0, pos + step10, pos + step11);       // what the first step reads
     while (count < cap) {
         const i64 nextA = pos + step10, nextB = pos + step11;
         if (nextA > limit) break;                                // run out of sampled signal (:49-51)
         const bool b_ok = nextB <= limit;                        // (:67-69)
         __syncthreads();
-        // ---- shared-memory prefetch (cp.async) of what the FOLLOWING step can touch: its windows sit within +-5 of the 10-/11-frame
-        //      successors of a group-A hit and the 10-frame successor of a group-B hit.  Double buffered: this step reads what the
-        //      previous step requested, so no global-memory latency is left on the per-step critical path. ----
+        // ---- what the FOLLOWING step can touch: its windows sit within +-5 of the 10-frame successor of a group-A hit, or of
+        //      pos + 10 + 11 frames (an A hit followed by an 11-frame step, or a B hit followed by a 10-frame step). ----
         const int cur = step_no & 1, nxt = cur ^ 1;
         if (src.lazy) {
-            const i64 centers[3] = {nextA + step10, nextA + step11, nextB + step10};
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                i64 lo = (centers[q] - 2 * max_offset - 2) * (i64)dec - nt1, hi = (centers[q] + 2 * max_offset + fft_len + 1) * (i64)dec;
-                bool okr = lo >= 8 && hi + 8 < src.n_iq && (hi - lo) * 2 + 32 <= PF_BYTES;
-                const uintptr_t a0 = ((uintptr_t)(raw + 2 * lo)) & ~(uintptr_t)15;
-                const int nchunk = okr ? (int)(((uintptr_t)(raw + 2 * hi) - a0 + 15) >> 4) : 0;
-                unsigned char *dstb = pf_buf + (nxt * 3 + q) * PF_STRIDE;
-                for (int ch = tid; ch < nchunk; ch += CHAIN_THREADS) {
-                    const unsigned sa = (unsigned)__cvta_generic_to_shared(dstb + 16 * ch + 16 * (ch >> 3));
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(a0 + 16 * (uintptr_t)ch));
-                }
-                if (tid == 0) {
-                    pf_lo[nxt][q] = okr ? (i64)(((const uint8_t *)a0 - raw) / 2) : 0;     // sample index of byte 0 (a0 >= raw, even offset)
-                    pf_hi[nxt][q] = okr ? pf_lo[nxt][q] + 8 * (i64)nchunk : 0;            // exclusive
-                }
-            }
+            prefetch(nxt, nextA + step10, nextA + step11);
+            asm volatile("cp.async.wait_group 1;");              // everything except the group just committed has landed
         }
-        asm volatile("cp.async.commit_group;");
-        asm volatile("cp.async.wait_group 1;");                  // everything except the group just committed has landed
         __syncthreads();
         // which prefetched range serves this step's groups?
         int srcA = -1, srcB = -1;
-        if (src.lazy && step_no > 0) {
+        if (src.lazy) {
             const i64 needA0 = (nextA - max_offset - 1) * (i64)dec - nt1, needA1 = (nextA + max_offset + fft_len - 1) * (i64)dec;
             const i64 needB0 = (nextB - max_offset - 1) * (i64)dec - nt1, needB1 = (nextB + max_offset + fft_len - 1) * (i64)dec;
-            for (int q = 0; q < 3; ++q) {
+            for (int q = 0; q < PF_RANGES; ++q) {
                 if (srcA < 0 && pf_hi[cur][q] > 0 && needA0 >= pf_lo[cur][q] && needA1 <= pf_hi[cur][q]) srcA = q;
                 if (srcB < 0 && pf_hi[cur][q] > 0 && needB0 >= pf_lo[cur][q] && needB1 <= pf_hi[cur][q]) srcB = q;
             }
@@ -1077,87 +1087,28 @@ __global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src,
                 const int g = i / ns, r = i % ns;
                 if (g == 1 && !b_ok) continue;
                 const int q = g == 0 ? srcA : srcB;
-                const unsigned char *pb = pf_buf + (cur * 3 + q) * PF_STRIDE;
+                const unsigned char *pb = pf_buf + (cur * PF_RANGES + q) * PF_STRIDE;
                 const i64 s0 = ((g == 0 ? nextA : nextB) - max_offset - 1 + r) * (i64)dec - nt1;   // oldest raw sample of this decimated sample
                 int bo = (int)(2 * (s0 - pf_lo[cur][q]));                                            // byte offset (unpadded)
                 double ar = 0.0, ai = 0.0;
                 for (int k = nt1; k >= 0; --k, bo += 2) {        // oldest tap first
-                    const uchar2 u = *reinterpret_cast<const uchar2 *>(pb + bo + 16 * (bo >> 7));
-                    ar = fma(c_taps[k], (double)u.x - mur, ar);
-                    ai = fma(c_taps[k], (double)u.y - mui, ai);
+                    const unsigned u = *reinterpret_cast<const unsigned short *>(pb + bo + 16 * (bo >> 7));
+                    ar = fma(c_taps[k], u8_to_f64(u & 0xffu) - mur, ar);
+                    ai = fma(c_taps[k], u8_to_f64(u >> 8) - mui, ai);
                 }
-                buf[g][r] = make_double2(ar, ai);
+                (g == 0 ? buf0 : buf1)[r] = make_double2(ar, ai);
             }
-        } else {
-        // the aligned words must stay inside this stream's row (the first samples of a capture use the scalar path)
-        const i64 lo_raw = (nextA - max_offset - 1) * (i64)dec - nt1, hi_raw = (nextB + max_offset + fft_len) * (i64)dec;
-        const bool staged = can_stage && lo_raw >= 4 && hi_raw + 4 < src.n_iq;
-        if (staged) {
-            // 8-byte aligned loads (4 IQ pairs each), all of a thread's loads for both groups in flight at once:
-            // one memory latency per step instead of one per sample
-            constexpr int MAXW = (CHAIN_MAXSTAGE + 3 + 3) / 4 / CHAIN_THREADS + 1;      // words per thread per group
-            uint2 wv[2][MAXW];
-            i64 r0g[2]; int offg[2], nwg[2];
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                const i64 d0 = (g == 0 ? nextA : nextB) - max_offset - 1;     // first decimated index (0-based)
-                r0g[g] = d0 * dec - nt1;                                      // first raw sample staged
-                const uintptr_t a = (uintptr_t)(raw + 2 * r0g[g]);
-                offg[g] = (int)((a & 7) >> 1);                                // samples between the aligned word and r0
-                nwg[g] = (g == 0 || b_ok) ? (n_stage + offg[g] + 3) / 4 : 0;
-                const uint2 *wp = reinterpret_cast<const uint2 *>(a & ~(uintptr_t)7);
-#pragma unroll
-                for (int q = 0; q < MAXW; ++q) {
-                    const int wi = tid + q * CHAIN_THREADS;
-                    wv[g][q] = (wi < nwg[g]) ? __ldg(wp + wi) : make_uint2(0u, 0u);
-                }
-            }
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                double2 *sg = stage + g * stage_cap;
-#pragma unroll
-                for (int q = 0; q < MAXW; ++q) {
-                    const int wi = tid + q * CHAIN_THREADS;
-                    if (wi < nwg[g]) {
-                        const unsigned w2[2] = {wv[g][q].x, wv[g][q].y};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int i = 4 * wi + e - offg[g];
-                            if (i >= 0 && i < n_stage) {
-                                const unsigned pr2 = w2[e >> 1] >> (16 * (e & 1));
-                                sg[i + (i >> 5)] = make_double2((double)(pr2 & 0xffu) - mur, (double)((pr2 >> 8) & 0xffu) - mui);
-                            }
-                        }
-                    }
-                }
-            }
-            __syncthreads();
+        } else {                                                 // first samples / last samples of a capture, materialised source
             for (int i = tid; i < 2 * ns; i += CHAIN_THREADS) {
                 const int g = i / ns, r = i % ns;
-                if (g == 1 && !b_ok) continue;
-                const double2 *sg = stage + g * stage_cap;
-                double ar = 0.0, ai = 0.0;
-                const int b0 = r * dec;
-                for (int k = nt1; k >= 0; --k) {                 // oldest tap first
-                    const int idx = b0 + nt1 - k;
-                    const double2 x = sg[idx + (idx >> 5)];
-                    ar = fma(c_taps[k], x.x, ar);
-                    ai = fma(c_taps[k], x.y, ai);
-                }
-                buf[g][r] = make_double2(ar, ai);
+                if (g == 0 || b_ok) (g == 0 ? buf0 : buf1)[r] = coarse_sample(src, c, stream, (g == 0 ? nextA : nextB) - max_offset - 1 + r);
             }
-        } else {
-            for (int i = tid; i < 2 * ns; i += CHAIN_THREADS) {
-                const int g = i / ns, r = i % ns;
-                if (g == 0 || b_ok) buf[g][r] = coarse_sample(src, c, stream, (g == 0 ? nextA : nextB) - max_offset - 1 + r);
-            }
-        }
         }
         __syncthreads();
         if (tid < 32) {
             double v = 0.0; bool h = false;
             const int g = tid / n_cand, r = tid % n_cand;
-            if (tid < 2 * n_cand && (g == 0 || b_ok)) { v = window_snr(buf[g] + r, fft_len, tw); h = (v - c.hit_avg_snr) > th; }
+            if (tid < 2 * n_cand && (g == 0 || b_ok)) { v = window_snr((g == 0 ? buf0 : buf1) + r, fft_len, tw); h = (v - c.hit_avg_snr) > th; }
             const unsigned mask = __ballot_sync(0xffffffffu, h);
             const unsigned mA = mask & ((1u << n_cand) - 1), mB = (mask >> n_cand) & ((1u << n_cand) - 1);
             int l = -1;
@@ -1172,6 +1123,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src,
         if (tid == 0) { pos_o[count] = (double)((pos - 1) * dr + 1); snr_o[count] = sh_snr; }
         ++count;
     }
+    asm volatile("cp.async.wait_group 0;");                      // no copy may still be in flight when the block retires
     if (tid == 0) ctl[stream].n_coarse = count;
 }
 
@@ -1340,7 +1292,11 @@ __global__ void __launch_bounds__(FB_THREADS, 4) fine_peak_band_kernel(WinSrc sr
     const i64 sp = (position - max_offset - 1) * osr + 1;
     double2 *win = sm;
     double2 *X = win + n_smp;
-    {   // level 0: only the staging scratch X is used; three passes keep it small (4 blocks per SM)
+    if (src.wcache && osr == 8) {   // tier 1 (fine_core8_kernel) left the filtered window in the cache: no staging, no FIR
+        const double2 *wc = src.wcache + ((i64)stream * src.wc_cap + burst) * B8_WLEN;
+        for (int i = tid; i < n_smp; i += FB_THREADS) win[i] = wc[B8_WPAD(i)];
+        __syncthreads();
+    } else {   // level 0: only the staging scratch X is used; three passes keep it small (4 blocks per SM)
         const int part_n = (n_smp + 2) / 3;
         for (int off = 0; off < n_smp; off += part_n)
             load_window(src, c, stream, sp - 1 + off, (n_smp - off < part_n) ? n_smp - off : part_n, win + off, X, X);
@@ -1775,7 +1731,7 @@ __device__ __forceinline__ double2 dft_col(const double2 *Tm, int k, int N, cons
 // (N*sum|u|^2 - sum_band P < max_band P); otherwise all N bins are evaluated.
 #define TONE_THREADS 256
 #define TONE_BAND 16
-__global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, int which /* 1: fine stage, 2: post-SCH */,
+__global__ void __launch_bounds__(TONE_THREADS, 3) tone_est_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, int which /* 1: fine stage, 2: post-SCH */,
                                                                const double *__restrict__ pos, int cap, int osr, const double2 *__restrict__ tw,
                                                                double *__restrict__ fo_out, double *__restrict__ gate_out) {
     extern __shared__ double2 sm[];
@@ -1794,7 +1750,7 @@ __global__ void __launch_bounds__(TONE_THREADS) tone_est_kernel(WinSrc src, cons
     double2 *u = sm, *A = u + N, *F = A + N;
     double2 *X = A, *Y = X + GSMCAL_XCAP(N);                  // the loader's scratch aliases the FFT work buffers
     const i64 sp = (i64)pos[(i64)stream * cap + burst];
-    load_window(src, c, stream, sp - 1, N, u, X, Y);
+    load_window(src, c, stream, sp - 1, N, u, X, Y, burst);       // burst: level 0 comes from the fine search's window cache when it covers the range
     // energy and phase slope -> band centre
     double epq[3] = {0.0, 0.0, 0.0};
     for (int n = tid; n < N; n += TONE_THREADS) {

@@ -276,6 +276,36 @@ def test_calibrate_batch_matches_function_chain(gpu, captures, coef47, tpl):
         _check_stream(got[d], oracle.calibrate_stream(raw[d], CARRIER, tpl, coef47))
 
 
+def test_osr8_fast_path_equals_round1_kernels(gpu, captures, coef47, tpl):
+    """fine_core8_kernel + filtered-window cache (tier 2 and both tone stages read it) against the generic tier-1 kernel that
+    re-filters in every stage (debug key 9): every output identical, ppm included (the cached samples are the same bits)."""
+    from gsmcal._lib import lib
+    _, raw = captures
+    new = gpu.calibrate_batch(raw, CARRIER, tpl, coef47)
+    lib().gsmcal_debug_set(9, 1)
+    try:
+        old = gpu.calibrate_batch(raw, CARRIER, tpl, coef47)
+    finally:
+        lib().gsmcal_debug_set(9, 0)
+    for d, (a, b) in enumerate(zip(new, old)):
+        for k in ("coarse_pos", "coarse_snr", "fcch_pos", "pos_info"):
+            assert np.array_equal(a[k], b[k]), k
+        assert a["sampling_ppm"] == b["sampling_ppm"] and a["flags"] & ~32 == b["flags"] & ~32
+        assert np.allclose(a["carrier_ppm"], b["carrier_ppm"], rtol=0, atol=1e-9)
+        if d < 2:
+            _check_stream(a, oracle.calibrate_stream(raw[d], CARRIER, tpl, coef47))
+
+
+def test_osr8_fast_path_other_tap_counts(gpu, captures, tpl):
+    """the 48- and 64-tap instantiations of the fast path (zero-padded on the old side) and a filter too long for it (generic path)"""
+    _, raw = captures
+    for order in (30, 47, 63, 70):
+        coef = oracle.fir1(order, 200e3 / FS)
+        got = gpu.calibrate_batch(raw[:2], CARRIER, tpl, coef)
+        for d in range(2):
+            _check_stream(got[d], oracle.calibrate_stream(raw[d], CARRIER, tpl, coef))
+
+
 def test_calibrate_batch_matches_golden(gpu, captures, coef47, tpl):
     _, raw = captures
     with open(os.path.join(GOLDEN, "pipeline_golden.json")) as f:
