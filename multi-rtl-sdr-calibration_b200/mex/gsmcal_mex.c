@@ -109,7 +109,10 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     (void)nlhs; init_once();
     if (nrhs < 2 || nrhs > 3) mexErrMsgIdAndTxt("gsmcal:nargin", "usage: r = fir_filter(coef, s [, decim])");
     size_t nt; const double *coef = real_vector(prhs[0], &nt);
-    int decim = nrhs == 3 ? (int)mxGetScalar(prhs[2]) : 1;
+    double decim_d = nrhs == 3 ? mxGetScalar(prhs[2]) : 1.0;
+    if (!(decim_d >= 1.0 && decim_d <= 1e9) || decim_d != floor(decim_d))      /* before any size is derived from it */
+        mexErrMsgIdAndTxt("gsmcal:decim", "fir_filter: decim must be a positive integer");
+    int decim = (int)decim_d;
     size_t rows = mxGetM(prhs[1]), cols = mxGetN(prhs[1]);
     int own; const double *s = get_c128(prhs[1], &own);
     size_t n_out = (rows + decim - 1) / decim;

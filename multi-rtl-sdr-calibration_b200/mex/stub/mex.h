@@ -1,5 +1,6 @@
-/* mex.h - minimal stand-in for the MATLAB/Octave MEX API (split-complex flavour, as Octave and pre-R2018a MATLAB),
- * enough to compile mex/gsmcal_mex.c and drive its gateways from a C test harness.  NOT a MATLAB replacement. */
+/* mex.h - minimal stand-in for the MATLAB/Octave MEX API, enough to compile mex/gsmcal_mex.c and drive its gateways from a C
+ * test harness.  NOT a MATLAB replacement.  Default: split complex (Octave, pre-R2018a MATLAB: mxGetPr/mxGetPi); with
+ * -DMX_HAS_INTERLEAVED_COMPLEX=1: the -R2018a flavour (mxGetComplexDoubles / mxGetDoubles, complex data interleaved in `re`). */
 #ifndef GSMCAL_STUB_MEX_H
 #define GSMCAL_STUB_MEX_H
 #include <math.h>
@@ -42,9 +43,18 @@ static mxArray *mxCreateNumericArray(size_t ndim, const size_t *dims, mxClassID 
     a->cls = cls; a->is_complex = (c == mxCOMPLEX); a->ndim = ndim;
     size_t n = 1; for (size_t i = 0; i < ndim; ++i) { a->dims[i] = dims[i]; n *= dims[i]; }
     size_t es = (cls == mxDOUBLE_CLASS) ? 8 : 1;
+#if defined(MX_HAS_INTERLEAVED_COMPLEX) && MX_HAS_INTERLEAVED_COMPLEX
+    a->re = calloc((n ? n : 1) * (a->is_complex ? 2 : 1), es); a->im = NULL;
+#else
     a->re = calloc(n ? n : 1, es); a->im = a->is_complex ? calloc(n ? n : 1, es) : NULL;
+#endif
     return a;
 }
+#if defined(MX_HAS_INTERLEAVED_COMPLEX) && MX_HAS_INTERLEAVED_COMPLEX
+typedef struct { double real, imag; } mxComplexDouble;
+static mxComplexDouble *mxGetComplexDoubles(const mxArray *a) { return (mxComplexDouble *)a->re; }
+static double *mxGetDoubles(const mxArray *a) { return (double *)a->re; }
+#endif
 static mxArray *mxCreateDoubleMatrix(size_t m, size_t n, mxComplexity c) { size_t d[2] = {m, n}; return mxCreateNumericArray(2, d, mxDOUBLE_CLASS, c); }
 static mxArray *mxCreateDoubleScalar(double v) { mxArray *a = mxCreateDoubleMatrix(1, 1, mxREAL); ((double *)a->re)[0] = v; return a; }
 static mxArray *mxCreateLogicalScalar(int v) { size_t d[2] = {1, 1}; mxArray *a = mxCreateNumericArray(2, d, mxLOGICAL_CLASS, mxREAL); ((unsigned char *)a->re)[0] = v ? 1 : 0; return a; }

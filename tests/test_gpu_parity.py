@@ -610,3 +610,68 @@ def test_submit_collect_matches_synchronous_call(gpu, captures, coef47, tpl):
     # slots are reusable, and the synchronous call still works in between
     again = gpu.calibrate_batch_submit(0, b.data_ptr(), N_SYNC, 3, CARRIER, tpl, coef47, cuda_stream=st, details=True).collect()
     assert [x["pos_info"].tolist() for x in again] == [y["pos_info"].tolist() for y in ref_b]
+
+
+# ---- deliberate fixtures through the DROP-IN entry points, each asserting the branch it took ----------------
+def _same_fine(got, ref, r_tol):
+    assert np.array_equal(got[0], ref[0])
+    assert (got[1] is None) == (ref[1] is None)
+    if ref[1] is not None:
+        assert len(got[1]) == len(ref[1]) and rel_err(got[1], ref[1]) < r_tol
+    assert (got[2] == ref[2]) if math.isinf(ref[2]) else got[2] == ref[2]
+    assert (got[3] == ref[3]) if math.isinf(ref[3]) else abs(got[3] - ref[3]) < 1e-3
+
+
+def test_appendix_a_fine_overrun_returns_four_positions(gpu):
+    import appendix_a_fixtures as fx
+    args, took = fx.fine_overrun_drops_to_four()                     # FCCH_fine_correction.m:135-137,142
+    ref, got = oracle.FCCH_fine_correction(*args), gpu.FCCH_fine_correction(*args)
+    assert took(ref) and took(got)
+    _same_fine(got, ref, 1e-13)                                      # r is resampled only on this path
+
+
+def test_appendix_a_fine_snr_gate_return(gpu):
+    import appendix_a_fixtures as fx
+    args, took = fx.fine_snr_gate_return()                           # FCCH_fine_correction.m:192-196
+    ref, got = oracle.FCCH_fine_correction(*args), gpu.FCCH_fine_correction(*args)
+    assert took(ref) and took(got)
+    _same_fine(got, ref, 1e-8)                                       # r is resampled and derotated
+
+
+def test_appendix_a_sch_paths(gpu, tpl):
+    import appendix_a_fixtures as fx
+    args, took, _ = fx.sch_e_zero_skips_interp1(tpl)                 # SCH_corr_rate_correction.m:120-128
+    ref, got = oracle.SCH_corr_rate_correction(*args), gpu.SCH_corr_rate_correction(*args)
+    assert took(ref) and took(got) and np.array_equal(got[0], ref[0]) and got[2] == ref[2] == 0.0
+    for build in (fx.sch_last_slot_does_not_fit, fx.sch_bcch_rows_run_out):      # :153-159, :167-178
+        args, took = build(tpl)
+        ref, got = oracle.SCH_corr_rate_correction(*args), gpu.SCH_corr_rate_correction(*args)
+        assert took(ref) and took(got)
+        assert np.array_equal(got[0], ref[0]) and got[2] == ref[2] and np.array_equal(got[1], ref[1])
+
+
+def test_planted_known_answers_through_the_c_abi(gpu, tpl):
+    """hand-derived answers (no oracle involved): templates planted on the ideal grid -> pos_info rows by the rules of
+    SCH_corr_rate_correction.m:138-181; tones planted at known starts -> FCCH_pos, 0 ppm sampling error, the planted carrier offset"""
+    osr, frame = 8, 10000
+    for gaps, flagged in (((10, 10, 10, 11, 10, 10), {5}), ((10, 10, 10, 10, 11, 10), {1, 6}), ((10, 10, 10, 10, 10), set())):
+        fcch = np.cumsum([2001] + [g * frame for g in gaps]).astype(np.float64)
+        n = int(fcch[-1]) + 10336 + 512 + 5 * frame
+        s = np.zeros(n, dtype=np.complex128)
+        for p in fcch:
+            s[int(p) + 10336 - 1:int(p) + 10336 - 1 + 512] = tpl
+        pos_info, r, ppm = gpu.SCH_corr_rate_correction(s, fcch, tpl, osr)
+        rows = []
+        for i, p in enumerate(fcch, 1):
+            rows += [[p, 0.0], [p + 10000, 1.0]] + ([[p + 10000 + k * frame, 2.0] for k in (1, 2, 3, 4)] if i in flagged else [])
+        assert pos_info.tolist() == rows and ppm == 0.0 and np.array_equal(r, s)
+    f_off = 2500.0
+    rg = np.random.default_rng(5)
+    starts = np.cumsum([30001] + [g * frame for g in (10, 10, 11, 10, 10)])
+    n = int(starts[-1]) + 3 * frame
+    s = 1e-3 * (rg.standard_normal(n) + 1j * rg.standard_normal(n))
+    for p in starts:
+        s[p - 1:p - 1 + 1184] += np.exp(2j * np.pi * (oracle.SYMBOL_RATE / 4 + f_off) * (p - 1 + np.arange(1184)) / FS)
+    base = np.round((starts - 1) / osr) + 1 + np.array([3, -7, 0, 11, -20, 5])
+    fpos, r, sppm, cppm = gpu.FCCH_fine_correction(s, base, osr, CARRIER)
+    assert fpos.tolist() == starts.astype(float).tolist() and sppm == 0.0 and abs(cppm - 1e6 * f_off / CARRIER) < 1e-3

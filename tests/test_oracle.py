@@ -378,3 +378,21 @@ def test_fine_correction_known_answer_on_planted_tones():
     # r = s .* exp(1i*n*comp) (:163-165): the tone sits on fs_sym/4 afterwards
     fo, _, _ = oracle.tone_freq_estimate(r, fpos, n_tone, FS)
     assert abs(oracle.matlab_mean(fo) - oracle.SYMBOL_RATE / 4) < 1e-6 and np.max(np.abs(fo - oracle.SYMBOL_RATE / 4)) < 2.0   # mean exact, bursts within noise
+
+
+# ---- SURVEY Appendix A paths that random captures rarely reach: the deliberate fixtures do drive the oracle there -------------
+def test_appendix_a_fixtures_take_their_branches():
+    import appendix_a_fixtures as fx
+    tpl = oracle.gsm_SCH_training_sequence_gen(8)
+    args, took = fx.fine_overrun_drops_to_four()
+    assert took(oracle.FCCH_fine_correction(*args))                 # FCCH_fine_correction.m:135-137,142
+    args, took = fx.fine_snr_gate_return()
+    info = {}
+    res = oracle.FCCH_fine_correction(*args, info)
+    assert took(res) and np.min(info["fine_gate_snr"]) < 5.0 - 3.0  # :192-196, well below the 5 dB gate
+    args, took, _ = fx.sch_e_zero_skips_interp1(tpl)
+    assert took(oracle.SCH_corr_rate_correction(*args))             # SCH_corr_rate_correction.m:120-128
+    args, took = fx.sch_last_slot_does_not_fit(tpl)
+    assert took(oracle.SCH_corr_rate_correction(*args))             # :153-159
+    args, took = fx.sch_bcch_rows_run_out(tpl)
+    assert took(oracle.SCH_corr_rate_correction(*args))             # :167-178
