@@ -517,6 +517,7 @@ def main():
     ap.add_argument("--persist-colsum", type=int, default=None)
     ap.add_argument("--no-hi-prio", action="store_true")
     ap.add_argument("--stages", action="store_true", help="also time the materialising per-stage kernels (raw2iq, FIR, resample, derotate)")
+    ap.add_argument("--debug", action="append", default=[], metavar="KEY=VALUE", help="gsmcal_debug_set(KEY, VALUE) before the run (A/B of kernel paths, see include/gsmcal.h)")
     ap.add_argument("--ingest", type=int, default=0, metavar="D",
                     help="instead of the benchmark: D loopback rtl_tcp replay servers -> gsmcal.ingest -> calibrate (SURVEY 8(f) row 1)")
     args = ap.parse_args()
@@ -565,6 +566,9 @@ def main():
     if args.persist_colsum is not None:
         L.gsmcal_debug_set(7, args.persist_colsum)
     L.gsmcal_debug_set(8, args.submit_groups)
+    for kv in args.debug:
+        k_, _, v_ = kv.partition("=")
+        L.gsmcal_debug_set(int(k_), int(v_))
     stream = torch.cuda.current_stream()
     rec_bytes = C.sizeof(StreamResult)
     gathered = torch.empty((world * sub * rec_bytes,), dtype=torch.uint8, device=dev) if world > 1 else None
@@ -688,7 +692,9 @@ def main():
         sync_step()
         for k, v in gsmcal.api.last_batch_stage_ms().items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v
-        tiers = {"tier2": int(L.gsmcal_debug_get(2)), "tier3": int(L.gsmcal_debug_get(1))}
+        tiers = {"tier2": int(L.gsmcal_debug_get(2)), "tier3": int(L.gsmcal_debug_get(1)),
+                 "tier1_proven_after_passes": {str(p_): int(L.gsmcal_debug_get(10 + p_)) for p_ in range(1, 9)},
+                 "tier1_left_open": int(L.gsmcal_debug_get(10))}
     L.gsmcal_debug_set(3, args.groups)
     stage_ms = {k: v / n_prof for k, v in stage_acc.items()}
 
@@ -783,6 +789,7 @@ def main():
                 "cpu_baseline": cpu_baseline, "stage_ms": stage_ms, "stage_ms_note": f"sequential pass over all {D} streams of rank 0 (one stream group)",
                 "streams_fully_calibrated": f"{n_ok}/{D} on rank 0", "oracle_agreement": agreement, "synchronous_call": sync_call,
                 "fine_search_allbin_fallback_bursts": tiers["tier3"], "fine_search_64bin_tier2_bursts": tiers["tier2"], "bursts_rank0": n_bursts,
+                "fine_search_tier1": {k: tiers.get(k) for k in ("tier1_proven_after_passes", "tier1_left_open")}, "debug_keys": args.debug,
                 "configs": configs, "reference_runtime_probe": probe_reference_runtimes(), "synthetic_generation_s": t_gen}
         if stages is not None:
             line["stage_rooflines"] = stages

@@ -216,9 +216,11 @@ int gsmcal_fcch_scan(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t n_ch
  * 3 = stream groups of gsmcal_calibrate_batch; 4 = pretend the tier-1/2 certificates failed; 5 = tier-3 list limit;
  * 6 = burst chain on high-priority streams (default 1); 7 = blocks per SM of a persistent high-priority column-sum kernel in
  * _submit (default 0 = per-group launches); 8 = stream groups inside a submitted batch (default 1); 9, value 1 = the generic tier-1 fine
- * search without the osr-8 fast path and its filtered-window cache (A/B and tests) */
+ * search without the osr-8 fast path and its filtered-window cache (A/B and tests); 10 = passes of 8 tracked bins in the osr-8 tier-1
+ * kernel (1..8, default 6); 11, value 1 = generic tone estimator for every burst (no tone8_kernel) */
 int gsmcal_debug_set(int key, int value);
-/* key 1: number of bursts of the last fine FCCH search whose band certificate failed (all-bin fallback ran) */
+/* key 1: number of bursts of the last fine FCCH search whose band certificate failed (all-bin fallback ran); 2: bursts that needed the
+ * 64-bin band kernel; 10 + p: bursts the osr-8 tier-1 kernel proved after p passes (p = 0: left open) */
 int64_t gsmcal_debug_get(int key);
 
 /* kernel-launch counter (all launches since the last reset, this process) - for bench.py's gpu_launches */

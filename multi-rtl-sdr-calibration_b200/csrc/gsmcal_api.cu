@@ -33,6 +33,9 @@ int g_debug_force_full = 0;       // tests: run the all-bin fine search for ever
 int g_debug_submit_groups = 1;    // stream groups inside a submitted batch
 int g_debug_persist_colsum = 0;   // submit/collect: blocks per SM of the persistent high-priority column-sum kernel (0 = per-group launches)
 int g_debug_hi_prio = 1;          // burst chain of each stream group on a high-priority CUDA stream
+int g_debug_core8_passes = B8_NPASS; // passes of 8 tracked bins in fine_core8_kernel (1..8)
+unsigned *g_last_pass_hist = nullptr;
+int g_debug_no_tone8 = 0;          // tests / A-B: 1 = generic tone estimator for every burst
 int g_debug_no_core8 = 0;         // tests / A-B: 1 = round-1 tier-1 kernel and no filtered-window cache
 
 int fail(int code, const char *fmt, ...) {
@@ -135,8 +138,8 @@ size_t tone_smem(int osr) {
 size_t sch_smem(int osr) {
     int L = 64 * osr, ns = 16 * osr - 5 * osr + 1 + L - 1;
     size_t slots = (size_t)(2 * ns + L + 8 + GSMCAL_XCAP(ns));
-    if (osr == 8) {     // register-tiled path: padded window + padded template + 192 partial-sum rows of 33 doubles behind X
-        size_t need = (size_t)(ns + L + 8) + (size_t)(ns + (ns >> 4) + 2) + (size_t)(L + (L >> 4) + 2) + (192 * 33 + 1) / 2 + 2;
+    if (osr == 8) {     // register-tiled path: padded window + padded template + 96 partial-sum rows of 9 doubles behind X
+        size_t need = (size_t)(ns + L + 8) + (size_t)(ns + (ns >> 4) + 2) + (size_t)(L + (L >> 4) + 2) + (96 * 9 + 1) / 2 + 2;
         if (slots < need) slots = need;
     }
     return slots * sizeof(double2);
@@ -152,6 +155,7 @@ int get_ctx(Ctx **out) {
         CU(cudaFuncSetAttribute(fine_core8_kernel<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, B8_SMEM));
         CU(cudaFuncSetAttribute(fine_core8_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, B8_SMEM));
         CU(cudaFuncSetAttribute(fine_core8_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, B8_SMEM));
+        CU(cudaFuncSetAttribute(tone8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T8_SMEM));
         CU(cudaFuncSetAttribute(tone_est_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(sch_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CU(cudaFuncSetAttribute(fir_full_tma_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -203,8 +207,9 @@ int set_taps(const double *coef, int n_taps, cudaStream_t st) {
 struct Work {
     StreamCtl *ctl; StreamResultDev *res;
     double *coarse_pos, *coarse_snr, *fine_raw, *fcch_pos, *fo, *gate, *sch_raw, *sch_pos, *post_pos, *pos_info, *snr_map, *power;
-    int *sch_edge, *need_full, *need_band, *fall_list, *fall_count, *fall_m; double *fall_best; unsigned char *kind; double2 *tpl;
+    int *sch_edge, *need_full, *need_band, *tone_need, *fall_list, *fall_count, *fall_m; double *fall_best; unsigned char *kind; double2 *tpl;
     i64 snr_stride;
+    unsigned *pass_hist;          // [16] fine_core8_kernel: bursts proven after p passes ([0] = left to the band kernel)
     double2 *wcache;              // [D][cap][B8_WLEN] or nullptr (set by attach_wcache)
     bool wc_valid;                // the fine search of this call filled the cache
 };
@@ -218,7 +223,7 @@ int make_work(DevBuf &wb, i64 D, int cap, i64 snr_len, int tpl_len, Work *w) {
     size_t per = sizeof(double) * D * cap;
     size_t o_cp = take(per), o_cs = take(per), o_fr = take(per), o_fp = take(per), o_fo = take(per), o_g = take(per), o_sr = take(per), o_sp = take(per), o_pp = take(per);
     size_t o_pi = take(per * 12), o_snr = take(sizeof(double) * D * snr_len), o_pw = take(sizeof(double) * D);
-    size_t o_se = take(sizeof(int) * D * cap), o_nf = take(sizeof(int) * D * cap), o_nb = take(sizeof(int) * D * cap), o_fl = take(sizeof(int) * D * cap), o_fc = take(sizeof(int) * D), o_fm = take(sizeof(int) * (size_t)FALL_GRID * 24 * kMaxGroups), o_fb = take(sizeof(double) * (size_t)FALL_GRID * 24 * kMaxGroups), o_k = take(D * cap), o_tpl = take(sizeof(double2) * (tpl_len > 0 ? tpl_len : 1));
+    size_t o_se = take(sizeof(int) * D * cap), o_nf = take(sizeof(int) * D * cap), o_nb = take(sizeof(int) * D * cap), o_tn = take(sizeof(int) * D * cap), o_fl = take(sizeof(int) * D * cap), o_fc = take(sizeof(int) * D), o_fm = take(sizeof(int) * (size_t)FALL_GRID * 24 * kMaxGroups), o_fb = take(sizeof(double) * (size_t)FALL_GRID * 24 * kMaxGroups), o_k = take(D * cap), o_tpl = take(sizeof(double2) * (tpl_len > 0 ? tpl_len : 1)), o_ph = take(sizeof(unsigned) * 16);
     void *base;
     TRY(wb.get(off, &base));
     char *b = static_cast<char *>(base);
@@ -226,8 +231,9 @@ int make_work(DevBuf &wb, i64 D, int cap, i64 snr_len, int tpl_len, Work *w) {
     w->coarse_pos = (double *)(b + o_cp); w->coarse_snr = (double *)(b + o_cs); w->fine_raw = (double *)(b + o_fr); w->fcch_pos = (double *)(b + o_fp);
     w->fo = (double *)(b + o_fo); w->gate = (double *)(b + o_g); w->sch_raw = (double *)(b + o_sr); w->sch_pos = (double *)(b + o_sp); w->post_pos = (double *)(b + o_pp);
     w->pos_info = (double *)(b + o_pi); w->snr_map = (double *)(b + o_snr); w->power = (double *)(b + o_pw);
-    w->sch_edge = (int *)(b + o_se); w->need_full = (int *)(b + o_nf); w->need_band = (int *)(b + o_nb); w->fall_list = (int *)(b + o_fl); w->fall_count = (int *)(b + o_fc); w->fall_m = (int *)(b + o_fm); w->fall_best = (double *)(b + o_fb); w->kind = (unsigned char *)(b + o_k); w->tpl = (double2 *)(b + o_tpl);
+    w->sch_edge = (int *)(b + o_se); w->need_full = (int *)(b + o_nf); w->need_band = (int *)(b + o_nb); w->tone_need = (int *)(b + o_tn); w->fall_list = (int *)(b + o_fl); w->fall_count = (int *)(b + o_fc); w->fall_m = (int *)(b + o_fm); w->fall_best = (double *)(b + o_fb); w->kind = (unsigned char *)(b + o_k); w->tpl = (double2 *)(b + o_tpl);
     w->snr_stride = snr_len;
+    w->pass_hist = (unsigned *)(b + o_ph);
     w->wcache = nullptr; w->wc_valid = false;
     return GSMCAL_OK;
 }
@@ -250,7 +256,7 @@ Work sub_work(const Work &w, i64 d0, int cap, int group) {
     s.ctl += d0; s.res += d0; s.power += d0;
     s.coarse_pos += d0 * cap; s.coarse_snr += d0 * cap; s.fine_raw += d0 * cap; s.fcch_pos += d0 * cap; s.fo += d0 * cap; s.gate += d0 * cap;
     s.sch_raw += d0 * cap; s.sch_pos += d0 * cap; s.post_pos += d0 * cap; s.pos_info += d0 * cap * 12; s.snr_map += d0 * w.snr_stride;
-    s.sch_edge += d0 * cap; s.need_full += d0 * cap; s.need_band += d0 * cap; s.kind += d0 * cap;
+    s.sch_edge += d0 * cap; s.need_full += d0 * cap; s.need_band += d0 * cap; s.tone_need += d0 * cap; s.kind += d0 * cap;
     s.fall_list += d0 * cap; s.fall_count += d0;
     s.fall_m += (size_t)group * FALL_GRID * 24; s.fall_best += (size_t)group * FALL_GRID * 24;
     if (s.wcache) s.wcache += (size_t)d0 * cap * B8_WLEN;
@@ -328,9 +334,9 @@ int run_fine_peak(Ctx &c, WinSrc src_peak, i64 n_iq, int osr, i64 D, int cap, Wo
     if (src_peak.lazy && osr == 8 && src_peak.n_taps <= 64 && !g_debug_no_core8) {
         // osr-8 fast path: FIR once per burst, filtered window cached for tier 2 and the tone stages
         const dim3 grid((unsigned)cap, (unsigned)D);
-        if (src_peak.n_taps == 47)      LAUNCH((fine_core8_kernel<47>), grid, B8_THREADS, B8_SMEM, st, src_peak.raw, n_iq, w.ctl, w.coarse_pos, cap, tw, w.fine_raw, w.need_band, g_debug_fail_tier2, w.wcache);
-        else if (src_peak.n_taps <= 48) LAUNCH((fine_core8_kernel<48>), grid, B8_THREADS, B8_SMEM, st, src_peak.raw, n_iq, w.ctl, w.coarse_pos, cap, tw, w.fine_raw, w.need_band, g_debug_fail_tier2, w.wcache);
-        else                            LAUNCH((fine_core8_kernel<64>), grid, B8_THREADS, B8_SMEM, st, src_peak.raw, n_iq, w.ctl, w.coarse_pos, cap, tw, w.fine_raw, w.need_band, g_debug_fail_tier2, w.wcache);
+        if (src_peak.n_taps == 47)      LAUNCH((fine_core8_kernel<47>), grid, B8_THREADS, B8_SMEM, st, src_peak.raw, n_iq, w.ctl, w.coarse_pos, cap, tw, w.fine_raw, w.need_band, g_debug_fail_tier2, w.wcache, g_debug_core8_passes, w.pass_hist);
+        else if (src_peak.n_taps <= 48) LAUNCH((fine_core8_kernel<48>), grid, B8_THREADS, B8_SMEM, st, src_peak.raw, n_iq, w.ctl, w.coarse_pos, cap, tw, w.fine_raw, w.need_band, g_debug_fail_tier2, w.wcache, g_debug_core8_passes, w.pass_hist);
+        else                            LAUNCH((fine_core8_kernel<64>), grid, B8_THREADS, B8_SMEM, st, src_peak.raw, n_iq, w.ctl, w.coarse_pos, cap, tw, w.fine_raw, w.need_band, g_debug_fail_tier2, w.wcache, g_debug_core8_passes, w.pass_hist);
         w.wc_valid = (w.wcache != nullptr);
         src_peak = with_cache(src_peak, w, cap);
     } else
@@ -346,10 +352,23 @@ int run_fine_peak(Ctx &c, WinSrc src_peak, i64 n_iq, int osr, i64 D, int cap, Wo
            (const int *)w.fall_list, (const int *)w.fall_count, g_debug_fall_limit);
     return GSMCAL_OK;
 }
+// per-burst tone estimate: with the filtered-window cache (osr 8) tone8_kernel does every burst it can certify and flags the others
+// for the generic row-FFT kernel; without a cache the generic kernel does them all
+int run_tone(WinSrc src, int which, const double *pos, int osr, i64 D, int cap, const double2 *tw, Work &w, cudaStream_t st) {
+    const int *need = nullptr;
+    if (src.lazy && src.wcache && osr == 8 && !g_debug_no_tone8) {
+        CU(cudaMemsetAsync(w.tone_need, 0, sizeof(int) * D * cap, st));
+        LAUNCH(tone8_kernel, dim3((unsigned)cap, (unsigned)D), T8_THREADS, T8_SMEM, st, src, w.ctl, which, pos, cap, tw, w.fo, w.gate, w.tone_need);
+        need = w.tone_need;
+    }
+    LAUNCH(tone_est_kernel, dim3((unsigned)cap, (unsigned)D), TONE_THREADS, tone_smem(osr), st, src, w.ctl, which, pos, cap, osr, tw, w.fo, w.gate, need);
+    return GSMCAL_OK;
+}
+
 int run_fine_rest(Ctx &c, WinSrc src_tone, i64 n_iq, int osr, double carrier_freq, i64 D, int cap, Work &w, cudaStream_t st) {
     const double2 *tw; TRY(get_twiddle(c, 148 * osr, st, &tw));
     LAUNCH(fine_ppm_kernel, (unsigned)D, PS_THREADS, (size_t)cap * 17 + 16, st, w.ctl, (int)D, cap, osr, n_iq, w.fine_raw, w.fcch_pos, w.kind);
-    LAUNCH(tone_est_kernel, dim3((unsigned)cap, (unsigned)D), TONE_THREADS, tone_smem(osr), st, src_tone, w.ctl, 1, w.fcch_pos, cap, osr, tw, w.fo, w.gate);
+    TRY(run_tone(src_tone, 1, w.fcch_pos, osr, D, cap, tw, w, st));
     LAUNCH(fine_carrier_kernel, (unsigned)D, PS_THREADS, (size_t)cap * 16, st, w.ctl, (int)D, cap, osr, carrier_freq, w.fo, w.gate);
     return GSMCAL_OK;
 }
@@ -367,7 +386,7 @@ int run_sch(WinSrc src, int osr, i64 D, int cap, Work &w, cudaStream_t st) {
 
 int run_post(Ctx &c, WinSrc src, int osr, double carrier_freq, i64 D, int cap, Work &w, bool want_res, cudaStream_t st) {
     const double2 *tw; TRY(get_twiddle(c, 148 * osr, st, &tw));
-    LAUNCH(tone_est_kernel, dim3((unsigned)cap, (unsigned)D), TONE_THREADS, tone_smem(osr), st, src, w.ctl, 2, w.post_pos, cap, osr, tw, w.fo, w.gate);
+    TRY(run_tone(src, 2, w.post_pos, osr, D, cap, tw, w, st));
     LAUNCH(post_carrier_kernel, (unsigned)D, PS_THREADS, (size_t)cap * 8, st, w.ctl, (int)D, cap, osr, carrier_freq, w.fo, want_res ? w.res : nullptr);
     return GSMCAL_OK;
 }
@@ -467,6 +486,12 @@ void gsmcal_release(void) {
 int64_t gsmcal_debug_get(int key) {
     // key 1: bursts of the last fine search (this device) that needed the all-bin fallback
     std::lock_guard<std::mutex> lk(g_mu);
+    if (key >= 10 && key < 26) {                                 // 10 + p: bursts the osr-8 tier-1 kernel proved after p passes (p = 0: left open)
+        if (!g_last_pass_hist) return 0;
+        unsigned v = 0;
+        if (cudaMemcpy(&v, g_last_pass_hist + (key - 10), sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        return (int64_t)v;
+    }
     if (key == 1 || key == 2) {
         const int *src = (key == 1) ? g_last_need_full : g_last_need_band;
         if (!src || g_last_need_full_n <= 0) return 0;
@@ -484,6 +509,8 @@ int gsmcal_debug_set(int key, int value) {
     if (key == 5) { g_debug_fall_limit = value < 0 ? 0 : (value > FALL_GRID ? FALL_GRID : value); return GSMCAL_OK; }
     if (key == 6) { g_debug_hi_prio = value ? 1 : 0; return GSMCAL_OK; }
     if (key == 9) { g_debug_no_core8 = value ? 1 : 0; return GSMCAL_OK; }
+    if (key == 11) { g_debug_no_tone8 = value ? 1 : 0; return GSMCAL_OK; }
+    if (key == 10) { g_debug_core8_passes = value < 1 ? 1 : (value > 8 ? 8 : value); return GSMCAL_OK; }
     if (key == 8) { g_debug_submit_groups = value < 1 ? 1 : (value > kMaxGroups / 2 ? kMaxGroups / 2 : value); return GSMCAL_OK; }
     if (key == 7) { g_debug_persist_colsum = value < 0 ? 0 : (value > 8 ? 8 : value); return GSMCAL_OK; }
     if (key == 3) { g_debug_groups = value < 1 ? 1 : (value > kMaxGroups / 2 ? kMaxGroups / 2 : value); return GSMCAL_OK; }
@@ -905,6 +932,8 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
     CU(cudaMemcpyAsync(w.tpl, tpl, sizeof(double2) * 64 * osr, cudaMemcpyHostToDevice, st));
     { const double2 *twp; TRY(get_twiddle(*c, 148 * osr, st, &twp)); }        // built on `st` before the groups fork
     g_last_need_full = w.need_full; g_last_need_band = w.need_band; g_last_need_full_n = (long long)D * cap;
+    g_last_pass_hist = w.pass_hist;
+    CU(cudaMemsetAsync(w.pass_hist, 0, sizeof(unsigned) * 16, st));
     g_stage_n = 0;
     // Streams are independent, so the batch is cut into groups that run the stage sequence on their own CUDA
     // streams: the latency-bound stages of one group (burst chain, per-stream solves) overlap the FP64-bound
@@ -1034,6 +1063,8 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
     CU(cudaMemsetAsync(w.need_band, 0, sizeof(int) * D * cap, fr));
     CU(cudaMemcpyAsync(w.tpl, h_tpl, sizeof(double2) * 64 * osr, cudaMemcpyHostToDevice, fr));
     g_last_need_full = w.need_full; g_last_need_band = w.need_band; g_last_need_full_n = (long long)D * cap;
+    g_last_pass_hist = w.pass_hist;
+    CU(cudaMemsetAsync(w.pass_hist, 0, sizeof(unsigned) * 16, fr));
     const size_t per = (size_t)2 * n_iq;
     std::vector<cudaEvent_t> ev_done;
     cudaEvent_t e_sum = nullptr;

@@ -22,12 +22,16 @@
 #define B8_BUF     2304                      // staged samples: 2208 + (NT-1 <= 63) + R-1, rounded up
 #define B8_CSL     71                        // row stride of the chunk prefix table (odd: bins fall into different banks)
 #define B8_SMEM    (B8_BUF * 16 + 8 * B8_CSL * 16 + 72 * 8 + 72 * 8 + 33 * 8 * 8)
+#define B8_NPASS   6                         // passes of 8 tracked bins each before a burst is handed to the 64-bin band kernel
+// offset from the band centre k0 of tracked bin j (0..7) in pass p: 8 bins around the tone, 8 more on both sides, then 8 at a time
+// towards the GMSK data energy (it sits ~37 bins below the FCCH tone)
+__device__ __forceinline__ int b8_bin_off(int pass, int j) { return pass == 0 ? j - 3 : (pass == 1 ? (j < 4 ? j - 7 : j + 1) : -8 * pass + 1 + j); }
 
 template <int NT>
 __global__ void __launch_bounds__(B8_THREADS, 4) fine_core8_kernel(const uint8_t *__restrict__ raw_all, i64 n_iq, const StreamCtl *__restrict__ ctl,
                                                                   const double *__restrict__ base_pos, int cap, const double2 *__restrict__ tw,
                                                                   double *__restrict__ fine_raw, int *__restrict__ need_band, int force_fail,
-                                                                  double2 *__restrict__ wcache) {
+                                                                  double2 *__restrict__ wcache, int n_pass, unsigned *__restrict__ pass_hist) {
     extern __shared__ __align__(128) unsigned char b8_sm[];
     double2 *B = reinterpret_cast<double2 *>(b8_sm);             // staged capture, then the filtered window (padded layout)
     double2 *CS = B + B8_BUF;                                    // [8][B8_CSL] prefix of chunk sums, bin-major
@@ -132,11 +136,12 @@ __global__ void __launch_bounds__(B8_THREADS, 4) fine_core8_kernel(const uint8_t
     __syncthreads();
     const int k0 = red_i[0];
     __syncthreads();
-    // Two passes at most (see fine_peak_core_kernel): pass 0 tracks k0-3 .. k0+4, pass 1 adds k0-7 .. k0-4 and k0+5 .. k0+8.
+    // Up to n_pass passes of 8 tracked bins (b8_bin_off): every pass adds its bins' power to the tracked sums of the certificate, which
+    // is re-checked after each; a burst leaves as soon as it is proven.  The 64-bin band kernel only sees what is still open then.
     double g_best = -1.0; int g_bestm = 0x7fffffff;
-    int ok = 0;
-    for (int pass = 0; pass < 2 && !ok; ++pass) {
-        if (pass == 1) {                                         // s[m] = s[m+N] - d[m] for m < 1024 (d was stored in place)
+    int ok = 0, pass = 0;
+    for (; pass < n_pass && !ok; ++pass) {
+        if (pass > 0) {                                          // s[m] = s[m+N] - d[m] for m < 1024 (d was stored in place)
             for (int m = tid; m < B8_NWIN - 1; m += B8_THREADS) {
                 const int i0 = B8_WPAD(m);
                 const double2 dd = B[i0], s_new = B[i0 + 33 * B8_WCH];
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(B8_THREADS, 4) fine_core8_kernel(const uint8_t
             const double2 s_last = bp[31];
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                int k = (k0 + ((pass == 0) ? 4 * q + b - 3 : (q == 0 ? b - 7 : b + 5))) % B8_N; if (k < 0) k += B8_N;
+                int k = (k0 + b8_bin_off(pass, 4 * q + b)) % B8_N; if (k < 0) k += B8_N;
                 kk[b] = k; z[b] = tw[k]; acc[b] = s_last;
             }
 #pragma unroll 31
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(B8_THREADS, 4) fine_core8_kernel(const uint8_t
         if (pass == 0 && tid == 0 && wcache) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the bulk store has read the window
         __syncthreads();
         const int g = tid >> 3, j = tid & 7;
-        int k = (k0 + ((pass == 0) ? j - 3 : (j < 4 ? j - 7 : j + 1))) % B8_N; if (k < 0) k += B8_N;
+        int k = (k0 + b8_bin_off(pass, j)) % B8_N; if (k < 0) k += B8_N;
         const double2 wk = tw[k];
         double xr, xi;
         {
@@ -257,7 +262,7 @@ __global__ void __launch_bounds__(B8_THREADS, 4) fine_core8_kernel(const uint8_t
                         const double yr = hi.x - lo.x, yi = hi.y - lo.y;
                         t2 += yr * yr + yi * yi;
                     }
-                    if (pass == 0) T2[gq * 8 + cand] = t2;
+                    T2[gq * 8 + cand] = t2;
                     const double r2 = (double)B8_N * e2 - t2;
                     bnd = sqrt_ub((double)(dch * B8_CH) * (e1 > 0.0 ? e1 : 0.0)) + sqrt_ub(r2 > 0.0 ? r2 : 0.0);
                 }
@@ -274,8 +279,257 @@ __global__ void __launch_bounds__(B8_THREADS, 4) fine_core8_kernel(const uint8_t
         ok = __syncthreads_and(ok);
     }
     if (tid == 0) {
+        if (pass_hist) atomicAdd(pass_hist + (ok ? pass : 0), 1u);             // [p] = bursts proven after p passes, [0] = left open
         if (wcache) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the bulk store is complete before the block retires
         *o = (double)(sp0 + 1 + g_bestm);                        // sp + max_idx - 1
         need_band[(i64)stream * cap + burst] = (ok && !force_fail) ? 0 : 1;       // force_fail: test hook, sends every burst to tier 2
+    }
+}
+
+// ===================================================================================================
+// K8 at osr 8 from the filtered-window cache: per-burst tone frequency (+ SNR gate)
+//   FCCH_fine_correction.m:143-155,185-189 (which = 1, level 1: resampled stream) and carrier_correct_post_SCH.m:58-72
+//   (which = 2, level 3: resampled, derotated, resampled again).
+// Same statements as tone_est_kernel, rebuilt for what the cached level-0 window makes possible: no staging, no FIR, two ping-pong
+// buffers (39 KB: 4 blocks per SM), and the two partial DFTs (8-bin band around the phase-slope estimate, 5 gate bins) by Horner's
+// rule over 10-sample segments with 4 bins (2 gate-bin pairs) per thread sharing every sample load.  A burst whose level-0 range is
+// not covered by its cached window, or whose Parseval certificates (integer bin, 5 dB gate) do not hold, is flagged in `need_old`
+// and recomputed by tone_est_kernel (all 1184 bins through the 37 x 32 row FFT).
+// ===================================================================================================
+#define T8_THREADS 256
+#define T8_SEG     10
+#define T8_NSEG    119                       // ceil(1184 / 10); the last segment is padded with zeros
+#define T8_BUF     1216
+#define T8_SMEM    (2 * T8_BUF * 16)
+__global__ void __launch_bounds__(T8_THREADS, 4) tone8_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, int which, const double *__restrict__ pos, int cap,
+                                                             const double2 *__restrict__ tw, double *__restrict__ fo_out, double *__restrict__ gate_out,
+                                                             int *__restrict__ need_old) {
+    extern __shared__ __align__(16) double2 t8_sm[];
+    double2 *P = t8_sm, *Q = t8_sm + T8_BUF;
+    __shared__ double red_n[24];
+    __shared__ double2 sh_base, sh_step;
+    __shared__ double sh_pb[8], sh_E, sh_pr;
+    __shared__ int sh_k0, sh_jbest, sh_flag;
+    const int burst = blockIdx.x, stream = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const StreamCtl c = ctl[stream];
+    const int nb = (which == 1) ? (c.tone1_enable ? c.n_fcch : 0) : (c.post_enable ? c.n_post_fcch : 0);
+    if (burst >= nb) return;
+    const i64 idx_o = (i64)stream * cap + burst;
+    constexpr int N = B8_N;
+    const double sampling_rate = ((1625.0 / 6.0) * 1e3) * 8.0;
+    const i64 start = (i64)pos[idx_o] - 1;
+    // ---- index ranges of the levels (load_window's arithmetic) ----
+    const i64 n0 = src.n_iq;
+    const bool use2 = (src.level == 3) && c.interp2_on;
+    const bool use1 = (src.level >= 1) && c.interp1_on;
+    const bool derot = (src.level >= 2) && c.derot1_on;
+    const double s1 = 1.0 + c.e1, s2 = 1.0 + c.e2;
+    const i64 len1 = use1 ? c.len1 : n0;
+    i64 a2 = start, b2 = start + N - 1, a1 = a2, b1 = b2, a0, b0;
+    if (use2) {
+        a1 = (i64)floor((double)a2 * s2);
+        b1 = (i64)floor((double)b2 * s2) + 1;
+        if (b1 > len1 - 1) b1 = len1 - 1;
+        if (a1 > b1) a1 = b1;
+    }
+    a0 = a1; b0 = b1;
+    if (use1) {
+        a0 = (i64)floor((double)a1 * s1);
+        b0 = (i64)floor((double)b1 * s1) + 1;
+        if (b0 > n0 - 1) b0 = n0 - 1;
+        if (a0 > b0) a0 = b0;
+    }
+    if (a0 < 0) a0 = 0;
+    if (b0 > n0 - 1) b0 = n0 - 1;
+    const int n_l0 = (int)(b0 - a0 + 1), n_l1 = (int)(b1 - a1 + 1);
+    const i64 wbase = ((i64)src.wc_pos[idx_o] - 65) * 8;
+    const bool covered = src.wcache && a0 >= wbase && b0 < wbase + B8_NSMP && n_l0 <= T8_BUF - 8 && n_l1 <= T8_BUF - 8 && start >= 0
+                         && (!derot || use1);                     // (derotation without resampling does not occur in the reference flow)
+    if (!covered) {                                              // block-uniform
+        if (tid == 0) need_old[idx_o] = 1;
+        return;
+    }
+    // ---- level 0 from the cache -> P ----
+    {
+        const double2 *wc = src.wcache + idx_o * B8_WLEN;
+        const int o = (int)(a0 - wbase);
+        for (int i = tid; i < n_l0; i += T8_THREADS) P[i] = wc[B8_WPAD(o + i)];
+        if (derot && tid == 0) { double sn, cs; sincos((double)a1 * c.dphi1, &sn, &cs); sh_base = make_double2(cs, sn); }
+    }
+    __syncthreads();
+    double2 *u = P, *spare = Q;                                  // u: the burst the stage works on; spare: the other buffer
+    if (use1) {                                                  // level 1 (+2): interp1 by (1+e1) [and derotation by dphi1] -> Q
+        double2 ph = make_double2(1.0, 0.0), st = make_double2(1.0, 0.0);
+        if (derot) {
+            double sn, cs;
+            sincos((double)tid * c.dphi1, &sn, &cs); ph = cmul(sh_base, make_double2(cs, sn));
+            sincos((double)T8_THREADS * c.dphi1, &sn, &cs); st = make_double2(cs, sn);
+        }
+        for (int i = tid; i < n_l1; i += T8_THREADS) {
+            const i64 j = a1 + i;
+            const double xq = (double)j * s1;
+            i64 i0 = (i64)floor(xq);
+            if (i0 > n0 - 1) i0 = n0 - 1;
+            const i64 i1 = (i0 + 1 > n0 - 1) ? n0 - 1 : i0 + 1;
+            double2 v = lerp_ref(P[i0 - a0], P[i1 - a0], xq - (double)i0);
+            if (derot) { v = cmul(v, ph); ph = cmul(ph, st); }
+            Q[i] = v;
+        }
+        __syncthreads();
+        u = Q; spare = P;
+        if (use2) {                                              // level 3: second interp1 by (1+e2) -> P
+            for (int i = tid; i < N; i += T8_THREADS) {
+                const double xq = (double)(a2 + i) * s2;
+                i64 i0 = (i64)floor(xq);
+                if (i0 > len1 - 1) i0 = len1 - 1;
+                const i64 i1 = (i0 + 1 > len1 - 1) ? len1 - 1 : i0 + 1;
+                P[i] = lerp_ref(Q[i0 - a1], Q[i1 - a1], xq - (double)i0);
+            }
+            u = P; spare = Q;
+        }
+    } else if (use2) {                                           // e1 path off, second interp1 only (no derotation here, see `covered`)
+        for (int i = tid; i < N; i += T8_THREADS) {
+            const double xq = (double)(a2 + i) * s2;
+            i64 i0 = (i64)floor(xq);
+            if (i0 > len1 - 1) i0 = len1 - 1;
+            const i64 i1 = (i0 + 1 > len1 - 1) ? len1 - 1 : i0 + 1;
+            Q[i] = lerp_ref(P[i0 - a1], P[i1 - a1], xq - (double)i0);
+        }
+        u = Q; spare = P;
+    }
+    if (tid < T8_SEG * T8_NSEG - N + 2) u[N + tid] = make_double2(0.0, 0.0);     // zero padding of the last Horner segment
+    __syncthreads();
+    // ---- energy and phase slope -> band centre ----
+    {
+        double epq[3] = {0.0, 0.0, 0.0};
+        for (int n = tid; n < N; n += T8_THREADS) {
+            const double2 v = u[n];
+            epq[0] = fma(v.x, v.x, fma(v.y, v.y, epq[0]));
+            if (n + 1 < N) { const double2 q = cmulc(u[n + 1], v); epq[1] += q.x; epq[2] += q.y; }
+        }
+        block_sum_n<3, false>(epq, red_n);
+        if (tid == 0) { sh_E = epq[0]; sh_k0 = (int)floor(atan2(epq[2], epq[1]) * (double)N / (2.0 * GSMCAL_PI) + 0.5); sh_flag = 0; }
+    }
+    __syncthreads();
+    const int k0 = sh_k0;
+    // ---- 8-bin band DFT by Horner's rule: thread = (10-sample segment, 4 bins); partial sums -> spare[bin][120] ----
+    if (tid < 2 * T8_NSEG) {
+        const int seg = tid >> 1, q = tid & 1, n0s = T8_SEG * seg;
+        double2 z[4], acc[4]; int kk[4];
+        const double2 s_last = u[n0s + T8_SEG - 1];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            int k = (k0 - 3 + 4 * q + b) % N; if (k < 0) k += N;
+            kk[b] = k; z[b] = tw[k]; acc[b] = s_last;
+        }
+#pragma unroll
+        for (int i = T8_SEG - 2; i >= 0; --i) {
+            const double2 s = u[n0s + i];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const double nr = fma(acc[b].x, z[b].x, fma(-acc[b].y, z[b].y, s.x));
+                const double ni = fma(acc[b].x, z[b].y, fma(acc[b].y, z[b].x, s.y));
+                acc[b] = make_double2(nr, ni);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) spare[(4 * q + b) * 120 + seg] = cmul(acc[b], tw[(n0s * kk[b]) % N]);
+    }
+    __syncthreads();
+    {   // warp b adds the partials of bin b
+        double xr = 0.0, xi = 0.0;
+        for (int sgi = lane; sgi < T8_NSEG; sgi += 32) { const double2 v = spare[warp * 120 + sgi]; xr += v.x; xi += v.y; }
+        xr = warp_sum(xr); xi = warp_sum(xi);
+        if (lane == 0) sh_pb[warp] = abs2_ref(make_double2(xr, xi));
+    }
+    __syncthreads();
+    if (tid == 0) {   // first maximum in fftshift-ed order (:149-150) and the Parseval certificate for every bin outside the band
+        double v = -1.0, band_sum = 0.0; int j_best = 0x7fffffff;
+        for (int b = 0; b < 8; ++b) {
+            int k = (k0 - 3 + b) % N; if (k < 0) k += N;
+            int j = k - N / 2; if (j < 0) j += N;
+            band_sum += sh_pb[b];
+            argmax_combine(v, j_best, sh_pb[b], j);
+        }
+        if (!((double)N * sh_E - band_sum < v * (1.0 - 1e-9))) sh_flag = 1;
+        sh_jbest = j_best;
+    }
+    __syncthreads();
+    if (sh_flag) {                                               // block-uniform: not certified, the row-FFT kernel takes the burst
+        if (tid == 0) need_old[idx_o] = 1;
+        return;
+    }
+    const int jr = sh_jbest + 1 - ((N / 2) + 1);                 // max_idx - (fft_len/2 + 1)
+    const double int_phase_rotate = 2.0 * GSMCAL_PI * (double)jr / (double)N;
+    // ---- integer-bin derotation (twiddle table entry n*jr mod N), unit phasors -> spare (:152-153) ----
+    {
+        int jm = jr % N; if (jm < 0) jm += N;
+        int tidx = (tid * jm) % N;
+        const int tinc = (T8_THREADS * jm) % N;
+        for (int n = tid; n < N; n += T8_THREADS, tidx = (tidx + tinc >= N) ? tidx + tinc - N : tidx + tinc) {
+            const double2 w = cmul(u[n], tw[tidx]);
+            u[n] = w;
+            const double h2 = fma(w.x, w.x, w.y * w.y);
+            const double inv = rsqrt(h2);
+            spare[n] = (h2 > 0.0) ? make_double2(w.x * inv, w.y * inv) : make_double2(1.0, 0.0);
+        }
+    }
+    __syncthreads();
+    {
+        double rri[2] = {0.0, 0.0};
+        for (int n = tid; n < N - 1; n += T8_THREADS) {
+            const double2 a = spare[n + 1], b = spare[n];
+            rri[0] += a.x * b.x + a.y * b.y;
+            rri[1] += a.y * b.x - a.x * b.y;
+        }
+        block_sum_n<2, false>(rri, red_n);
+        if (tid == 0) {
+            const double pr = atan2(rri[1] / (double)(N - 1), rri[0] / (double)(N - 1));
+            sh_pr = pr;
+            fo_out[idx_o] = sampling_rate * (int_phase_rotate + pr) / (2 * GSMCAL_PI);
+            double sn, cs; sincos(pr, &sn, &cs); sh_step = make_double2(cs, sn);      // exp(+i*phi): one step back in n
+        }
+    }
+    if (which != 1) return;
+    __syncthreads();
+    // ---- SNR gate (:185-196): bins 0, +-1, +-2 of the finely derotated burst by Horner's rule, thread = (segment, bin pair);
+    //      sig >= 10^0.5 (N*E - sig) proves the burst passes the 5 dB gate (Parseval; derotation keeps the energy) ----
+    const double phase_rotate = sh_pr;
+    if (tid < 2 * T8_NSEG) {
+        const int seg = tid >> 1, q = tid & 1, n0s = T8_SEG * seg, n_last = n0s + T8_SEG - 1;
+        const double2 zp = tw[q + 1], zm = make_double2(zp.x, -zp.y);      // W^{+(q+1)}, W^{-(q+1)}
+        double sn, cs; sincos((double)n_last * phase_rotate, &sn, &cs);
+        double2 ph = make_double2(cs, -sn);                      // exp(-i*n*phi) at the segment's last sample
+        const double2 st = sh_step;
+        double2 accp, accm, acc0;
+        {
+            const double2 v = cmul(u[n_last], ph);
+            accp = v; accm = v; acc0 = v;
+        }
+#pragma unroll
+        for (int i = T8_SEG - 2; i >= 0; --i) {
+            ph = cmul(ph, st);
+            const double2 v = cmul(u[n0s + i], ph);
+            accp = make_double2(fma(accp.x, zp.x, fma(-accp.y, zp.y, v.x)), fma(accp.x, zp.y, fma(accp.y, zp.x, v.y)));
+            accm = make_double2(fma(accm.x, zm.x, fma(-accm.y, zm.y, v.x)), fma(accm.x, zm.y, fma(accm.y, zm.x, v.y)));
+            acc0.x += v.x; acc0.y += v.y;
+        }
+        const double2 t = tw[(n0s * (q + 1)) % N];               // W^{+n0 (q+1)}; its conjugate for the negative bin
+        spare[(2 * q) * 120 + seg] = cmul(accp, t);
+        spare[(2 * q + 1) * 120 + seg] = cmul(accm, make_double2(t.x, -t.y));
+        if (q == 0) spare[4 * 120 + seg] = acc0;
+    }
+    __syncthreads();
+    if (warp < 5) {
+        double xr = 0.0, xi = 0.0;
+        for (int sgi = lane; sgi < T8_NSEG; sgi += 32) { const double2 v = spare[warp * 120 + sgi]; xr += v.x; xi += v.y; }
+        xr = warp_sum(xr); xi = warp_sum(xi);
+        if (lane == 0) sh_pb[warp] = xr * xr + xi * xi;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const double sig5 = ((sh_pb[0] + sh_pb[1]) + (sh_pb[2] + sh_pb[3])) + sh_pb[4];
+        if (sig5 >= 3.16227766016838 * (1.0 + 1e-9) * ((double)N * sh_E - sig5)) gate_out[idx_o] = 99.0;      // "certified above the 5 dB gate"
+        else need_old[idx_o] = 1;                                // evaluate the 110 gate bins exactly
     }
 }

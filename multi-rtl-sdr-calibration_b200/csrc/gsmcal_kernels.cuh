@@ -133,15 +133,18 @@ __device__ __forceinline__ void fir_taps_const(const double2 *__restrict__ xb, d
 }
 #define LW_R 5
 template <int NT>
-__device__ __forceinline__ void fir_groups_c(const double2 *__restrict__ X, double2 *__restrict__ l0, int n_l0, int tid, int nt) {
-    const int n_grp = (n_l0 + LW_R - 1) / LW_R;
-    for (int gi = tid; gi < n_grp; gi += nt) {
-        double ar[LW_R], ai[LW_R];
-        fir_taps_const<NT, LW_R, 6>(X + LW_R * gi, ar, ai);
-        const int base = LW_R * gi;
+__device__ __forceinline__ void fir_group_one(const double2 *__restrict__ X, double2 *__restrict__ l0, int n_l0, int gi) {
+    double ar[LW_R], ai[LW_R];
+    fir_taps_const<NT, LW_R, 6>(X + LW_R * gi, ar, ai);
+    const int base = LW_R * gi;
 #pragma unroll
-        for (int r = 0; r < LW_R; ++r) if (base + r < n_l0) l0[base + r] = make_double2(ar[r], ai[r]);
-    }
+    for (int r = 0; r < LW_R; ++r) if (base + r < n_l0) l0[base + r] = make_double2(ar[r], ai[r]);
+}
+template <int NT>
+__device__ __forceinline__ void fir_groups_c(const double2 *__restrict__ X, double2 *__restrict__ l0, int n_l0, int tid) {
+    // one group per thread, straight-line code (the caller guarantees ceil(n_l0 / LW_R) <= blockDim.x): inside a loop over groups the
+    // compiler hoists all 2*NT tap registers out of it and spills uniform registers
+    if (LW_R * tid < n_l0) fir_group_one<NT>(X, l0, n_l0, tid);
 }
 // exact uint8 -> double without the quarter-rate I2F: the integer sits in the low mantissa bits of 2^52
 __device__ __forceinline__ double u8_to_f64(unsigned v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
@@ -204,9 +207,10 @@ __device__ void load_window(const WinSrc &src, const StreamCtl &c, int stream, i
     // thread evaluates it while the others stage and filter; it is read after the barriers below
     __shared__ double2 lw_base;
     if (derot && use1 && tid == 0) { double sn, cs; sincos((double)a1 * c.dphi1, &sn, &cs); lw_base = make_double2(cs, sn); }
-    const int nt_sel = (src.n_taps == 47) ? 47 : ((src.n_taps <= 48) ? 48 : (src.n_taps <= 64 ? 64 : 0));   // unrolled FIR variants (taps zero-padded on the old side)
-    const int nt1 = (nt_sel ? nt_sel : src.n_taps) - 1;
     const int n_l0 = (int)(b0 - a0 + 1);
+    // unrolled FIR variants (taps zero-padded on the old side), one group of LW_R outputs per thread; longer windows or filters take the rolled loop
+    const int nt_sel = ((n_l0 + LW_R - 1) / LW_R > nt) ? 0 : ((src.n_taps == 47) ? 47 : ((src.n_taps <= 48) ? 48 : (src.n_taps <= 64 ? 64 : 0)));
+    const int nt1 = (nt_sel ? nt_sel : src.n_taps) - 1;
     const int n_raw = n_l0 + nt1;
     double2 *l0 = (use1 || use2) ? Y : dst;
     // the fine search left this burst's filtered window in the cache: level 0 is a copy, no staging, no FIR
@@ -246,9 +250,9 @@ __device__ void load_window(const WinSrc &src, const StreamCtl &c, int stream, i
     }
     if (tid < 8) X[n_raw + tid] = make_double2(0.0, 0.0);        // the last output group reads up to LW_R-1 samples past the window
     __syncthreads();
-    if (nt_sel == 47) fir_groups_c<47>(X, l0, n_l0, tid, nt);
-    else if (nt_sel == 48) fir_groups_c<48>(X, l0, n_l0, tid, nt);
-    else if (nt_sel == 64) fir_groups_c<64>(X, l0, n_l0, tid, nt);
+    if (nt_sel == 47) fir_groups_c<47>(X, l0, n_l0, tid);
+    else if (nt_sel == 48) fir_groups_c<48>(X, l0, n_l0, tid);
+    else if (nt_sel == 64) fir_groups_c<64>(X, l0, n_l0, tid);
     else {
         // generic tap count: 3 consecutive outputs per thread from a sliding register window of taps
         const int n_grp = (n_l0 + 2) / 3;
@@ -1733,7 +1737,7 @@ __device__ __forceinline__ double2 dft_col(const double2 *Tm, int k, int N, cons
 #define TONE_BAND 16
 __global__ void __launch_bounds__(TONE_THREADS, 3) tone_est_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, int which /* 1: fine stage, 2: post-SCH */,
                                                                const double *__restrict__ pos, int cap, int osr, const double2 *__restrict__ tw,
-                                                               double *__restrict__ fo_out, double *__restrict__ gate_out) {
+                                                               double *__restrict__ fo_out, double *__restrict__ gate_out, const int *__restrict__ need) {
     extern __shared__ double2 sm[];
     __shared__ double red_v[8];
     __shared__ int red_i[8];
@@ -1745,6 +1749,7 @@ __global__ void __launch_bounds__(TONE_THREADS, 3) tone_est_kernel(WinSrc src, c
     const StreamCtl c = ctl[stream];
     const int nb = (which == 1) ? (c.tone1_enable ? c.n_fcch : 0) : (c.post_enable ? c.n_post_fcch : 0);
     if (burst >= nb) return;
+    if (need && !need[(i64)stream * cap + burst]) return;       // tone8_kernel (osr-8 fast path) already did this burst
     const int N = 148 * osr;
     const double sampling_rate = ((1625.0 / 6.0) * 1e3) * (double)osr;
     double2 *u = sm, *A = u + N, *F = A + N;
@@ -1884,9 +1889,10 @@ __global__ void __launch_bounds__(TONE_THREADS, 3) tone_est_kernel(WinSrc src, c
 // K9  SCH training-sequence correlation   SCH_corr_rate_correction.m:37-63
 // ===================================================================================================
 #define SCH_THREADS 256
-#define SCH_LPG 12      // lags per warp
+#define SCH_LPG 6       // lags per warp and pass
+#define SCH_PASSES 2
 #define SCH_NSL 16      // template samples per lane
-__global__ void __launch_bounds__(SCH_THREADS, 2) sch_corr_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ fcch_pos, int cap,
+__global__ void __launch_bounds__(SCH_THREADS, 4) sch_corr_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ fcch_pos, int cap,
                                                               int osr, const double2 *__restrict__ tpl, double *__restrict__ sch_raw, int *__restrict__ sch_edge) {
     extern __shared__ double2 sm[];
     __shared__ double red_v[8];
@@ -1939,50 +1945,61 @@ __global__ void __launch_bounds__(SCH_THREADS, 2) sch_corr_kernel(WinSrc src, co
         }
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = SCH_THREADS >> 5;
-    if (L == 32 * SCH_NSL && n_lag <= nw * SCH_LPG) {
-        // register-tiled correlation: warp w owns lags [12w, 12w+12), lane owns template samples [16*lane, 16*lane+16);
-        // a 12-deep sliding register window of the burst is advanced one sample per step (2 shared loads per 12 MACs).
-        // Both arrays are re-laid out with one pad slot per 16 samples so the 256-byte lane stride is conflict free.
+    if (L == 32 * SCH_NSL && n_lag <= SCH_PASSES * nw * SCH_LPG) {
+        // register-tiled correlation: per pass warp w owns lags [6(8p+w), +6), lane owns template samples [16*lane, 16*lane+16);
+        // a 6-deep sliding register window of the burst is advanced one sample per step (2 shared loads per 6 complex MACs).
+        // Both arrays are re-laid out with one pad slot per 16 samples so the 256-byte lane stride is conflict free.  Two passes
+        // of 6 lags (instead of one of 12) keep the kernel at 64 registers, and the lane partials are folded to 8 lanes by shuffles
+        // before they go through shared memory (7 KB instead of 50 KB): 4 blocks per SM instead of 2.
         double2 *wp = X, *tp = X + (n_smp + (n_smp >> 4) + 2);      // X and Y are contiguous: 924 + 608 slots >= 640 + 544
         for (int i = threadIdx.x; i < n_smp; i += SCH_THREADS) wp[i + (i >> 4)] = win[i];
         for (int i = threadIdx.x; i < L; i += SCH_THREADS) tp[i + (i >> 4)] = t[i];
         __syncthreads();
-        double ar[SCH_LPG], ai[SCH_LPG];
-        double2 wr_[SCH_LPG];
+        double *part = reinterpret_cast<double *>(tp + (L + (L >> 4) + 2));      // [2 * nw * SCH_LPG][9]
+        const int nb = SCH_NSL * lane;
+#pragma unroll 1
+        for (int pass = 0; pass < SCH_PASSES; ++pass) {
+            double ar[SCH_LPG], ai[SCH_LPG];
+            double2 wr_[SCH_LPG];
 #pragma unroll
-        for (int l = 0; l < SCH_LPG; ++l) { ar[l] = 0.0; ai[l] = 0.0; }
-        const int l0 = SCH_LPG * w, nb = SCH_NSL * lane;
+            for (int l = 0; l < SCH_LPG; ++l) { ar[l] = 0.0; ai[l] = 0.0; }
+            const int l0 = SCH_LPG * (pass * nw + w);
 #pragma unroll
-        for (int l = 0; l < SCH_LPG - 1; ++l) { const int i = l0 + nb + l; wr_[l] = (i < n_smp) ? wp[i + (i >> 4)] : make_double2(0.0, 0.0); }
+            for (int l = 0; l < SCH_LPG - 1; ++l) { const int i = l0 + nb + l; wr_[l] = (i < n_smp) ? wp[i + (i >> 4)] : make_double2(0.0, 0.0); }
 #pragma unroll
-        for (int n = 0; n < SCH_NSL; ++n) {
-            const int iw = l0 + nb + n + SCH_LPG - 1, it = nb + n;
-            wr_[SCH_LPG - 1] = (iw < n_smp) ? wp[iw + (iw >> 4)] : make_double2(0.0, 0.0);
-            const double2 tt = tp[it + (it >> 4)];
+            for (int n = 0; n < SCH_NSL; ++n) {
+                const int iw = l0 + nb + n + SCH_LPG - 1, it = nb + n;
+                wr_[SCH_LPG - 1] = (iw < n_smp) ? wp[iw + (iw >> 4)] : make_double2(0.0, 0.0);
+                const double2 tt = tp[it + (it >> 4)];
 #pragma unroll
-            for (int l = 0; l < SCH_LPG; ++l) {                  // conj(ts) .* window
-                ar[l] = fma(wr_[l].x, tt.x, fma(wr_[l].y, tt.y, ar[l]));
-                ai[l] = fma(wr_[l].y, tt.x, fma(-wr_[l].x, tt.y, ai[l]));
+                for (int l = 0; l < SCH_LPG; ++l) {              // conj(ts) .* window
+                    ar[l] = fma(wr_[l].x, tt.x, fma(wr_[l].y, tt.y, ar[l]));
+                    ai[l] = fma(wr_[l].y, tt.x, fma(-wr_[l].x, tt.y, ai[l]));
+                }
+#pragma unroll
+                for (int l = 0; l < SCH_LPG - 1; ++l) wr_[l] = wr_[l + 1];
             }
+            // fold 32 lanes to 8 (lanes 0..7 hold the sums of lanes {i, i+8, i+16, i+24}), then rows (lag, re|im) of 9 doubles
 #pragma unroll
-            for (int l = 0; l < SCH_LPG - 1; ++l) wr_[l] = wr_[l + 1];
-        }
-        // sum over the 32 lanes through shared memory (24 shuffle trees per warp cost half as many instructions as the MACs above):
-        // row (lag, re|im) of 33 doubles, lane-major, then one thread per row
-        double *part = reinterpret_cast<double *>(tp + (L + (L >> 4) + 2));
+            for (int l = 0; l < SCH_LPG; ++l) {
+                ar[l] += __shfl_down_sync(0xffffffffu, ar[l], 16); ai[l] += __shfl_down_sync(0xffffffffu, ai[l], 16);
+                ar[l] += __shfl_down_sync(0xffffffffu, ar[l], 8);  ai[l] += __shfl_down_sync(0xffffffffu, ai[l], 8);
+            }
+            if (pass > 0) __syncthreads();                       // the rows of the previous pass have been consumed
+            if (lane < 8) {
 #pragma unroll
-        for (int l = 0; l < SCH_LPG; ++l) {
-            part[(2 * (l0 + l)) * 33 + lane] = ar[l];
-            part[(2 * (l0 + l) + 1) * 33 + lane] = ai[l];
-        }
-        __syncthreads();
-        if (threadIdx.x < 2 * nw * SCH_LPG) {
-            const double *row = part + threadIdx.x * 33;
-            double s0 = 0.0, s1 = 0.0;
-#pragma unroll 8
-            for (int i = 0; i < 32; i += 2) { s0 += row[i]; s1 += row[i + 1]; }
-            const int lag = threadIdx.x >> 1;
-            if (lag < n_lag) { if (threadIdx.x & 1) corr_i[lag] = s0 + s1; else corr[lag] = s0 + s1; }
+                for (int l = 0; l < SCH_LPG; ++l) {
+                    part[(2 * (SCH_LPG * w + l)) * 9 + lane] = ar[l];
+                    part[(2 * (SCH_LPG * w + l) + 1) * 9 + lane] = ai[l];
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x < 2 * nw * SCH_LPG) {
+                const double *row = part + threadIdx.x * 9;
+                const double s0 = (row[0] + row[1]) + (row[2] + row[3]), s1 = (row[4] + row[5]) + (row[6] + row[7]);
+                const int lag = SCH_LPG * pass * nw + (threadIdx.x >> 1);
+                if (lag < n_lag) { if (threadIdx.x & 1) corr_i[lag] = s0 + s1; else corr[lag] = s0 + s1; }
+            }
         }
     } else {
         for (int lag = w; lag < n_lag; lag += nw) {              // generic shapes: one warp per lag

@@ -296,6 +296,27 @@ def test_osr8_fast_path_equals_round1_kernels(gpu, captures, coef47, tpl):
             _check_stream(a, oracle.calibrate_stream(raw[d], CARRIER, tpl, coef47))
 
 
+def test_tone8_equals_generic_tone_estimator(gpu, captures, coef47, tpl):
+    """tone8_kernel (cache-fed, Horner band DFT, certified gate) against tone_est_kernel for every burst (debug key 11); also with
+    fewer tier-1 passes (key 10) so that more bursts reach the 64-bin band kernel"""
+    from gsmcal._lib import lib
+    _, raw = captures
+    new = gpu.calibrate_batch(raw, CARRIER, tpl, coef47)
+    outs = []
+    for key, val, back in ((11, 1, 0), (10, 1, 6)):
+        lib().gsmcal_debug_set(key, val)
+        try:
+            outs.append(gpu.calibrate_batch(raw, CARRIER, tpl, coef47))
+        finally:
+            lib().gsmcal_debug_set(key, back)
+    for old in outs:
+        for a, b in zip(new, old):
+            for k in ("coarse_pos", "fcch_pos", "pos_info"):
+                assert np.array_equal(a[k], b[k]), k
+            assert a["sampling_ppm"] == b["sampling_ppm"]
+            assert np.allclose(a["carrier_ppm"], b["carrier_ppm"], rtol=0, atol=1e-9)
+
+
 def test_osr8_fast_path_other_tap_counts(gpu, captures, tpl):
     """the 48- and 64-tap instantiations of the fast path (zero-padded on the old side) and a filter too long for it (generic path)"""
     _, raw = captures
