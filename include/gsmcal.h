@@ -15,6 +15,14 @@
  *     through the count/length outputs (-1 means "the scalar -1") so a gateway can rebuild them.
  *   - every compute call runs hand-written sm_100a kernels; there is no CPU fallback: without a CUDA
  *     device the call fails with GSMCAL_ERR_CUDA.
+ *
+ * Limits that the reference (MATLAB, unbounded) does not have; every one is checked and reported as GSMCAL_ERR_ARG:
+ *   - oversampling_ratio 1..8 in FCCH_fine_correction / SCH_corr_rate_correction / carrier_correct_post_SCH / calibrate_batch
+ *     (shared-memory windows are sized for 148*8 samples; the reference scripts only ever use 8);
+ *   - fft_len <= 128 in the moving-FFT functions (FCCH_coarse_position uses 16);
+ *   - n_taps <= 128 (GSMCAL_MAX_TAPS: the numerator lives in constant memory; the reference uses 47 / 31 / 64 / 60 / 30);
+ *   - at most 65,535 streams (columns) per call (CUDA grid y dimension);
+ *   - calls are serialised by one process-wide mutex (the MEX entry is single-threaded anyway); _collect / _cancel wait outside it.
  */
 #ifndef GSMCAL_H
 #define GSMCAL_H
@@ -197,6 +205,11 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
                                   int oversampling_ratio, int coarse_decimation_ratio, gsmcal_stream_result *results,
                                   double *coarse_pos, double *coarse_snr, double *fcch_pos, double *pos_info, void *cuda_stream);
 int gsmcal_calibrate_batch_collect(int slot);
+/* Gives `slot` back without delivering results (waits for the batch; the result pointers passed to _submit are never written).
+ * For callers that abandon a submitted batch: the slot would otherwise stay busy and keep pointers into freed memory.
+ * _submit, _collect and _cancel of one slot must be called from threads that selected the same device (gsmcal_set_device is
+ * per thread; slots belong to the device). */
+int gsmcal_calibrate_batch_cancel(int slot);
 
 /* CUDA-event times (ms) of the stages of the last gsmcal_calibrate_batch call on this process:
  * [0] uint8 column sums (+ H2D when raw is on the host) [1] coarse FCCH [2] fine FCCH sliding-DFT peak search
@@ -217,7 +230,7 @@ int gsmcal_fcch_scan(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t n_ch
  * 6 = burst chain on high-priority streams (default 1); 7 = blocks per SM of a persistent high-priority column-sum kernel in
  * _submit (default 0 = per-group launches); 8 = stream groups inside a submitted batch (default 1); 9, value 1 = the generic tier-1 fine
  * search without the osr-8 fast path and its filtered-window cache (A/B and tests); 10 = passes of 8 tracked bins in the osr-8 tier-1
- * kernel (1..8, default 6); 11, value 1 = generic tone estimator for every burst (no tone8_kernel) */
+ * kernel (1..8, default 8); 11, value 1 = generic tone estimator for every burst (no tone8_kernel) */
 int gsmcal_debug_set(int key, int value);
 /* key 1: number of bursts of the last fine FCCH search whose band certificate failed (all-bin fallback ran); 2: bursts that needed the
  * 64-bin band kernel; 10 + p: bursts the osr-8 tier-1 kernel proved after p passes (p = 0: left open) */

@@ -85,8 +85,11 @@ struct Slot {
     gsmcal_stream_result *results = nullptr; double *coarse_pos = nullptr, *coarse_snr = nullptr, *fcch_pos = nullptr, *pos_info = nullptr;
     size_t n_res = 0, n_per = 0;                                // bytes of the result records / of one D*cap double array
 };
+constexpr int kNumStageEvents = 8;
 struct Ctx {
     bool attrs = false;
+    cudaEvent_t stage_ev[kNumStageEvents];
+    bool stage_ev_ok = false;
     Slot slots[kSlots];
     DevBuf in, out, work, tplbuf, wc;
     std::map<int, double2 *> tw;     // N -> exp(-2*pi*i*j/N)
@@ -95,18 +98,16 @@ struct Ctx {
 };
 std::map<int, Ctx> g_ctx;
 
-// per-stage CUDA-event timing of the last gsmcal_calibrate_batch call (events are recorded on the call's stream)
-constexpr int kNumStageEvents = 8;
-cudaEvent_t g_stage_ev[kNumStageEvents];
-bool g_stage_ev_ok = false;
+// per-stage CUDA-event timing of the last gsmcal_calibrate_batch call (events are recorded on the call's stream; they belong to the
+// device's Ctx - an event of another device cannot be recorded on this one's streams)
 int g_stage_n = 0;
 float g_stage_ms[kNumStageEvents];
-int stage_mark(cudaStream_t st) {
-    if (!g_stage_ev_ok) {
-        for (int i = 0; i < kNumStageEvents; ++i) CU(cudaEventCreate(&g_stage_ev[i]));
-        g_stage_ev_ok = true;
+int stage_mark(Ctx &c, cudaStream_t st) {
+    if (!c.stage_ev_ok) {
+        for (int i = 0; i < kNumStageEvents; ++i) CU(cudaEventCreate(&c.stage_ev[i]));
+        c.stage_ev_ok = true;
     }
-    if (g_stage_n < kNumStageEvents) CU(cudaEventRecord(g_stage_ev[g_stage_n++], st));
+    if (g_stage_n < kNumStageEvents) CU(cudaEventRecord(c.stage_ev[g_stage_n++], st));
     return GSMCAL_OK;
 }
 
@@ -167,6 +168,9 @@ int get_ctx(Ctx **out) {
         CU(cudaFuncSetAttribute(post_carrier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CU(cudaFuncSetAttribute(fir_decim_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CU(cudaFuncSetAttribute(fir_decim_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CU(cudaFuncSetAttribute(fcch_demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));      // (attributes are per device:
+        CU(cudaFuncSetAttribute(fde_template_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));    //  all of them live here, keyed by
+        CU(cudaFuncSetAttribute(sch_demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));       //  the device's Ctx)
         c.attrs = true;
     }
     *out = &c;
@@ -460,11 +464,13 @@ int gsmcal_set_device(int device) {
 }
 void gsmcal_release(void) {
     std::lock_guard<std::mutex> lk(g_mu);
+    g_last_need_full = nullptr; g_last_need_band = nullptr; g_last_need_full_n = 0; g_last_pass_hist = nullptr;   // they point into the workspaces freed below
     for (auto &kv : g_ctx) {
         cudaSetDevice(kv.first);
         kv.second.in.release(); kv.second.out.release(); kv.second.work.release(); kv.second.tplbuf.release(); kv.second.wc.release();
         for (auto &t : kv.second.tw) cudaFree(t.second);
         kv.second.tw.clear();
+        if (kv.second.stage_ev_ok) { for (cudaEvent_t e : kv.second.stage_ev) cudaEventDestroy(e); kv.second.stage_ev_ok = false; }
         for (cudaStream_t s2 : kv.second.side) cudaStreamDestroy(s2);
         kv.second.side.clear();
         for (cudaStream_t s2 : kv.second.side_hi) cudaStreamDestroy(s2);
@@ -953,7 +959,7 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
     if (raw_mem == GSMCAL_MEM_HOST) CU(cudaStreamWaitEvent(cp, ev_fork, 0));
     std::vector<cudaEvent_t> ev_done;
     const size_t per = (size_t)2 * n_iq;
-    if (timing) TRY(stage_mark(st));
+    if (timing) TRY(stage_mark(*c, st));
     for (int g = 0; g < n_groups; ++g) {
         const i64 d0 = D * g / n_groups, d1 = D * (g + 1) / n_groups, nd = d1 - d0;
         cudaStream_t sg = (n_groups == 1) ? st : c->side[g];
@@ -975,7 +981,7 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
             CU(cudaEventRecord(ev, st)); CU(cudaStreamWaitEvent(sg, ev, 0)); CU(cudaEventDestroy(ev));
         }
         LAUNCH(mean_kernel, (unsigned)((nd + 127) / 128), 128, 0, sg, ws.ctl, (int)nd, n_iq);
-        if (timing) TRY(stage_mark(sg));
+        if (timing) TRY(stage_mark(*c, sg));
         if (sg != st && g_debug_hi_prio) {
             // the coarse stage is a handful of small latency-bound kernels (a 0.8 ms dependent burst chain): on the group's own stream
             // their blocks queue behind the thousands of pending blocks of the other groups' FP64 kernels.  A high-priority stream
@@ -988,15 +994,15 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
             CU(cudaEventDestroy(e1)); CU(cudaEventDestroy(e2));
         } else
         TRY(run_coarse(lazy_src(graw, n_iq, n_taps, 0, dec), len_dec, p, nd, cap, ws, sg));
-        if (timing) TRY(stage_mark(sg));
+        if (timing) TRY(stage_mark(*c, sg));
         TRY(run_fine_peak(*c, lazy_src(graw, n_iq, n_taps, 0, 1), n_iq, osr, nd, cap, ws, sg));
-        if (timing) TRY(stage_mark(sg));
+        if (timing) TRY(stage_mark(*c, sg));
         TRY(run_fine_rest(*c, with_cache(lazy_src(graw, n_iq, n_taps, 1, 1), ws, cap), n_iq, osr, carrier_freq, nd, cap, ws, sg));
-        if (timing) TRY(stage_mark(sg));
+        if (timing) TRY(stage_mark(*c, sg));
         TRY(run_sch(lazy_src(graw, n_iq, n_taps, 2, 1), osr, nd, cap, ws, sg));
-        if (timing) TRY(stage_mark(sg));
+        if (timing) TRY(stage_mark(*c, sg));
         TRY(run_post(*c, with_cache(lazy_src(graw, n_iq, n_taps, 3, 1), ws, cap), osr, carrier_freq, nd, cap, ws, true, sg));
-        if (timing) TRY(stage_mark(sg));
+        if (timing) TRY(stage_mark(*c, sg));
         if (sg != st) {
             cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             CU(cudaEventRecord(ev, sg));
@@ -1011,7 +1017,7 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
     if (fcch_pos) CU(cudaMemcpyAsync(fcch_pos, w.fcch_pos, sizeof(double) * D * cap, cudaMemcpyDeviceToHost, st));
     if (pos_info) CU(cudaMemcpyAsync(pos_info, w.pos_info, sizeof(double) * D * cap * 12, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    if (timing) for (int i = 0; i + 1 < g_stage_n; ++i) CU(cudaEventElapsedTime(&g_stage_ms[i], g_stage_ev[i], g_stage_ev[i + 1]));
+    if (timing) for (int i = 0; i + 1 < g_stage_n; ++i) CU(cudaEventElapsedTime(&g_stage_ms[i], c->stage_ev[i], c->stage_ev[i + 1]));
     if (!timing) g_stage_n = 0;
     return GSMCAL_OK;
 }
@@ -1131,6 +1137,26 @@ int gsmcal_calibrate_batch_collect(int slot) {
     if (sl.coarse_snr) memcpy(sl.coarse_snr, h_arr + sl.n_per, sl.n_per);
     if (sl.fcch_pos) memcpy(sl.fcch_pos, h_arr + 2 * sl.n_per, sl.n_per);
     if (sl.pos_info) memcpy(sl.pos_info, h_arr + 3 * sl.n_per, 12 * sl.n_per);
+    sl.busy = false;
+    return GSMCAL_OK;
+}
+
+int gsmcal_calibrate_batch_cancel(int slot) {
+    // gives the slot back without delivering results: waits for the batch (its kernels read the capture and write the slot's own
+    // staging, never the caller's result pointers, which are only touched by _collect) and forgets the pointers
+    cudaEvent_t done;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (slot < 0 || slot >= kSlots) return fail(GSMCAL_ERR_ARG, "calibrate_batch_cancel: slot must be 0..%d", kSlots - 1);
+        Ctx *c; TRY(get_ctx(&c));
+        if (!c->slots[slot].busy) return GSMCAL_OK;
+        done = c->slots[slot].done;
+    }
+    CU(cudaEventSynchronize(done));
+    std::lock_guard<std::mutex> lk(g_mu);
+    Ctx *c; TRY(get_ctx(&c));
+    Slot &sl = c->slots[slot];
+    sl.results = nullptr; sl.coarse_pos = sl.coarse_snr = sl.fcch_pos = sl.pos_info = nullptr;
     sl.busy = false;
     return GSMCAL_OK;
 }

@@ -22,13 +22,13 @@
 #define B8_BUF     2304                      // staged samples: 2208 + (NT-1 <= 63) + R-1, rounded up
 #define B8_CSL     71                        // row stride of the chunk prefix table (odd: bins fall into different banks)
 #define B8_SMEM    (B8_BUF * 16 + 8 * B8_CSL * 16 + 72 * 8 + 72 * 8 + 33 * 8 * 8)
-#define B8_NPASS   6                         // passes of 8 tracked bins each before a burst is handed to the 64-bin band kernel
+#define B8_NPASS   8                         // passes of 8 tracked bins each before a burst is handed to the 64-bin band kernel
 // offset from the band centre k0 of tracked bin j (0..7) in pass p: 8 bins around the tone, 8 more on both sides, then 8 at a time
 // towards the GMSK data energy (it sits ~37 bins below the FCCH tone)
 __device__ __forceinline__ int b8_bin_off(int pass, int j) { return pass == 0 ? j - 3 : (pass == 1 ? (j < 4 ? j - 7 : j + 1) : -8 * pass + 1 + j); }
 
 template <int NT>
-__global__ void __launch_bounds__(B8_THREADS, 4) fine_core8_kernel(const uint8_t *__restrict__ raw_all, i64 n_iq, const StreamCtl *__restrict__ ctl,
+__global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ raw_all, i64 n_iq, const StreamCtl *__restrict__ ctl,
                                                                   const double *__restrict__ base_pos, int cap, const double2 *__restrict__ tw,
                                                                   double *__restrict__ fine_raw, int *__restrict__ need_band, int force_fail,
                                                                   double2 *__restrict__ wcache, int n_pass, unsigned *__restrict__ pass_hist) {
@@ -140,8 +140,10 @@ __global__ void __launch_bounds__(B8_THREADS, 4) fine_core8_kernel(const uint8_t
     // is re-checked after each; a burst leaves as soon as it is proven.  The 64-bin band kernel only sees what is still open then.
     double g_best = -1.0; int g_bestm = 0x7fffffff;
     int ok = 0, pass = 0;
+    bool is_diff = false;                                        // B[0..1024) holds the differences d[m] instead of the samples (block-uniform)
     for (; pass < n_pass && !ok; ++pass) {
-        if (pass > 0) {                                          // s[m] = s[m+N] - d[m] for m < 1024 (d was stored in place)
+        if (is_diff) {                                           // s[m] = s[m+N] - d[m] for m < 1024 (d was stored in place)
+            is_diff = false;
             for (int m = tid; m < B8_NWIN - 1; m += B8_THREADS) {
                 const int i0 = B8_WPAD(m);
                 const double2 dd = B[i0], s_new = B[i0 + 33 * B8_WCH];
@@ -206,31 +208,54 @@ __global__ void __launch_bounds__(B8_THREADS, 4) fine_core8_kernel(const uint8_t
             xr = yr * t.x + yi * t.y;
             xi = yi * t.x - yr * t.y;
         }
-        for (int m = tid; m < B8_NWIN - 1; m += B8_THREADS) {    // d[m] = s[m+N] - s[m] in place
-            const int i0 = B8_WPAD(m);
-            const double2 s_old = B[i0], s_new = B[i0 + 33 * B8_WCH];
-            B[i0] = make_double2(s_new.x - s_old.x, s_new.y - s_old.y);
-        }
+        // ---- which (segment, bin) pairs can hold the maximum at all?  |X_{m+1}[k]| <= |X_m[k]| + |s[m]| + |s[m+N]|, so the windows of
+        //      segment g stay below |X_{32g}[k]| + slack_g; the largest segment-start power (and the best of earlier passes) is a lower
+        //      bound of the final maximum.  Only the few segments around the burst slide; for the bins of the later passes usually none. ----
+        const double p0 = fma(xr, xr, xi * xi);
+        double gl = p0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gl = fmax(gl, __shfl_xor_sync(0xffffffffu, gl, o));
+        if (lane == 0) red_v[warp] = gl;
         __syncthreads();
-        const double wr = wk.x, wi = -wk.y;
-        double best = -1.0; int bestm = 0x7fffffff;
+        gl = fmax(fmax(fmax(red_v[0], red_v[1]), fmax(red_v[2], red_v[3])), fmax(fmax(red_v[4], red_v[5]), fmax(red_v[6], red_v[7])));
+        if (pass > 0) gl = fmax(gl, g_best);
+        bool need;
         {
-            const double2 *dp = B + 33 * g;                      // d[32 g + i] sits at 33 g + i
-            const int m0 = 32 * g;
-#pragma unroll 8
-            for (int i = 0; i < 32; ++i) {
-                const double p = fma(xr, xr, xi * xi);
-                if (p > best) { best = p; bestm = m0 + i; }
-                if (i < 31 || g == B8_NSEG - 1) {
-                    const double2 d = dp[i];
-                    const double tr = xr + d.x, ti = xi + d.y;
-                    xr = fma(tr, wr, -(ti * wi));
-                    xi = fma(tr, wi, ti * wr);
-                }
+            const double slack = (g < B8_NSEG - 1) ? sqrt_ub(31.0 * E31[g]) + sqrt_ub(31.0 * E31[g + B8_WCH])
+                                                   : sqrt_ub(32.0 * (PE[g + 1] - PE[g])) + sqrt_ub(32.0 * (PE[g + B8_WCH + 1] - PE[g + B8_WCH]));
+            const double bound = (sqrt_ub(p0) + slack) * (1.0 + 1e-9);
+            need = !(bound * bound < gl * (1.0 - 1e-6));
+        }
+        const int any_need = __syncthreads_or(need ? 1 : 0);      // (also orders the reads of red_v before block_argmax reuses it)
+        double best = -1.0; int bestm = 0x7fffffff;
+        if (any_need) {
+            for (int m = tid; m < B8_NWIN - 1; m += B8_THREADS) {    // d[m] = s[m+N] - s[m] in place
+                const int i0 = B8_WPAD(m);
+                const double2 s_old = B[i0], s_new = B[i0 + 33 * B8_WCH];
+                B[i0] = make_double2(s_new.x - s_old.x, s_new.y - s_old.y);
             }
-            if (g == B8_NSEG - 1) {                              // the last segment also owns window 1024
-                const double p = fma(xr, xr, xi * xi);
-                if (p > best) { best = p; bestm = m0 + 32; }
+            is_diff = true;
+            __syncthreads();
+            if (need) {
+                const double wr = wk.x, wi = -wk.y;
+                const double2 *dp = B + 33 * g;                      // d[32 g + i] sits at 33 g + i
+                int besti = 0;
+#pragma unroll 8
+                for (int i = 0; i < 32; ++i) {
+                    const double p = fma(xr, xr, xi * xi);
+                    if (p > best) { best = p; besti = i; }
+                    if (i < 31 || g == B8_NSEG - 1) {
+                        const double2 d = dp[i];
+                        const double tr = xr + d.x, ti = xi + d.y;
+                        xr = fma(tr, wr, -(ti * wi));
+                        xi = fma(tr, wi, ti * wr);
+                    }
+                }
+                if (g == B8_NSEG - 1) {                              // the last segment also owns window 1024
+                    const double p = fma(xr, xr, xi * xi);
+                    if (p > best) { best = p; besti = 32; }
+                }
+                bestm = 32 * g + besti;
             }
         }
         block_argmax(best, bestm, red_v, red_i);
@@ -301,7 +326,7 @@ __global__ void __launch_bounds__(B8_THREADS, 4) fine_core8_kernel(const uint8_t
 #define T8_NSEG    119                       // ceil(1184 / 10); the last segment is padded with zeros
 #define T8_BUF     1216
 #define T8_SMEM    (2 * T8_BUF * 16)
-__global__ void __launch_bounds__(T8_THREADS, 4) tone8_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, int which, const double *__restrict__ pos, int cap,
+__global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, int which, const double *__restrict__ pos, int cap,
                                                              const double2 *__restrict__ tw, double *__restrict__ fo_out, double *__restrict__ gate_out,
                                                              int *__restrict__ need_old) {
     extern __shared__ __align__(16) double2 t8_sm[];
@@ -309,6 +334,7 @@ __global__ void __launch_bounds__(T8_THREADS, 4) tone8_kernel(WinSrc src, const 
     __shared__ double red_n[24];
     __shared__ double2 sh_base, sh_step;
     __shared__ double sh_pb[8], sh_E, sh_pr;
+    __shared__ double2 sh_x[8];
     __shared__ int sh_k0, sh_jbest, sh_flag;
     const int burst = blockIdx.x, stream = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const StreamCtl c = ctl[stream];
@@ -440,19 +466,29 @@ __global__ void __launch_bounds__(T8_THREADS, 4) tone8_kernel(WinSrc src, const 
         double xr = 0.0, xi = 0.0;
         for (int sgi = lane; sgi < T8_NSEG; sgi += 32) { const double2 v = spare[warp * 120 + sgi]; xr += v.x; xi += v.y; }
         xr = warp_sum(xr); xi = warp_sum(xi);
-        if (lane == 0) sh_pb[warp] = abs2_ref(make_double2(xr, xi));
+        if (lane == 0) sh_x[warp] = make_double2(xr, xi);
     }
     __syncthreads();
-    if (tid == 0) {   // first maximum in fftshift-ed order (:149-150) and the Parseval certificate for every bin outside the band
-        double v = -1.0, band_sum = 0.0; int j_best = 0x7fffffff;
-        for (int b = 0; b < 8; ++b) {
-            int k = (k0 - 3 + b) % N; if (k < 0) k += N;
-            int j = k - N / 2; if (j < 0) j += N;
-            band_sum += sh_pb[b];
-            argmax_combine(v, j_best, sh_pb[b], j);
+    if (warp == 0) {   // first maximum in fftshift-ed order (:149-150) and the Parseval certificate for every bin outside the band;
+                       // abs(.)^2 of the 8 bins by 8 lanes of ONE warp (hypot is ~150 instructions: not once per warp)
+        double pw = 0.0, v = -1.0; int j = 0x7fffffff;
+        if (lane < 8) {
+            int k = (k0 - 3 + lane) % N; if (k < 0) k += N;
+            j = k - N / 2; if (j < 0) j += N;
+            pw = abs2_ref(sh_x[lane]); v = pw;
         }
-        if (!((double)N * sh_E - band_sum < v * (1.0 - 1e-9))) sh_flag = 1;
-        sh_jbest = j_best;
+        double band_sum = pw;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            band_sum += __shfl_down_sync(0xffffffffu, band_sum, o);
+            const double v2 = __shfl_down_sync(0xffffffffu, v, o);
+            const int j2 = __shfl_down_sync(0xffffffffu, j, o);
+            argmax_combine(v, j, v2, j2);
+        }
+        if (lane == 0) {
+            if (!((double)N * sh_E - band_sum < v * (1.0 - 1e-9))) sh_flag = 1;
+            sh_jbest = j;
+        }
     }
     __syncthreads();
     if (sh_flag) {                                               // block-uniform: not certified, the row-FFT kernel takes the burst

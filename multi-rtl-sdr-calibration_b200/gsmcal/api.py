@@ -343,9 +343,25 @@ class PendingBatch:
 
     def __init__(self, slot, D, cap, res, arrays, keep):
         self.slot, self.D, self.cap, self.res, self.arrays, self._keep = slot, D, cap, res, arrays, keep
+        self._open = True
+
+    def cancel(self):
+        """Give the slot back without results (the library never writes this object's arrays after that)."""
+        if self._open:
+            self._open = False
+            check(lib().gsmcal_calibrate_batch_cancel(self.slot))
+
+    def __del__(self):                       # a dropped PendingBatch must not leave its slot busy with dangling pointers
+        try:
+            self.cancel()
+        except Exception:
+            pass
 
     def collect(self, details: bool | None = None):
+        if not self._open:
+            raise GsmcalError(-1, "this batch was already collected or cancelled")
         check(lib().gsmcal_calibrate_batch_collect(self.slot))
+        self._open = False
         if self.arrays is None or details is False:
             return self.res
         return _unpack_results(self.res, self.D, self.cap, *self.arrays)

@@ -26,7 +26,8 @@ CMD_SET_FREQ, CMD_SET_RATE, CMD_SET_GAIN_MODE, CMD_SET_GAIN = 1, 2, 3, 4
 
 
 def _send_cmd(sock: socket.socket, cmd: int, param: int) -> None:
-    sock.sendall(struct.pack(">BI", cmd, int(param) & 0xFFFFFFFF))
+    param = min(max(int(param), 0), 0xFFFFFFFF)                  # MATLAB's uint32() saturates (a negative gain becomes 0, not 4e9)
+    sock.sendall(struct.pack(">BI", cmd, param))
 
 
 def set_freq_tcp(sock: socket.socket, freq: float) -> socket.socket:
@@ -92,10 +93,12 @@ class DongleIngest:
         self.bytes_read = 0
 
     # ------------------------------------------------------------------------------------------------------------
-    def _read_rows(self, buf: np.ndarray, rows: list[int], errors: list) -> None:
-        """One worker: multiplex its sockets, recv_into straight into the pinned rows."""
+    def _read_rows(self, buf: np.ndarray, rows: list[int], errors: list, stop: threading.Event) -> None:
+        """One worker: multiplex its sockets, recv_into straight into the pinned rows.  A failure in ANY worker sets `stop`, so the
+        others leave within one poll interval instead of writing into the buffer until their own timeout; the selector is always
+        closed and the sockets are handed back blocking, so a retry of read_capture starts from a clean state."""
+        sel = selectors.DefaultSelector()
         try:
-            sel = selectors.DefaultSelector()
             need = 2 * self.num_sample
             views = {d: memoryview(buf[d]) for d in rows}
             got = {d: 0 for d in rows}
@@ -103,11 +106,17 @@ class DongleIngest:
                 self.socks[d].setblocking(False)
                 sel.register(self.socks[d], selectors.EVENT_READ, d)
             left = len(rows)
-            while left:
-                ev = sel.select(self.timeout)
+            waited = 0.0
+            poll = min(0.2, self.timeout)
+            while left and not stop.is_set():
+                ev = sel.select(poll)
                 if not ev:
-                    raise TimeoutError(f"rtl_tcp read timed out; short rows: "
-                                       f"{[(d, got[d]) for d in rows if got[d] < need][:4]}")
+                    waited += poll
+                    if waited >= self.timeout:
+                        raise TimeoutError(f"rtl_tcp read timed out; short rows: "
+                                           f"{[(d, got[d]) for d in rows if got[d] < need][:4]}")
+                    continue
+                waited = 0.0
                 for key, _ in ev:
                     d = key.data
                     n = key.fileobj.recv_into(views[d][got[d]:need])
@@ -117,19 +126,27 @@ class DongleIngest:
                     if got[d] == need:
                         sel.unregister(key.fileobj)
                         left -= 1
-            sel.close()
         except Exception as e:                                      # surfaced by read_capture on the calling thread
             errors.append(e)
+            stop.set()
+        finally:
+            sel.close()
+            for d in rows:
+                try:
+                    self.socks[d].settimeout(self.timeout)
+                except OSError:
+                    pass
 
     def read_capture(self, buf: np.ndarray) -> np.ndarray:
         """The `fread(tcp_obj{i}, 2*num_sample, 'uint8')` loop of gsm_sync_demod.m:95-98 for all dongles at once."""
         D = len(self.socks)
         errors: list = []
+        stop = threading.Event()
         parts = [list(range(t, D, self.n_threads)) for t in range(self.n_threads)]
-        threads = [threading.Thread(target=self._read_rows, args=(buf, rows, errors), daemon=True) for rows in parts[1:]]
+        threads = [threading.Thread(target=self._read_rows, args=(buf, rows, errors, stop), daemon=True) for rows in parts[1:]]
         for t in threads:
             t.start()
-        self._read_rows(buf, parts[0], errors)
+        self._read_rows(buf, parts[0], errors, stop)
         for t in threads:
             t.join()
         if errors:

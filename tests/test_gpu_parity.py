@@ -303,7 +303,7 @@ def test_tone8_equals_generic_tone_estimator(gpu, captures, coef47, tpl):
     _, raw = captures
     new = gpu.calibrate_batch(raw, CARRIER, tpl, coef47)
     outs = []
-    for key, val, back in ((11, 1, 0), (10, 1, 6)):
+    for key, val, back in ((11, 1, 0), (10, 1, 8)):
         lib().gsmcal_debug_set(key, val)
         try:
             outs.append(gpu.calibrate_batch(raw, CARRIER, tpl, coef47))

@@ -59,6 +59,42 @@ def test_lockstep_captures_are_byte_exact_and_greeting_is_flushed():
             s.close()
 
 
+def test_negative_gain_saturates_like_uint32():
+    """MATLAB's uint32(gain) saturates at 0 (set_gain_tcp.m:10); a two's-complement wrap would ask the tuner for 4e9 tenths of a dB"""
+    srv = _servers(1, 4096)[0]
+    try:
+        import socket
+        s = socket.create_connection((srv.host, srv.port))
+        ingest.set_gain_tcp(s, -7)
+        assert _wait_cmds(srv, 2) == [(3, 1), (4, 0)]
+        s.close()
+    finally:
+        srv.close()
+
+
+def test_one_failing_dongle_stops_all_readers_and_leaves_sockets_usable():
+    """a dongle that stalls must not leave the other reader threads writing into the buffer until their own timeout, and the
+    sockets of the healthy dongles must come back blocking (a retry starts clean)"""
+    D, N = 4, 20000
+    srvs = _servers(D, 2 * N, seed=5)
+    try:
+        ing = ingest.DongleIngest([(s.host, s.port) for s in srvs], N, 957.4e6, 2166666.67, n_threads=4, timeout=1.0)
+        ing.flush()
+        srvs[2].close()                           # dongle 2 goes away
+        time.sleep(0.2)
+        t0 = time.time()
+        with pytest.raises((ConnectionError, TimeoutError, OSError)):
+            for _ in range(50):
+                ing.read_capture(ing.buffers[0])
+        assert time.time() - t0 < 20
+        for d in (0, 1, 3):
+            assert ing.socks[d].gettimeout() == 1.0      # handed back in blocking-with-timeout mode
+        ing.close()
+    finally:
+        for s in srvs:
+            s.close()
+
+
 def test_short_stream_raises():
     srv = _servers(1, 1000)[0]
     try:
