@@ -6,7 +6,9 @@
  * these symbols and shadows the .m file.  Citations are file:line into the reference.
  *
  * Conventions (all entry points)
- *   - plain pointers + sizes; HOST memory unless a parameter says otherwise; caller allocates outputs.
+ *   - plain pointers + sizes; HOST memory unless a parameter says otherwise; caller allocates outputs.  Host buffers may be
+ *     pageable (an mxArray, a NumPy array): transfers above 32 MB then go through the library's own multi-threaded pinned staging
+ *     ring (~4x the rate of cudaMemcpy from pageable memory); pinned / registered buffers are used directly.
  *   - matrices are column-major as MATLAB holds them; one stream (dongle / scanned frequency) per column.
  *   - complex128 is interleaved (re,im) pairs of doubles ("double[2]").
  *   - positions / indices are 1-based doubles exactly as the reference returns them.
@@ -72,6 +74,13 @@ int gsmcal_chn_filter_taps (int which /* 8 or 4 */, double *coef /* >=60 */, int
  *      scan_band_power_spectrum.m:80-85 (coef NULL, decim 1); multi_rtl_sdr_split_scanner.m:154-156 ---- */
 int gsmcal_band_power_u8(const uint8_t *a, int64_t n_iq, int64_t n_col, const double *coef, int n_taps,
                          int decim, double *power /* n_col, linear */);
+
+/* diversity scanner, multi_rtl_sdr_diversity_scanner.m:150-176: every dongle scans the same band.
+ * s_all: (2*n_iq) x n_freq x n_dongle uint8 as the script holds it (:118-131).  power_spectrum: n_dongle x n_freq (column-major),
+ * power_spectrum(i,:) = mean(abs(r_flt(1:decim:end,:)).^2, 1) of dongle i (:152-156); power_spectrum_combine: 1 x n_freq =
+ * mean(power_spectrum, 1) (:172), linear units.  The combination runs on the device (one kernel after the per-column means). */
+int gsmcal_diversity_power_u8(const uint8_t *s_all, int64_t n_iq, int64_t n_freq, int64_t n_dongle, const double *coef, int n_taps,
+                              int decim, double *power_spectrum, double *power_spectrum_combine);
 
 /* ---- K3  [hit_flag,hit_idx,hit_avg_snr,hit_snr] = move_fft_snr_runtime_avg(s,mv_len,fft_len,th)
  *          move_fft_snr_runtime_avg.m:5-50.   No hit: 0, -1, inf, inf.  fft_len <= 128. ---- */
@@ -230,10 +239,12 @@ int gsmcal_fcch_scan(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t n_ch
  * 6 = burst chain on high-priority streams (default 1); 7 = blocks per SM of a persistent high-priority column-sum kernel in
  * _submit (default 0 = per-group launches); 8 = stream groups inside a submitted batch (default 1); 9, value 1 = the generic tier-1 fine
  * search without the osr-8 fast path and its filtered-window cache (A/B and tests); 10 = passes of 8 tracked bins in the osr-8 tier-1
- * kernel (1..8, default 8); 11, value 1 = generic tone estimator for every burst (no tone8_kernel) */
+ * kernel (1..8, default 8); 11, value 1 = generic tone estimator for every burst (no tone8_kernel); 12, value 1 = plain cudaMemcpyAsync
+ * for pageable host buffers instead of the library's multi-threaded pinned staging ring */
 int gsmcal_debug_set(int key, int value);
 /* key 1: number of bursts of the last fine FCCH search whose band certificate failed (all-bin fallback ran); 2: bursts that needed the
- * 64-bin band kernel; 10 + p: bursts the osr-8 tier-1 kernel proved after p passes (p = 0: left open) */
+ * 64-bin band kernel; 10 + p: bursts the osr-8 tier-1 kernel proved after p passes (p = 0: left open); 30: bytes moved through the
+ * pinned staging ring so far */
 int64_t gsmcal_debug_get(int key);
 
 /* kernel-launch counter (all launches since the last reset, this process) - for bench.py's gpu_launches */

@@ -13,6 +13,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "chn_filter_taps.inc"
@@ -85,8 +86,11 @@ struct Slot {
     gsmcal_stream_result *results = nullptr; double *coarse_pos = nullptr, *coarse_snr = nullptr, *fcch_pos = nullptr, *pos_info = nullptr;
     size_t n_res = 0, n_per = 0;                                // bytes of the result records / of one D*cap double array
 };
+#include "gsmcal_hostcopy.inc"
+
 constexpr int kNumStageEvents = 8;
 struct Ctx {
+    StageRing ring;                  // pinned staging for pageable host buffers
     bool attrs = false;
     cudaEvent_t stage_ev[kNumStageEvents];
     bool stage_ev_ok = false;
@@ -171,6 +175,15 @@ int get_ctx(Ctx **out) {
         CU(cudaFuncSetAttribute(fcch_demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));      // (attributes are per device:
         CU(cudaFuncSetAttribute(fde_template_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));    //  all of them live here, keyed by
         CU(cudaFuncSetAttribute(sch_demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));       //  the device's Ctx)
+        // The front of batch k+1 (column sums, mean, SNR map, first-hit scan, burst chain) is meant to run BESIDE the FP64 burst kernels of
+        // batch k, whose blocks need the SM in its maximum-shared-memory configuration.  A kernel that prefers a different L1/shared
+        // split cannot be placed on such an SM until it drains, so the front kernels ask for the same carve-out.
+        CU(cudaFuncSetAttribute(colsum_u8_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CU(cudaFuncSetAttribute(colsum_u8_persist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CU(cudaFuncSetAttribute(mean_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CU(cudaFuncSetAttribute(snr_map_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CU(cudaFuncSetAttribute(first_hit_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CU(cudaFuncSetAttribute(coarse_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         c.attrs = true;
     }
     *out = &c;
@@ -467,7 +480,7 @@ void gsmcal_release(void) {
     g_last_need_full = nullptr; g_last_need_band = nullptr; g_last_need_full_n = 0; g_last_pass_hist = nullptr;   // they point into the workspaces freed below
     for (auto &kv : g_ctx) {
         cudaSetDevice(kv.first);
-        kv.second.in.release(); kv.second.out.release(); kv.second.work.release(); kv.second.tplbuf.release(); kv.second.wc.release();
+        kv.second.ring.release(); kv.second.in.release(); kv.second.out.release(); kv.second.work.release(); kv.second.tplbuf.release(); kv.second.wc.release();
         for (auto &t : kv.second.tw) cudaFree(t.second);
         kv.second.tw.clear();
         if (kv.second.stage_ev_ok) { for (cudaEvent_t e : kv.second.stage_ev) cudaEventDestroy(e); kv.second.stage_ev_ok = false; }
@@ -492,6 +505,7 @@ void gsmcal_release(void) {
 int64_t gsmcal_debug_get(int key) {
     // key 1: bursts of the last fine search (this device) that needed the all-bin fallback
     std::lock_guard<std::mutex> lk(g_mu);
+    if (key == 30) return (int64_t)g_staged_bytes.load();           // bytes that went through the pinned staging ring (pageable host buffers)
     if (key >= 10 && key < 26) {                                 // 10 + p: bursts the osr-8 tier-1 kernel proved after p passes (p = 0: left open)
         if (!g_last_pass_hist) return 0;
         unsigned v = 0;
@@ -516,6 +530,7 @@ int gsmcal_debug_set(int key, int value) {
     if (key == 6) { g_debug_hi_prio = value ? 1 : 0; return GSMCAL_OK; }
     if (key == 9) { g_debug_no_core8 = value ? 1 : 0; return GSMCAL_OK; }
     if (key == 11) { g_debug_no_tone8 = value ? 1 : 0; return GSMCAL_OK; }
+    if (key == 12) { g_debug_no_staging = value ? 1 : 0; return GSMCAL_OK; }
     if (key == 10) { g_debug_core8_passes = value < 1 ? 1 : (value > 8 ? 8 : value); return GSMCAL_OK; }
     if (key == 8) { g_debug_submit_groups = value < 1 ? 1 : (value > kMaxGroups / 2 ? kMaxGroups / 2 : value); return GSMCAL_OK; }
     if (key == 7) { g_debug_persist_colsum = value < 0 ? 0 : (value > 8 ? 8 : value); return GSMCAL_OK; }
@@ -540,13 +555,12 @@ int gsmcal_raw2iq_u8(const uint8_t *a, int64_t n_iq, int64_t n_col, double *b) {
     TRY(c->in.get((size_t)2 * n_iq * n_col, &din));
     TRY(c->out.get(sizeof(double2) * (size_t)n_iq * n_col, &dout));
     TRY(make_work(c->work, n_col, 1, 1, 0, &w));
-    CU(cudaMemcpyAsync(din, a, (size_t)2 * n_iq * n_col, cudaMemcpyHostToDevice, st));
+    TRY(copy_h2d(c->ring, g_device, din, a, (size_t)2 * n_iq * n_col, st));
     CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * n_col, st));
     TRY(run_colsum_u8((const uint8_t *)din, n_iq, n_col, w.ctl, st));
     i64 gx = (n_iq + 256 * 8 - 1) / (256 * 8); if (gx > 148 * 16) gx = 148 * 16; if (gx < 1) gx = 1;
     LAUNCH(raw2iq_store_kernel, dim3((unsigned)gx, (unsigned)n_col), 256, 0, st, (const uint8_t *)din, n_iq, w.ctl, (double2 *)dout);
-    CU(cudaMemcpyAsync(b, dout, sizeof(double2) * (size_t)n_iq * n_col, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    TRY(copy_d2h(c->ring, g_device, b, dout, sizeof(double2) * (size_t)n_iq * n_col, st));
     return GSMCAL_OK;
 }
 
@@ -563,13 +577,12 @@ int gsmcal_raw2iq_f64(const double *a, int64_t n_iq, int64_t n_col, double *b) {
     TRY(c->in.get(sizeof(double) * (size_t)2 * n_iq * n_col, &din));
     TRY(c->out.get(sizeof(double2) * (size_t)n_iq * n_col, &dout));
     TRY(make_work(c->work, n_col, 1, 1, 0, &w));
-    CU(cudaMemcpyAsync(din, a, sizeof(double) * (size_t)2 * n_iq * n_col, cudaMemcpyHostToDevice, st));
+    TRY(copy_h2d(c->ring, g_device, din, a, sizeof(double) * (size_t)2 * n_iq * n_col, st));
     CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * n_col, st));
     i64 gx = (n_iq + 256 * 8 - 1) / (256 * 8); if (gx > 148 * 16) gx = 148 * 16; if (gx < 1) gx = 1;
     LAUNCH(colsum_f64_kernel, dim3((unsigned)gx, (unsigned)n_col), 256, 0, st, (const double *)din, n_iq, w.ctl);
     LAUNCH(raw2iq_store_f64_kernel, dim3((unsigned)gx, (unsigned)n_col), 256, 0, st, (const double *)din, n_iq, w.ctl, (double2 *)dout);
-    CU(cudaMemcpyAsync(b, dout, sizeof(double2) * (size_t)n_iq * n_col, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    TRY(copy_d2h(c->ring, g_device, b, dout, sizeof(double2) * (size_t)n_iq * n_col, st));
     return GSMCAL_OK;
 }
 
@@ -603,10 +616,9 @@ int gsmcal_fir_filter(const double *coef, int n_taps, const double *s, int64_t n
     TRY(c->in.get(sizeof(double2) * (size_t)n * n_col, &din));
     TRY(c->out.get(sizeof(double2) * (size_t)n_out * n_col, &dout));
     TRY(set_taps(coef, n_taps, st));
-    CU(cudaMemcpyAsync(din, s, sizeof(double2) * (size_t)n * n_col, cudaMemcpyHostToDevice, st));
+    TRY(copy_h2d(c->ring, g_device, din, s, sizeof(double2) * (size_t)n * n_col, st));
     TRY(run_fir<false>(din, n, n, nullptr, n_taps, decim, n_col, (double2 *)dout, n_out, nullptr, st));
-    CU(cudaMemcpyAsync(r, dout, sizeof(double2) * (size_t)n_out * n_col, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    TRY(copy_d2h(c->ring, g_device, r, dout, sizeof(double2) * (size_t)n_out * n_col, st));
     return GSMCAL_OK;
 }
 
@@ -622,12 +634,11 @@ int gsmcal_raw2iq_fir_u8(const uint8_t *a, int64_t n_iq, int64_t n_col, const do
     TRY(c->out.get(sizeof(double2) * (size_t)n_out * n_col, &dout));
     TRY(make_work(c->work, n_col, 1, 1, 0, &w));
     TRY(set_taps(coef, n_taps, st));
-    CU(cudaMemcpyAsync(din, a, (size_t)2 * n_iq * n_col, cudaMemcpyHostToDevice, st));
+    TRY(copy_h2d(c->ring, g_device, din, a, (size_t)2 * n_iq * n_col, st));
     CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * n_col, st));
     TRY(run_colsum_u8((const uint8_t *)din, n_iq, n_col, w.ctl, st));
     TRY(run_fir<true>(din, n_iq, 2 * n_iq, w.ctl, n_taps, decim, n_col, (double2 *)dout, n_out, nullptr, st));
-    CU(cudaMemcpyAsync(r, dout, sizeof(double2) * (size_t)n_out * n_col, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    TRY(copy_d2h(c->ring, g_device, r, dout, sizeof(double2) * (size_t)n_out * n_col, st));
     return GSMCAL_OK;
 }
 
@@ -649,7 +660,7 @@ int gsmcal_band_power_u8(const uint8_t *a, int64_t n_iq, int64_t n_col, const do
     TRY(c->in.get((size_t)2 * n_iq * n_col, &din));
     TRY(make_work(c->work, n_col, 1, 1, 0, &w));
     if (coef) TRY(set_taps(coef, n_taps, st));
-    CU(cudaMemcpyAsync(din, a, (size_t)2 * n_iq * n_col, cudaMemcpyHostToDevice, st));
+    TRY(copy_h2d(c->ring, g_device, din, a, (size_t)2 * n_iq * n_col, st));
     CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * n_col, st));
     CU(cudaMemsetAsync(w.power, 0, sizeof(double) * n_col, st));
     TRY(run_colsum_u8((const uint8_t *)din, n_iq, n_col, w.ctl, st));
@@ -666,6 +677,31 @@ int gsmcal_band_power_u8(const uint8_t *a, int64_t n_iq, int64_t n_col, const do
     return GSMCAL_OK;
 }
 
+int gsmcal_diversity_power_u8(const uint8_t *s_all, int64_t n_iq, int64_t n_freq, int64_t n_dongle, const double *coef, int n_taps, int decim,
+                              double *power_spectrum, double *power_spectrum_combine) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!s_all || !coef || !power_spectrum || !power_spectrum_combine || n_iq < 1 || n_freq < 1 || n_dongle < 1 || decim < 1)
+        return fail(GSMCAL_ERR_ARG, "diversity_power: bad arguments");
+    const i64 n_col = n_freq * n_dongle;
+    Ctx *c; TRY(get_ctx(&c));
+    cudaStream_t st = 0;
+    void *din; Work w;
+    TRY(c->in.get((size_t)2 * n_iq * n_col, &din));
+    TRY(make_work(c->work, n_col, 3, 1, 0, &w));                  // cap 3: room for power | per-dongle spectrum | combination in the [D][cap] arrays
+    TRY(set_taps(coef, n_taps, st));
+    TRY(copy_h2d(c->ring, g_device, din, s_all, (size_t)2 * n_iq * n_col, st));
+    CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * n_col, st));
+    CU(cudaMemsetAsync(w.power, 0, sizeof(double) * n_col, st));
+    TRY(run_colsum_u8((const uint8_t *)din, n_iq, n_col, w.ctl, st));
+    const i64 n_out = (n_iq + decim - 1) / decim;
+    TRY(run_fir<true>(din, n_iq, 2 * n_iq, w.ctl, n_taps, decim, n_col, nullptr, n_out, w.power, st));
+    LAUNCH(diversity_combine_kernel, (unsigned)((n_freq + 127) / 128), 128, 0, st, w.power, n_out, (int)n_freq, (int)n_dongle, w.fo, w.gate);
+    CU(cudaMemcpyAsync(power_spectrum, w.fo, sizeof(double) * n_col, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(power_spectrum_combine, w.gate, sizeof(double) * n_freq, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return GSMCAL_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 static int snr_windows(const double *s, int64_t len, int fft_len, i64 w0, i64 n_win, Ctx **cout, Work *w, cudaStream_t st) {
     if (!s || len < 1 || fft_len < 1 || fft_len > 128) return fail(GSMCAL_ERR_ARG, "moving fft: bad arguments (fft_len <= 128)");
@@ -673,7 +709,7 @@ static int snr_windows(const double *s, int64_t len, int fft_len, i64 w0, i64 n_
     void *din;
     TRY(c->in.get(sizeof(double2) * (size_t)len, &din));
     TRY(make_work(c->work, 1, 1, n_win > 0 ? n_win : 1, 0, w));
-    CU(cudaMemcpyAsync(din, s, sizeof(double2) * (size_t)len, cudaMemcpyHostToDevice, st));
+    TRY(copy_h2d(c->ring, g_device, din, s, sizeof(double2) * (size_t)len, st));
     CU(cudaMemsetAsync(w->ctl, 0, sizeof(StreamCtl), st));
     if (n_win > 0) {
         WinSrc src = mat_src((const double2 *)din, len, len, 0);
@@ -743,7 +779,7 @@ int gsmcal_FCCH_coarse_position(const double *s, int64_t len, int decimation_rat
     cudaStream_t st = 0; void *din; Work w;
     TRY(c->in.get(sizeof(double2) * (size_t)len, &din));
     TRY(make_work(c->work, 1, cap, p.n_first, 0, &w));
-    CU(cudaMemcpyAsync(din, s, sizeof(double2) * (size_t)len, cudaMemcpyHostToDevice, st));
+    TRY(copy_h2d(c->ring, g_device, din, s, sizeof(double2) * (size_t)len, st));
     CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl), st));
     TRY(run_coarse(mat_src((const double2 *)din, len, len, 0), len, p, 1, cap, w, st));
     StreamCtl h;
@@ -777,7 +813,7 @@ int gsmcal_FCCH_fine_correction(const double *s, int64_t n, const double *base_p
     const int cap = (int)n_base;
     TRY(c->in.get(sizeof(double2) * (size_t)n, &din));
     TRY(make_work(c->work, 1, cap, 1, 0, &w));
-    CU(cudaMemcpyAsync(din, s, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, st));
+    TRY(copy_h2d(c->ring, g_device, din, s, sizeof(double2) * (size_t)n, st));
     StreamCtl h; memset(&h, 0, sizeof h); h.n_coarse = cap;
     CU(cudaMemcpyAsync(w.ctl, &h, sizeof h, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(w.coarse_pos, base_position, sizeof(double) * cap, cudaMemcpyHostToDevice, st));
@@ -797,8 +833,7 @@ int gsmcal_FCCH_fine_correction(const double *s, int64_t n, const double *base_p
         else {
             void *dout; TRY(c->out.get(sizeof(double2) * (size_t)h.len1, &dout));
             TRY(run_resample_derotate((const double2 *)din, n, h.e1, h.interp1_on, h.dphi1, h.derot1_on, (double2 *)dout, h.len1, st));
-            CU(cudaMemcpyAsync(r, dout, sizeof(double2) * (size_t)h.len1, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
+            TRY(copy_d2h(c->ring, g_device, r, dout, sizeof(double2) * (size_t)h.len1, st));
         }
     }
     return GSMCAL_OK;
@@ -825,7 +860,7 @@ int gsmcal_SCH_corr_rate_correction(const double *s, int64_t n, const double *FC
     cudaStream_t st = 0; void *din; Work w;
     TRY(c->in.get(sizeof(double2) * (size_t)n, &din));
     TRY(make_work(c->work, 1, cap, 1, L, &w));
-    CU(cudaMemcpyAsync(din, s, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, st));
+    TRY(copy_h2d(c->ring, g_device, din, s, sizeof(double2) * (size_t)n, st));
     CU(cudaMemcpyAsync(w.tpl, tpl, sizeof(double2) * L, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(w.fcch_pos, FCCH_pos, sizeof(double) * cap, cudaMemcpyHostToDevice, st));
     StreamCtl h; memset(&h, 0, sizeof h); h.n_fcch = cap; h.sch_enable = 1; h.len1 = n;
@@ -848,8 +883,7 @@ int gsmcal_SCH_corr_rate_correction(const double *s, int64_t n, const double *FC
         else {
             void *dout; TRY(c->out.get(sizeof(double2) * (size_t)h.len2, &dout));
             TRY(run_resample_derotate((const double2 *)din, n, h.e2, 1, 0.0, 0, (double2 *)dout, h.len2, st));
-            CU(cudaMemcpyAsync(r, dout, sizeof(double2) * (size_t)h.len2, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
+            TRY(copy_d2h(c->ring, g_device, r, dout, sizeof(double2) * (size_t)h.len2, st));
         }
     }
     return GSMCAL_OK;
@@ -881,7 +915,7 @@ int gsmcal_carrier_correct_post_SCH(const double *s, int64_t n, const double *po
     TRY(c->in.get(sizeof(double2) * (size_t)n, &din));
     TRY(c->out.get(sizeof(double2) * (size_t)n, &dout));
     TRY(make_work(c->work, 1, cap, 1, 0, &w));
-    CU(cudaMemcpyAsync(din, s, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, st));
+    TRY(copy_h2d(c->ring, g_device, din, s, sizeof(double2) * (size_t)n, st));
     CU(cudaMemcpyAsync(w.post_pos, fpos.data(), sizeof(double) * cap, cudaMemcpyHostToDevice, st));
     StreamCtl h; memset(&h, 0, sizeof h); h.post_enable = 1; h.n_post_fcch = cap; h.len2 = n;
     h.sppm1 = h.sppm2 = h.cppm1 = INFINITY;
@@ -892,8 +926,7 @@ int gsmcal_carrier_correct_post_SCH(const double *s, int64_t n, const double *po
     CU(cudaStreamSynchronize(st));
     *carrier_ppm = h.cppm2;
     TRY(run_resample_derotate((const double2 *)din, n, 0.0, 0, h.dphi2, 1, (double2 *)dout, n, st));
-    CU(cudaMemcpyAsync(r, dout, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    TRY(copy_d2h(c->ring, g_device, r, dout, sizeof(double2) * (size_t)n, st));
     *r_len = n;
     return GSMCAL_OK;
 }
@@ -967,7 +1000,7 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
         Work ws = sub_work(w, d0, cap, g);
         const uint8_t *graw = draw + d0 * per;
         if (raw_mem == GSMCAL_MEM_HOST) {
-            CU(cudaMemcpyAsync((void *)graw, raw + d0 * per, per * nd, cudaMemcpyHostToDevice, cp));
+            TRY(copy_h2d(c->ring, g_device, (void *)graw, raw + d0 * per, per * nd, cp));
             cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             CU(cudaEventRecord(ev, cp)); CU(cudaStreamWaitEvent(sg, ev, 0)); CU(cudaEventDestroy(ev));
             TRY(run_colsum_u8(graw, n_iq, nd, ws.ctl, sg));
@@ -1185,7 +1218,7 @@ int gsmcal_fcch_scan(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t n_ch
     const uint8_t *draw = raw;
     if (raw_mem == GSMCAL_MEM_HOST) {
         void *din; TRY(c->in.get((size_t)2 * n_iq * n_chan, &din));
-        CU(cudaMemcpyAsync(din, raw, (size_t)2 * n_iq * n_chan, cudaMemcpyHostToDevice, st));
+        TRY(copy_h2d(c->ring, g_device, din, raw, (size_t)2 * n_iq * n_chan, st));
         draw = (const uint8_t *)din;
     }
     CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * n_chan, st));

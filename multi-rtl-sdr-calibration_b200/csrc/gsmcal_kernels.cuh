@@ -2267,6 +2267,45 @@ __global__ void __launch_bounds__(PS_THREADS) post_carrier_kernel(StreamCtl *ctl
     }
 }
 
+// ===================================================================================================
+// r_correct of the batched pipeline: the stream gsm_sync_demod.m:120 hands to SCH_demod (:145), straight from the uint8 capture:
+//   filter(coef,1,raw2iq(a)) -> interp1 by (1+e1) (FCCH_fine_correction.m:125) -> .*exp(1i*n*dphi1) (:165)
+//   -> interp1 by (1+e2) (SCH_corr_rate_correction.m:127) -> .*exp(1i*n*dphi2) (carrier_correct_post_SCH.m:83)
+// One pass, 2 bytes in and 16 bytes out per sample (the function-by-function chain moves 178).  Persistent blocks walk tiles of MAT_T
+// outputs; the levels are load_window's, the last derotation uses one slow-path sincos per tile.  FP64-bound by the 47-tap FIR.
+// ===================================================================================================
+#define MAT_T 1200
+#define MAT_THREADS 256
+__global__ void __launch_bounds__(MAT_THREADS) materialise_r_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, double2 *__restrict__ r_out, i64 r_stride,
+                                                                   i64 tiles_per_stream) {
+    extern __shared__ double2 sm[];
+    __shared__ double2 base2;
+    double2 *dst = sm, *X = dst + MAT_T, *Y = X + GSMCAL_XCAP(MAT_T + 8);
+    const int stream = blockIdx.y, tid = threadIdx.x;
+    const StreamCtl c = ctl[stream];
+    if (c.len3 < 0) return;                                      // r = -1 on this stream's path: nothing to materialise
+    double2 *o = r_out + (i64)stream * r_stride;
+    double2 st2 = make_double2(1.0, 0.0), ph_t = make_double2(1.0, 0.0);
+    {
+        double sn, cs;
+        sincos((double)tid * c.dphi2, &sn, &cs); ph_t = make_double2(cs, sn);
+        sincos((double)MAT_THREADS * c.dphi2, &sn, &cs); st2 = make_double2(cs, sn);
+    }
+    for (i64 tile = blockIdx.x; tile < tiles_per_stream; tile += gridDim.x) {
+        const i64 j0 = tile * MAT_T;
+        if (j0 >= c.len3) break;
+        const int count = (c.len3 - j0 < MAT_T) ? (int)(c.len3 - j0) : MAT_T;
+        __syncthreads();                                         // the previous tile's reads of dst are done
+        if (tid == 0) { double sn, cs; sincos((double)j0 * c.dphi2, &sn, &cs); base2 = make_double2(cs, sn); }
+        load_window(src, c, stream, j0, count, dst, X, Y);       // level 3; ends with a barrier
+        double2 ph = cmul(base2, ph_t);
+        for (int i = tid; i < count; i += MAT_THREADS) {
+            __stcs(o + j0 + i, cmul(dst[i], ph));
+            ph = cmul(ph, st2);
+        }
+    }
+}
+
 // FCCH scanner acceptance: multi_rtl_sdr_gsm_FCCH_scanner.m:165-186
 __global__ void scan_accept_kernel(const StreamCtl *ctl, int n_chan, int cap, const double *__restrict__ position, const double *__restrict__ snr,
                                    double *__restrict__ snr_out, double *__restrict__ num_hit) {
@@ -2289,6 +2328,21 @@ __global__ void scan_accept_kernel(const StreamCtl *ctl, int n_chan, int cap, co
         }
     }
     snr_out[ch] = s; num_hit[ch] = h;
+}
+
+// multi_rtl_sdr_diversity_scanner.m:150-176: per-dongle mean power (:155) and the incoherent combination over dongles
+// (mean(power_spectrum, 1), :172), both on the device: power_acc[i * n_freq + f] holds sum(abs(r_flt(1:decim:end, f)).^2) of dongle i.
+__global__ void diversity_combine_kernel(const double *__restrict__ power_acc, i64 n_out, int n_freq, int n_dongle,
+                                         double *__restrict__ power_spectrum /* n_dongle x n_freq, column-major */, double *__restrict__ combine) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_freq) return;
+    double acc = 0.0;
+    for (int i = 0; i < n_dongle; ++i) {                         // MATLAB sums a column top to bottom
+        const double p = power_acc[(i64)i * n_freq + f] / (double)n_out;
+        power_spectrum[(i64)f * n_dongle + i] = p;
+        acc += p;
+    }
+    combine[f] = acc / (double)n_dongle;
 }
 
 __global__ void mean_kernel(StreamCtl *ctl, int n_streams, i64 n_iq) {

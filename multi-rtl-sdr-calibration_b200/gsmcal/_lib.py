@@ -35,6 +35,7 @@ SIGNATURES = {
     "gsmcal_chn_filter_4x": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p]),
     "gsmcal_chn_filter_taps": (C.c_int, [C.c_int, C.c_void_p, c_ip]),
     "gsmcal_band_power_u8": (C.c_int, [C.c_void_p, c_i64, c_i64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "gsmcal_diversity_power_u8": (C.c_int, [C.c_void_p, c_i64, c_i64, c_i64, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "gsmcal_move_fft_snr_runtime_avg": (C.c_int, [C.c_void_p, c_i64, C.c_int, C.c_int, C.c_double, c_ip, c_dp, c_dp, c_dp]),
     "gsmcal_move_fft_snr_trace": (C.c_int, [C.c_void_p, c_i64, C.c_int, C.c_void_p]),
     "gsmcal_specific_fft_snr_fix_avg": (C.c_int, [C.c_void_p, c_i64, c_i64, c_i64, C.c_int, C.c_double, C.c_double, c_ip, c_dp, c_dp]),

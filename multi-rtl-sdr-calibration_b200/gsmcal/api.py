@@ -412,9 +412,14 @@ def fcch_scan(raw, coef, osr: int = 8, coarse_dr: int = 8):
 
 def diversity_power_spectrum(s_all_u8, coef, decim: int):
     """multi_rtl_sdr_diversity_scanner.m:150-176: every dongle scans the same band; per-dongle mean power after
-    raw2iq -> filter -> r(1:decim:end), then the incoherent mean across dongles.  s_all_u8: [2N, n_freq, n_dongle] uint8.
-    Returns (power_spectrum [n_dongle, n_freq], power_spectrum_combine [n_freq]), linear units."""
+    raw2iq -> filter -> r(1:decim:end), then the incoherent mean across dongles - one library call, the combination runs on the
+    device.  s_all_u8: [2N, n_freq, n_dongle] uint8.  Returns (power_spectrum [n_dongle, n_freq], power_spectrum_combine [n_freq]),
+    linear units."""
     s_all_u8 = np.asarray(s_all_u8, dtype=np.uint8)
-    per = np.stack([band_power(s_all_u8[:, :, i], coef, decim) for i in range(s_all_u8.shape[2])], axis=0)
-    combine = per.sum(axis=0) / per.shape[0]                      # mean(power_spectrum, 1)
-    return per, combine
+    rows, n_freq, n_dongle = s_all_u8.shape
+    buf = np.ascontiguousarray(np.transpose(s_all_u8, (2, 1, 0)))            # column-major 2N x n_freq x n_dongle == C order [dongle][freq][2N]
+    coef = np.ascontiguousarray(coef, dtype=np.float64)
+    per = np.empty((n_freq, n_dongle))                                        # column-major n_dongle x n_freq
+    combine = np.empty(n_freq)
+    check(lib().gsmcal_diversity_power_u8(_ptr(buf), rows // 2, n_freq, n_dongle, _ptr(coef), len(coef), int(decim), _ptr(per), _ptr(combine)))
+    return per.T.copy(), combine

@@ -7,7 +7,8 @@ import subprocess
 CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
 LIB = os.path.join(CSRC, "libgsmcal.so")
 SOURCES = ["gsmcal_api.cu"]
-DEPS = ["gsmcal_api.cu", "gsmcal_kernels.cuh", "gsmcal_demod.cuh", "gsmcal_demod_api.inc", "chn_filter_taps.inc", "../../include/gsmcal.h"]
+DEPS = ["gsmcal_api.cu", "gsmcal_kernels.cuh", "gsmcal_burst8.cuh", "gsmcal_hostcopy.inc", "gsmcal_demod.cuh", "gsmcal_demod_api.inc", "chn_filter_taps.inc",
+        "../../include/gsmcal.h"]
 
 
 def needs_build() -> bool:

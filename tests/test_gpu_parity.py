@@ -604,6 +604,63 @@ def test_diversity_scanner_combine(gpu):
     assert rel_err(per, ref) < 1e-12 and rel_err(comb, ref.mean(axis=0)) < 1e-12
 
 
+def test_split_and_diversity_scanners_at_the_reference_size(gpu):
+    """multi_rtl_sdr_split_scanner.m:40-57,154-156 at its own size (501 frequencies x 204,800 IQ at 2.048 MS/s, fir1(63, 0.05/2.048), /20)
+    and the diversity scanner's device-side combination over 2 dongles at the same size (multi_rtl_sdr_diversity_scanner.m:150-176).
+    The oracle filters 1002 columns of 204,800 samples: the slow part of this test is the CPU."""
+    rng = np.random.default_rng(17)
+    s_all = np.clip(np.round(rng.standard_normal((2 * 204800, 501, 2)) * rng.uniform(3, 40, size=(1, 501, 2)) + 127.5), 0, 255).astype(np.uint8)
+    coef = oracle.fir1(63, 0.05 / 2.048)
+    ref = np.stack([np.concatenate([oracle.band_power(s_all[:, f0:f0 + 64, i], coef, 20) for f0 in range(0, 501, 64)]) for i in range(2)], axis=0)
+    assert rel_err(gpu.band_power(s_all[:, :, 0], coef, 20), ref[0]) < 1e-12               # split scanner: 501 frequencies, one dongle's share
+    per, comb = gpu.diversity_power_spectrum(s_all, coef, 20)
+    assert per.shape == (2, 501) and comb.shape == (501,)
+    assert rel_err(per, ref) < 1e-12 and rel_err(comb, ref.sum(axis=0) / 2) < 1e-12
+
+
+def test_submit_cancel_gives_the_slot_back(gpu, captures, coef47, tpl):
+    import torch
+    _, raw = captures
+    a = torch.from_numpy(raw[:2].copy()).cuda()
+    torch.cuda.synchronize()
+    n_iq = raw.shape[1] // 2
+    p = gpu.calibrate_batch_submit(0, a.data_ptr(), n_iq, 2, CARRIER, tpl, coef47)
+    with pytest.raises(gpu.GsmcalError):                              # the slot is busy until collected or cancelled
+        gpu.calibrate_batch_submit(0, a.data_ptr(), n_iq, 2, CARRIER, tpl, coef47)
+    p.cancel()
+    with pytest.raises(gpu.GsmcalError):
+        p.collect()
+    q = gpu.calibrate_batch_submit(0, a.data_ptr(), n_iq, 2, CARRIER, tpl, coef47, details=True)
+    del p                                                             # a dropped, cancelled handle must not touch the slot again
+    got = q.collect()
+    _check_stream(got[0], oracle.calibrate_stream(raw[0], CARRIER, tpl, coef47))
+    r = gpu.calibrate_batch_submit(1, a.data_ptr(), n_iq, 2, CARRIER, tpl, coef47)
+    del r                                                             # dropped without collect: __del__ cancels, the slot is free again
+    gpu.calibrate_batch_submit(1, a.data_ptr(), n_iq, 2, CARRIER, tpl, coef47).collect()
+
+
+def test_second_device_after_the_first(gpu, captures, coef47, tpl):
+    """per-device state (kernel attributes, stage events, twiddles, workspaces): device 1 used after device 0 in one process.
+    Fewer than 8 streams takes the single-group path that records the stage events."""
+    if gpu.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    _, raw = captures
+    a = gpu.calibrate_batch(raw[:2], CARRIER, tpl, coef47)
+    gpu.set_device(1)
+    try:
+        b = gpu.calibrate_batch(raw[:2], CARRIER, tpl, coef47)
+        r = oracle.fir_filter(coef47, oracle.raw2iq(raw[0])[:, 0])
+        pinfo = a[0]["pos_info"]
+        d1 = gpu.FCCH_demod(r, pinfo, 8, CARRIER)                    # opts into > 48 KB of dynamic shared memory on device 1
+        s1 = gpu.SCH_demod(r, pinfo, tpl, 8)
+    finally:
+        gpu.set_device(0)
+    d0 = gpu.FCCH_demod(r, pinfo, 8, CARRIER)
+    for x, y in zip(a, b):
+        assert np.array_equal(x["pos_info"], y["pos_info"]) and x["total_carrier_ppm"] == y["total_carrier_ppm"]
+    assert np.array_equal(d0["max_idx"], d1["max_idx"]) and s1 is not None
+
+
 # ---- submit / collect: several batches in flight give the results of the synchronous call ---------------------------------------
 def test_submit_collect_matches_synchronous_call(gpu, captures, coef47, tpl):
     import torch
@@ -696,3 +753,27 @@ def test_planted_known_answers_through_the_c_abi(gpu, tpl):
     base = np.round((starts - 1) / osr) + 1 + np.array([3, -7, 0, 11, -20, 5])
     fpos, r, sppm, cppm = gpu.FCCH_fine_correction(s, base, osr, CARRIER)
     assert fpos.tolist() == starts.astype(float).tolist() and sppm == 0.0 and abs(cppm - 1e6 * f_off / CARRIER) < 1e-3
+
+
+def test_pageable_host_buffers_go_through_the_staging_ring(gpu, captures, coef47, tpl):
+    """NumPy arrays are pageable (like an mxArray): transfers above 32 MB use the library's pinned staging ring, both directions;
+    results are the bytes a plain cudaMemcpy delivers (debug key 12 switches the ring off)."""
+    from gsmcal._lib import lib
+    rng = np.random.default_rng(3)
+    n = 3_000_001                                                   # 48 MB of complex128 per column, odd length
+    s = rng.standard_normal((n, 2)) + 1j * rng.standard_normal((n, 2))
+    coef = oracle.fir1(46, 0.09)
+    before = int(lib().gsmcal_debug_get(30))
+    got = gpu.fir_filter(coef, s)
+    moved = int(lib().gsmcal_debug_get(30)) - before
+    assert moved >= 2 * s.nbytes                                    # in and out went through the ring
+    lib().gsmcal_debug_set(12, 1)
+    try:
+        plain = gpu.fir_filter(coef, s)
+        assert int(lib().gsmcal_debug_get(30)) - before == moved
+    finally:
+        lib().gsmcal_debug_set(12, 0)
+    assert np.array_equal(got, plain)
+    assert rel_err(got[:50000], oracle.fir_filter(coef, s[:50000])) < 1e-14
+    a = rng.integers(0, 256, size=(2 * 20_000_003, 1), dtype=np.uint8)      # 40 MB uint8 -> 320 MB complex128 back
+    assert np.array_equal(gpu.raw2iq(a), oracle.raw2iq(a))
