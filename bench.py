@@ -41,15 +41,17 @@ TOTAL_STREAMS = 1024                 # BASELINE config 5
 SUB_BATCH = 128                      # streams per submitted batch (2 batches in flight)
 METRIC = "calibrated IQ MSamples/s"
 
-# fp64 operations (one DFMA = 2) the kernels execute per FCCH burst, by tier/stage; DESIGN.md section 4 derives them.
-# Only the arithmetic the algorithm needs is counted (FIR taps x samples, DFT accumulations, slides, correlations); index
-# math, certificates, reductions and conversions are not, so `achieved` is a lower bound of the FP64 instruction rate.
-FLOP_PER_BURST = {
-    "fine_tier1": 2 * (2254 * 47 * 2 + 2208 * 8 * 5 + 1025 * 8 * 8),            # FIR + chunk sums (8 bins) + slide
-    "fine_tier1_pass2": 2 * (2208 * 8 * 5 + 1025 * 8 * 8),                        # second 8-bin pass (no FIR)
-    "fine_tier2": 2 * (2254 * 47 * 2 + 2208 * 64 * 5 + 1025 * 64 * 8),          # 64-bin band: FIR + piece sums + slide
-    "tone": 2 * (1230 * 47 * 2 + 1184 * 16 * 4 + 1184 * 24),                     # FIR + 16-bin band DFT + phasors/gate sums
-    "sch": 2 * (646 * 47 * 2 + 89 * 512 * 4),                                    # FIR + 89-lag x 512-tap correlation
+# Algorithmic fp64 work per FCCH burst (FMA counts; one FMA = 2 flop) of the osr-8 kernels, DESIGN.md section 4 derives them.  Only
+# the arithmetic the algorithm needs is counted - FIR taps x samples, Horner DFT accumulations, correlation MACs, the per-sample
+# complex multiplies of the tone stage; slides, certificates, index math, reductions and conversions are NOT, so `achieved` is a
+# lower bound of the FP64 instruction rate (ncu's pipe-active figure sits beside it in the roofline object).
+FMA_PER_BURST = {
+    "fine_fir": 2208 * 47 * 2,                    # 47-tap FIR over the 2208-sample search window, once per burst (fine_core8_kernel)
+    "fine_pass": 2208 * 8 * 4,                    # chunk sums of one pass: 8 tracked bins, Horner, 4 FMA per sample and bin
+    "fine_tier2": 2208 * 64 * 5 + 1025 * 64 * 8,  # 64-bin band kernel on the cached window: piece sums + slide
+    "tone1": 1184 * (8 * 4 + 4 * 4 + 4 + 4 + 4),  # 8-bin Horner band DFT, 4 gate bins, gate phasor, integer-bin derotation, phasor ratios
+    "tone2": 1184 * (8 * 4 + 4 + 4),              # post-SCH stage: no gate
+    "sch": 646 * 47 * 2 + 89 * 512 * 4,           # FIR of the SCH window + 89-lag x 512-tap correlation
 }
 
 
@@ -508,6 +510,7 @@ def main():
     ap.add_argument("--sub-batch", type=int, default=SUB_BATCH, help="streams per submitted batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-r-correct", action="store_true", help="skip the figure that also materialises r_correct")
     ap.add_argument("--no-oracle-check", action="store_true")
     ap.add_argument("--oracle-check", type=int, default=32, help="streams of the timed workload compared with the oracle (side leg)")
     ap.add_argument("--configs", default="auto", choices=["auto", "on", "off", "quick"], help="timings of BASELINE configs 1-4 (auto: on at N=1)")
@@ -704,10 +707,14 @@ def main():
     L.gsmcal_fp64_peak(C.byref(fp64), C.c_void_p(stream.cuda_stream))
     n_bursts = sum(max(r.n_coarse, 0) for r in res if r.n_coarse >= 5)
     n_tone1 = sum(max(r.n_fcch, 0) for r in res)
-    fine_flop = (n_bursts * FLOP_PER_BURST["fine_tier1"] + facts.get("tier1_pass2_share", 0.22) * n_bursts * FLOP_PER_BURST["fine_tier1_pass2"]
-                 + tiers["tier2"] * FLOP_PER_BURST["fine_tier2"])
-    stage_flop = {"fine_peak": fine_flop, "fine_tone": n_tone1 * FLOP_PER_BURST["tone"], "sch": n_tone1 * FLOP_PER_BURST["sch"],
-                  "post": n_tone1 * FLOP_PER_BURST["tone"]}
+    hist = tiers.get("tier1_proven_after_passes", {})
+    open_b = tiers.get("tier1_left_open", 0)
+    n_pass_total = sum(int(p_) * n_ for p_, n_ in hist.items()) + open_b * int(L.gsmcal_debug_get(40) or 8)   # passes executed over all bursts
+    if n_pass_total <= 0:
+        n_pass_total = n_bursts
+    fine_fma = n_bursts * FMA_PER_BURST["fine_fir"] + n_pass_total * FMA_PER_BURST["fine_pass"] + tiers["tier2"] * FMA_PER_BURST["fine_tier2"]
+    stage_flop = {"fine_peak": 2.0 * fine_fma, "fine_tone": 2.0 * n_tone1 * FMA_PER_BURST["tone1"], "sch": 2.0 * n_tone1 * FMA_PER_BURST["sch"],
+                  "post": 2.0 * n_tone1 * FMA_PER_BURST["tone2"]}
     stage_tflops = {k: stage_flop[k] / (stage_ms[k] * 1e-3) / 1e12 for k in stage_flop if stage_ms.get(k)}
     burst_stages = [k for k in ("fine_peak", "fine_tone", "sch", "post") if k in stage_ms]
     dominant = max(burst_stages, key=lambda k: stage_ms[k]) if burst_stages else None
@@ -721,8 +728,8 @@ def main():
                     "frac": (stage_tflops.get(dominant) / fp64.value) if fp64.value else None,
                     "peak_source": "measured here: gsmcal_fp64_peak (register-only DFMA kernel, CUDA events); MEASURED_PEAKS.json has no FP64 figure",
                     "algorithmic_flop_per_launch": stage_flop[dominant], "ms": stage_ms[dominant],
-                    "counted": "FIR taps x samples, DFT accumulations, slides / correlation MACs over ALL tiers (FLOP_PER_BURST in bench.py, DESIGN.md section 4); "
-                               "certificates, index math, reductions are not counted",
+                    "counted": "FIR taps x samples, Horner DFT accumulations of every executed pass, band-kernel sums and slides, correlation MACs "
+                               "(FMA_PER_BURST in bench.py, DESIGN.md section 4); tier-1 slides, certificates, index math, reductions are not counted",
                     "ncu_fp64_pipe_active_pct": facts.get("fp64_pipe_active_pct", {}).get(dominant),
                     "traffic": facts.get("dram_bytes_per_launch", {}).get(dominant), "traffic_source": facts.get("source"),
                     "all_burst_stages_tflops": stage_tflops,
@@ -735,6 +742,46 @@ def main():
     hbm_floor_ms = D * 2 * n_iq / (hbm_peak * 1e9) * 1e3
     whole_path = {"hbm_floor_ms_per_step": hbm_floor_ms, "frac_of_hbm_floor": hbm_floor_ms / ms_per_step if ms_per_step else None,
                   "note": "2 B per IQ sample read once is the HBM floor of the whole path on one rank; the step is FP64-bound"}
+
+    # ---- the same pipeline when it also MATERIALISES r_correct (what the reference chain and the oracle produce on the way and hand
+    #      to SCH_demod, gsm_sync_demod.m:120,145): gsmcal_calibrate_batch_r writes it in one fused pass, 2 B in + 16 B out per sample ----
+    with_r = None
+    if not args.no_r_correct:
+        try:
+            sub_r = max(1, min(D, 64))
+            r_buf = torch.empty((sub_r, n_iq), dtype=torch.complex128, device=dev)
+
+            def step_r():
+                for c0 in range(0, D, sub_r):
+                    nd = min(sub_r, D - c0)
+                    rr = gsmcal.calibrate_batch(None, CARRIER, tpl, coef, device_ptr=raw.data_ptr() + c0 * row_bytes, n_iq=n_iq, n_streams=nd,
+                                                cuda_stream=stream.cuda_stream, details=False, r_device_ptr=r_buf.data_ptr())
+                    gather(rr)
+            step_r()
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_r = 2
+            r0.record(stream)
+            for _ in range(n_r):
+                step_r()
+            r1.record(stream)
+            barrier()
+            ms_r = r0.elapsed_time(r1) / n_r
+            if world > 1:
+                t = torch.tensor([ms_r], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_r = float(t.item())
+            gbs = D * n_iq * 18 / (ms_r * 1e-3) / 1e9
+            with_r = {"value": total_iq / (ms_r * 1e-3) / 1e6, "unit": "MS/s", "ms_per_step": ms_r, "steps": n_r,
+                      "algorithmic_bytes_per_iq": 18, "achieved_GBs_per_gpu": gbs, "frac_hbm": gbs / measured_peaks()[0],
+                      "streams_per_call": sub_r, "r_correct_bytes_per_step": D * n_iq * 16,
+                      "api": "gsmcal_calibrate_batch_r, r_correct written to a device buffer (complex128, reused per call)",
+                      "note": "like-for-like with the CPU arm, which materialises the corrected stream; bounded by the fp64 47-tap FIR "
+                              "(94 DFMA per sample), not by HBM"}
+            del r_buf
+            torch.cuda.empty_cache()
+        except Exception as ex:      # noqa: BLE001
+            with_r = {"error": repr(ex)}
 
     # ---- e2e: same call with host buffers -----------------------------------------------------------------
     e2e = None
@@ -784,7 +831,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": dict(workload_config(world, D, n_iq, scaling), batches_in_flight=depth, streams_per_submitted_batch=sub),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "e2e": e2e, "with_r_correct": with_r, "gpu_launches": int(launches),
                 "roofline": roofline, "roofline_hbm": roofline_hbm, "whole_path": whole_path, "fp64_peak_tflops_measured": fp64.value,
                 "cpu_baseline": cpu_baseline, "stage_ms": stage_ms, "stage_ms_note": f"sequential pass over all {D} streams of rank 0 (one stream group)",
                 "streams_fully_calibrated": f"{n_ok}/{D} on rank 0", "oracle_agreement": agreement, "synchronous_call": sync_call,

@@ -204,6 +204,18 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
                            double *coarse_pos, double *coarse_snr, double *fcch_pos, double *pos_info,
                            void *cuda_stream);
 
+/* The same call that also MATERIALISES r_correct, the corrected stream gsm_sync_demod.m:120 hands to SCH_demod (:145):
+ *   filter(coef,1,raw2iq(a)) -> interp1 by (1+e1) -> .*exp(1i*n*dphi1) -> interp1 by (1+e2) -> .*exp(1i*n*dphi2)
+ * (FCCH_fine_correction.m:125,165; SCH_corr_rate_correction.m:127; carrier_correct_post_SCH.m:83), written in one fused pass from
+ * the uint8 capture: 2 bytes in, 16 bytes out per sample.  r_correct: n_streams rows of r_stride complex128 (r_stride >= n_iq), in
+ * HOST or DEVICE memory (r_mem); row d holds results[d].r_len[2] samples, nothing is written when that is -1 (r = -1). */
+int gsmcal_calibrate_batch_r(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t n_streams,
+                             double carrier_freq, const double *sch_training_sequence,
+                             const double *coef, int n_taps, int oversampling_ratio, int coarse_decimation,
+                             gsmcal_stream_result *results,
+                             double *coarse_pos, double *coarse_snr, double *fcch_pos, double *pos_info,
+                             void *cuda_stream, double *r_correct, int r_mem, int64_t r_stride);
+
 /* The same pipeline with several batches in flight (continuous captures): _submit enqueues batch `slot` (0..3) on the library's
  * own streams once the caller's `cuda_stream` has produced the DEVICE-resident capture, and returns; _collect waits for that batch
  * and fills the result pointers given to _submit (they must stay valid until then).  The latency-bound front of one batch

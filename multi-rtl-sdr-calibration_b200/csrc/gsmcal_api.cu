@@ -163,6 +163,7 @@ int get_ctx(Ctx **out) {
         CU(cudaFuncSetAttribute(tone8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T8_SMEM));
         CU(cudaFuncSetAttribute(tone_est_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(sch_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CU(cudaFuncSetAttribute(materialise_r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CU(cudaFuncSetAttribute(fir_full_tma_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CU(cudaFuncSetAttribute(fir_full_tma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CU(cudaFuncSetAttribute(coarse_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -505,6 +506,7 @@ void gsmcal_release(void) {
 int64_t gsmcal_debug_get(int key) {
     // key 1: bursts of the last fine search (this device) that needed the all-bin fallback
     std::lock_guard<std::mutex> lk(g_mu);
+    if (key == 40) return (int64_t)g_debug_core8_passes;
     if (key == 30) return (int64_t)g_staged_bytes.load();           // bytes that went through the pinned staging ring (pageable host buffers)
     if (key >= 10 && key < 26) {                                 // 10 + p: bursts the osr-8 tier-1 kernel proved after p passes (p = 0: left open)
         if (!g_last_pass_hist) return 0;
@@ -944,10 +946,12 @@ int gsmcal_total_ppm_calculation(const double *ppm_in, int64_t n, double *ppm_ou
 }
 
 // ---------------------------------------------------------------------------------------------------
-int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t D, double carrier_freq, const double *tpl,
-                           const double *coef, int n_taps, int osr, int coarse_dr, gsmcal_stream_result *results,
-                           double *coarse_pos, double *coarse_snr, double *fcch_pos, double *pos_info, void *cuda_stream) {
+static int calibrate_batch_impl(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t D, double carrier_freq, const double *tpl,
+                                const double *coef, int n_taps, int osr, int coarse_dr, gsmcal_stream_result *results,
+                                double *coarse_pos, double *coarse_snr, double *fcch_pos, double *pos_info, void *cuda_stream,
+                                double *r_out, int r_mem, int64_t r_stride) {
     std::lock_guard<std::mutex> lk(g_mu);
+    if (r_out && r_stride < n_iq) return fail(GSMCAL_ERR_ARG, "calibrate_batch_r: r_stride must be >= n_iq");
     if (!raw || !tpl || !coef || !results || n_iq < 1 || D < 1 || osr < 1 || osr > 8) return fail(GSMCAL_ERR_ARG, "calibrate_batch: bad arguments (osr 1..8)");
     CoarseParams p; TRY(coarse_params(coarse_dr, &p));
     const int dec = osr * coarse_dr;
@@ -1044,6 +1048,16 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
     }
     for (cudaEvent_t ev : ev_done) { CU(cudaStreamWaitEvent(st, ev, 0)); CU(cudaEventDestroy(ev)); }   // join (after ALL groups are enqueued)
     CU(cudaEventDestroy(ev_fork));
+    if (r_out) {
+        // r_correct (gsm_sync_demod.m:120 -> :145) for every stream whose chain completed: one fused pass from the uint8 capture
+        double2 *r_dev = (double2 *)r_out;
+        if (r_mem == GSMCAL_MEM_HOST) { void *p; TRY(c->out.get(sizeof(double2) * (size_t)r_stride * D, &p)); r_dev = (double2 *)p; }
+        const i64 tiles = (n_iq + MAT_T - 1) / MAT_T;
+        i64 gx = (148 * 3 + D - 1) / D; if (gx < 1) gx = 1; if (gx > tiles) gx = tiles;
+        const size_t smem = sizeof(double2) * (size_t)(MAT_T + GSMCAL_XCAP(MAT_T + 8) + MAT_T + 16);
+        LAUNCH(materialise_r_kernel, dim3((unsigned)gx, (unsigned)D), MAT_THREADS, smem, st, lazy_src(draw, n_iq, n_taps, 3, 1), w.ctl, r_dev, (i64)r_stride, tiles);
+        if (r_mem == GSMCAL_MEM_HOST) TRY(copy_d2h(c->ring, g_device, r_out, r_dev, sizeof(double2) * (size_t)r_stride * D, st));
+    }
     CU(cudaMemcpyAsync(results, w.res, sizeof(StreamResultDev) * D, cudaMemcpyDeviceToHost, st));
     if (coarse_pos) CU(cudaMemcpyAsync(coarse_pos, w.coarse_pos, sizeof(double) * D * cap, cudaMemcpyDeviceToHost, st));
     if (coarse_snr) CU(cudaMemcpyAsync(coarse_snr, w.coarse_snr, sizeof(double) * D * cap, cudaMemcpyDeviceToHost, st));
@@ -1053,6 +1067,22 @@ int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_
     if (timing) for (int i = 0; i + 1 < g_stage_n; ++i) CU(cudaEventElapsedTime(&g_stage_ms[i], c->stage_ev[i], c->stage_ev[i + 1]));
     if (!timing) g_stage_n = 0;
     return GSMCAL_OK;
+}
+
+int gsmcal_calibrate_batch(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t D, double carrier_freq, const double *tpl,
+                           const double *coef, int n_taps, int osr, int coarse_dr, gsmcal_stream_result *results,
+                           double *coarse_pos, double *coarse_snr, double *fcch_pos, double *pos_info, void *cuda_stream) {
+    return calibrate_batch_impl(raw, raw_mem, n_iq, D, carrier_freq, tpl, coef, n_taps, osr, coarse_dr, results, coarse_pos, coarse_snr, fcch_pos, pos_info,
+                                cuda_stream, nullptr, GSMCAL_MEM_DEVICE, 0);
+}
+
+int gsmcal_calibrate_batch_r(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t D, double carrier_freq, const double *tpl,
+                             const double *coef, int n_taps, int osr, int coarse_dr, gsmcal_stream_result *results,
+                             double *coarse_pos, double *coarse_snr, double *fcch_pos, double *pos_info, void *cuda_stream,
+                             double *r_correct, int r_mem, int64_t r_stride) {
+    if (!r_correct) return fail(GSMCAL_ERR_ARG, "calibrate_batch_r: null r_correct");
+    return calibrate_batch_impl(raw, raw_mem, n_iq, D, carrier_freq, tpl, coef, n_taps, osr, coarse_dr, results, coarse_pos, coarse_snr, fcch_pos, pos_info,
+                                cuda_stream, r_correct, r_mem, r_stride);
 }
 
 // ---- submit / collect: the same pipeline, several batches in flight -----------------------------------------------------------

@@ -2276,7 +2276,7 @@ __global__ void __launch_bounds__(PS_THREADS) post_carrier_kernel(StreamCtl *ctl
 // ===================================================================================================
 #define MAT_T 1200
 #define MAT_THREADS 256
-__global__ void __launch_bounds__(MAT_THREADS) materialise_r_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, double2 *__restrict__ r_out, i64 r_stride,
+__global__ void __launch_bounds__(MAT_THREADS, 3) materialise_r_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, double2 *__restrict__ r_out, i64 r_stride,
                                                                    i64 tiles_per_stream) {
     extern __shared__ double2 sm[];
     __shared__ double2 base2;

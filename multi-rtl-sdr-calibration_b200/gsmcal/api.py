@@ -307,7 +307,7 @@ def _unpack_results(res, D, cap, coarse_pos, coarse_snr, fcch_pos, pos_info):
 
 def calibrate_batch(raw, carrier_freq: float, sch_training_sequence, coef, osr: int = 8, coarse_dr: int = 8,
                     device_ptr: int | None = None, n_iq: int | None = None, n_streams: int | None = None,
-                    cuda_stream: int = 0, details: bool = True):
+                    cuda_stream: int = 0, details: bool = True, r_correct=None, r_device_ptr: int | None = None):
     """gsm_sync_demod.m:107-124 for every row of `raw` ([D, 2N] uint8, row d == dongle d's fread column).
 
     `raw` is a host NumPy array, or pass device_ptr/n_iq/n_streams for a capture already resident in HBM.
@@ -331,8 +331,18 @@ def calibrate_batch(raw, carrier_freq: float, sch_training_sequence, coef, osr: 
     else:
         coarse_pos = coarse_snr = fcch_pos = pos_info = None
         ptrs = [None] * 4
-    check(lib().gsmcal_calibrate_batch(ptr, mem, int(n_iq), D, float(carrier_freq), _ptr(tpl), _ptr(coef), len(coef),
-                                       int(osr), int(coarse_dr), C.cast(res, C.c_void_p), *ptrs, C.c_void_p(cuda_stream)))
+    if r_correct is None and r_device_ptr is None:
+        check(lib().gsmcal_calibrate_batch(ptr, mem, int(n_iq), D, float(carrier_freq), _ptr(tpl), _ptr(coef), len(coef),
+                                           int(osr), int(coarse_dr), C.cast(res, C.c_void_p), *ptrs, C.c_void_p(cuda_stream)))
+    else:
+        # r_correct: a [D, n_iq] complex128 host array to fill, or r_device_ptr: a device buffer of D * n_iq complex128
+        if r_device_ptr is not None:
+            rp, rmem = C.c_void_p(int(r_device_ptr)), 1
+        else:
+            assert r_correct.dtype == np.complex128 and r_correct.flags.c_contiguous and r_correct.shape == (D, n_iq)
+            rp, rmem = _ptr(r_correct), 0
+        check(lib().gsmcal_calibrate_batch_r(ptr, mem, int(n_iq), D, float(carrier_freq), _ptr(tpl), _ptr(coef), len(coef),
+                                             int(osr), int(coarse_dr), C.cast(res, C.c_void_p), *ptrs, C.c_void_p(cuda_stream), rp, rmem, int(n_iq)))
     if not details:
         return res
     return _unpack_results(res, D, cap, coarse_pos, coarse_snr, fcch_pos, pos_info)

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2e_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/r2e_pytest.log
 tail -8 gpurun_out/r2e_pytest.log
-B="python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --configs off --no-oracle-check"
+B="python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --configs off --no-oracle-check --no-r-correct"
 run() { name=$1; shift; timeout 600 $B "$@" > gpurun_out/r2e_bench_$name.json 2> gpurun_out/r2e_bench_$name.err; echo "bench $name rc=$?"
   python - <<PY
 import json

@@ -777,3 +777,26 @@ def test_pageable_host_buffers_go_through_the_staging_ring(gpu, captures, coef47
     assert rel_err(got[:50000], oracle.fir_filter(coef, s[:50000])) < 1e-14
     a = rng.integers(0, 256, size=(2 * 20_000_003, 1), dtype=np.uint8)      # 40 MB uint8 -> 320 MB complex128 back
     assert np.array_equal(gpu.raw2iq(a), oracle.raw2iq(a))
+
+
+def test_calibrate_batch_r_materialises_r_correct(gpu, captures, coef47, tpl):
+    """gsmcal_calibrate_batch_r: the corrected stream gsm_sync_demod.m:120 hands to SCH_demod, written in one fused pass from the uint8
+    capture (filter -> interp1(e1) -> derotate -> interp1(e2) -> derotate), against the oracle's function-by-function r_final; rows of
+    streams whose chain did not complete (r = -1) are left untouched."""
+    _, raw = captures
+    specs = [synth.StreamSpec(seed=21, n_samples=N_SYNC, noise_only=True)]
+    raw4 = np.concatenate([raw[:3], synth.generate_batch(specs).numpy()], axis=0)
+    D, n_iq = raw4.shape[0], raw4.shape[1] // 2
+    r = np.full((D, n_iq), 7.0 + 7.0j, dtype=np.complex128)
+    got = gpu.calibrate_batch(raw4, CARRIER, tpl, coef47, r_correct=r)
+    for d in range(D):
+        ref = oracle.calibrate_stream(raw4[d], CARRIER, tpl, coef47)
+        _check_stream(got[d], ref)
+        if ref["r_final"] is None:
+            assert got[d]["r_len"][2] == -1 and np.all(r[d] == 7.0 + 7.0j)
+        else:
+            n = got[d]["r_len"][2]
+            assert n == len(ref["r_final"])
+            assert rel_err(r[d, :n], ref["r_final"]) < 1e-8          # two derotations with n*dphi up to 1e5..1e6 rad
+            assert np.all(r[d, n:] == 7.0 + 7.0j)
+    assert got[3]["r_len"][2] == -1
