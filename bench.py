@@ -38,7 +38,7 @@ FS = SYMBOL_RATE * 8
 CARRIER = 957.4e6
 N_IQ_10S = 21666667
 TOTAL_STREAMS = 1024                 # BASELINE config 5
-SUB_BATCH = 128                      # streams per submitted batch (2 batches in flight)
+SUB_BATCH = 512                      # streams per submitted batch (2 batches in flight)
 METRIC = "calibrated IQ MSamples/s"
 
 # Algorithmic fp64 work per FCCH burst (FMA counts; one FMA = 2 flop) of the osr-8 kernels, DESIGN.md section 4 derives them.  Only
@@ -433,7 +433,7 @@ def run_configs(gsmcal, synth, workers, quick=False):
     def chain_case(name, D, n, note):
         specs = [synth.random_spec(5000 + d, n) for d in range(D)]
         raw = synth.generate_batch(specs, device="cuda").cpu().numpy()
-        cols = np.ascontiguousarray(raw.T)                       # 2N x D as the script holds it
+        cols = raw.T                                             # 2N x D as the script holds it (column-major, like a MATLAB matrix: no copy)
         dropin_chain(gsmcal, cols[:, :1], tpl, coef)             # warm-up (allocations, module load)
         t0 = time.perf_counter(); got = dropin_chain(gsmcal, cols, tpl, coef); t_drop = time.perf_counter() - t0
         gsmcal.calibrate_batch(raw[:1], CARRIER, tpl, coef, details=False)
@@ -476,11 +476,11 @@ def run_configs(gsmcal, synth, workers, quick=False):
                     "channels_with_carrier": int(sum(1 for c in range(nf) if num_hit[c] > 0)), "results_agree_with_oracle": bool(agree)}
         # config 4: scan_band_power_spectrum.m:80-85 (251 x 2 x 12,288 IQ) and multi_rtl_sdr_split_scanner.m:154-156 (501 x 204,800 IQ, fir1(63), /20)
         rng = np.random.default_rng(44)
-        a = np.clip(np.round(rng.standard_normal((2 * 12288, 502)) * 20 + 127.5), 0, 255).astype(np.uint8)
+        a = np.clip(np.round(rng.standard_normal((502, 2 * 12288)) * 20 + 127.5), 0, 255).astype(np.uint8).T     # column-major 24576 x 502
         gsmcal.band_power(a[:, :2])
         t0 = time.perf_counter(); p_gpu = gsmcal.band_power(a); t_gpu = time.perf_counter() - t0
         t0 = time.perf_counter(); p_ref = oracle.band_power(a); t_ref = time.perf_counter() - t0
-        b = np.clip(np.round(rng.standard_normal((2 * 204800, 501)) * 20 + 127.5), 0, 255).astype(np.uint8)
+        b = np.clip(np.round(rng.standard_normal((501, 2 * 204800)) * 20 + 127.5), 0, 255).astype(np.uint8).T   # column-major 409600 x 501
         coef63 = gsmcal.fir1(63, 0.05 / 2.048)
         gsmcal.band_power(b[:, :2], coef63, 20)
         t0 = time.perf_counter(); q_gpu = gsmcal.band_power(b, coef63, 20); t_gpu2 = time.perf_counter() - t0
@@ -698,6 +698,11 @@ def main():
         tiers = {"tier2": int(L.gsmcal_debug_get(2)), "tier3": int(L.gsmcal_debug_get(1)),
                  "tier1_proven_after_passes": {str(p_): int(L.gsmcal_debug_get(10 + p_)) for p_ in range(1, 9)},
                  "tier1_left_open": int(L.gsmcal_debug_get(10))}
+        if "13=1" in args.debug:                 # per-phase cycles of fine_core8_kernel (thread 0 of every block, clock64)
+            names = ["staging", "fir", "energies_k0", "chunk_sums", "prefix", "segment_starts", "diff_slide", "argmax", "certificate"]
+            blocks = max(1, int(L.gsmcal_debug_get(65)))
+            tiers["core8_phase_cycles_per_block"] = {n_: int(L.gsmcal_debug_get(50 + i_)) / blocks for i_, n_ in enumerate(names)}
+            tiers["core8_blocks"] = blocks
     L.gsmcal_debug_set(3, args.groups)
     stage_ms = {k: v / n_prof for k, v in stage_acc.items()}
 
@@ -731,7 +736,9 @@ def main():
                     "counted": "FIR taps x samples, Horner DFT accumulations of every executed pass, band-kernel sums and slides, correlation MACs "
                                "(FMA_PER_BURST in bench.py, DESIGN.md section 4); tier-1 slides, certificates, index math, reductions are not counted",
                     "ncu_fp64_pipe_active_pct": facts.get("fp64_pipe_active_pct", {}).get(dominant),
-                    "traffic": facts.get("dram_bytes_per_launch", {}).get(dominant), "traffic_source": facts.get("source"),
+                    "traffic": (int(facts["dram_bytes_per_launch"][dominant] * D / facts["streams_profiled"])
+                                if facts.get("dram_bytes_per_launch", {}).get(dominant) and facts.get("streams_profiled") else None),
+                    "traffic_source": (facts.get("source", "") + "; scaled by streams per launch") if facts else None,
                     "all_burst_stages_tflops": stage_tflops,
                     "all_burst_stages_frac": {k: v / fp64.value for k, v in stage_tflops.items()} if fp64.value else None}
     ratio = facts.get("colsum_dram_ratio")
@@ -836,7 +843,8 @@ def main():
                 "cpu_baseline": cpu_baseline, "stage_ms": stage_ms, "stage_ms_note": f"sequential pass over all {D} streams of rank 0 (one stream group)",
                 "streams_fully_calibrated": f"{n_ok}/{D} on rank 0", "oracle_agreement": agreement, "synchronous_call": sync_call,
                 "fine_search_allbin_fallback_bursts": tiers["tier3"], "fine_search_64bin_tier2_bursts": tiers["tier2"], "bursts_rank0": n_bursts,
-                "fine_search_tier1": {k: tiers.get(k) for k in ("tier1_proven_after_passes", "tier1_left_open")}, "debug_keys": args.debug,
+                "fine_search_tier1": {k: tiers.get(k) for k in ("tier1_proven_after_passes", "tier1_left_open", "core8_phase_cycles_per_block", "core8_blocks") if k in tiers},
+                "debug_keys": args.debug,
                 "configs": configs, "reference_runtime_probe": probe_reference_runtimes(), "synthetic_generation_s": t_gen}
         if stages is not None:
             line["stage_rooflines"] = stages

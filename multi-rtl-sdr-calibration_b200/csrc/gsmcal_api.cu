@@ -36,6 +36,7 @@ int g_debug_persist_colsum = 0;   // submit/collect: blocks per SM of the persis
 int g_debug_hi_prio = 1;          // burst chain of each stream group on a high-priority CUDA stream
 int g_debug_core8_passes = B8_NPASS; // passes of 8 tracked bins in fine_core8_kernel (1..8)
 unsigned *g_last_pass_hist = nullptr;
+int g_debug_prof = 0;              // fine_core8_kernel accumulates per-phase cycle counts (debug_get 50..65)
 int g_debug_no_tone8 = 0;          // tests / A-B: 1 = generic tone estimator for every burst
 int g_debug_no_core8 = 0;         // tests / A-B: 1 = round-1 tier-1 kernel and no filtered-window cache
 
@@ -157,9 +158,10 @@ int get_ctx(Ctx **out) {
         CU(cudaFuncSetAttribute(fine_peak_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(fine_peak_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(fine_peak_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CU(cudaFuncSetAttribute(fine_core8_kernel<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, B8_SMEM));
-        CU(cudaFuncSetAttribute(fine_core8_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, B8_SMEM));
-        CU(cudaFuncSetAttribute(fine_core8_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, B8_SMEM));
+        CU(cudaFuncSetAttribute(fine_core8_kernel<47, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B8_SMEM));
+        CU(cudaFuncSetAttribute(fine_core8_kernel<47, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B8_SMEM));
+        CU(cudaFuncSetAttribute(fine_core8_kernel<48, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B8_SMEM));
+        CU(cudaFuncSetAttribute(fine_core8_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B8_SMEM));
         CU(cudaFuncSetAttribute(tone8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T8_SMEM));
         CU(cudaFuncSetAttribute(tone_est_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         CU(cudaFuncSetAttribute(sch_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -176,15 +178,6 @@ int get_ctx(Ctx **out) {
         CU(cudaFuncSetAttribute(fcch_demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));      // (attributes are per device:
         CU(cudaFuncSetAttribute(fde_template_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));    //  all of them live here, keyed by
         CU(cudaFuncSetAttribute(sch_demod_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));       //  the device's Ctx)
-        // The front of batch k+1 (column sums, mean, SNR map, first-hit scan, burst chain) is meant to run BESIDE the FP64 burst kernels of
-        // batch k, whose blocks need the SM in its maximum-shared-memory configuration.  A kernel that prefers a different L1/shared
-        // split cannot be placed on such an SM until it drains, so the front kernels ask for the same carve-out.
-        CU(cudaFuncSetAttribute(colsum_u8_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CU(cudaFuncSetAttribute(colsum_u8_persist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CU(cudaFuncSetAttribute(mean_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CU(cudaFuncSetAttribute(snr_map_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CU(cudaFuncSetAttribute(first_hit_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CU(cudaFuncSetAttribute(coarse_chain_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         c.attrs = true;
     }
     *out = &c;
@@ -241,7 +234,7 @@ int make_work(DevBuf &wb, i64 D, int cap, i64 snr_len, int tpl_len, Work *w) {
     size_t per = sizeof(double) * D * cap;
     size_t o_cp = take(per), o_cs = take(per), o_fr = take(per), o_fp = take(per), o_fo = take(per), o_g = take(per), o_sr = take(per), o_sp = take(per), o_pp = take(per);
     size_t o_pi = take(per * 12), o_snr = take(sizeof(double) * D * snr_len), o_pw = take(sizeof(double) * D);
-    size_t o_se = take(sizeof(int) * D * cap), o_nf = take(sizeof(int) * D * cap), o_nb = take(sizeof(int) * D * cap), o_tn = take(sizeof(int) * D * cap), o_fl = take(sizeof(int) * D * cap), o_fc = take(sizeof(int) * D), o_fm = take(sizeof(int) * (size_t)FALL_GRID * 24 * kMaxGroups), o_fb = take(sizeof(double) * (size_t)FALL_GRID * 24 * kMaxGroups), o_k = take(D * cap), o_tpl = take(sizeof(double2) * (tpl_len > 0 ? tpl_len : 1)), o_ph = take(sizeof(unsigned) * 16);
+    size_t o_se = take(sizeof(int) * D * cap), o_nf = take(sizeof(int) * D * cap), o_nb = take(sizeof(int) * D * cap), o_tn = take(sizeof(int) * D * cap), o_fl = take(sizeof(int) * D * cap), o_fc = take(sizeof(int) * D), o_fm = take(sizeof(int) * (size_t)FALL_GRID * 24 * kMaxGroups), o_fb = take(sizeof(double) * (size_t)FALL_GRID * 24 * kMaxGroups), o_k = take(D * cap), o_tpl = take(sizeof(double2) * (tpl_len > 0 ? tpl_len : 1)), o_ph = take(sizeof(unsigned) * 16 + sizeof(unsigned long long) * 16);
     void *base;
     TRY(wb.get(off, &base));
     char *b = static_cast<char *>(base);
@@ -352,9 +345,13 @@ int run_fine_peak(Ctx &c, WinSrc src_peak, i64 n_iq, int osr, i64 D, int cap, Wo
     if (src_peak.lazy && osr == 8 && src_peak.n_taps <= 64 && !g_debug_no_core8) {
         // osr-8 fast path: FIR once per burst, filtered window cached for tier 2 and the tone stages
         const dim3 grid((unsigned)cap, (unsigned)D);
-        if (src_peak.n_taps == 47)      LAUNCH((fine_core8_kernel<47>), grid, B8_THREADS, B8_SMEM, st, src_peak.raw, n_iq, w.ctl, w.coarse_pos, cap, tw, w.fine_raw, w.need_band, g_debug_fail_tier2, w.wcache, g_debug_core8_passes, w.pass_hist);
-        else if (src_peak.n_taps <= 48) LAUNCH((fine_core8_kernel<48>), grid, B8_THREADS, B8_SMEM, st, src_peak.raw, n_iq, w.ctl, w.coarse_pos, cap, tw, w.fine_raw, w.need_band, g_debug_fail_tier2, w.wcache, g_debug_core8_passes, w.pass_hist);
-        else                            LAUNCH((fine_core8_kernel<64>), grid, B8_THREADS, B8_SMEM, st, src_peak.raw, n_iq, w.ctl, w.coarse_pos, cap, tw, w.fine_raw, w.need_band, g_debug_fail_tier2, w.wcache, g_debug_core8_passes, w.pass_hist);
+#define CORE8_ARGS src_peak.raw, n_iq, w.ctl, w.coarse_pos, cap, tw, w.fine_raw, w.need_band, g_debug_fail_tier2, w.wcache, g_debug_core8_passes, w.pass_hist, \
+                   (unsigned long long *)(w.pass_hist + 16)
+        if (src_peak.n_taps == 47 && g_debug_prof) LAUNCH((fine_core8_kernel<47, true>), grid, B8_THREADS, B8_SMEM, st, CORE8_ARGS);
+        else if (src_peak.n_taps == 47) LAUNCH((fine_core8_kernel<47, false>), grid, B8_THREADS, B8_SMEM, st, CORE8_ARGS);
+        else if (src_peak.n_taps <= 48) LAUNCH((fine_core8_kernel<48, false>), grid, B8_THREADS, B8_SMEM, st, CORE8_ARGS);
+        else                            LAUNCH((fine_core8_kernel<64, false>), grid, B8_THREADS, B8_SMEM, st, CORE8_ARGS);
+#undef CORE8_ARGS
         w.wc_valid = (w.wcache != nullptr);
         src_peak = with_cache(src_peak, w, cap);
     } else
@@ -507,6 +504,12 @@ int64_t gsmcal_debug_get(int key) {
     // key 1: bursts of the last fine search (this device) that needed the all-bin fallback
     std::lock_guard<std::mutex> lk(g_mu);
     if (key == 40) return (int64_t)g_debug_core8_passes;
+    if (key >= 50 && key < 66) {                                 // per-phase cycle sums of fine_core8_kernel (debug key 13), [15] = blocks
+        if (!g_last_pass_hist) return 0;
+        unsigned long long v = 0;
+        if (cudaMemcpy(&v, (unsigned long long *)(g_last_pass_hist + 16) + (key - 50), sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        return (int64_t)v;
+    }
     if (key == 30) return (int64_t)g_staged_bytes.load();           // bytes that went through the pinned staging ring (pageable host buffers)
     if (key >= 10 && key < 26) {                                 // 10 + p: bursts the osr-8 tier-1 kernel proved after p passes (p = 0: left open)
         if (!g_last_pass_hist) return 0;
@@ -533,6 +536,7 @@ int gsmcal_debug_set(int key, int value) {
     if (key == 9) { g_debug_no_core8 = value ? 1 : 0; return GSMCAL_OK; }
     if (key == 11) { g_debug_no_tone8 = value ? 1 : 0; return GSMCAL_OK; }
     if (key == 12) { g_debug_no_staging = value ? 1 : 0; return GSMCAL_OK; }
+    if (key == 13) { g_debug_prof = value ? 1 : 0; return GSMCAL_OK; }
     if (key == 10) { g_debug_core8_passes = value < 1 ? 1 : (value > 8 ? 8 : value); return GSMCAL_OK; }
     if (key == 8) { g_debug_submit_groups = value < 1 ? 1 : (value > kMaxGroups / 2 ? kMaxGroups / 2 : value); return GSMCAL_OK; }
     if (key == 7) { g_debug_persist_colsum = value < 0 ? 0 : (value > 8 ? 8 : value); return GSMCAL_OK; }
@@ -976,7 +980,7 @@ static int calibrate_batch_impl(const uint8_t *raw, int raw_mem, int64_t n_iq, i
     { const double2 *twp; TRY(get_twiddle(*c, 148 * osr, st, &twp)); }        // built on `st` before the groups fork
     g_last_need_full = w.need_full; g_last_need_band = w.need_band; g_last_need_full_n = (long long)D * cap;
     g_last_pass_hist = w.pass_hist;
-    CU(cudaMemsetAsync(w.pass_hist, 0, sizeof(unsigned) * 16, st));
+    CU(cudaMemsetAsync(w.pass_hist, 0, sizeof(unsigned) * 16 + sizeof(unsigned long long) * 16, st));
     g_stage_n = 0;
     // Streams are independent, so the batch is cut into groups that run the stage sequence on their own CUDA
     // streams: the latency-bound stages of one group (burst chain, per-stream solves) overlap the FP64-bound
@@ -1056,7 +1060,13 @@ static int calibrate_batch_impl(const uint8_t *raw, int raw_mem, int64_t n_iq, i
         i64 gx = (148 * 3 + D - 1) / D; if (gx < 1) gx = 1; if (gx > tiles) gx = tiles;
         const size_t smem = sizeof(double2) * (size_t)(MAT_T + GSMCAL_XCAP(MAT_T + 8) + MAT_T + 16);
         LAUNCH(materialise_r_kernel, dim3((unsigned)gx, (unsigned)D), MAT_THREADS, smem, st, lazy_src(draw, n_iq, n_taps, 3, 1), w.ctl, r_dev, (i64)r_stride, tiles);
-        if (r_mem == GSMCAL_MEM_HOST) TRY(copy_d2h(c->ring, g_device, r_out, r_dev, sizeof(double2) * (size_t)r_stride * D, st));
+        if (r_mem == GSMCAL_MEM_HOST) {                          // only the r_len[2] samples of every completed stream go back (nothing else is written)
+            CU(cudaMemcpyAsync(results, w.res, sizeof(StreamResultDev) * D, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (i64 d = 0; d < D; ++d)
+                if (results[d].r_len[2] > 0)
+                    TRY(copy_d2h(c->ring, g_device, r_out + 2 * (size_t)r_stride * d, r_dev + (size_t)r_stride * d, sizeof(double2) * (size_t)results[d].r_len[2], st));
+        }
     }
     CU(cudaMemcpyAsync(results, w.res, sizeof(StreamResultDev) * D, cudaMemcpyDeviceToHost, st));
     if (coarse_pos) CU(cudaMemcpyAsync(coarse_pos, w.coarse_pos, sizeof(double) * D * cap, cudaMemcpyDeviceToHost, st));
@@ -1133,7 +1143,7 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
     CU(cudaMemcpyAsync(w.tpl, h_tpl, sizeof(double2) * 64 * osr, cudaMemcpyHostToDevice, fr));
     g_last_need_full = w.need_full; g_last_need_band = w.need_band; g_last_need_full_n = (long long)D * cap;
     g_last_pass_hist = w.pass_hist;
-    CU(cudaMemsetAsync(w.pass_hist, 0, sizeof(unsigned) * 16, fr));
+    CU(cudaMemsetAsync(w.pass_hist, 0, sizeof(unsigned) * 16 + sizeof(unsigned long long) * 16, fr));
     const size_t per = (size_t)2 * n_iq;
     std::vector<cudaEvent_t> ev_done;
     cudaEvent_t e_sum = nullptr;

@@ -27,11 +27,12 @@
 // towards the GMSK data energy (it sits ~37 bins below the FCCH tone)
 __device__ __forceinline__ int b8_bin_off(int pass, int j) { return pass == 0 ? j - 3 : (pass == 1 ? (j < 4 ? j - 7 : j + 1) : -8 * pass + 1 + j); }
 
-template <int NT>
+template <int NT, bool PROF>
 __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ raw_all, i64 n_iq, const StreamCtl *__restrict__ ctl,
                                                                   const double *__restrict__ base_pos, int cap, const double2 *__restrict__ tw,
                                                                   double *__restrict__ fine_raw, int *__restrict__ need_band, int force_fail,
-                                                                  double2 *__restrict__ wcache, int n_pass, unsigned *__restrict__ pass_hist) {
+                                                                  double2 *__restrict__ wcache, int n_pass, unsigned *__restrict__ pass_hist,
+                                                                  unsigned long long *__restrict__ prof) {
     extern __shared__ __align__(128) unsigned char b8_sm[];
     double2 *B = reinterpret_cast<double2 *>(b8_sm);             // staged capture, then the filtered window (padded layout)
     double2 *CS = B + B8_BUF;                                    // [8][B8_CSL] prefix of chunk sums, bin-major
@@ -42,6 +43,9 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
     __shared__ int red_i[8];
     __shared__ double scan_sv[16];
     const int burst = blockIdx.x, stream = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // debug hook (gsmcal_debug_set key 13): thread 0 adds the cycles between phase marks to prof[phase]; prof[15] counts blocks
+    long long t_prev = PROF ? clock64() : 0;
+#define B8_MARK(ph) do { if (PROF && tid == 0) { const long long t_now = clock64(); atomicAdd(prof + (ph), (unsigned long long)(t_now - t_prev)); t_prev = t_now; } } while (0)
     const StreamCtl c = ctl[stream];
     if (c.n_coarse < 5 || burst >= c.n_coarse) return;
     const i64 len_s = n_iq / 8;
@@ -76,6 +80,7 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
         if (tid < B8_R + 7) B[NRAW + tid] = make_double2(0.0, 0.0);
     }
     __syncthreads();
+    B8_MARK(0);                                                  // staging (global-memory latency)
     // ---- FIR, 9 outputs per thread, in place: all reads happen before the barrier, all writes after it ----
     {
         constexpr int NGRP = (B8_NSMP + B8_R - 1) / B8_R;        // 246 <= 256: one round
@@ -91,6 +96,7 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
         }
     }
     __syncthreads();
+    B8_MARK(1);                                                  // FIR
     // ---- the filtered window goes to the cache with ONE TMA bulk store (reads shared memory asynchronously: waited for below,
     //      before the window is overwritten by differences) ----
     if (wcache && tid == 0) {
@@ -136,6 +142,7 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
     __syncthreads();
     const int k0 = red_i[0];
     __syncthreads();
+    B8_MARK(2);                                                  // energies, phase slope, k0
     // Up to n_pass passes of 8 tracked bins (b8_bin_off): every pass adds its bins' power to the tracked sums of the certificate, which
     // is re-checked after each; a burst leaves as soon as it is proven.  The 64-bin band kernel only sees what is still open then.
     double g_best = -1.0; int g_bestm = 0x7fffffff;
@@ -177,6 +184,7 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
                 CS[(4 * q + b) * B8_CSL + cch + 1] = cmul(acc[b], tw[(32 * cch * kk[b]) % B8_N]);
         }
         __syncthreads();
+        B8_MARK(3);                                              // (restore +) chunk sums
         {   // prefix over chunks: warp b scans bin b (lanes own 3 consecutive chunks)
             double2 *row = CS + warp * B8_CSL;
             constexpr int per = (B8_NCH + 31) / 32;
@@ -197,6 +205,7 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
         }
         if (pass == 0 && tid == 0 && wcache) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the bulk store has read the window
         __syncthreads();
+        B8_MARK(4);                                              // prefix over chunks
         const int g = tid >> 3, j = tid & 7;
         int k = (k0 + b8_bin_off(pass, j)) % B8_N; if (k < 0) k += B8_N;
         const double2 wk = tw[k];
@@ -227,6 +236,7 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
             need = !(bound * bound < gl * (1.0 - 1e-6));
         }
         const int any_need = __syncthreads_or(need ? 1 : 0);      // (also orders the reads of red_v before block_argmax reuses it)
+        B8_MARK(5);                                              // segment starts, which segments slide
         double best = -1.0; int bestm = 0x7fffffff;
         if (any_need) {
             for (int m = tid; m < B8_NWIN - 1; m += B8_THREADS) {    // d[m] = s[m+N] - s[m] in place
@@ -258,7 +268,9 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
                 bestm = 32 * g + besti;
             }
         }
+        B8_MARK(6);                                              // differences + slide
         block_argmax(best, bestm, red_v, red_i);
+        B8_MARK(7);                                              // block argmax
         if (pass == 0) { g_best = best; g_bestm = bestm; }
         else if (best > g_best || (best == g_best && bestm < g_bestm)) break;   // the extra bins would move the argmax: leave it to tier 2
         // ---- certificate at every segment-start window c = 32 g (g = 0..32), straight from the chunk prefix tables: for any split of
@@ -302,7 +314,9 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
             }
         }
         ok = __syncthreads_and(ok);
+        B8_MARK(8);                                              // certificate
     }
+    if (PROF && tid == 0) atomicAdd(prof + 15, 1ull);
     if (tid == 0) {
         if (pass_hist) atomicAdd(pass_hist + (ok ? pass : 0), 1u);             // [p] = bursts proven after p passes, [0] = left open
         if (wcache) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the bulk store is complete before the block retires

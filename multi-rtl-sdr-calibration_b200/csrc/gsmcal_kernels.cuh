@@ -1892,7 +1892,7 @@ __global__ void __launch_bounds__(TONE_THREADS, 3) tone_est_kernel(WinSrc src, c
 #define SCH_LPG 6       // lags per warp and pass
 #define SCH_PASSES 2
 #define SCH_NSL 16      // template samples per lane
-__global__ void __maxnreg__(56) sch_corr_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ fcch_pos, int cap,
+__global__ void __launch_bounds__(SCH_THREADS, 4) sch_corr_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ fcch_pos, int cap,
                                                               int osr, const double2 *__restrict__ tpl, double *__restrict__ sch_raw, int *__restrict__ sch_edge) {
     extern __shared__ double2 sm[];
     __shared__ double red_v[8];

@@ -57,5 +57,56 @@ def launches(path):
         print(f"{name[:60]:60s} {n:8d} {ns / 1e3:12.1f} {100 * ns / tot:6.2f}%")
 
 
+def _rows(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        yield dict(zip(hdr, r)), dict(zip(hdr, units))
+
+
+def _num(x):
+    return float(str(x).replace(",", ""))
+
+
+def _bytes(v, unit):
+    return _num(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+
+
+def facts(burst_rep, colsum_rep, streams_profiled, n_iq):
+    """roofline_facts.json for bench.py: numbers that only an ncu capture can give (fp64 pipe utilisation and DRAM bytes per launch of the
+    burst kernels at the profiled size, DRAM bytes of the column-sum kernel against its algorithmic bytes)."""
+    import json
+    stage_of = {"fine_core8_kernel": "fine_peak", "sch_corr_kernel": "sch"}
+    pipe, dram, seen_tone = {}, {}, 0
+    for d, u in _rows(burst_rep):
+        name = d["Kernel Name"].split("(")[0].replace("void ", "").split("<")[0]
+        if name == "tone8_kernel":
+            seen_tone += 1
+            stage = "fine_tone" if seen_tone == 1 else "post"
+        elif name in stage_of:
+            stage = stage_of[name]
+        else:
+            continue
+        pipe[stage] = _num(d["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"])
+        dram[stage] = int(_bytes(d["dram__bytes_read.sum"], u["dram__bytes_read.sum"]) + _bytes(d["dram__bytes_write.sum"], u["dram__bytes_write.sum"]))
+    col = {}
+    for d, u in _rows(colsum_rep):
+        if d["Kernel Name"].startswith("colsum_u8_kernel"):
+            rd = _bytes(d["dram__bytes_read.sum"], u["dram__bytes_read.sum"]); wr = _bytes(d["dram__bytes_write.sum"], u["dram__bytes_write.sum"])
+            grid = d.get("launch__grid_size", "")
+            col = {"dram_bytes": int(rd + wr)}
+            break
+    out = {"source": f"ncu --set full --clock-control none, {os.path.basename(burst_rep)} ({streams_profiled} streams x {n_iq} IQ in one synchronous call, one launch per kernel)",
+           "streams_profiled": streams_profiled, "fp64_pipe_active_pct": pipe, "dram_bytes_per_launch": dram,
+           "colsum_source": f"ncu --set full --clock-control none, {os.path.basename(colsum_rep)} (32-stream launch of the bench command: 1,386,666,688 algorithmic bytes)",
+           "colsum_dram_ratio": (col.get("dram_bytes", 0) / 1386666688.0) if col else None}
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"rep": rep, "list": launches}[sys.argv[1]](sys.argv[2])
+    import os
+    if sys.argv[1] == "facts":
+        facts(sys.argv[2], sys.argv[3], int(sys.argv[4]), int(sys.argv[5]))
+    else:
+        {"rep": rep, "list": launches}[sys.argv[1]](sys.argv[2])
