@@ -294,9 +294,25 @@ def oracle_agreement(gsmcal, raw, res, n_iq, tpl, coef, count, workers):
     hist = {}
     for o in outcomes:
         hist[o] = hist.get(o, 0) + 1
-    pick = [d for d in range(D) if outcomes[d] != "calibrated"][:count]
-    fill = [d for d in np.linspace(0, D - 1, num=min(D, count)).astype(int).tolist() if d not in pick]
-    pick = sorted(set(pick + fill[:max(0, count - len(pick))]))
+    # every outcome kind is represented: round-robin over the non-calibrating kinds (up to 3/4 of the budget, rare kinds first), the rest
+    # evenly spaced fully calibrating streams
+    by_kind = {}
+    for d in range(D):
+        if outcomes[d] != "calibrated":
+            by_kind.setdefault(outcomes[d], []).append(d)
+    pick, budget = [], (3 * count) // 4
+    kinds = sorted(by_kind, key=lambda k_: len(by_kind[k_]))
+    i_ = 0
+    while len(pick) < budget and any(by_kind[k_] for k_ in kinds):
+        k_ = kinds[i_ % len(kinds)]
+        if by_kind[k_]:
+            pick.append(by_kind[k_].pop(0))
+        i_ += 1
+    cal = [d for d in range(D) if outcomes[d] == "calibrated"]
+    if cal:
+        want = max(0, count - len(pick))
+        pick += [cal[i] for i in sorted(set(np.linspace(0, len(cal) - 1, num=min(len(cal), want)).astype(int).tolist()))]
+    pick = sorted(set(pick))
     got = {}
     for d in pick:
         got[d] = gsmcal.calibrate_batch(None, CARRIER, tpl, coef, device_ptr=raw[d].data_ptr(), n_iq=n_iq, n_streams=1)[0]
@@ -727,8 +743,8 @@ def main():
     colsum_gbs = (D * 2 * n_iq) / (stage_ms.get("colsum_u8", float("nan")) * 1e-3) / 1e9
     roofline = None
     if dominant:
-        roofline = {"kernel": {"fine_peak": "fine_peak_core_kernel (+ fine_peak_band_kernel for the bursts it cannot certify)",
-                               "fine_tone": "tone_est_kernel", "sch": "sch_corr_kernel", "post": "tone_est_kernel"}[dominant],
+        roofline = {"kernel": {"fine_peak": "fine_core8_kernel (+ fine_peak_band_kernel for the bursts it cannot certify)",
+                               "fine_tone": "tone8_kernel", "sch": "sch_corr_kernel", "post": "tone8_kernel"}[dominant],
                     "stage": dominant, "bound": "fp64", "achieved": stage_tflops.get(dominant), "peak": fp64.value, "unit": "TFLOP/s",
                     "frac": (stage_tflops.get(dominant) / fp64.value) if fp64.value else None,
                     "peak_source": "measured here: gsmcal_fp64_peak (register-only DFMA kernel, CUDA events); MEASURED_PEAKS.json has no FP64 figure",

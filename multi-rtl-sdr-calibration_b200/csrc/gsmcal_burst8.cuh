@@ -46,10 +46,14 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
     // debug hook (gsmcal_debug_set key 13): thread 0 adds the cycles between phase marks to prof[phase]; prof[15] counts blocks
     long long t_prev = PROF ? clock64() : 0;
 #define B8_MARK(ph) do { if (PROF && tid == 0) { const long long t_now = clock64(); atomicAdd(prof + (ph), (unsigned long long)(t_now - t_prev)); t_prev = t_now; } } while (0)
-    const StreamCtl c = ctl[stream];
-    if (c.n_coarse < 5 || burst >= c.n_coarse) return;
+    // the three things the block needs from global memory before it can address the capture are fetched side by side (one latency,
+    // not three): the burst's coarse position, the stream's burst count and its mean
+    const double pos_d = __ldg(base_pos + (i64)stream * cap + burst);      // (always inside the [D][cap] array; garbage beyond n_coarse is not used)
+    const int n_coarse = ctl[stream].n_coarse;
+    struct { double mu_re, mu_im; } c = {ctl[stream].mu_re, ctl[stream].mu_im};
+    if (n_coarse < 5 || burst >= n_coarse) return;
     const i64 len_s = n_iq / 8;
-    const i64 position = (i64)base_pos[(i64)stream * cap + burst];
+    const i64 position = (i64)pos_d;
     double *o = fine_raw + (i64)stream * cap + burst;
     if (position + 64 > len_s - 148 + 1) {                       // run out of sampled signal (:35-38)
         if (tid == 0) *o = INFINITY;
@@ -108,23 +112,22 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
     }
     // ---- chunk energies: thread = (chunk, half), 16 samples each, the start rotated per lane so a quarter-warp reads 8 banks ----
     {
-        double se = 0.0, se31 = 0.0;
+        double se = 0.0, e_last = 0.0;
         const int cch = tid >> 1, h = tid & 1;
         if (tid < 2 * B8_NCH) {
             const double2 *bp = B + 33 * cch + 16 * h;
             const int rot = (tid + 1) >> 1;
-#pragma unroll 4
+#pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const int idx = (i + rot) & 15;
-                const double2 v = bp[idx];
-                const double e = fma(v.x, v.x, v.y * v.y);
-                se += e;
-                if (!(h == 1 && idx == 15)) se31 += e;
+                const double2 v = bp[(i + rot) & 15];
+                se = fma(v.x, v.x, fma(v.y, v.y, se));
             }
+            if (h == 0) { const double2 v = B[33 * cch + 31]; e_last = fma(v.x, v.x, v.y * v.y); }
         }
         if (warp < 5) {                                          // 138 tasks live in warps 0..4; the halves of a chunk are lane neighbours
-            const double se_o = __shfl_xor_sync(0xffffffffu, se, 1), se31_o = __shfl_xor_sync(0xffffffffu, se31, 1);
-            if (tid < 2 * B8_NCH && h == 0) { PE[cch + 1] = se + se_o; E31[cch] = se31 + se31_o; }
+            const double se_o = __shfl_xor_sync(0xffffffffu, se, 1);
+            // E31 = E32 - |s[31]|^2: the rounding of the difference (1e-16 of E32) is far inside the 1e-9 / 1e-6 margins of the certificate
+            if (tid < 2 * B8_NCH && h == 0) { const double e32 = se + se_o; PE[cch + 1] = e32; E31[cch] = fmax(e32 - e_last, 0.0) * (1.0 + 1e-12); }
         }
         if (tid == 0) PE[0] = 0.0;
     }
@@ -136,7 +139,9 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
             pq[0] += q2.x; pq[1] += q2.y;
         }
         block_sum_n<2, false>(pq, scan_sv);                      // (its barriers also publish PE / E31)
-        if (tid == 0) red_i[0] = (int)floor(atan2(pq[1], pq[0]) * (double)B8_N / (2.0 * GSMCAL_PI) + 0.5);   // one atan2 per block
+        // (the band centre only selects WHICH bins are tracked - the certificate decides correctness - so the fp32 atan2 is enough:
+        //  it is ~5x shorter on the one thread the whole block waits for)
+        if (tid == 0) red_i[0] = (int)floorf(atan2f((float)pq[1], (float)pq[0]) * (float)(B8_N / (2.0 * GSMCAL_PI)) + 0.5f);
     }
     if (warp == 1) warp_scan_smem(PE, B8_NCH + 1, lane);         // PE[i] = sum_{n < 32 i} |s[n]|^2
     __syncthreads();
@@ -235,7 +240,9 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
             const double bound = (sqrt_ub(p0) + slack) * (1.0 + 1e-9);
             need = !(bound * bound < gl * (1.0 - 1e-6));
         }
-        const int any_need = __syncthreads_or(need ? 1 : 0);      // (also orders the reads of red_v before block_argmax reuses it)
+        // pass 0 always slides somewhere (the segment that holds the largest start), so only the later passes vote; the barrier inside the
+        // branch below (or block_argmax's first one) orders the reads of red_v before it is reused
+        const int any_need = (pass == 0) ? 1 : __syncthreads_or(need ? 1 : 0);
         B8_MARK(5);                                              // segment starts, which segments slide
         double best = -1.0; int bestm = 0x7fffffff;
         if (any_need) {
@@ -280,6 +287,7 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
         //   sum_{i=c}^{c+30} (|s[i]| + |s[i+N]|) <= sqrt(31*E31[g]) + sqrt(31*E31[g+37])        (Cauchy-Schwarz). ----
         ok = 1;
         for (int w0 = 0; w0 <= B8_NSEG; w0 += B8_THREADS / 8) {
+            if (w0 > 0 && warp > 0) break;                       // the second round is window 32 alone: 8 threads of warp 0
             const int gq = w0 + (tid >> 3), cand = tid & 7;
             double bnd = INFINITY;
             if (gq <= B8_NSEG && cand < 7) {
@@ -351,13 +359,15 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
     __shared__ double2 sh_x[8];
     __shared__ int sh_k0, sh_jbest, sh_flag;
     const int burst = blockIdx.x, stream = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const i64 idx_o = (i64)stream * cap + burst;
+    // fetched side by side with the control block (one global-memory latency instead of three); garbage beyond the burst count is not used
+    const double pos_d = __ldg(pos + idx_o), wpos_d = src.wcache ? __ldg(src.wc_pos + idx_o) : 0.0;
     const StreamCtl c = ctl[stream];
     const int nb = (which == 1) ? (c.tone1_enable ? c.n_fcch : 0) : (c.post_enable ? c.n_post_fcch : 0);
     if (burst >= nb) return;
-    const i64 idx_o = (i64)stream * cap + burst;
     constexpr int N = B8_N;
     const double sampling_rate = ((1625.0 / 6.0) * 1e3) * 8.0;
-    const i64 start = (i64)pos[idx_o] - 1;
+    const i64 start = (i64)pos_d - 1;
     // ---- index ranges of the levels (load_window's arithmetic) ----
     const i64 n0 = src.n_iq;
     const bool use2 = (src.level == 3) && c.interp2_on;
@@ -382,7 +392,7 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
     if (a0 < 0) a0 = 0;
     if (b0 > n0 - 1) b0 = n0 - 1;
     const int n_l0 = (int)(b0 - a0 + 1), n_l1 = (int)(b1 - a1 + 1);
-    const i64 wbase = ((i64)src.wc_pos[idx_o] - 65) * 8;
+    const i64 wbase = ((i64)wpos_d - 65) * 8;
     const bool covered = src.wcache && a0 >= wbase && b0 < wbase + B8_NSMP && n_l0 <= T8_BUF - 8 && n_l1 <= T8_BUF - 8 && start >= 0
                          && (!derot || use1);                     // (derotation without resampling does not occur in the reference flow)
     if (!covered) {                                              // block-uniform
@@ -448,7 +458,7 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
             if (n + 1 < N) { const double2 q = cmulc(u[n + 1], v); epq[1] += q.x; epq[2] += q.y; }
         }
         block_sum_n<3, false>(epq, red_n);
-        if (tid == 0) { sh_E = epq[0]; sh_k0 = (int)floor(atan2(epq[2], epq[1]) * (double)N / (2.0 * GSMCAL_PI) + 0.5); sh_flag = 0; }
+        if (tid == 0) { sh_E = epq[0]; sh_k0 = (int)floorf(atan2f((float)epq[2], (float)epq[1]) * (float)(N / (2.0 * GSMCAL_PI)) + 0.5f); sh_flag = 0; }   // fp32: see fine_core8_kernel
     }
     __syncthreads();
     const int k0 = sh_k0;
