@@ -800,3 +800,26 @@ def test_calibrate_batch_r_materialises_r_correct(gpu, captures, coef47, tpl):
             assert rel_err(r[d, :n], ref["r_final"]) < 1e-8          # two derotations with n*dphi up to 1e5..1e6 rad
             assert np.all(r[d, n:] == 7.0 + 7.0j)
     assert got[3]["r_len"][2] == -1
+
+
+def test_bench_workload_streams_match_the_oracle(gpu, coef47, tpl):
+    """32 of bench.py's own 10 s streams (BASELINE config 5, seeds = stream indices) - half of them streams that do NOT fully calibrate
+    in the timed run (SCH spacing failures, short chains, the SCH edge abort, the SNR-gate stream) - through the batched pipeline and
+    through oracle.calibrate_stream on a process pool; bench.py's own comparison code, so the bench line's `oracle_agreement` is tested."""
+    import sys
+    torch = pytest.importorskip("torch")
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    n_iq = bench.N_IQ_10S
+    failing = [48, 59, 94, 100, 122, 126, 179, 183, 218, 224, 300, 307, 309, 319, 332, 336]      # non-calibrating in profiles/r2*_bench*.json
+    seeds = sorted(set(failing + list(range(0, 1024, 64))))
+    raw = torch.empty((len(seeds), 2 * n_iq), dtype=torch.uint8, device="cuda")
+    for i, sd in enumerate(seeds):
+        synth.generate_stream(synth.random_spec(sd, n_iq), "cuda", raw[i])
+    torch.cuda.synchronize()
+    res = gpu.calibrate_batch(None, CARRIER, tpl, coef47, device_ptr=raw.data_ptr(), n_iq=n_iq, n_streams=len(seeds), details=False)
+    rep = bench.oracle_agreement(gpu, raw, res, n_iq, tpl, coef47, len(seeds), os.cpu_count() or 4)
+    assert rep["oracle_agrees"] == f"{len(seeds)}/{len(seeds)}", rep
+    assert len(rep["checked_streams"]) == len(seeds)
+    hist = rep["outcome_histogram_rank0"]
+    assert hist.get("calibrated", 0) >= 8 and sum(v for k, v in hist.items() if k != "calibrated") >= 8, hist
