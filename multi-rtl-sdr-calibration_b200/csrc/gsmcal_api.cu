@@ -36,6 +36,9 @@ int g_debug_persist_colsum = 0;   // submit/collect: blocks per SM of the persis
 int g_debug_hi_prio = 1;          // burst chain of each stream group on a high-priority CUDA stream
 int g_debug_core8_passes = B8_NPASS; // passes of 8 tracked bins in fine_core8_kernel (1..8)
 unsigned *g_last_pass_hist = nullptr;
+int g_debug_persist_threads = 256;  // block size of the persistent column-sum kernel (debug key 15)
+int g_debug_timeline = 0;          // submit/collect print the device timeline of every batch to stderr (A/B of overlap)
+cudaEvent_t g_tl_base = nullptr;
 int g_debug_prof = 0;              // fine_core8_kernel accumulates per-phase cycle counts (debug_get 50..65)
 int g_debug_no_tone8 = 0;          // tests / A-B: 1 = generic tone estimator for every burst
 int g_debug_no_core8 = 0;         // tests / A-B: 1 = round-1 tier-1 kernel and no filtered-window cache
@@ -82,6 +85,8 @@ struct Slot {
     cudaStream_t front = nullptr, front_hi = nullptr;
     std::vector<cudaStream_t> grp, hi;
     cudaEvent_t done = nullptr;
+    cudaEvent_t tl[4] = {nullptr, nullptr, nullptr, nullptr};   // debug key 14: front start, column sums done, burst chain done, FP64 stages done
+    bool tl_on = false;
     bool busy = false;
     char *stage = nullptr; size_t stage_cap = 0;               // pinned host staging of the results
     gsmcal_stream_result *results = nullptr; double *coarse_pos = nullptr, *coarse_snr = nullptr, *fcch_pos = nullptr, *pos_info = nullptr;
@@ -303,7 +308,7 @@ int run_colsum_u8_persist(const uint8_t *raw, i64 n_iq, i64 D, StreamCtl *ctl, i
     if (((uintptr_t)raw & 1) != 0) return fail(GSMCAL_ERR_ARG, "uint8 capture must start on an even address");
     const i64 chunk = 512 * 1024;
     i64 chunks = (2 * n_iq + chunk - 1) / chunk; if (chunks < 1) chunks = 1;
-    LAUNCH(colsum_u8_persist_kernel, (unsigned)blocks, 256, 0, st, raw, n_iq, chunk, chunks, D, ctl);
+    LAUNCH(colsum_u8_persist_kernel, (unsigned)blocks, g_debug_persist_threads, 0, st, raw, n_iq, chunk, chunks, D, ctl);
     return GSMCAL_OK;
 }
 
@@ -537,6 +542,8 @@ int gsmcal_debug_set(int key, int value) {
     if (key == 11) { g_debug_no_tone8 = value ? 1 : 0; return GSMCAL_OK; }
     if (key == 12) { g_debug_no_staging = value ? 1 : 0; return GSMCAL_OK; }
     if (key == 13) { g_debug_prof = value ? 1 : 0; return GSMCAL_OK; }
+    if (key == 14) { g_debug_timeline = value ? 1 : 0; return GSMCAL_OK; }
+    if (key == 15) { g_debug_persist_threads = (value == 64 || value == 128) ? value : 256; return GSMCAL_OK; }
     if (key == 10) { g_debug_core8_passes = value < 1 ? 1 : (value > 8 ? 8 : value); return GSMCAL_OK; }
     if (key == 8) { g_debug_submit_groups = value < 1 ? 1 : (value > kMaxGroups / 2 ? kMaxGroups / 2 : value); return GSMCAL_OK; }
     if (key == 7) { g_debug_persist_colsum = value < 0 ? 0 : (value > 8 ? 8 : value); return GSMCAL_OK; }
@@ -1147,6 +1154,12 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
     const size_t per = (size_t)2 * n_iq;
     std::vector<cudaEvent_t> ev_done;
     cudaEvent_t e_sum = nullptr;
+    sl.tl_on = g_debug_timeline != 0;
+    if (sl.tl_on) {
+        if (!sl.tl[0]) for (auto &e : sl.tl) CU(cudaEventCreate(&e));
+        if (!g_tl_base) { CU(cudaEventCreate(&g_tl_base)); CU(cudaEventRecord(g_tl_base, fr)); }
+        CU(cudaEventRecord(sl.tl[0], fr));
+    }
     if (g_debug_persist_colsum > 0) {
         // all column sums in ONE persistent launch of fixed footprint on the high-priority front stream (see colsum_u8_persist_kernel)
         int n_sm = 148; CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, g_device));
@@ -1154,6 +1167,7 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
         CU(cudaEventRecord(e_in, fr)); CU(cudaStreamWaitEvent(sl.front_hi, e_in, 0)); CU(cudaEventDestroy(e_in));
         TRY(run_colsum_u8_persist(raw_dev, n_iq, D, w.ctl, n_sm * g_debug_persist_colsum, sl.front_hi));
         CU(cudaEventRecord(e_sum, sl.front_hi));
+        if (sl.tl_on) CU(cudaEventRecord(sl.tl[1], sl.front_hi));
     }
     for (int g = 0; g < n_groups; ++g) {
         const i64 d0 = D * g / n_groups, d1 = D * (g + 1) / n_groups, nd = d1 - d0;
@@ -1165,10 +1179,12 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
         else {
             TRY(run_colsum_u8(graw, n_iq, nd, ws.ctl, fr));     // HBM-bound sums back to back on the front stream (group 0 first)
             CU(cudaEventRecord(e0, fr)); CU(cudaStreamWaitEvent(sh, e0, 0));
+            if (sl.tl_on && g == n_groups - 1) CU(cudaEventRecord(sl.tl[1], fr));
         }
         LAUNCH(mean_kernel, (unsigned)((nd + 127) / 128), 128, 0, sh, ws.ctl, (int)nd, n_iq);
         TRY(run_coarse(lazy_src(graw, n_iq, n_taps, 0, dec), len_dec, p, nd, cap, ws, sh));      // latency-bound chain: high priority
         CU(cudaEventRecord(e1, sh)); CU(cudaStreamWaitEvent(sg, e1, 0));
+        if (sl.tl_on && g == n_groups - 1) CU(cudaEventRecord(sl.tl[2], sh));
         CU(cudaEventDestroy(e0)); CU(cudaEventDestroy(e1));
         TRY(run_fine_peak(*c, lazy_src(graw, n_iq, n_taps, 0, 1), n_iq, osr, nd, cap, ws, sg));
         TRY(run_fine_rest(*c, with_cache(lazy_src(graw, n_iq, n_taps, 1, 1), ws, cap), n_iq, osr, carrier_freq, nd, cap, ws, sg));
@@ -1176,6 +1192,7 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
         TRY(run_post(*c, with_cache(lazy_src(graw, n_iq, n_taps, 3, 1), ws, cap), osr, carrier_freq, nd, cap, ws, true, sg));
         cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CU(cudaEventRecord(ev, sg));
+        if (sl.tl_on && g == n_groups - 1) CU(cudaEventRecord(sl.tl[3], sg));
         ev_done.push_back(ev);
     }
     if (e_sum) CU(cudaEventDestroy(e_sum));
@@ -1204,6 +1221,12 @@ int gsmcal_calibrate_batch_collect(int slot) {
     std::lock_guard<std::mutex> lk(g_mu);
     Ctx *c; TRY(get_ctx(&c));
     Slot &sl = c->slots[slot];
+    if (sl.tl_on && g_tl_base) {
+        float t[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], g_tl_base, sl.tl[i]);
+        fprintf(stderr, "[gsmcal timeline] slot %d: front start %.3f ms, column sums done %.3f, burst chain done %.3f, FP64 stages done %.3f\n", slot, t[0], t[1], t[2], t[3]);
+        cudaGetLastError();
+    }
     const char *h_res = sl.stage, *h_arr = sl.stage + align_up(sl.n_res);
     memcpy(sl.results, h_res, sl.n_res);
     if (sl.coarse_pos) memcpy(sl.coarse_pos, h_arr, sl.n_per);

@@ -444,16 +444,17 @@ __device__ __forceinline__ void colsum_u8_chunk(const uint8_t *__restrict__ raw,
         i64 c1 = c0 + chunk_bytes; if (c1 > body) c1 = body;
         const uint4 *v = reinterpret_cast<const uint4 *>(p + head);
         const i64 i0 = c0 / 16, i1 = c1 / 16;
+        const int nt = blockDim.x;                               // 256 (grid form) or a smaller persistent block
         i64 i = i0 + threadIdx.x;
-        for (; i + 3 * 256 < i1; i += 4 * 256) {
-            uint4 a = __ldg(v + i), b = __ldg(v + i + 256), c = __ldg(v + i + 512), d = __ldg(v + i + 768);
+        for (; i + 3 * nt < i1; i += 4 * nt) {
+            uint4 a = __ldg(v + i), b = __ldg(v + i + nt), c = __ldg(v + i + 2 * nt), d = __ldg(v + i + 3 * nt);
 #define GSMCAL_ACC(w) si = __dp4a((w), 0x00010001u, si); sq = __dp4a((w), 0x01000100u, sq);
             GSMCAL_ACC(a.x) GSMCAL_ACC(a.y) GSMCAL_ACC(a.z) GSMCAL_ACC(a.w)
             GSMCAL_ACC(b.x) GSMCAL_ACC(b.y) GSMCAL_ACC(b.z) GSMCAL_ACC(b.w)
             GSMCAL_ACC(c.x) GSMCAL_ACC(c.y) GSMCAL_ACC(c.z) GSMCAL_ACC(c.w)
             GSMCAL_ACC(d.x) GSMCAL_ACC(d.y) GSMCAL_ACC(d.z) GSMCAL_ACC(d.w)
         }
-        for (; i < i1; i += 256) {
+        for (; i < i1; i += nt) {
             uint4 a = __ldg(v + i);
             GSMCAL_ACC(a.x) GSMCAL_ACC(a.y) GSMCAL_ACC(a.z) GSMCAL_ACC(a.w)
         }
@@ -462,8 +463,8 @@ __device__ __forceinline__ void colsum_u8_chunk(const uint8_t *__restrict__ raw,
     li = si; lq = sq;
     if (chunk_id == 0) {                                          // ragged head / tail bytes, scalar
         const i64 hb = (head < total) ? head : total;
-        for (i64 j = threadIdx.x; j < hb; j += 256) { if (j & 1) lq += p[j]; else li += p[j]; }
-        for (i64 j = hb + body + threadIdx.x; j < total; j += 256) { if (j & 1) lq += p[j]; else li += p[j]; }
+        for (i64 j = threadIdx.x; j < hb; j += blockDim.x) { if (j & 1) lq += p[j]; else li += p[j]; }
+        for (i64 j = hb + body + threadIdx.x; j < total; j += blockDim.x) { if (j & 1) lq += p[j]; else li += p[j]; }
     }
     for (int o = 16; o > 0; o >>= 1) {
         li += __shfl_down_sync(0xffffffffu, li, o);
