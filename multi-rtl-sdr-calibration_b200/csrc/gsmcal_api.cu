@@ -37,6 +37,7 @@ int g_debug_hi_prio = 1;          // burst chain of each stream group on a high-
 int g_debug_core8_passes = B8_NPASS; // passes of 8 tracked bins in fine_core8_kernel (1..8)
 unsigned *g_last_pass_hist = nullptr;
 int g_debug_persist_threads = 256;  // block size of the persistent column-sum kernel (debug key 15)
+int g_debug_gate = 1;              // submit: the FP64 stages of a batch wait for the previous batch to finish (its front does not)
 int g_debug_timeline = 0;          // submit/collect print the device timeline of every batch to stderr (A/B of overlap)
 cudaEvent_t g_tl_base = nullptr;
 int g_debug_prof = 0;              // fine_core8_kernel accumulates per-phase cycle counts (debug_get 50..65)
@@ -97,6 +98,7 @@ struct Slot {
 constexpr int kNumStageEvents = 8;
 struct Ctx {
     StageRing ring;                  // pinned staging for pageable host buffers
+    int last_slot = -1;              // slot of the most recently submitted batch (submit/collect pipeline)
     bool attrs = false;
     cudaEvent_t stage_ev[kNumStageEvents];
     bool stage_ev_ok = false;
@@ -543,6 +545,7 @@ int gsmcal_debug_set(int key, int value) {
     if (key == 12) { g_debug_no_staging = value ? 1 : 0; return GSMCAL_OK; }
     if (key == 13) { g_debug_prof = value ? 1 : 0; return GSMCAL_OK; }
     if (key == 14) { g_debug_timeline = value ? 1 : 0; return GSMCAL_OK; }
+    if (key == 16) { g_debug_gate = value ? 1 : 0; return GSMCAL_OK; }
     if (key == 15) { g_debug_persist_threads = (value == 64 || value == 128) ? value : 256; return GSMCAL_OK; }
     if (key == 10) { g_debug_core8_passes = value < 1 ? 1 : (value > 8 ? 8 : value); return GSMCAL_OK; }
     if (key == 8) { g_debug_submit_groups = value < 1 ? 1 : (value > kMaxGroups / 2 ? kMaxGroups / 2 : value); return GSMCAL_OK; }
@@ -1185,6 +1188,11 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
         TRY(run_coarse(lazy_src(graw, n_iq, n_taps, 0, dec), len_dec, p, nd, cap, ws, sh));      // latency-bound chain: high priority
         CU(cudaEventRecord(e1, sh)); CU(cudaStreamWaitEvent(sg, e1, 0));
         if (sl.tl_on && g == n_groups - 1) CU(cudaEventRecord(sl.tl[2], sh));
+        // Stagger the batches: without this, two batches in flight run in lockstep (their kernels interleave at equal priority and
+        // both finish together), so both fronts execute while nothing else does.  Gated, the FP64 stages of batch k+1 start when batch k
+        // is done, and the front of batch k+1 (column sums, burst chain: HBM- and latency-bound) runs UNDER the FP64 stages of batch k.
+        if (g_debug_gate && c->last_slot >= 0 && c->last_slot != slot && c->slots[c->last_slot].busy)
+            CU(cudaStreamWaitEvent(sg, c->slots[c->last_slot].done, 0));
         CU(cudaEventDestroy(e0)); CU(cudaEventDestroy(e1));
         TRY(run_fine_peak(*c, lazy_src(graw, n_iq, n_taps, 0, 1), n_iq, osr, nd, cap, ws, sg));
         TRY(run_fine_rest(*c, with_cache(lazy_src(graw, n_iq, n_taps, 1, 1), ws, cap), n_iq, osr, carrier_freq, nd, cap, ws, sg));
@@ -1205,6 +1213,7 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
     CU(cudaEventRecord(sl.done, fr));
     sl.results = results; sl.coarse_pos = coarse_pos; sl.coarse_snr = coarse_snr; sl.fcch_pos = fcch_pos; sl.pos_info = pos_info;
     sl.busy = true;
+    c->last_slot = slot;
     return GSMCAL_OK;
 }
 
