@@ -37,7 +37,7 @@ int g_debug_hi_prio = 1;          // burst chain of each stream group on a high-
 int g_debug_core8_passes = B8_NPASS; // passes of 8 tracked bins in fine_core8_kernel (1..8)
 unsigned *g_last_pass_hist = nullptr;
 int g_debug_persist_threads = 256;  // block size of the persistent column-sum kernel (debug key 15)
-int g_debug_gate = 1;              // submit: the FP64 stages of a batch wait for the previous batch to finish (its front does not)
+int g_debug_gate = 0;              // debug key 16: FP64 stages of a batch wait for the previous batch (staggered pipeline) - measured slower, see DESIGN.md
 int g_debug_timeline = 0;          // submit/collect print the device timeline of every batch to stderr (A/B of overlap)
 cudaEvent_t g_tl_base = nullptr;
 int g_debug_prof = 0;              // fine_core8_kernel accumulates per-phase cycle counts (debug_get 50..65)
@@ -1024,9 +1024,17 @@ static int calibrate_batch_impl(const uint8_t *raw, int raw_mem, int64_t n_iq, i
             TRY(run_colsum_u8(graw, n_iq, nd, ws.ctl, sg));
         } else if (sg == st) {
             TRY(run_colsum_u8(graw, n_iq, nd, ws.ctl, sg));
+        } else if (g_debug_persist_colsum > 0 && g_debug_hi_prio && g > 0) {
+            // device input, groups after the first: the column sums as ONE persistent launch of small fixed footprint on the group's
+            // high-priority stream, so they run BESIDE the FP64 stages of the previous group (which the gate below keeps ahead)
+            cudaStream_t sh = c->side_hi[g];
+            int n_sm = 148; CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, g_device));
+            CU(cudaStreamWaitEvent(sh, ev_fork, 0));
+            TRY(run_colsum_u8_persist(graw, n_iq, nd, ws.ctl, n_sm * g_debug_persist_colsum, sh));
+            cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            CU(cudaEventRecord(ev, sh)); CU(cudaStreamWaitEvent(sg, ev, 0)); CU(cudaEventDestroy(ev));
         } else {
-            // device input: the HBM-bound column sums of all groups run back to back on the caller's stream, so group 0
-            // gets the whole bandwidth first and its latency-bound burst chain starts while the others are still summing
+            // device input: the HBM-bound column sums run on the caller's stream (group 0 gets the whole bandwidth first)
             TRY(run_colsum_u8(graw, n_iq, nd, ws.ctl, st));
             cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             CU(cudaEventRecord(ev, st)); CU(cudaStreamWaitEvent(sg, ev, 0)); CU(cudaEventDestroy(ev));
@@ -1190,9 +1198,11 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
         TRY(run_coarse(lazy_src(graw, n_iq, n_taps, 0, dec), len_dec, p, nd, cap, ws, sh));      // latency-bound chain: high priority
         CU(cudaEventRecord(e1, sh)); CU(cudaStreamWaitEvent(sg, e1, 0));
         if (sl.tl_on && g == n_groups - 1) CU(cudaEventRecord(sl.tl[2], sh));
-        // Stagger the batches: without this, two batches in flight run in lockstep (their kernels interleave at equal priority and
-        // both finish together), so both fronts execute while nothing else does.  Gated, the FP64 stages of batch k+1 start when batch k
-        // is done, and the front of batch k+1 (column sums, burst chain: HBM- and latency-bound) runs UNDER the FP64 stages of batch k.
+        // Optional (debug key 16): stagger the batches.  Two batches in flight run in lockstep (their kernels interleave at equal priority
+        // and both finish together), so both fronts execute while nothing else does.  Gated, the FP64 stages of batch k+1 start when
+        // batch k is done and the front of batch k+1 runs UNDER the FP64 stages of batch k.  Measured (profiles/r2j_timeline_staggered.txt):
+        // the overlap happens but does not pay - the column sums saturate HBM and stretch the latency-bound phases of the FP64 kernels by
+        // more than their own 6 ms (36.6-39.9 ms per step against 35.5 ms in lockstep) - so it is off by default.
         if (g_debug_gate && c->last_slot >= 0 && c->last_slot != slot && c->slots[c->last_slot].busy)
             CU(cudaStreamWaitEvent(sg, c->slots[c->last_slot].done, 0));
         CU(cudaEventDestroy(e0)); CU(cudaEventDestroy(e1));
