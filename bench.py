@@ -675,6 +675,18 @@ def main():
     clocks = sampler.stop()
     launches = gsmcal.launch_count()
     ms = ev0.elapsed_time(ev1)
+    pipelined_phases = None
+    if "13=1" in args.debug:                      # phase cycles of the last two batches of the timed run (the one before the last ran under the next front)
+        cn = ["staging", "fir", "energies_k0", "chunk_sums", "prefix", "segment_starts", "diff_slide", "argmax", "certificate"]
+        tn = ["cache_load", "interp_levels", "energy_k0", "horner_band", "totals_argmax", "derot_unit_phasors", "ratio_atan2", "gate_horner", "gate_sums"]
+        pipelined_phases = {}
+        for off_, which_ in ((150, "batch_before_last"), (50, "last_batch")):
+            ent = {}
+            for base_, label_, nm in ((0, "core8", cn), (16, "tone8_fine", tn), (32, "tone8_post", tn)):
+                nb_ = max(1, int(L.gsmcal_debug_get(off_ + base_ + 15)))
+                ent[label_] = {n_: round(int(L.gsmcal_debug_get(off_ + base_ + i_)) / nb_, 1) for i_, n_ in enumerate(nm)}
+                ent[label_]["total"] = round(sum(ent[label_].values()), 1)
+            pipelined_phases[which_] = ent
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -719,6 +731,10 @@ def main():
             blocks = max(1, int(L.gsmcal_debug_get(65)))
             tiers["core8_phase_cycles_per_block"] = {n_: int(L.gsmcal_debug_get(50 + i_)) / blocks for i_, n_ in enumerate(names)}
             tiers["core8_blocks"] = blocks
+            tnames = ["cache_load", "interp_levels", "energy_k0", "horner_band", "totals_argmax", "derot_unit_phasors", "ratio_atan2", "gate_horner", "gate_sums"]
+            for base_, label_ in ((66, "tone8_fine"), (82, "tone8_post")):
+                tb = max(1, int(L.gsmcal_debug_get(base_ + 15)))
+                tiers[label_ + "_phase_cycles_per_block"] = {n_: int(L.gsmcal_debug_get(base_ + i_)) / tb for i_, n_ in enumerate(tnames)}
     L.gsmcal_debug_set(3, args.groups)
     stage_ms = {k: v / n_prof for k, v in stage_acc.items()}
 
@@ -859,7 +875,9 @@ def main():
                 "cpu_baseline": cpu_baseline, "stage_ms": stage_ms, "stage_ms_note": f"sequential pass over all {D} streams of rank 0 (one stream group)",
                 "streams_fully_calibrated": f"{n_ok}/{D} on rank 0", "oracle_agreement": agreement, "synchronous_call": sync_call,
                 "fine_search_allbin_fallback_bursts": tiers["tier3"], "fine_search_64bin_tier2_bursts": tiers["tier2"], "bursts_rank0": n_bursts,
-                "fine_search_tier1": {k: tiers.get(k) for k in ("tier1_proven_after_passes", "tier1_left_open", "core8_phase_cycles_per_block", "core8_blocks") if k in tiers},
+                "pipelined_phase_cycles_per_block": pipelined_phases,
+                "fine_search_tier1": {k: tiers.get(k) for k in ("tier1_proven_after_passes", "tier1_left_open", "core8_phase_cycles_per_block", "core8_blocks",
+                                                                 "tone8_fine_phase_cycles_per_block", "tone8_post_phase_cycles_per_block") if k in tiers},
                 "debug_keys": args.debug,
                 "configs": configs, "reference_runtime_probe": probe_reference_runtimes(), "synthetic_generation_s": t_gen}
         if stages is not None:

@@ -35,9 +35,12 @@ int g_debug_submit_groups = 1;    // stream groups inside a submitted batch
 int g_debug_persist_colsum = 0;   // submit/collect: blocks per SM of the persistent high-priority column-sum kernel (0 = per-group launches)
 int g_debug_hi_prio = 1;          // burst chain of each stream group on a high-priority CUDA stream
 int g_debug_core8_passes = B8_NPASS; // passes of 8 tracked bins in fine_core8_kernel (1..8)
-unsigned *g_last_pass_hist = nullptr;
+unsigned *g_last_pass_hist = nullptr, *g_prev_pass_hist = nullptr;   // counters of the last / the one-before-last batch (debug_get 50.., 150..)
 int g_debug_persist_threads = 256;  // block size of the persistent column-sum kernel (debug key 15)
-int g_debug_gate = 0;              // debug key 16: FP64 stages of a batch wait for the previous batch (staggered pipeline) - measured slower, see DESIGN.md
+int g_debug_sch56 = 0;             // debug key 19: sch_corr_kernel capped at 56 registers
+int g_debug_trickle = 2;           // debug key 17: ring stages (x 4 KB) of colsum_u8_trickle_kernel in submit/collect, 0 = off (plain column-sum launches)
+int g_debug_trickle_blocks = 3;    // debug key 18: its blocks per SM (3 x 2 stages: 22 GB in 7 ms under the FP64 stages, profiles/r2q)
+int g_debug_gate = 1;              // debug key 16: submit/collect staggers the batches - the FP64 stages of batch k+1 wait for batch k, its front runs under them
 int g_debug_timeline = 0;          // submit/collect print the device timeline of every batch to stderr (A/B of overlap)
 cudaEvent_t g_tl_base = nullptr;
 int g_debug_prof = 0;              // fine_core8_kernel accumulates per-phase cycle counts (debug_get 50..65)
@@ -86,7 +89,8 @@ struct Slot {
     cudaStream_t front = nullptr, front_hi = nullptr;
     std::vector<cudaStream_t> grp, hi;
     cudaEvent_t done = nullptr;
-    cudaEvent_t tl[4] = {nullptr, nullptr, nullptr, nullptr};   // debug key 14: front start, column sums done, burst chain done, FP64 stages done
+    cudaEvent_t tl[8] = {};                                     // debug key 14: front start, column sums done, burst chain done, FP64 stages done,
+                                                                // FP64 stages start, fine search done, fine tone done, SCH done
     bool tl_on = false;
     bool busy = false;
     char *stage = nullptr; size_t stage_cap = 0;               // pinned host staging of the results
@@ -169,9 +173,13 @@ int get_ctx(Ctx **out) {
         CU(cudaFuncSetAttribute(fine_core8_kernel<47, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B8_SMEM));
         CU(cudaFuncSetAttribute(fine_core8_kernel<48, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B8_SMEM));
         CU(cudaFuncSetAttribute(fine_core8_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B8_SMEM));
-        CU(cudaFuncSetAttribute(tone8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T8_SMEM));
+        CU(cudaFuncSetAttribute(tone8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T8_SMEM));
+        CU(cudaFuncSetAttribute(tone8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T8_SMEM));
         CU(cudaFuncSetAttribute(tone_est_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        CU(cudaFuncSetAttribute(sch_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CU(cudaFuncSetAttribute(sch_corr_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CU(cudaFuncSetAttribute(sch_corr_kernel<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CU(cudaFuncSetAttribute(colsum_u8_trickle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * (TRK_STAGE + 8)));
+        CU(cudaFuncSetAttribute(colsum_u8_trickle_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CU(cudaFuncSetAttribute(materialise_r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CU(cudaFuncSetAttribute(fir_full_tma_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CU(cudaFuncSetAttribute(fir_full_tma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -241,7 +249,7 @@ int make_work(DevBuf &wb, i64 D, int cap, i64 snr_len, int tpl_len, Work *w) {
     size_t per = sizeof(double) * D * cap;
     size_t o_cp = take(per), o_cs = take(per), o_fr = take(per), o_fp = take(per), o_fo = take(per), o_g = take(per), o_sr = take(per), o_sp = take(per), o_pp = take(per);
     size_t o_pi = take(per * 12), o_snr = take(sizeof(double) * D * snr_len), o_pw = take(sizeof(double) * D);
-    size_t o_se = take(sizeof(int) * D * cap), o_nf = take(sizeof(int) * D * cap), o_nb = take(sizeof(int) * D * cap), o_tn = take(sizeof(int) * D * cap), o_fl = take(sizeof(int) * D * cap), o_fc = take(sizeof(int) * D), o_fm = take(sizeof(int) * (size_t)FALL_GRID * 24 * kMaxGroups), o_fb = take(sizeof(double) * (size_t)FALL_GRID * 24 * kMaxGroups), o_k = take(D * cap), o_tpl = take(sizeof(double2) * (tpl_len > 0 ? tpl_len : 1)), o_ph = take(sizeof(unsigned) * 16 + sizeof(unsigned long long) * 16);
+    size_t o_se = take(sizeof(int) * D * cap), o_nf = take(sizeof(int) * D * cap), o_nb = take(sizeof(int) * D * cap), o_tn = take(sizeof(int) * D * cap), o_fl = take(sizeof(int) * D * cap), o_fc = take(sizeof(int) * D), o_fm = take(sizeof(int) * (size_t)FALL_GRID * 24 * kMaxGroups), o_fb = take(sizeof(double) * (size_t)FALL_GRID * 24 * kMaxGroups), o_k = take(D * cap), o_tpl = take(sizeof(double2) * (tpl_len > 0 ? tpl_len : 1)), o_ph = take(sizeof(unsigned) * 16 + sizeof(unsigned long long) * 48);
     void *base;
     TRY(wb.get(off, &base));
     char *b = static_cast<char *>(base);
@@ -314,6 +322,14 @@ int run_colsum_u8_persist(const uint8_t *raw, i64 n_iq, i64 D, StreamCtl *ctl, i
     return GSMCAL_OK;
 }
 
+int run_colsum_u8_trickle(const uint8_t *raw, i64 n_iq, i64 D, StreamCtl *ctl, int blocks, int n_stage, cudaStream_t st) {
+    if (((uintptr_t)raw & 1) != 0) return fail(GSMCAL_ERR_ARG, "uint8 capture must start on an even address");
+    const i64 chunk = 512 * 1024;
+    i64 chunks = (2 * n_iq + chunk - 1) / chunk; if (chunks < 1) chunks = 1;
+    LAUNCH(colsum_u8_trickle_kernel, (unsigned)blocks, 32, (size_t)n_stage * (TRK_STAGE + 8), st, raw, n_iq, chunk, chunks, D, ctl, n_stage);
+    return GSMCAL_OK;
+}
+
 struct CoarseParams { int fft_len, mv_len, step10, step11, dr; i64 n_first; double th; };
 double host_mround(double x) { return x >= 0 ? floor(x + 0.5) : -floor(-x + 0.5); }
 int coarse_params(int dr, CoarseParams *p) {
@@ -380,7 +396,9 @@ int run_tone(WinSrc src, int which, const double *pos, int osr, i64 D, int cap, 
     const int *need = nullptr;
     if (src.lazy && src.wcache && osr == 8 && !g_debug_no_tone8) {
         CU(cudaMemsetAsync(w.tone_need, 0, sizeof(int) * D * cap, st));
-        LAUNCH(tone8_kernel, dim3((unsigned)cap, (unsigned)D), T8_THREADS, T8_SMEM, st, src, w.ctl, which, pos, cap, tw, w.fo, w.gate, w.tone_need);
+        unsigned long long *prof = (unsigned long long *)(w.pass_hist + 16) + 16 * which;      // [1]: fine stage, [2]: post stage (debug key 13)
+        if (g_debug_prof) LAUNCH(tone8_kernel<true>, dim3((unsigned)cap, (unsigned)D), T8_THREADS, T8_SMEM, st, src, w.ctl, which, pos, cap, tw, w.fo, w.gate, w.tone_need, prof);
+        else              LAUNCH(tone8_kernel<false>, dim3((unsigned)cap, (unsigned)D), T8_THREADS, T8_SMEM, st, src, w.ctl, which, pos, cap, tw, w.fo, w.gate, w.tone_need, prof);
         need = w.tone_need;
     }
     LAUNCH(tone_est_kernel, dim3((unsigned)cap, (unsigned)D), TONE_THREADS, tone_smem(osr), st, src, w.ctl, which, pos, cap, osr, tw, w.fo, w.gate, need);
@@ -401,7 +419,8 @@ int run_fine(Ctx &c, WinSrc src_peak, WinSrc src_tone, i64 n_iq, int osr, double
 }
 
 int run_sch(WinSrc src, int osr, i64 D, int cap, Work &w, cudaStream_t st) {
-    LAUNCH(sch_corr_kernel, dim3((unsigned)cap, (unsigned)D), SCH_THREADS, sch_smem(osr), st, src, w.ctl, w.fcch_pos, cap, osr, w.tpl, w.sch_raw, w.sch_edge);
+    if (g_debug_sch56) LAUNCH(sch_corr_kernel<56>, dim3((unsigned)cap, (unsigned)D), SCH_THREADS, sch_smem(osr), st, src, w.ctl, w.fcch_pos, cap, osr, w.tpl, w.sch_raw, w.sch_edge);
+    else               LAUNCH(sch_corr_kernel<64>, dim3((unsigned)cap, (unsigned)D), SCH_THREADS, sch_smem(osr), st, src, w.ctl, w.fcch_pos, cap, osr, w.tpl, w.sch_raw, w.sch_edge);
     LAUNCH(sch_ppm_kernel, (unsigned)D, PS_THREADS, (size_t)cap * 21 + 16, st, w.ctl, (int)D, cap, osr, w.sch_raw, w.sch_edge, w.sch_pos, w.kind, w.pos_info, w.post_pos);
     return GSMCAL_OK;
 }
@@ -482,7 +501,7 @@ int gsmcal_set_device(int device) {
 }
 void gsmcal_release(void) {
     std::lock_guard<std::mutex> lk(g_mu);
-    g_last_need_full = nullptr; g_last_need_band = nullptr; g_last_need_full_n = 0; g_last_pass_hist = nullptr;   // they point into the workspaces freed below
+    g_last_need_full = nullptr; g_last_need_band = nullptr; g_last_need_full_n = 0; g_last_pass_hist = nullptr; g_prev_pass_hist = nullptr;   // they point into the workspaces freed below
     for (auto &kv : g_ctx) {
         cudaSetDevice(kv.first);
         kv.second.ring.release(); kv.second.in.release(); kv.second.out.release(); kv.second.work.release(); kv.second.tplbuf.release(); kv.second.wc.release();
@@ -511,7 +530,13 @@ int64_t gsmcal_debug_get(int key) {
     // key 1: bursts of the last fine search (this device) that needed the all-bin fallback
     std::lock_guard<std::mutex> lk(g_mu);
     if (key == 40) return (int64_t)g_debug_core8_passes;
-    if (key >= 50 && key < 66) {                                 // per-phase cycle sums of fine_core8_kernel (debug key 13), [15] = blocks
+    if (key >= 150 && key < 198) {                               // the same counters of the batch submitted before the last one (other slot)
+        if (!g_prev_pass_hist) return 0;
+        unsigned long long v = 0;
+        if (cudaMemcpy(&v, (unsigned long long *)(g_prev_pass_hist + 16) + (key - 150), sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        return (int64_t)v;
+    }
+    if (key >= 50 && key < 98) {                                 // per-phase cycle sums (debug key 13), [15] = blocks: 50.. fine_core8, 66.. tone8 (fine), 82.. tone8 (post)
         if (!g_last_pass_hist) return 0;
         unsigned long long v = 0;
         if (cudaMemcpy(&v, (unsigned long long *)(g_last_pass_hist + 16) + (key - 50), sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
@@ -546,6 +571,9 @@ int gsmcal_debug_set(int key, int value) {
     if (key == 13) { g_debug_prof = value ? 1 : 0; return GSMCAL_OK; }
     if (key == 14) { g_debug_timeline = value ? 1 : 0; return GSMCAL_OK; }
     if (key == 16) { g_debug_gate = value ? 1 : 0; return GSMCAL_OK; }
+    if (key == 19) { g_debug_sch56 = value != 0; return GSMCAL_OK; }
+    if (key == 17) { g_debug_trickle = value < 0 ? 0 : (value > 24 ? 24 : value); return GSMCAL_OK; }
+    if (key == 18) { g_debug_trickle_blocks = value < 1 ? 1 : (value > 4 ? 4 : value); return GSMCAL_OK; }
     if (key == 15) { g_debug_persist_threads = (value == 64 || value == 128) ? value : 256; return GSMCAL_OK; }
     if (key == 10) { g_debug_core8_passes = value < 1 ? 1 : (value > 8 ? 8 : value); return GSMCAL_OK; }
     if (key == 8) { g_debug_submit_groups = value < 1 ? 1 : (value > kMaxGroups / 2 ? kMaxGroups / 2 : value); return GSMCAL_OK; }
@@ -990,7 +1018,7 @@ static int calibrate_batch_impl(const uint8_t *raw, int raw_mem, int64_t n_iq, i
     { const double2 *twp; TRY(get_twiddle(*c, 148 * osr, st, &twp)); }        // built on `st` before the groups fork
     g_last_need_full = w.need_full; g_last_need_band = w.need_band; g_last_need_full_n = (long long)D * cap;
     g_last_pass_hist = w.pass_hist;
-    CU(cudaMemsetAsync(w.pass_hist, 0, sizeof(unsigned) * 16 + sizeof(unsigned long long) * 16, st));
+    CU(cudaMemsetAsync(w.pass_hist, 0, sizeof(unsigned) * 16 + sizeof(unsigned long long) * 48, st));
     g_stage_n = 0;
     // Streams are independent, so the batch is cut into groups that run the stage sequence on their own CUDA
     // streams: the latency-bound stages of one group (burst chain, per-stream solves) overlap the FP64-bound
@@ -1154,7 +1182,9 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
     char *h_res = sl.stage, *h_arr = sl.stage + align_up(sl.n_res), *h_tpl = h_arr + 15 * sl.n_per;
     memcpy(h_tpl, tpl, sizeof(double2) * 64 * osr);              // the caller's template may be pageable and short-lived
     { const double2 *twp; TRY(get_twiddle(*c, 148 * osr, st, &twp)); }
-    cudaStream_t fr = sl.front;
+    // normal-priority kernels of different streams are dispatched in arrival order: behind the 10^5 queued blocks of the previous batch's fine
+    // search even a memset waits milliseconds (device timeline, debug key 14), so the staggered mode runs the whole front at high priority
+    cudaStream_t fr = (g_debug_trickle > 0 || g_debug_gate) ? sl.front_hi : sl.front;
     cudaEvent_t ev_in; CU(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
     CU(cudaEventRecord(ev_in, st)); CU(cudaStreamWaitEvent(fr, ev_in, 0)); CU(cudaEventDestroy(ev_in));     // the capture is ready on the caller's stream
     CU(cudaMemsetAsync(w.ctl, 0, sizeof(StreamCtl) * D, fr));
@@ -1162,8 +1192,8 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
     CU(cudaMemsetAsync(w.need_band, 0, sizeof(int) * D * cap, fr));
     CU(cudaMemcpyAsync(w.tpl, h_tpl, sizeof(double2) * 64 * osr, cudaMemcpyHostToDevice, fr));
     g_last_need_full = w.need_full; g_last_need_band = w.need_band; g_last_need_full_n = (long long)D * cap;
-    g_last_pass_hist = w.pass_hist;
-    CU(cudaMemsetAsync(w.pass_hist, 0, sizeof(unsigned) * 16 + sizeof(unsigned long long) * 16, fr));
+    g_prev_pass_hist = g_last_pass_hist; g_last_pass_hist = w.pass_hist;
+    CU(cudaMemsetAsync(w.pass_hist, 0, sizeof(unsigned) * 16 + sizeof(unsigned long long) * 48, fr));
     const size_t per = (size_t)2 * n_iq;
     std::vector<cudaEvent_t> ev_done;
     cudaEvent_t e_sum = nullptr;
@@ -1173,12 +1203,14 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
         if (!g_tl_base) { CU(cudaEventCreate(&g_tl_base)); CU(cudaEventRecord(g_tl_base, fr)); }
         CU(cudaEventRecord(sl.tl[0], fr));
     }
-    if (g_debug_persist_colsum > 0) {
-        // all column sums in ONE persistent launch of fixed footprint on the high-priority front stream (see colsum_u8_persist_kernel)
+    if (g_debug_persist_colsum > 0 || g_debug_trickle > 0) {
+        // all column sums in ONE persistent launch of fixed footprint on the high-priority front stream (see colsum_u8_persist_kernel,
+        // colsum_u8_trickle_kernel)
         int n_sm = 148; CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, g_device));
         cudaEvent_t e_in; CU(cudaEventCreateWithFlags(&e_in, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&e_sum, cudaEventDisableTiming));
         CU(cudaEventRecord(e_in, fr)); CU(cudaStreamWaitEvent(sl.front_hi, e_in, 0)); CU(cudaEventDestroy(e_in));
-        TRY(run_colsum_u8_persist(raw_dev, n_iq, D, w.ctl, n_sm * g_debug_persist_colsum, sl.front_hi));
+        if (g_debug_persist_colsum > 0) TRY(run_colsum_u8_persist(raw_dev, n_iq, D, w.ctl, n_sm * g_debug_persist_colsum, sl.front_hi));
+        else TRY(run_colsum_u8_trickle(raw_dev, n_iq, D, w.ctl, n_sm * g_debug_trickle_blocks, g_debug_trickle, sl.front_hi));
         CU(cudaEventRecord(e_sum, sl.front_hi));
         if (sl.tl_on) CU(cudaEventRecord(sl.tl[1], sl.front_hi));
     }
@@ -1198,17 +1230,22 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
         TRY(run_coarse(lazy_src(graw, n_iq, n_taps, 0, dec), len_dec, p, nd, cap, ws, sh));      // latency-bound chain: high priority
         CU(cudaEventRecord(e1, sh)); CU(cudaStreamWaitEvent(sg, e1, 0));
         if (sl.tl_on && g == n_groups - 1) CU(cudaEventRecord(sl.tl[2], sh));
-        // Optional (debug key 16): stagger the batches.  Two batches in flight run in lockstep (their kernels interleave at equal priority
-        // and both finish together), so both fronts execute while nothing else does.  Gated, the FP64 stages of batch k+1 start when
-        // batch k is done and the front of batch k+1 runs UNDER the FP64 stages of batch k.  Measured (profiles/r2j_timeline_staggered.txt):
-        // the overlap happens but does not pay - the column sums saturate HBM and stretch the latency-bound phases of the FP64 kernels by
-        // more than their own 6 ms (36.6-39.9 ms per step against 35.5 ms in lockstep) - so it is off by default.
+        // Staggered batches (debug key 16, default on).  Ungated, two batches in flight run in lockstep (normal-priority kernels are dispatched
+        // in arrival order, so their stages interleave and both finish together) and both fronts execute while nothing else does.  Gated,
+        // the FP64 stages of batch k+1 start when batch k is done and the front of batch k+1 - on the high-priority stream, with the
+        // column sums as the small-footprint TMA-ring kernel - runs UNDER the FP64 stages of batch k.  Device timelines and the cost of the
+        // overlap (the ring's shared-memory traffic, the burst chain's register footprint): profiles/r2n, r2p, r2q and DESIGN.md section 8.
         if (g_debug_gate && c->last_slot >= 0 && c->last_slot != slot && c->slots[c->last_slot].busy)
             CU(cudaStreamWaitEvent(sg, c->slots[c->last_slot].done, 0));
         CU(cudaEventDestroy(e0)); CU(cudaEventDestroy(e1));
+        const bool tl_g = sl.tl_on && g == n_groups - 1;
+        if (tl_g) CU(cudaEventRecord(sl.tl[4], sg));
         TRY(run_fine_peak(*c, lazy_src(graw, n_iq, n_taps, 0, 1), n_iq, osr, nd, cap, ws, sg));
+        if (tl_g) CU(cudaEventRecord(sl.tl[5], sg));
         TRY(run_fine_rest(*c, with_cache(lazy_src(graw, n_iq, n_taps, 1, 1), ws, cap), n_iq, osr, carrier_freq, nd, cap, ws, sg));
+        if (tl_g) CU(cudaEventRecord(sl.tl[6], sg));
         TRY(run_sch(lazy_src(graw, n_iq, n_taps, 2, 1), osr, nd, cap, ws, sg));
+        if (tl_g) CU(cudaEventRecord(sl.tl[7], sg));
         TRY(run_post(*c, with_cache(lazy_src(graw, n_iq, n_taps, 3, 1), ws, cap), osr, carrier_freq, nd, cap, ws, true, sg));
         cudaEvent_t ev; CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         CU(cudaEventRecord(ev, sg));
@@ -1243,9 +1280,11 @@ int gsmcal_calibrate_batch_collect(int slot) {
     Ctx *c; TRY(get_ctx(&c));
     Slot &sl = c->slots[slot];
     if (sl.tl_on && g_tl_base) {
-        float t[4] = {0, 0, 0, 0};
-        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], g_tl_base, sl.tl[i]);
-        fprintf(stderr, "[gsmcal timeline] slot %d: front start %.3f ms, column sums done %.3f, burst chain done %.3f, FP64 stages done %.3f\n", slot, t[0], t[1], t[2], t[3]);
+        float t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < 8; ++i) cudaEventElapsedTime(&t[i], g_tl_base, sl.tl[i]);
+        fprintf(stderr, "[gsmcal timeline] slot %d: front start %.3f ms, column sums done %.3f, burst chain done %.3f, FP64 stages start %.3f, "
+                        "fine search +%.3f, fine tone +%.3f, SCH +%.3f, post +%.3f, done %.3f\n",
+                slot, t[0], t[1], t[2], t[4], t[5] - t[4], t[6] - t[5], t[7] - t[6], t[3] - t[7], t[3]);
         cudaGetLastError();
     }
     const char *h_res = sl.stage, *h_arr = sl.stage + align_up(sl.n_res);

@@ -348,10 +348,13 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
 #define T8_NSEG    119                       // ceil(1184 / 10); the last segment is padded with zeros
 #define T8_BUF     1216
 #define T8_SMEM    (2 * T8_BUF * 16)
+template <bool PROF>
 __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, int which, const double *__restrict__ pos, int cap,
                                                              const double2 *__restrict__ tw, double *__restrict__ fo_out, double *__restrict__ gate_out,
-                                                             int *__restrict__ need_old) {
+                                                             int *__restrict__ need_old, unsigned long long *__restrict__ prof) {
     extern __shared__ __align__(16) double2 t8_sm[];
+    long long t_prev = PROF ? clock64() : 0;                     // debug hook as in fine_core8_kernel: prof[ph] += cycles, prof[15] = blocks
+#define T8_MARK(ph) do { if (PROF && threadIdx.x == 0) { const long long t_now = clock64(); atomicAdd(prof + (ph), (unsigned long long)(t_now - t_prev)); t_prev = t_now; } } while (0)
     double2 *P = t8_sm, *Q = t8_sm + T8_BUF;
     __shared__ double red_n[24];
     __shared__ double2 sh_base, sh_step;
@@ -363,9 +366,9 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
     // fetched side by side with the control block (one global-memory latency instead of three); garbage beyond the burst count is not used
     const double pos_d = __ldg(pos + idx_o), wpos_d = src.wcache ? __ldg(src.wc_pos + idx_o) : 0.0;
     const StreamCtl c = ctl[stream];
+    constexpr int N = B8_N;
     const int nb = (which == 1) ? (c.tone1_enable ? c.n_fcch : 0) : (c.post_enable ? c.n_post_fcch : 0);
     if (burst >= nb) return;
-    constexpr int N = B8_N;
     const double sampling_rate = ((1625.0 / 6.0) * 1e3) * 8.0;
     const i64 start = (i64)pos_d - 1;
     // ---- index ranges of the levels (load_window's arithmetic) ----
@@ -407,6 +410,7 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
         if (derot && tid == 0) { double sn, cs; sincos((double)a1 * c.dphi1, &sn, &cs); sh_base = make_double2(cs, sn); }
     }
     __syncthreads();
+    T8_MARK(0);                                                  // level 0 from the cache (global-memory latency)
     double2 *u = P, *spare = Q;                                  // u: the burst the stage works on; spare: the other buffer
     if (use1) {                                                  // level 1 (+2): interp1 by (1+e1) [and derotation by dphi1] -> Q
         double2 ph = make_double2(1.0, 0.0), st = make_double2(1.0, 0.0);
@@ -449,6 +453,7 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
     }
     if (tid < T8_SEG * T8_NSEG - N + 2) u[N + tid] = make_double2(0.0, 0.0);     // zero padding of the last Horner segment
     __syncthreads();
+    T8_MARK(1);                                                  // interp1 / derotation levels
     // ---- energy and phase slope -> band centre ----
     {
         double epq[3] = {0.0, 0.0, 0.0};
@@ -461,6 +466,7 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
         if (tid == 0) { sh_E = epq[0]; sh_k0 = (int)floorf(atan2f((float)epq[2], (float)epq[1]) * (float)(N / (2.0 * GSMCAL_PI)) + 0.5f); sh_flag = 0; }   // fp32: see fine_core8_kernel
     }
     __syncthreads();
+    T8_MARK(2);                                                  // energy, phase slope, band centre
     const int k0 = sh_k0;
     // ---- 8-bin band DFT by Horner's rule: thread = (10-sample segment, 4 bins); partial sums -> spare[bin][120] ----
     if (tid < 2 * T8_NSEG) {
@@ -486,6 +492,7 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
         for (int b = 0; b < 4; ++b) spare[(4 * q + b) * 120 + seg] = cmul(acc[b], tw[(n0s * kk[b]) % N]);
     }
     __syncthreads();
+    T8_MARK(3);                                                  // Horner band DFT
     {   // warp b adds the partials of bin b
         double xr = 0.0, xi = 0.0;
         for (int sgi = lane; sgi < T8_NSEG; sgi += 32) { const double2 v = spare[warp * 120 + sgi]; xr += v.x; xi += v.y; }
@@ -515,6 +522,7 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
         }
     }
     __syncthreads();
+    T8_MARK(4);                                                  // bin totals, argmax, certificate
     if (sh_flag) {                                               // block-uniform: not certified, the row-FFT kernel takes the burst
         if (tid == 0) need_old[idx_o] = 1;
         return;
@@ -535,6 +543,7 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
         }
     }
     __syncthreads();
+    T8_MARK(5);                                                  // integer-bin derotation, unit phasors
     {
         double rri[2] = {0.0, 0.0};
         for (int n = tid; n < N - 1; n += T8_THREADS) {
@@ -550,6 +559,8 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
             double sn, cs; sincos(pr, &sn, &cs); sh_step = make_double2(cs, sn);      // exp(+i*phi): one step back in n
         }
     }
+    T8_MARK(6);                                                  // phasor-ratio mean, atan2, fo
+    if (PROF && which != 1 && tid == 0) atomicAdd(prof + 15, 1ull);
     if (which != 1) return;
     __syncthreads();
     // ---- SNR gate (:185-196): bins 0, +-1, +-2 of the finely derotated burst by Horner's rule, thread = (segment, bin pair);
@@ -580,6 +591,7 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
         if (q == 0) spare[4 * 120 + seg] = acc0;
     }
     __syncthreads();
+    T8_MARK(7);                                                  // gate: Horner over the finely derotated burst
     if (warp < 5) {
         double xr = 0.0, xi = 0.0;
         for (int sgi = lane; sgi < T8_NSEG; sgi += 32) { const double2 v = spare[warp * 120 + sgi]; xr += v.x; xi += v.y; }
@@ -592,4 +604,6 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
         if (sig5 >= 3.16227766016838 * (1.0 + 1e-9) * ((double)N * sh_E - sig5)) gate_out[idx_o] = 99.0;      // "certified above the 5 dB gate"
         else need_old[idx_o] = 1;                                // evaluate the 110 gate bins exactly
     }
+    T8_MARK(8);                                                  // gate sums, certificate
+    if (PROF && tid == 0) atomicAdd(prof + 15, 1ull);
 }

@@ -486,6 +486,117 @@ __global__ void __launch_bounds__(256) colsum_u8_persist_kernel(const uint8_t *_
     for (i64 w = blockIdx.x; w < total; w += gridDim.x) colsum_u8_chunk(raw, n_iq, chunk_bytes, ctl, (int)(w / n_chunks), w % n_chunks);
 }
 
+// "trickle" form for the staggered submit/collect pipeline (debug key 17): ONE warp per block, one block per SM, the bytes brought in by
+// TMA bulk copies (cp.async.bulk -> UBLKCP) into a ring of 4 KB stages that complete on mbarriers.  What is in flight lives in shared
+// memory, not in registers, so the footprint is 1 K registers + the ring (it fits beside four blocks of every FP64 kernel of the previous
+// batch), and the ring size bounds the HBM rate (ring bytes / memory latency per SM): the sums of batch k+1 trickle in under the FP64
+// stages of batch k instead of saturating HBM in front of them.  Same exact integer sums as colsum_u8_chunk, same (stream, chunk) units.
+#define TRK_STAGE 4096
+__global__ void __launch_bounds__(32) colsum_u8_trickle_kernel(const uint8_t *__restrict__ raw, i64 n_iq, i64 chunk_bytes, i64 n_chunks, i64 n_streams,
+                                                               StreamCtl *ctl, int n_stage) {
+    extern __shared__ __align__(128) unsigned char trk_sm[];     // [n_stage][TRK_STAGE] bytes, then n_stage mbarriers
+    const int lane = threadIdx.x;
+    const unsigned sm0 = (unsigned)__cvta_generic_to_shared(trk_sm), bar0 = sm0 + (unsigned)n_stage * TRK_STAGE;
+    if (lane == 0) {
+        for (int s = 0; s < n_stage; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * s));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    __syncwarp();
+    const i64 total_units = n_chunks * n_streams, total = 2 * n_iq;
+    struct Cur { i64 w, off, len; const uint8_t *base; };        // unit, byte offset inside it, its length, its first byte (16-byte aligned)
+    auto open_unit = [&](Cur &c) {                               // skips empty units; len = 0 when the block has no more work
+        for (; c.w < total_units; c.w += gridDim.x) {
+            const int stream = (int)(c.w / n_chunks);
+            const i64 chunk_id = c.w % n_chunks;
+            const uint8_t *p = raw + (i64)stream * total;
+            const i64 head = (16 - ((uintptr_t)p & 15)) & 15;
+            const i64 body = ((total - (head < total ? head : total)) / 16) * 16;
+            const i64 c0 = chunk_id * chunk_bytes;
+            i64 c1 = c0 + chunk_bytes; if (c1 > body) c1 = body;
+            if (c1 > c0 || chunk_id == 0) { c.off = 0; c.len = c1 > c0 ? c1 - c0 : 0; c.base = p + head + c0; return; }
+        }
+        c.off = 0; c.len = 0; c.base = nullptr;
+    };
+    // the producer cursor only visits units that have bytes; the consumer also visits empty chunk-0 units (ragged head / tail)
+    auto prod_next = [&](Cur &c) {
+        c.off += TRK_STAGE;
+        if (c.off >= c.len) { do { c.w += gridDim.x; open_unit(c); } while (c.w < total_units && c.len == 0); }
+    };
+    auto issue = [&](const Cur &c, int stage) {                  // lane 0 only
+        const i64 left = c.len - c.off;
+        const unsigned bytes = (unsigned)(left < TRK_STAGE ? left : TRK_STAGE);
+        const unsigned bar = bar0 + 8 * stage;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes));
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(sm0 + (unsigned)stage * TRK_STAGE), "l"(c.base + c.off), "r"(bytes), "r"(bar) : "memory");
+    };
+    Cur prod; prod.w = blockIdx.x; open_unit(prod);
+    while (prod.w < total_units && prod.len == 0) { prod.w += gridDim.x; open_unit(prod); }
+    Cur cons; cons.w = blockIdx.x; open_unit(cons);
+    for (int s = 0; s < n_stage; ++s)
+        if (prod.w < total_units) { if (lane == 0) issue(prod, s); prod_next(prod); }
+    int stage = 0; unsigned phase = 0;
+    unsigned si = 0, sq = 0;
+    while (cons.w < total_units) {
+        if (cons.len > 0) {
+            const i64 left = cons.len - cons.off;
+            const int bytes = (int)(left < TRK_STAGE ? left : TRK_STAGE);
+            {
+                unsigned done = 0;
+                const unsigned bar = bar0 + 8 * stage;
+                while (!done)
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                 : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+            }
+            const uint4 *v = reinterpret_cast<const uint4 *>(trk_sm + (size_t)stage * TRK_STAGE);
+            unsigned ti = 0, tq = 0, ui = 0, uq = 0, wi = 0, wq = 0;     // four independent dp4a chains per column
+#define GSMCAL_ACC2(w, a, b) a = __dp4a((w), 0x00010001u, a); b = __dp4a((w), 0x01000100u, b);
+            if (bytes == TRK_STAGE) {                            // all eight 16-byte loads in flight before the first use (one warp: latency is exposed)
+                uint4 a[TRK_STAGE / 512];
+#pragma unroll
+                for (int k = 0; k < TRK_STAGE / 512; ++k) a[k] = v[lane + 32 * k];
+#pragma unroll
+                for (int k = 0; k < TRK_STAGE / 512; ++k) {
+                    GSMCAL_ACC2(a[k].x, si, sq) GSMCAL_ACC2(a[k].y, ti, tq) GSMCAL_ACC2(a[k].z, ui, uq) GSMCAL_ACC2(a[k].w, wi, wq)
+                }
+            } else {
+                for (int i = lane; 16 * i < bytes; i += 32) {
+                    const uint4 a = v[i];
+                    GSMCAL_ACC2(a.x, si, sq) GSMCAL_ACC2(a.y, ti, tq) GSMCAL_ACC2(a.z, ui, uq) GSMCAL_ACC2(a.w, wi, wq)
+                }
+            }
+#undef GSMCAL_ACC2
+            ti += ui; tq += uq; si += wi; sq += wq;
+            si += ti; sq += tq;
+            __syncwarp();                                        // every lane has read the stage before it is refilled
+            if (prod.w < total_units) { if (lane == 0) issue(prod, stage); prod_next(prod); }
+            if (++stage == n_stage) { stage = 0; phase ^= 1u; }
+            cons.off += TRK_STAGE;
+        }
+        if (cons.off >= cons.len) {                              // unit done (at most 512 KB: the 32-bit lane sums cannot overflow)
+            const int stream = (int)(cons.w / n_chunks);
+            u64 li = si, lq = sq; si = 0; sq = 0;
+            if (cons.w % n_chunks == 0) {                        // ragged head / tail bytes, scalar
+                const uint8_t *p = raw + (i64)stream * total;
+                const i64 head = (16 - ((uintptr_t)p & 15)) & 15;
+                const i64 body = ((total - (head < total ? head : total)) / 16) * 16;
+                const i64 hb = (head < total) ? head : total;
+                for (i64 j = lane; j < hb; j += 32) { if (j & 1) lq += p[j]; else li += p[j]; }
+                for (i64 j = hb + body + lane; j < total; j += 32) { if (j & 1) lq += p[j]; else li += p[j]; }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                li += __shfl_down_sync(0xffffffffu, li, o);
+                lq += __shfl_down_sync(0xffffffffu, lq, o);
+            }
+            if (lane == 0) {
+                if (li) atomicAdd(&ctl[stream].sum_i, li);
+                if (lq) atomicAdd(&ctl[stream].sum_q, lq);
+            }
+            cons.w += gridDim.x; open_unit(cons);
+        }
+    }
+}
+
 // b = c - mean: one thread per IQ pair, 2-byte load, 16-byte store (warp stores 512 contiguous bytes)
 __global__ void __launch_bounds__(256) raw2iq_store_kernel(const uint8_t *__restrict__ raw, i64 n_iq, const StreamCtl *__restrict__ ctl, double2 *__restrict__ out) {
     const int stream = blockIdx.y;
@@ -1893,7 +2004,8 @@ __global__ void __launch_bounds__(TONE_THREADS, 3) tone_est_kernel(WinSrc src, c
 #define SCH_LPG 6       // lags per warp and pass
 #define SCH_PASSES 2
 #define SCH_NSL 16      // template samples per lane
-__global__ void __launch_bounds__(SCH_THREADS, 4) sch_corr_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ fcch_pos, int cap,
+template <int MAXR>     // 64: four blocks fill the register file; 56 (a few spilled values) leaves room for the trickle column sums of the next batch
+__global__ void __maxnreg__(MAXR) sch_corr_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ fcch_pos, int cap,
                                                               int osr, const double2 *__restrict__ tpl, double *__restrict__ sch_raw, int *__restrict__ sch_edge) {
     extern __shared__ double2 sm[];
     __shared__ double red_v[8];

@@ -690,6 +690,40 @@ def test_submit_collect_matches_synchronous_call(gpu, captures, coef47, tpl):
     assert [x["pos_info"].tolist() for x in again] == [y["pos_info"].tolist() for y in ref_b]
 
 
+@pytest.mark.parametrize("gate,stages,blocks,sch56", [(1, 7, 1, 1), (1, 2, 3, 0), (1, 24, 1, 1), (0, 0, 1, 0), (1, 0, 1, 0), (0, 3, 2, 0)])
+def test_submit_collect_trickle_column_sums_and_staggered_batches(gpu, captures, coef47, tpl, gate, stages, blocks, sch56):
+    """debug keys 16-19: column sums by the TMA-ring kernel (ragged stream starts: 2*N_RAG is not a multiple of 16) or by plain launches,
+    FP64 stages gated behind the previous batch or in lockstep, SCH kernel at 56 registers - same records as the synchronous call,
+    bit for bit.  (The default is gate on, 2 stages x 3 blocks per SM.)"""
+    import torch
+    from gsmcal._lib import lib
+    _, raw = captures
+    N_RAG = N_SYNC - 3                                             # stream d starts 10*d bytes past a 16-byte boundary
+    a = torch.from_numpy(np.ascontiguousarray(raw[:3, :2 * N_RAG])).cuda()
+    b = torch.from_numpy(np.ascontiguousarray(raw[1:6, :2 * N_RAG])).cuda()
+    torch.cuda.synchronize()
+    st = torch.cuda.current_stream().cuda_stream
+    ref_a = gpu.calibrate_batch(None, CARRIER, tpl, coef47, device_ptr=a.data_ptr(), n_iq=N_RAG, n_streams=3, cuda_stream=st)
+    ref_b = gpu.calibrate_batch(None, CARRIER, tpl, coef47, device_ptr=b.data_ptr(), n_iq=N_RAG, n_streams=5, cuda_stream=st)
+    for key, val in ((16, gate), (17, stages), (18, blocks), (19, sch56)):
+        lib().gsmcal_debug_set(key, val)
+    try:
+        pend = [gpu.calibrate_batch_submit(0, a.data_ptr(), N_RAG, 3, CARRIER, tpl, coef47, cuda_stream=st, details=True),
+                gpu.calibrate_batch_submit(1, b.data_ptr(), N_RAG, 5, CARRIER, tpl, coef47, cuda_stream=st, details=True)]
+        got = [pend[0].collect()]
+        pend.append(gpu.calibrate_batch_submit(0, b.data_ptr(), N_RAG, 5, CARRIER, tpl, coef47, cuda_stream=st, details=True))
+        got += [pend[1].collect(), pend[2].collect()]
+    finally:
+        for key, val in ((16, 1), (17, 2), (18, 3), (19, 0)):       # the library defaults
+            lib().gsmcal_debug_set(key, val)
+    for g, ref in zip(got, (ref_a, ref_b, ref_b)):
+        assert len(g) == len(ref)
+        for x, y in zip(g, ref):
+            for k in ("coarse_pos", "coarse_snr", "fcch_pos", "pos_info"):
+                np.testing.assert_array_equal(x[k], y[k])
+            assert x["sampling_ppm"] == y["sampling_ppm"] and x["carrier_ppm"] == y["carrier_ppm"] and x["flags"] == y["flags"]
+
+
 # ---- SURVEY Appendix A: deliberate fixtures through the DROP-IN entry points, each asserting the branch it took ----------------
 def _same_fine(got, ref, r_tol):
     assert np.array_equal(got[0], ref[0])
