@@ -89,12 +89,15 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
     {
         constexpr int NGRP = (B8_NSMP + B8_R - 1) / B8_R;        // 246 <= 256: one round
         double ar[B8_R], ai[B8_R];
-        if (tid < NGRP) fir_taps_const<NT, B8_R>(B + B8_R * tid, ar, ai);
+        // thread -> output group by an odd multiplier: the loads stay conflict-free (57 = 1 mod 8) and the padded stores of a quarter-warp
+        // collide 1.2x instead of 2x (consecutive groups step over a pad slot every 3.6 lanes)
+        const int grp = (57 * tid) & (B8_THREADS - 1);
+        if (grp < NGRP) fir_taps_const<NT, B8_R>(B + B8_R * grp, ar, ai);
         __syncthreads();
-        if (tid < NGRP) {
+        if (grp < NGRP) {
 #pragma unroll
             for (int r = 0; r < B8_R; ++r) {
-                const int i = B8_R * tid + r;
+                const int i = B8_R * grp + r;
                 if (i < B8_NSMP) B[B8_WPAD(i)] = make_double2(ar[r], ai[r]);
             }
         }
@@ -134,9 +137,19 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
     // ---- band centre from the phase slope of the centre window ----
     {
         double pq[2] = {0.0, 0.0};
-        for (int n = 512 + tid; n < 512 + B8_N - 1; n += B8_THREADS) {
-            const double2 q2 = cmulc(B[B8_WPAD(n + 1)], B[B8_WPAD(n)]);
-            pq[0] += q2.x; pq[1] += q2.y;
+        if (5 * tid < B8_N - 1) {                                // 5 consecutive pairs per thread: 6 loads instead of 10
+            const int n0 = 512 + 5 * tid;
+            double2 prev = B[B8_WPAD(n0)];
+#pragma unroll
+            for (int k = 1; k <= 5; ++k) {
+                const int n = n0 + k;
+                if (n < 512 + B8_N) {
+                    const double2 v = B[B8_WPAD(n)];
+                    const double2 q2 = cmulc(v, prev);
+                    pq[0] += q2.x; pq[1] += q2.y;
+                    prev = v;
+                }
+            }
         }
         block_sum_n<2, false>(pq, scan_sv);                      // (its barriers also publish PE / E31)
         // (the band centre only selects WHICH bins are tracked - the certificate decides correctness - so the fp32 atan2 is enough:
@@ -184,9 +197,15 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
                     acc[b] = make_double2(nr, ni);
                 }
             }
+            // W^(32 c k) of the thread's four (consecutive) bins from two table entries, W^(32 c (k+1)) = W^(32 c k) W^(32 c): a scattered
+            // 16-byte table read costs one L1 wavefront per lane, and the L1/shared data pipe is the busiest unit of this kernel
+            double2 rot = tw[(32 * cch * kk[0]) % B8_N];
+            const double2 rstep = tw[(32 * cch) % B8_N];
 #pragma unroll
-            for (int b = 0; b < 4; ++b)
-                CS[(4 * q + b) * B8_CSL + cch + 1] = cmul(acc[b], tw[(32 * cch * kk[b]) % B8_N]);
+            for (int b = 0; b < 4; ++b) {
+                CS[(4 * q + b) * B8_CSL + cch + 1] = cmul(acc[b], rot);
+                rot = cmul(rot, rstep);
+            }
         }
         __syncthreads();
         B8_MARK(3);                                              // (restore +) chunk sums
@@ -343,6 +362,23 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
 // not covered by its cached window, or whose Parseval certificates (integer bin, 5 dB gate) do not hold, is flagged in `need_old`
 // and recomputed by tone_est_kernel (all 1184 bins through the 37 x 32 row FFT).
 // ===================================================================================================
+#define T8_K 5                               // consecutive samples per thread in the fused passes
+// interp1 'linear' of consecutive outputs (load_window's arithmetic): the upper neighbour of one output is the lower neighbour of the next
+// except where the resampling ratio makes the source index skip or repeat, so it is kept in registers
+struct T8Lerp {
+    i64 prev_i1 = -1;
+    double2 prev_hi = {0.0, 0.0};
+    __device__ __forceinline__ double2 next(const double2 *S, i64 a_src, i64 last, i64 j, double s) {
+        const double xq = (double)j * s;
+        i64 i0 = (i64)floor(xq);
+        if (i0 > last) i0 = last;
+        const i64 i1 = (i0 + 1 > last) ? last : i0 + 1;
+        const double2 lo = (i0 == prev_i1) ? prev_hi : S[i0 - a_src];
+        const double2 hi = (i1 == i0) ? lo : S[i1 - a_src];
+        prev_i1 = i1; prev_hi = hi;
+        return lerp_ref(lo, hi, xq - (double)i0);
+    }
+};
 #define T8_THREADS 256
 #define T8_SEG     10
 #define T8_NSEG    119                       // ceil(1184 / 10); the last segment is padded with zeros
@@ -411,72 +447,94 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
     }
     __syncthreads();
     T8_MARK(0);                                                  // level 0 from the cache (global-memory latency)
+    // The L1/shared-memory data pipe is the busiest unit of this kernel (ncu: 68 % against 34 % for the FP64 pipe), so the passes below
+    // give every thread T8_K CONSECUTIVE samples: interp1 re-uses the upper neighbour of one output as the lower neighbour of the next
+    // (K+1 loads for K outputs instead of 2K), and the sums over neighbouring samples (energy + phase slope here, the phasor ratios
+    // after the band DFT) are taken from registers while the samples are produced - they cost no shared-memory reads of their own.
+    // A stride of 5 x 16 bytes keeps the 128-bit accesses of a quarter-warp on different banks.
+    const int nf = T8_K * tid;                                   // first sample of the thread (237 threads cover the burst)
     double2 *u = P, *spare = Q;                                  // u: the burst the stage works on; spare: the other buffer
+    double epq[3] = {0.0, 0.0, 0.0};                             // energy, sum of x[n+1] * conj(x[n])
+    auto energy_pair = [&](int k, int n, const double2 v, double2 &prev) {     // v = final-level sample n (k: its number in the thread)
+        if (k < T8_K) epq[0] = fma(v.x, v.x, fma(v.y, v.y, epq[0]));
+        if (k > 0) { const double2 q = cmulc(v, prev); epq[1] += q.x; epq[2] += q.y; }
+        prev = v;
+    };
     if (use1) {                                                  // level 1 (+2): interp1 by (1+e1) [and derotation by dphi1] -> Q
         double2 ph = make_double2(1.0, 0.0), st = make_double2(1.0, 0.0);
         if (derot) {
             double sn, cs;
-            sincos((double)tid * c.dphi1, &sn, &cs); ph = cmul(sh_base, make_double2(cs, sn));
-            sincos((double)T8_THREADS * c.dphi1, &sn, &cs); st = make_double2(cs, sn);
+            sincos((double)nf * c.dphi1, &sn, &cs); ph = cmul(sh_base, make_double2(cs, sn));
+            sincos(c.dphi1, &sn, &cs); st = make_double2(cs, sn);
         }
-        for (int i = tid; i < n_l1; i += T8_THREADS) {
-            const i64 j = a1 + i;
-            const double xq = (double)j * s1;
-            i64 i0 = (i64)floor(xq);
-            if (i0 > n0 - 1) i0 = n0 - 1;
-            const i64 i1 = (i0 + 1 > n0 - 1) ? n0 - 1 : i0 + 1;
-            double2 v = lerp_ref(P[i0 - a0], P[i1 - a0], xq - (double)i0);
-            if (derot) { v = cmul(v, ph); ph = cmul(ph, st); }
-            Q[i] = v;
+        T8Lerp lc;
+        double2 prev = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k <= T8_K; ++k) {                        // (the K+1-th sample only feeds the pair sum when this level is the final one)
+            const int i = nf + k;
+            if (i < n_l1 && (k < T8_K || !use2)) {
+                double2 v = lc.next(P, a0, n0 - 1, a1 + i, s1);
+                if (derot) { v = cmul(v, ph); ph = cmul(ph, st); }
+                if (k < T8_K) Q[i] = v;
+                if (!use2 && i < N) energy_pair(k, i, v, prev);
+            }
         }
-        __syncthreads();
         u = Q; spare = P;
         if (use2) {                                              // level 3: second interp1 by (1+e2) -> P
-            for (int i = tid; i < N; i += T8_THREADS) {
-                const double xq = (double)(a2 + i) * s2;
-                i64 i0 = (i64)floor(xq);
-                if (i0 > len1 - 1) i0 = len1 - 1;
-                const i64 i1 = (i0 + 1 > len1 - 1) ? len1 - 1 : i0 + 1;
-                P[i] = lerp_ref(Q[i0 - a1], Q[i1 - a1], xq - (double)i0);
+            __syncthreads();
+            T8Lerp l2;
+#pragma unroll
+            for (int k = 0; k <= T8_K; ++k) {
+                const int i = nf + k;
+                if (i < N) {
+                    const double2 v = l2.next(Q, a1, len1 - 1, a2 + i, s2);
+                    if (k < T8_K) P[i] = v;
+                    energy_pair(k, i, v, prev);
+                }
             }
             u = P; spare = Q;
         }
     } else if (use2) {                                           // e1 path off, second interp1 only (no derotation here, see `covered`)
-        for (int i = tid; i < N; i += T8_THREADS) {
-            const double xq = (double)(a2 + i) * s2;
-            i64 i0 = (i64)floor(xq);
-            if (i0 > len1 - 1) i0 = len1 - 1;
-            const i64 i1 = (i0 + 1 > len1 - 1) ? len1 - 1 : i0 + 1;
-            Q[i] = lerp_ref(P[i0 - a1], P[i1 - a1], xq - (double)i0);
+        T8Lerp l2;
+        double2 prev = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k <= T8_K; ++k) {
+            const int i = nf + k;
+            if (i < N) {
+                const double2 v = l2.next(P, a1, len1 - 1, a2 + i, s2);
+                if (k < T8_K) Q[i] = v;
+                energy_pair(k, i, v, prev);
+            }
         }
         u = Q; spare = P;
+    } else {                                                     // level 0 is the burst
+        double2 prev = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k <= T8_K; ++k) {
+            const int i = nf + k;
+            if (i < N) energy_pair(k, i, P[i], prev);
+        }
     }
     if (tid < T8_SEG * T8_NSEG - N + 2) u[N + tid] = make_double2(0.0, 0.0);     // zero padding of the last Horner segment
-    __syncthreads();
-    T8_MARK(1);                                                  // interp1 / derotation levels
+    T8_MARK(1);                                                  // interp1 / derotation levels (+ energy and phase slope on the fly)
     // ---- energy and phase slope -> band centre ----
-    {
-        double epq[3] = {0.0, 0.0, 0.0};
-        for (int n = tid; n < N; n += T8_THREADS) {
-            const double2 v = u[n];
-            epq[0] = fma(v.x, v.x, fma(v.y, v.y, epq[0]));
-            if (n + 1 < N) { const double2 q = cmulc(u[n + 1], v); epq[1] += q.x; epq[2] += q.y; }
-        }
-        block_sum_n<3, false>(epq, red_n);
-        if (tid == 0) { sh_E = epq[0]; sh_k0 = (int)floorf(atan2f((float)epq[2], (float)epq[1]) * (float)(N / (2.0 * GSMCAL_PI)) + 0.5f); sh_flag = 0; }   // fp32: see fine_core8_kernel
-    }
+    block_sum_n<3, false>(epq, red_n);
+    if (tid == 0) { sh_E = epq[0]; sh_k0 = (int)floorf(atan2f((float)epq[2], (float)epq[1]) * (float)(N / (2.0 * GSMCAL_PI)) + 0.5f); sh_flag = 0; }   // fp32: see fine_core8_kernel
     __syncthreads();
-    T8_MARK(2);                                                  // energy, phase slope, band centre
+    T8_MARK(2);                                                  // block sums, band centre
     const int k0 = sh_k0;
-    // ---- 8-bin band DFT by Horner's rule: thread = (10-sample segment, 4 bins); partial sums -> spare[bin][120] ----
+    // ---- 8-bin band DFT by Horner's rule: thread = (10-sample segment, 4 bins); partial sums -> spare[bin][120], the rows of the
+    //      upper four bins shifted by 4 slots so the two threads of a segment store to different banks ----
     if (tid < 2 * T8_NSEG) {
         const int seg = tid >> 1, q = tid & 1, n0s = T8_SEG * seg;
-        double2 z[4], acc[4]; int kk[4];
+        double2 z[4], acc[4];
         const double2 s_last = u[n0s + T8_SEG - 1];
+        int kf = 0;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             int k = (k0 - 3 + 4 * q + b) % N; if (k < 0) k += N;
-            kk[b] = k; z[b] = tw[k]; acc[b] = s_last;
+            if (b == 0) kf = k;
+            z[b] = tw[k]; acc[b] = s_last;
         }
 #pragma unroll
         for (int i = T8_SEG - 2; i >= 0; --i) {
@@ -488,14 +546,22 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
                 acc[b] = make_double2(nr, ni);
             }
         }
+        // W^(n0 k) of the four bins from two table entries: W^(n0 (k+1)) = W^(n0 k) W^n0 (scattered 16-byte table reads cost a
+        // wavefront per lane on the L1 data pipe)
+        double2 rot = tw[(n0s * kf) % N];
+        const double2 rstep = tw[n0s];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) spare[(4 * q + b) * 120 + seg] = cmul(acc[b], tw[(n0s * kk[b]) % N]);
+        for (int b = 0; b < 4; ++b) {
+            spare[(4 * q + b) * 120 + 4 * q + seg] = cmul(acc[b], rot);
+            rot = cmul(rot, rstep);
+        }
     }
     __syncthreads();
     T8_MARK(3);                                                  // Horner band DFT
     {   // warp b adds the partials of bin b
         double xr = 0.0, xi = 0.0;
-        for (int sgi = lane; sgi < T8_NSEG; sgi += 32) { const double2 v = spare[warp * 120 + sgi]; xr += v.x; xi += v.y; }
+        const double2 *row = spare + warp * 120 + 4 * (warp >> 2);
+        for (int sgi = lane; sgi < T8_NSEG; sgi += 32) { const double2 v = row[sgi]; xr += v.x; xi += v.y; }
         xr = warp_sum(xr); xi = warp_sum(xi);
         if (lane == 0) sh_x[warp] = make_double2(xr, xi);
     }
@@ -529,28 +595,36 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
     }
     const int jr = sh_jbest + 1 - ((N / 2) + 1);                 // max_idx - (fft_len/2 + 1)
     const double int_phase_rotate = 2.0 * GSMCAL_PI * (double)jr / (double)N;
-    // ---- integer-bin derotation (twiddle table entry n*jr mod N), unit phasors -> spare (:152-153) ----
+    // ---- integer-bin derotation (:152-153) -> g (the other buffer; the SNR gate reads it), unit phasors and the mean phasor ratio of
+    //      neighbours from registers: the twiddle of the thread's first sample from the table, then one step per sample ----
+    double2 *g = spare;
     {
         int jm = jr % N; if (jm < 0) jm += N;
-        int tidx = (tid * jm) % N;
-        const int tinc = (T8_THREADS * jm) % N;
-        for (int n = tid; n < N; n += T8_THREADS, tidx = (tidx + tinc >= N) ? tidx + tinc - N : tidx + tinc) {
-            const double2 w = cmul(u[n], tw[tidx]);
-            u[n] = w;
-            const double h2 = fma(w.x, w.x, w.y * w.y);
-            const double inv = rsqrt(h2);
-            spare[n] = (h2 > 0.0) ? make_double2(w.x * inv, w.y * inv) : make_double2(1.0, 0.0);
-        }
-    }
-    __syncthreads();
-    T8_MARK(5);                                                  // integer-bin derotation, unit phasors
-    {
         double rri[2] = {0.0, 0.0};
-        for (int n = tid; n < N - 1; n += T8_THREADS) {
-            const double2 a = spare[n + 1], b = spare[n];
-            rri[0] += a.x * b.x + a.y * b.y;
-            rri[1] += a.y * b.x - a.x * b.y;
+        if (nf < N) {
+            double2 ph = tw[(nf * jm) % N];
+            const double2 stp = tw[jm];
+            double2 eprev = make_double2(1.0, 0.0);
+#pragma unroll
+            for (int k = 0; k <= T8_K; ++k) {
+                const int n = nf + k;
+                if (n < N) {
+                    const double2 w = cmul(u[n], ph);
+                    ph = cmul(ph, stp);
+                    if (k < T8_K && which == 1) g[n] = w;
+                    const double h2 = fma(w.x, w.x, w.y * w.y);
+                    const double inv = rsqrt(h2);
+                    const double2 e = (h2 > 0.0) ? make_double2(w.x * inv, w.y * inv) : make_double2(1.0, 0.0);
+                    if (k > 0) {
+                        rri[0] += e.x * eprev.x + e.y * eprev.y;
+                        rri[1] += e.y * eprev.x - e.x * eprev.y;
+                    }
+                    eprev = e;
+                }
+            }
         }
+        if (which == 1 && tid < T8_SEG * T8_NSEG - N + 2) g[N + tid] = make_double2(0.0, 0.0);
+        T8_MARK(5);                                              // integer-bin derotation, unit phasors, ratios
         block_sum_n<2, false>(rri, red_n);
         if (tid == 0) {
             const double pr = atan2(rri[1] / (double)(N - 1), rri[0] / (double)(N - 1));
@@ -559,12 +633,13 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
             double sn, cs; sincos(pr, &sn, &cs); sh_step = make_double2(cs, sn);      // exp(+i*phi): one step back in n
         }
     }
-    T8_MARK(6);                                                  // phasor-ratio mean, atan2, fo
+    T8_MARK(6);                                                  // block sums, atan2, fo
     if (PROF && which != 1 && tid == 0) atomicAdd(prof + 15, 1ull);
     if (which != 1) return;
     __syncthreads();
     // ---- SNR gate (:185-196): bins 0, +-1, +-2 of the finely derotated burst by Horner's rule, thread = (segment, bin pair);
-    //      sig >= 10^0.5 (N*E - sig) proves the burst passes the 5 dB gate (Parseval; derotation keeps the energy) ----
+    //      sig >= 10^0.5 (N*E - sig) proves the burst passes the 5 dB gate (Parseval; derotation keeps the energy).  Partial sums go to
+    //      the buffer the burst came from (rows 2.. shifted by 4 slots: different banks for the two threads of a segment) ----
     const double phase_rotate = sh_pr;
     if (tid < 2 * T8_NSEG) {
         const int seg = tid >> 1, q = tid & 1, n0s = T8_SEG * seg, n_last = n0s + T8_SEG - 1;
@@ -574,27 +649,28 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
         const double2 st = sh_step;
         double2 accp, accm, acc0;
         {
-            const double2 v = cmul(u[n_last], ph);
+            const double2 v = cmul(g[n_last], ph);
             accp = v; accm = v; acc0 = v;
         }
 #pragma unroll
         for (int i = T8_SEG - 2; i >= 0; --i) {
             ph = cmul(ph, st);
-            const double2 v = cmul(u[n0s + i], ph);
+            const double2 v = cmul(g[n0s + i], ph);
             accp = make_double2(fma(accp.x, zp.x, fma(-accp.y, zp.y, v.x)), fma(accp.x, zp.y, fma(accp.y, zp.x, v.y)));
             accm = make_double2(fma(accm.x, zm.x, fma(-accm.y, zm.y, v.x)), fma(accm.x, zm.y, fma(accm.y, zm.x, v.y)));
             acc0.x += v.x; acc0.y += v.y;
         }
         const double2 t = tw[(n0s * (q + 1)) % N];               // W^{+n0 (q+1)}; its conjugate for the negative bin
-        spare[(2 * q) * 120 + seg] = cmul(accp, t);
-        spare[(2 * q + 1) * 120 + seg] = cmul(accm, make_double2(t.x, -t.y));
-        if (q == 0) spare[4 * 120 + seg] = acc0;
+        u[(2 * q) * 120 + 4 * q + seg] = cmul(accp, t);
+        u[(2 * q + 1) * 120 + 4 * q + seg] = cmul(accm, make_double2(t.x, -t.y));
+        if (q == 0) u[4 * 120 + 4 + seg] = acc0;
     }
     __syncthreads();
     T8_MARK(7);                                                  // gate: Horner over the finely derotated burst
     if (warp < 5) {
         double xr = 0.0, xi = 0.0;
-        for (int sgi = lane; sgi < T8_NSEG; sgi += 32) { const double2 v = spare[warp * 120 + sgi]; xr += v.x; xi += v.y; }
+        const double2 *row = u + warp * 120 + (warp >= 2 ? 4 : 0);
+        for (int sgi = lane; sgi < T8_NSEG; sgi += 32) { const double2 v = row[sgi]; xr += v.x; xi += v.y; }
         xr = warp_sum(xr); xi = warp_sum(xi);
         if (lane == 0) sh_pb[warp] = xr * xr + xi * xi;
     }

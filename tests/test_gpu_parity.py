@@ -504,7 +504,9 @@ def test_tier3_multiblock_search_equals_all_bin_search(gpu, captures, coef47, tp
             assert lib().gsmcal_debug_get(1) > 0
             for a, b in zip(t3, full):
                 assert np.array_equal(a["fcch_pos"], b["fcch_pos"]) and np.array_equal(a["pos_info"], b["pos_info"])
-                assert a["sampling_ppm"] == b["sampling_ppm"] and a["carrier_ppm"] == b["carrier_ppm"]
+                assert a["sampling_ppm"] == b["sampling_ppm"]
+                # the forced all-bin path estimates the tone with tone_est_kernel, the tiers with tone8_kernel (same statements, other summation order)
+                assert np.allclose(a["carrier_ppm"], b["carrier_ppm"], rtol=0, atol=1e-9)
     finally:
         lib().gsmcal_debug_set(4, 0)
         lib().gsmcal_debug_set(5, 256)
