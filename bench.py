@@ -686,6 +686,10 @@ def main():
                 nb_ = max(1, int(L.gsmcal_debug_get(off_ + base_ + 15)))
                 ent[label_] = {n_: round(int(L.gsmcal_debug_get(off_ + base_ + i_)) / nb_, 1) for i_, n_ in enumerate(nm)}
                 ent[label_]["total"] = round(sum(ent[label_].values()), 1)
+            steps_ = max(1, int(L.gsmcal_debug_get(off_ + 48 + 7)))
+            ent["coarse_chain_per_step"] = {n_: round(int(L.gsmcal_debug_get(off_ + 48 + i_)) / steps_, 1) for i_, n_ in
+                                            enumerate(["prefetch_wait", "fir_fast", "fir_slow", "decision_after_snr", "window_snr"])}
+            ent["coarse_chain_per_step"]["steps_per_block"] = round(steps_ / max(1, int(L.gsmcal_debug_get(off_ + 48 + 6))), 1)
             pipelined_phases[which_] = ent
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -768,6 +772,12 @@ def main():
                     "counted": "FIR taps x samples, Horner DFT accumulations of every executed pass, band-kernel sums and slides, correlation MACs "
                                "(FMA_PER_BURST in bench.py, DESIGN.md section 4); tier-1 slides, certificates, index math, reductions are not counted",
                     "ncu_fp64_pipe_active_pct": facts.get("fp64_pipe_active_pct", {}).get(dominant),
+                    "ncu_l1_data_pipe_pct": facts.get("l1_data_pipe_pct", {}).get(dominant),
+                    "ncu_issue_active_pct": facts.get("issue_active_pct", {}).get(dominant),
+                    "ncu_note": "the L1/shared-memory data pipe (complex128 operands: every 16-byte access of a warp is 4 wavefronts) is busier than the FP64 "
+                                "pipe in every burst kernel; utilisation of all stages in ncu_all_stages",
+                    "ncu_all_stages": {k: {"fp64_pipe_pct": facts.get("fp64_pipe_active_pct", {}).get(k), "l1_data_pipe_pct": facts.get("l1_data_pipe_pct", {}).get(k),
+                                           "issue_active_pct": facts.get("issue_active_pct", {}).get(k)} for k in burst_stages},
                     "traffic": (int(facts["dram_bytes_per_launch"][dominant] * D / facts["streams_profiled"])
                                 if facts.get("dram_bytes_per_launch", {}).get(dominant) and facts.get("streams_profiled") else None),
                     "traffic_source": (facts.get("source", "") + "; scaled by streams per launch") if facts else None,
@@ -780,7 +790,7 @@ def main():
                     "note": "the only whole-stream (HBM-proportional) pass of the fused pipeline, 2 B per IQ sample"}
     hbm_floor_ms = D * 2 * n_iq / (hbm_peak * 1e9) * 1e3
     whole_path = {"hbm_floor_ms_per_step": hbm_floor_ms, "frac_of_hbm_floor": hbm_floor_ms / ms_per_step if ms_per_step else None,
-                  "note": "2 B per IQ sample read once is the HBM floor of the whole path on one rank; the step is FP64-bound"}
+                  "note": "2 B per IQ sample read once is the HBM floor of the whole path on one rank; the step is bound by the burst kernels (FP64 + shared-memory pipes)"}
 
     # ---- the same pipeline when it also MATERIALISES r_correct (what the reference chain and the oracle produce on the way and hand
     #      to SCH_demod, gsm_sync_demod.m:120,145): gsmcal_calibrate_batch_r writes it in one fused pass, 2 B in + 16 B out per sample ----

@@ -249,7 +249,7 @@ int make_work(DevBuf &wb, i64 D, int cap, i64 snr_len, int tpl_len, Work *w) {
     size_t per = sizeof(double) * D * cap;
     size_t o_cp = take(per), o_cs = take(per), o_fr = take(per), o_fp = take(per), o_fo = take(per), o_g = take(per), o_sr = take(per), o_sp = take(per), o_pp = take(per);
     size_t o_pi = take(per * 12), o_snr = take(sizeof(double) * D * snr_len), o_pw = take(sizeof(double) * D);
-    size_t o_se = take(sizeof(int) * D * cap), o_nf = take(sizeof(int) * D * cap), o_nb = take(sizeof(int) * D * cap), o_tn = take(sizeof(int) * D * cap), o_fl = take(sizeof(int) * D * cap), o_fc = take(sizeof(int) * D), o_fm = take(sizeof(int) * (size_t)FALL_GRID * 24 * kMaxGroups), o_fb = take(sizeof(double) * (size_t)FALL_GRID * 24 * kMaxGroups), o_k = take(D * cap), o_tpl = take(sizeof(double2) * (tpl_len > 0 ? tpl_len : 1)), o_ph = take(sizeof(unsigned) * 16 + sizeof(unsigned long long) * 48);
+    size_t o_se = take(sizeof(int) * D * cap), o_nf = take(sizeof(int) * D * cap), o_nb = take(sizeof(int) * D * cap), o_tn = take(sizeof(int) * D * cap), o_fl = take(sizeof(int) * D * cap), o_fc = take(sizeof(int) * D), o_fm = take(sizeof(int) * (size_t)FALL_GRID * 24 * kMaxGroups), o_fb = take(sizeof(double) * (size_t)FALL_GRID * 24 * kMaxGroups), o_k = take(D * cap), o_tpl = take(sizeof(double2) * (tpl_len > 0 ? tpl_len : 1)), o_ph = take(sizeof(unsigned) * 16 + sizeof(unsigned long long) * 64);
     void *base;
     TRY(wb.get(off, &base));
     char *b = static_cast<char *>(base);
@@ -352,10 +352,12 @@ int run_coarse(WinSrc src, i64 len, const CoarseParams &p, i64 D, int cap, Work 
            src, w.ctl, (i64)0, n_win, p.fft_len, w.snr_map, w.snr_stride);
     LAUNCH(first_hit_scan_kernel, (unsigned)((D + 3) / 4), 128, 0, st, w.snr_map, w.snr_stride, n_win, p.mv_len, p.th, w.ctl, (int)D);
     const size_t chain_smem = sizeof(double2) * (size_t)(p.fft_len + 2 * (2 * 5 + p.fft_len));    // twiddles + the two candidate groups
-    LAUNCH(coarse_chain_kernel, (unsigned)D, CHAIN_THREADS, chain_smem, st, src, w.ctl, len, p.fft_len, p.th, p.step10, p.step11, p.dr, cap, w.coarse_pos, w.coarse_snr);
+    LAUNCH(coarse_chain_kernel, (unsigned)D, CHAIN_THREADS, chain_smem, st, src, w.ctl, len, p.fft_len, p.th, p.step10, p.step11, p.dr, cap, w.coarse_pos, w.coarse_snr,
+           g_debug_prof ? (unsigned long long *)(w.pass_hist + 16) + 48 : nullptr);
     return GSMCAL_OK;
 }
 
+constexpr int kNeedGroup = 8;      // bursts per block of the fallback kernels that run behind a need-mask (tone_est_kernel, tier 2)
 int run_fine_peak(Ctx &c, WinSrc src_peak, i64 n_iq, int osr, i64 D, int cap, Work &w, cudaStream_t st) {
     const double2 *tw; TRY(get_twiddle(c, 148 * osr, st, &tw));
     if (g_debug_force_full || (osr % 4) != 0) {      // the band kernel's 16-sample certificate grid needs osr % 4 == 0
@@ -380,11 +382,11 @@ int run_fine_peak(Ctx &c, WinSrc src_peak, i64 n_iq, int osr, i64 D, int cap, Wo
     } else
     LAUNCH(fine_peak_core_kernel, dim3((unsigned)cap, (unsigned)D), FC_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw, w.need_band, g_debug_fail_tier2);
     CU(cudaMemsetAsync(w.fall_count, 0, sizeof(int), st));
-    LAUNCH(fine_peak_band_kernel, dim3((unsigned)cap, (unsigned)D), FB_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw,
-           (const int *)w.need_band, w.need_full, 0, w.fall_list, w.fall_count, w.fall_best, w.fall_m, g_debug_fail_tier2);
+    LAUNCH(fine_peak_band_kernel, dim3((unsigned)((cap + kNeedGroup - 1) / kNeedGroup), (unsigned)D), FB_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw,
+           (const int *)w.need_band, w.need_full, 0, w.fall_list, w.fall_count, w.fall_best, w.fall_m, g_debug_fail_tier2, kNeedGroup);
     const int nb3 = (148 * osr + FB_BINS - 1) / FB_BINS;
     LAUNCH(fine_peak_band_kernel, dim3((unsigned)nb3, (unsigned)FALL_GRID), FB_THREADS, fine_band_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw,
-           (const int *)nullptr, (int *)nullptr, 1, w.fall_list, w.fall_count, w.fall_best, w.fall_m, g_debug_fall_limit);
+           (const int *)nullptr, (int *)nullptr, 1, w.fall_list, w.fall_count, w.fall_best, w.fall_m, g_debug_fall_limit, 1);
     LAUNCH(fine_fall_combine_kernel, FALL_GRID / 128, 128, 0, st, w.fall_list, w.fall_count, w.fall_best, w.fall_m, nb3, w.coarse_pos, cap, osr, w.fine_raw, w.ctl, g_debug_fall_limit);
     LAUNCH(fine_peak_full_kernel, 296, kFineThreads, fine_smem(osr), st, src_peak, w.ctl, w.coarse_pos, cap, osr, n_iq, tw, w.fine_raw,
            (const int *)w.fall_list, (const int *)w.fall_count, g_debug_fall_limit);
@@ -401,7 +403,8 @@ int run_tone(WinSrc src, int which, const double *pos, int osr, i64 D, int cap, 
         else              LAUNCH(tone8_kernel<false>, dim3((unsigned)cap, (unsigned)D), T8_THREADS, T8_SMEM, st, src, w.ctl, which, pos, cap, tw, w.fo, w.gate, w.tone_need, prof);
         need = w.tone_need;
     }
-    LAUNCH(tone_est_kernel, dim3((unsigned)cap, (unsigned)D), TONE_THREADS, tone_smem(osr), st, src, w.ctl, which, pos, cap, osr, tw, w.fo, w.gate, need);
+    const int gsz = need ? kNeedGroup : 1;                       // behind tone8_kernel's mask: groups of bursts per block (few or none are flagged)
+    LAUNCH(tone_est_kernel, dim3((unsigned)((cap + gsz - 1) / gsz), (unsigned)D), TONE_THREADS, tone_smem(osr), st, src, w.ctl, which, pos, cap, osr, tw, w.fo, w.gate, need, gsz);
     return GSMCAL_OK;
 }
 
@@ -530,13 +533,13 @@ int64_t gsmcal_debug_get(int key) {
     // key 1: bursts of the last fine search (this device) that needed the all-bin fallback
     std::lock_guard<std::mutex> lk(g_mu);
     if (key == 40) return (int64_t)g_debug_core8_passes;
-    if (key >= 150 && key < 198) {                               // the same counters of the batch submitted before the last one (other slot)
+    if (key >= 150 && key < 214) {                               // the same counters of the batch submitted before the last one (other slot)
         if (!g_prev_pass_hist) return 0;
         unsigned long long v = 0;
         if (cudaMemcpy(&v, (unsigned long long *)(g_prev_pass_hist + 16) + (key - 150), sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
         return (int64_t)v;
     }
-    if (key >= 50 && key < 98) {                                 // per-phase cycle sums (debug key 13), [15] = blocks: 50.. fine_core8, 66.. tone8 (fine), 82.. tone8 (post)
+    if (key >= 50 && key < 114) {                                 // per-phase cycle sums (debug key 13), [15] = blocks: 50.. fine_core8, 66.. tone8 (fine), 82.. tone8 (post)
         if (!g_last_pass_hist) return 0;
         unsigned long long v = 0;
         if (cudaMemcpy(&v, (unsigned long long *)(g_last_pass_hist + 16) + (key - 50), sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
@@ -1018,7 +1021,7 @@ static int calibrate_batch_impl(const uint8_t *raw, int raw_mem, int64_t n_iq, i
     { const double2 *twp; TRY(get_twiddle(*c, 148 * osr, st, &twp)); }        // built on `st` before the groups fork
     g_last_need_full = w.need_full; g_last_need_band = w.need_band; g_last_need_full_n = (long long)D * cap;
     g_last_pass_hist = w.pass_hist;
-    CU(cudaMemsetAsync(w.pass_hist, 0, sizeof(unsigned) * 16 + sizeof(unsigned long long) * 48, st));
+    CU(cudaMemsetAsync(w.pass_hist, 0, sizeof(unsigned) * 16 + sizeof(unsigned long long) * 64, st));
     g_stage_n = 0;
     // Streams are independent, so the batch is cut into groups that run the stage sequence on their own CUDA
     // streams: the latency-bound stages of one group (burst chain, per-stream solves) overlap the FP64-bound
@@ -1193,7 +1196,7 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
     CU(cudaMemcpyAsync(w.tpl, h_tpl, sizeof(double2) * 64 * osr, cudaMemcpyHostToDevice, fr));
     g_last_need_full = w.need_full; g_last_need_band = w.need_band; g_last_need_full_n = (long long)D * cap;
     g_prev_pass_hist = g_last_pass_hist; g_last_pass_hist = w.pass_hist;
-    CU(cudaMemsetAsync(w.pass_hist, 0, sizeof(unsigned) * 16 + sizeof(unsigned long long) * 48, fr));
+    CU(cudaMemsetAsync(w.pass_hist, 0, sizeof(unsigned) * 16 + sizeof(unsigned long long) * 64, fr));
     const size_t per = (size_t)2 * n_iq;
     std::vector<cudaEvent_t> ev_done;
     cudaEvent_t e_sum = nullptr;

@@ -1115,7 +1115,11 @@ __global__ void specific_hit_kernel(const double *__restrict__ snr, i64 n, doubl
 #define PF_STRIDE (PF_BYTES + PF_BYTES / 8 + 32)   // with one 16-byte pad per 128 bytes (bank spreading for the 128-byte window stride)
 #define PF_RANGES 2                // candidate ranges per step: after a 10-frame step, after an 11-frame step
 __global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src, StreamCtl *ctl, i64 len, int fft_len, double th, int step10, int step11,
-                                                                    int dr, int cap, double *__restrict__ position, double *__restrict__ snr_out) {
+                                                                    int dr, int cap, double *__restrict__ position, double *__restrict__ snr_out,
+                                                                    unsigned long long *__restrict__ prof) {
+    // debug key 13: thread 0 adds the cycles between the marks of a step to prof[phase], prof[7] counts steps, prof[6] blocks
+    long long t_prev = prof ? clock64() : 0;
+#define CH_MARK(ph) do { if (prof && threadIdx.x == 0) { const long long t_now = clock64(); atomicAdd(prof + (ph), (unsigned long long)(t_now - t_prev)); t_prev = t_now; } } while (0)
     // Each step evaluates the 11 windows around the 10-frame prediction (:47-58) AND the 11 around the 11-frame
     // prediction (:65-76) at once; the second set is only consulted when the first has no hit, as in the reference.
     // Lazy source: the raw bytes a step can touch are prefetched one step ahead into a double-buffered shared-memory ring with
@@ -1198,6 +1202,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src,
         }
         const bool fast = src.lazy && srcA >= 0 && (srcB >= 0 || !b_ok);
         ++step_no;
+        CH_MARK(0);                                              // prefetch issue, wait for the previous one, range lookup
         if (fast) {
             for (int i = tid; i < 2 * ns; i += CHAIN_THREADS) {
                 const int g = i / ns, r = i % ns;
@@ -1221,10 +1226,12 @@ __global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src,
             }
         }
         __syncthreads();
+        CH_MARK(fast ? 1 : 2);                                   // the 2 x 26 decimated samples (FIR over the prefetched bytes / slow path)
         if (tid < 32) {
             double v = 0.0; bool h = false;
             const int g = tid / n_cand, r = tid % n_cand;
             if (tid < 2 * n_cand && (g == 0 || b_ok)) { v = window_snr((g == 0 ? buf0 : buf1) + r, fft_len, tw); h = (v - c.hit_avg_snr) > th; }
+            CH_MARK(4);                                          // (inside phase 3) the window SNRs alone
             const unsigned mask = __ballot_sync(0xffffffffu, h);
             const unsigned mA = mask & ((1u << n_cand) - 1), mB = (mask >> n_cand) & ((1u << n_cand) - 1);
             int l = -1;
@@ -1233,6 +1240,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src,
             if (tid == 0) { sh_hit = l; sh_snr = hv; }
         }
         __syncthreads();
+        CH_MARK(3);                                              // 22 window SNRs, first hit
+        if (prof && tid == 0) atomicAdd(prof + 7, 1ull);
         const int l = sh_hit;
         if (l < 0) break;
         pos = (l < n_cand) ? nextA - max_offset + l : nextB - max_offset + (l - n_cand);
@@ -1240,6 +1249,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src,
         ++count;
     }
     asm volatile("cp.async.wait_group 0;");                      // no copy may still be in flight when the block retires
+    if (prof && tid == 0) atomicAdd(prof + 6, 1ull);
     if (tid == 0) ctl[stream].n_coarse = count;
 }
 
@@ -1370,11 +1380,18 @@ __global__ void __launch_bounds__(320) fine_peak_full_kernel(WinSrc src, StreamC
 #define FB_THREADS (FB_BINS * FB_SEGS)
 #define FB_LO 48
 #define FB_CERT 16
-__global__ void __launch_bounds__(FB_THREADS, 4) fine_peak_band_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ base_pos, int cap,
-                                                                   int osr, i64 len_s_ov, const double2 *__restrict__ tw, double *__restrict__ fine_raw,
-                                                                   const int *__restrict__ need_band, int *__restrict__ need_full,
-                                                                   int mode, int *__restrict__ fall_list, int *__restrict__ fall_count,
-                                                                   double *__restrict__ fall_best, int *__restrict__ fall_m, int force_fail) {
+// Fallback kernels behind a `need` mask (the bursts an earlier tier could not certify - few or none): a block owns `gsz` consecutive
+// bursts of a stream and runs the body for the flagged ones: 1/gsz of the blocks to dispatch, an unflagged group costs one 4-byte load per thread.
+__device__ __forceinline__ unsigned group_mask(const int *__restrict__ need, i64 row0, int first, int gsz, int cap) {
+    const int lane = threadIdx.x & 31;
+    const bool f = lane < gsz && first + lane < cap && (need == nullptr || need[row0 + first + lane] != 0);
+    return __ballot_sync(0xffffffffu, f);                        // every warp evaluates the same mask: block-uniform without a barrier
+}
+__device__ __forceinline__ void fine_peak_band_body(const WinSrc &src, const StreamCtl *__restrict__ ctl, const double *__restrict__ base_pos, int cap,
+                                                    int osr, i64 len_s_ov, const double2 *__restrict__ tw, double *__restrict__ fine_raw,
+                                                    int *__restrict__ need_full,
+                                                    int mode, int *__restrict__ fall_list, int *__restrict__ fall_count,
+                                                    double *__restrict__ fall_best, int *__restrict__ fall_m, int force_fail, int burst, int stream) {
     // mode 0 (tier 2): grid (cap, streams); the band sits around the tone and must pass the certificate, otherwise the
     //                  burst is appended to fall_list.
     // mode 1 (tier 3): grid (ceil(N/64), FALL_GRID); block (z, y) searches bins [64z, 64z+64) of the y-th listed burst, no
@@ -1384,13 +1401,6 @@ __global__ void __launch_bounds__(FB_THREADS, 4) fine_peak_band_kernel(WinSrc sr
     __shared__ int red_i[8];
     __shared__ double part[2 * (8 * 128 / FB_CERT + 2)];
     __shared__ double scan_sv[16];
-    int burst = blockIdx.x, stream = blockIdx.y;
-    if (mode == 1) {
-        const int cnt = *fall_count;
-        if ((int)blockIdx.y >= cnt || cnt > force_fail) return;    // in mode 1 `force_fail` carries the list-length limit of this tier
-        const int id = fall_list[blockIdx.y];
-        stream = id / cap; burst = id % cap;
-    } else if (need_band && !need_band[(i64)blockIdx.y * cap + blockIdx.x]) return;   // tier 1 already proved this burst
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const StreamCtl c = ctl[stream];
     if (c.n_coarse < 5 || burst >= c.n_coarse) return;
@@ -1541,6 +1551,28 @@ __global__ void __launch_bounds__(FB_THREADS, 4) fine_peak_band_kernel(WinSrc sr
             need_full[(i64)stream * cap + burst] = ok ? 0 : 1;
             if (!ok) fall_list[atomicAdd(fall_count, 1)] = stream * cap + burst;
         }
+    }
+}
+__global__ void __launch_bounds__(FB_THREADS, 4) fine_peak_band_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, const double *__restrict__ base_pos, int cap,
+                                                                   int osr, i64 len_s_ov, const double2 *__restrict__ tw, double *__restrict__ fine_raw,
+                                                                   const int *__restrict__ need_band, int *__restrict__ need_full,
+                                                                   int mode, int *__restrict__ fall_list, int *__restrict__ fall_count,
+                                                                   double *__restrict__ fall_best, int *__restrict__ fall_m, int force_fail, int gsz /* mode 0: 1..32 */) {
+    if (mode == 1) {
+        const int cnt = *fall_count;
+        if ((int)blockIdx.y >= cnt || cnt > force_fail) return;    // in mode 1 `force_fail` carries the list-length limit of this tier
+        const int id = fall_list[blockIdx.y];
+        fine_peak_band_body(src, ctl, base_pos, cap, osr, len_s_ov, tw, fine_raw, need_full, mode, fall_list, fall_count, fall_best, fall_m, force_fail, id % cap, id / cap);
+        return;
+    }
+    // mode 0: a block owns gsz consecutive bursts of a stream and searches the ones tier 1 left open (see tone_est_kernel)
+    const int stream = blockIdx.y, first = blockIdx.x * gsz;
+    unsigned m = group_mask(need_band, (i64)stream * cap, first, gsz, cap);
+    while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        fine_peak_band_body(src, ctl, base_pos, cap, osr, len_s_ov, tw, fine_raw, need_full, mode, fall_list, fall_count, fall_best, fall_m, force_fail, first + b, stream);
+        if (m) __syncthreads();
     }
 }
 
@@ -1847,9 +1879,9 @@ __device__ __forceinline__ double2 dft_col(const double2 *Tm, int k, int N, cons
 // (N*sum|u|^2 - sum_band P < max_band P); otherwise all N bins are evaluated.
 #define TONE_THREADS 256
 #define TONE_BAND 16
-__global__ void __launch_bounds__(TONE_THREADS, 3) tone_est_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, int which /* 1: fine stage, 2: post-SCH */,
-                                                               const double *__restrict__ pos, int cap, int osr, const double2 *__restrict__ tw,
-                                                               double *__restrict__ fo_out, double *__restrict__ gate_out, const int *__restrict__ need) {
+__device__ __forceinline__ void tone_est_body(const WinSrc &src, const StreamCtl *__restrict__ ctl, int which /* 1: fine stage, 2: post-SCH */,
+                                              const double *__restrict__ pos, int cap, int osr, const double2 *__restrict__ tw,
+                                              double *__restrict__ fo_out, double *__restrict__ gate_out, const int burst, const int stream) {
     extern __shared__ double2 sm[];
     __shared__ double red_v[8];
     __shared__ int red_i[8];
@@ -1857,11 +1889,10 @@ __global__ void __launch_bounds__(TONE_THREADS, 3) tone_est_kernel(WinSrc src, c
     __shared__ double red_n[80];
     __shared__ int sh_k0;
     __shared__ double sh_pr;
-    const int burst = blockIdx.x, stream = blockIdx.y, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     const StreamCtl c = ctl[stream];
     const int nb = (which == 1) ? (c.tone1_enable ? c.n_fcch : 0) : (c.post_enable ? c.n_post_fcch : 0);
     if (burst >= nb) return;
-    if (need && !need[(i64)stream * cap + burst]) return;       // tone8_kernel (osr-8 fast path) already did this burst
     const int N = 148 * osr;
     const double sampling_rate = ((1625.0 / 6.0) * 1e3) * (double)osr;
     double2 *u = sm, *A = u + N, *F = A + N;
@@ -1995,6 +2026,19 @@ __global__ void __launch_bounds__(TONE_THREADS, 3) tone_est_kernel(WinSrc src, c
     }
     block_sum_n<2, false>(sn2, red_n);
     if (tid == 0) gate_out[(i64)stream * cap + burst] = 10.0 * log10(sn2[0] / sn2[1]);
+}
+// (group_mask: see fine_peak_band_kernel)
+__global__ void __launch_bounds__(TONE_THREADS, 3) tone_est_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, int which, const double *__restrict__ pos, int cap,
+                                                               int osr, const double2 *__restrict__ tw, double *__restrict__ fo_out,
+                                                               double *__restrict__ gate_out, const int *__restrict__ need, int gsz /* 1..32 */) {
+    const int stream = blockIdx.y, first = blockIdx.x * gsz;
+    unsigned m = group_mask(need, (i64)stream * cap, first, gsz, cap);
+    while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        tone_est_body(src, ctl, which, pos, cap, osr, tw, fo_out, gate_out, first + b, stream);
+        if (m) __syncthreads();                                  // the next burst reuses the shared buffers
+    }
 }
 
 // ===================================================================================================

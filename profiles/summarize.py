@@ -18,7 +18,9 @@ KEYS = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__lsu_writeback_active_mem_lgds.sum.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
 
 
 def rep(path):
@@ -78,7 +80,7 @@ def facts(burst_rep, colsum_rep, streams_profiled, n_iq):
     burst kernels at the profiled size, DRAM bytes of the column-sum kernel against its algorithmic bytes)."""
     import json
     stage_of = {"fine_core8_kernel": "fine_peak", "sch_corr_kernel": "sch"}
-    pipe, dram, seen_tone = {}, {}, 0
+    pipe, dram, l1pipe, issue, seen_tone = {}, {}, {}, {}, 0
     for d, u in _rows(burst_rep):
         name = d["Kernel Name"].split("(")[0].replace("void ", "").split("<")[0]
         if name == "tone8_kernel":
@@ -89,6 +91,8 @@ def facts(burst_rep, colsum_rep, streams_profiled, n_iq):
         else:
             continue
         pipe[stage] = _num(d["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"])
+        l1pipe[stage] = _num(d["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"])     # shared-memory + global wavefronts on the L1 data pipe
+        issue[stage] = _num(d["smsp__issue_active.avg.pct_of_peak_sustained_active"])
         dram[stage] = int(_bytes(d["dram__bytes_read.sum"], u["dram__bytes_read.sum"]) + _bytes(d["dram__bytes_write.sum"], u["dram__bytes_write.sum"]))
     col = {}
     for d, u in _rows(colsum_rep):
@@ -98,7 +102,7 @@ def facts(burst_rep, colsum_rep, streams_profiled, n_iq):
             col = {"dram_bytes": int(rd + wr)}
             break
     out = {"source": f"ncu --set full --clock-control none, {os.path.basename(burst_rep)} ({streams_profiled} streams x {n_iq} IQ in one synchronous call, one launch per kernel)",
-           "streams_profiled": streams_profiled, "fp64_pipe_active_pct": pipe, "dram_bytes_per_launch": dram,
+           "streams_profiled": streams_profiled, "fp64_pipe_active_pct": pipe, "l1_data_pipe_pct": l1pipe, "issue_active_pct": issue, "dram_bytes_per_launch": dram,
            "colsum_source": f"ncu --set full --clock-control none, {os.path.basename(colsum_rep)} (32-stream launch of the bench command: 1,386,666,688 algorithmic bytes)",
            "colsum_dram_ratio": (col.get("dram_bytes", 0) / 1386666688.0) if col else None}
     print(json.dumps(out, indent=1))
