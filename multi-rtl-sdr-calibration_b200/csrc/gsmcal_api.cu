@@ -31,12 +31,14 @@ int g_debug_groups = 4;           // stream groups per batch (1 = strictly seque
 int g_debug_fall_limit = FALL_GRID;  // tier 3 handles work lists up to this length (tests set 0 to exercise the single-block list mode)
 int g_debug_fail_tier2 = 0;       // tests: pretend the 64-bin certificate failed
 int g_debug_force_full = 0;       // tests: run the all-bin fine search for every burst
-int g_debug_submit_groups = 1;    // stream groups inside a submitted batch
+int g_debug_submit_groups = 2;    // stream groups inside a submitted batch (debug key 8)
 int g_debug_persist_colsum = 0;   // submit/collect: blocks per SM of the persistent high-priority column-sum kernel (0 = per-group launches)
 int g_debug_hi_prio = 1;          // burst chain of each stream group on a high-priority CUDA stream
 int g_debug_core8_passes = B8_NPASS; // passes of 8 tracked bins in fine_core8_kernel (1..8)
 unsigned *g_last_pass_hist = nullptr, *g_prev_pass_hist = nullptr;   // counters of the last / the one-before-last batch (debug_get 50.., 150..)
 int g_debug_persist_threads = 256;  // block size of the persistent column-sum kernel (debug key 15)
+int g_debug_chain_serial = 0;      // debug key 21: the burst chains of a batch's stream groups run one after the other
+int g_debug_chain_lo = 0;          // debug key 22: ... on normal-priority streams (they only take what the FP64 blocks leave free)
 int g_debug_sch56 = 0;             // debug key 19: sch_corr_kernel capped at 56 registers
 int g_debug_trickle = 2;           // debug key 17: ring stages (x 4 KB) of colsum_u8_trickle_kernel in submit/collect, 0 = off (plain column-sum launches)
 int g_debug_trickle_blocks = 3;    // debug key 18: its blocks per SM (3 x 2 stages: 22 GB in 7 ms under the FP64 stages, profiles/r2q)
@@ -87,6 +89,7 @@ constexpr int kSlots = 4;
 struct Slot {
     DevBuf work, wc;                                            // wc: filtered-window cache of the osr-8 fast path
     cudaStream_t front = nullptr, front_hi = nullptr;
+    std::vector<cudaStream_t> co;                               // debug key 22: normal-priority streams for the burst chains
     std::vector<cudaStream_t> grp, hi;
     cudaEvent_t done = nullptr;
     cudaEvent_t tl[8] = {};                                     // debug key 14: front start, column sums done, burst chain done, FP64 stages done,
@@ -519,6 +522,8 @@ void gsmcal_release(void) {
             if (sl.done) { cudaEventSynchronize(sl.done); cudaEventDestroy(sl.done); sl.done = nullptr; }
             for (cudaStream_t s2 : sl.grp) cudaStreamDestroy(s2);
             for (cudaStream_t s2 : sl.hi) cudaStreamDestroy(s2);
+            for (cudaStream_t s2 : sl.co) cudaStreamDestroy(s2);
+            sl.co.clear();
             if (sl.front) cudaStreamDestroy(sl.front);
             if (sl.front_hi) cudaStreamDestroy(sl.front_hi);
             sl.front_hi = nullptr;
@@ -574,6 +579,8 @@ int gsmcal_debug_set(int key, int value) {
     if (key == 13) { g_debug_prof = value ? 1 : 0; return GSMCAL_OK; }
     if (key == 14) { g_debug_timeline = value ? 1 : 0; return GSMCAL_OK; }
     if (key == 16) { g_debug_gate = value ? 1 : 0; return GSMCAL_OK; }
+    if (key == 21) { g_debug_chain_serial = value != 0; return GSMCAL_OK; }
+    if (key == 22) { g_debug_chain_lo = value != 0; return GSMCAL_OK; }
     if (key == 19) { g_debug_sch56 = value != 0; return GSMCAL_OK; }
     if (key == 17) { g_debug_trickle = value < 0 ? 0 : (value > 24 ? 24 : value); return GSMCAL_OK; }
     if (key == 18) { g_debug_trickle_blocks = value < 1 ? 1 : (value > 4 ? 4 : value); return GSMCAL_OK; }
@@ -1162,7 +1169,8 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
     Slot &sl = c->slots[slot];
     if (sl.busy) return fail(GSMCAL_ERR_ARG, "calibrate_batch_submit: slot %d still holds an uncollected batch", slot);
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    int n_groups = g_debug_submit_groups;                       // 1: with batches in flight the overlap comes from the next batch; groups only add grid tails
+    int n_groups = g_debug_submit_groups;                       // 2: in the staggered pipeline a batch's stages run alone, so the per-stream kernels and
+                                                                // the grid tails of one half overlap the burst kernels of the other (31.15 -> 30.85 ms, profiles/r2x)
     if (D < 2 * n_groups) n_groups = 1;
     if (!sl.front) { CU(cudaStreamCreateWithFlags(&sl.front, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)); }
     int lo_p = 0, hi_p = 0; CU(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
@@ -1217,9 +1225,11 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
         CU(cudaEventRecord(e_sum, sl.front_hi));
         if (sl.tl_on) CU(cudaEventRecord(sl.tl[1], sl.front_hi));
     }
+    if (g_debug_chain_lo) while ((int)sl.co.size() < n_groups) { cudaStream_t s2; CU(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking)); sl.co.push_back(s2); }
+    cudaEvent_t e_chain_prev = nullptr;
     for (int g = 0; g < n_groups; ++g) {
         const i64 d0 = D * g / n_groups, d1 = D * (g + 1) / n_groups, nd = d1 - d0;
-        cudaStream_t sg = sl.grp[g], sh = sl.hi[g];
+        cudaStream_t sg = sl.grp[g], sh = g_debug_chain_lo ? sl.co[g] : sl.hi[g];
         Work ws = sub_work(w, d0, cap, g);
         const uint8_t *graw = raw_dev + d0 * per;
         cudaEvent_t e0, e1; CU(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
@@ -1229,9 +1239,12 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
             CU(cudaEventRecord(e0, fr)); CU(cudaStreamWaitEvent(sh, e0, 0));
             if (sl.tl_on && g == n_groups - 1) CU(cudaEventRecord(sl.tl[1], fr));
         }
+        if (g_debug_chain_serial && e_chain_prev) CU(cudaStreamWaitEvent(sh, e_chain_prev, 0));
         LAUNCH(mean_kernel, (unsigned)((nd + 127) / 128), 128, 0, sh, ws.ctl, (int)nd, n_iq);
         TRY(run_coarse(lazy_src(graw, n_iq, n_taps, 0, dec), len_dec, p, nd, cap, ws, sh));      // latency-bound chain: high priority
         CU(cudaEventRecord(e1, sh)); CU(cudaStreamWaitEvent(sg, e1, 0));
+        if (e_chain_prev) CU(cudaEventDestroy(e_chain_prev));
+        e_chain_prev = e1;
         if (sl.tl_on && g == n_groups - 1) CU(cudaEventRecord(sl.tl[2], sh));
         // Staggered batches (debug key 16, default on).  Ungated, two batches in flight run in lockstep (normal-priority kernels are dispatched
         // in arrival order, so their stages interleave and both finish together) and both fronts execute while nothing else does.  Gated,
@@ -1240,7 +1253,7 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
         // overlap (the ring's shared-memory traffic, the burst chain's register footprint): profiles/r2n, r2p, r2q and DESIGN.md section 8.
         if (g_debug_gate && c->last_slot >= 0 && c->last_slot != slot && c->slots[c->last_slot].busy)
             CU(cudaStreamWaitEvent(sg, c->slots[c->last_slot].done, 0));
-        CU(cudaEventDestroy(e0)); CU(cudaEventDestroy(e1));
+        CU(cudaEventDestroy(e0));
         const bool tl_g = sl.tl_on && g == n_groups - 1;
         if (tl_g) CU(cudaEventRecord(sl.tl[4], sg));
         TRY(run_fine_peak(*c, lazy_src(graw, n_iq, n_taps, 0, 1), n_iq, osr, nd, cap, ws, sg));
@@ -1256,6 +1269,7 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
         ev_done.push_back(ev);
     }
     if (e_sum) CU(cudaEventDestroy(e_sum));
+    if (e_chain_prev) CU(cudaEventDestroy(e_chain_prev));
     for (cudaEvent_t ev : ev_done) { CU(cudaStreamWaitEvent(fr, ev, 0)); CU(cudaEventDestroy(ev)); }
     CU(cudaMemcpyAsync(h_res, w.res, sl.n_res, cudaMemcpyDeviceToHost, fr));
     if (coarse_pos) CU(cudaMemcpyAsync(h_arr, w.coarse_pos, sl.n_per, cudaMemcpyDeviceToHost, fr));

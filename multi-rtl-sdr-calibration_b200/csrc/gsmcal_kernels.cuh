@@ -1111,10 +1111,12 @@ __global__ void specific_hit_kernel(const double *__restrict__ snr, i64 n, doubl
 // K4  burst chain  FCCH_coarse_position.m:32-91 - one warp per stream, 11 candidate windows per step
 // ===================================================================================================
 #define CHAIN_THREADS 64
-#define PF_BYTES 5632              // raw bytes one prefetched candidate range may hold ((2*5+2*5+16+3)*64+46 samples at dec 64)
+#define PF_BYTES 5120              // raw bytes one prefetched candidate range may hold ((2*5+2*5+16+3)*64+46 samples at dec 64 = 5084 B + alignment)
 #define PF_STRIDE (PF_BYTES + PF_BYTES / 8 + 32)   // with one 16-byte pad per 128 bytes (bank spreading for the 128-byte window stride)
 #define PF_RANGES 2                // candidate ranges per step: after a 10-frame step, after an 11-frame step
-__global__ void __launch_bounds__(CHAIN_THREADS) coarse_chain_kernel(WinSrc src, StreamCtl *ctl, i64 len, int fft_len, double th, int step10, int step11,
+// 112 registers and 24 KB: three chains fit into the registers and shared memory one retiring FP64 block (56 x 256 registers, 40-50 KB)
+// frees, so the high-priority chains of batch k+1 displace a third fewer blocks of batch k's burst kernels
+__global__ void __maxnreg__(112) coarse_chain_kernel(WinSrc src, StreamCtl *ctl, i64 len, int fft_len, double th, int step10, int step11,
                                                                     int dr, int cap, double *__restrict__ position, double *__restrict__ snr_out,
                                                                     unsigned long long *__restrict__ prof) {
     // debug key 13: thread 0 adds the cycles between the marks of a step to prof[phase], prof[7] counts steps, prof[6] blocks
