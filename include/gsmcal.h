@@ -218,8 +218,10 @@ int gsmcal_calibrate_batch_r(const uint8_t *raw, int raw_mem, int64_t n_iq, int6
 
 /* The same pipeline with several batches in flight (continuous captures): _submit enqueues batch `slot` (0..3) on the library's
  * own streams once the caller's `cuda_stream` has produced the DEVICE-resident capture, and returns; _collect waits for that batch
- * and fills the result pointers given to _submit (they must stay valid until then).  The latency-bound front of one batch
- * (column sums, ~0.8 ms dependent burst chain) then runs underneath the FP64-bound kernels of the previous one.
+ * and fills the result pointers given to _submit (they must stay valid until then).  Batches are staggered on the device: the
+ * burst kernels of batch k+1 start when batch k is done, and the front of batch k+1 - the exact column sums (a one-warp-per-block
+ * kernel that brings the bytes in with TMA bulk copies, small enough to sit beside the burst kernels) and the dependent burst chain,
+ * both on a high-priority stream - runs underneath the burst kernels of batch k.
  * Results are identical to gsmcal_calibrate_batch.  The capture must not be overwritten before _collect returns. */
 int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq, int64_t n_streams, double carrier_freq,
                                   const double *sch_training_sequence, const double *coef, int n_taps,
@@ -249,10 +251,15 @@ int gsmcal_fcch_scan(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t n_ch
 /* test / tuning hooks: key 0, value 1 = run the all-bin fine FCCH search for every burst (no band-limited fast path);
  * 3 = stream groups of gsmcal_calibrate_batch; 4 = pretend the tier-1/2 certificates failed; 5 = tier-3 list limit;
  * 6 = burst chain on high-priority streams (default 1); 7 = blocks per SM of a persistent high-priority column-sum kernel in
- * _submit (default 0 = per-group launches); 8 = stream groups inside a submitted batch (default 1); 9, value 1 = the generic tier-1 fine
+ * _submit (default 0 = off); 8 = stream groups inside a submitted batch (default 2); 9, value 1 = the generic tier-1 fine
  * search without the osr-8 fast path and its filtered-window cache (A/B and tests); 10 = passes of 8 tracked bins in the osr-8 tier-1
  * kernel (1..8, default 8); 11, value 1 = generic tone estimator for every burst (no tone8_kernel); 12, value 1 = plain cudaMemcpyAsync
- * for pageable host buffers instead of the library's multi-threaded pinned staging ring */
+ * for pageable host buffers instead of the library's multi-threaded pinned staging ring; 13, value 1 = per-phase clock64 counters in
+ * fine_core8_kernel / tone8_kernel / coarse_chain_kernel (gsmcal_debug_get 50.. / 150..); 14, value 1 = device timeline of every
+ * submitted batch on stderr; 15 = threads of the persistent column-sum kernel; 16 = stagger submitted batches (default 1; 0 = two
+ * batches in lockstep); 17 = 4 KB ring stages per block of the TMA column-sum kernel of _submit (default 2; 0 = plain launches);
+ * 18 = its blocks per SM (default 3); 19, value 1 = SCH correlation kernel capped at 56 registers; 21, value 1 = the burst chains of a
+ * batch's stream groups one after the other; 22, value 1 = burst chains on normal-priority streams */
 int gsmcal_debug_set(int key, int value);
 /* key 1: number of bursts of the last fine FCCH search whose band certificate failed (all-bin fallback ran); 2: bursts that needed the
  * 64-bin band kernel; 10 + p: bursts the osr-8 tier-1 kernel proved after p passes (p = 0: left open); 30: bytes moved through the
