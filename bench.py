@@ -561,7 +561,13 @@ def main():
     numa = numa_pin(local_rank)
     gsmcal.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL's kernels on a high-priority stream: at normal priority the 11 KB record gather would queue behind the 10^5 blocks of the
+        # running fine search (kernels of different streams are dispatched in arrival order)
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
+        except Exception:      # noqa: BLE001
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     host_cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
@@ -593,13 +599,25 @@ def main():
     gathered = torch.empty((world * sub * rec_bytes,), dtype=torch.uint8, device=dev) if world > 1 else None
     row_bytes = 2 * n_iq
 
-    def gather(records):
-        """the only exchange on the path: fixed-size per-stream result records over NCCL/NVLink"""
+    gathers = []                 # (work handle, source tensor) of the record gathers in flight
+
+    def gather(records, in_flight=False):
+        """the only exchange on the path: fixed-size per-stream result records over NCCL/NVLink.  in_flight (the submit/collect pipeline):
+        asynchronous, because the caller's stream must not wait for it - the next batch's front is ordered behind that stream and has to
+        start under the running burst kernels - and the handles are waited for by gather_wait() before the step's clock stops."""
         if world > 1:
             b = bytearray(bytes(records))
             b.extend(b"\0" * (sub * rec_bytes - len(b)))
             t = torch.frombuffer(b, dtype=torch.uint8).to(dev, non_blocking=True)
-            dist.all_gather_into_tensor(gathered, t)
+            if in_flight:
+                gathers.append((dist.all_gather_into_tensor(gathered, t, async_op=True), t))
+            else:
+                dist.all_gather_into_tensor(gathered, t)
+
+    def gather_wait():
+        for wk, _t in gathers:
+            wk.wait()
+        gathers.clear()
 
     def barrier():
         if world > 1:
@@ -628,7 +646,7 @@ def main():
             b, p = self.pend[slot]
             r = p.collect()
             self.pend[slot] = None
-            gather(r)
+            gather(r, in_flight=True)
             self.last[b] = r
 
         def run(self, k):
@@ -654,6 +672,7 @@ def main():
                 slot = (self.ctr + j) % depth
                 if self.pend[slot] is not None:
                     self._finish(slot)
+            gather_wait()                                # every rank holds every record before the clock stops
             return [r for part in self.last if part is not None for r in part]
 
     pipe = Pipe()
