@@ -424,6 +424,31 @@ def test_full_size_streams_match_oracle(gpu, captures_10s, coef47, tpl):
         assert abs(got[d]["total_carrier_ppm"] - specs[d].carrier_ppm) < 1.6
 
 
+def test_full_size_staggered_submit_collect_equals_synchronous_call(gpu, coef47, tpl):
+    """BASELINE-size rows (43 333 334 bytes: every row starts 6 bytes further from a 16-byte boundary, so the TMA-ring column sums peel
+    heads and tails), two batches of four streams in flight with the library defaults (staggered, two stream groups per batch)."""
+    torch = pytest.importorskip("torch")
+    specs = [synth.random_spec(seed, N_10S) for seed in (201, 202, 203, 204, 205)]
+    raw = synth.generate_batch(specs, device="cuda")
+    torch.cuda.synchronize()
+    st = torch.cuda.current_stream().cuda_stream
+    row = raw.shape[1]
+    ref_a = gpu.calibrate_batch(None, CARRIER, tpl, coef47, device_ptr=raw.data_ptr(), n_iq=N_10S, n_streams=4, cuda_stream=st)
+    ref_b = gpu.calibrate_batch(None, CARRIER, tpl, coef47, device_ptr=raw.data_ptr() + row, n_iq=N_10S, n_streams=4, cuda_stream=st)
+    pend = [gpu.calibrate_batch_submit(0, raw.data_ptr(), N_10S, 4, CARRIER, tpl, coef47, cuda_stream=st, details=True),
+            gpu.calibrate_batch_submit(1, raw.data_ptr() + row, N_10S, 4, CARRIER, tpl, coef47, cuda_stream=st, details=True)]
+    got = [pend[0].collect()]
+    pend.append(gpu.calibrate_batch_submit(0, raw.data_ptr(), N_10S, 4, CARRIER, tpl, coef47, cuda_stream=st, details=True))
+    got += [pend[1].collect(), pend[2].collect()]
+    for g, ref in zip(got, (ref_a, ref_b, ref_a)):
+        for x, y in zip(g, ref):
+            for k in ("coarse_pos", "coarse_snr", "fcch_pos", "pos_info"):
+                np.testing.assert_array_equal(x[k], y[k])
+            assert x["sampling_ppm"] == y["sampling_ppm"] and x["carrier_ppm"] == y["carrier_ppm"] and x["flags"] == y["flags"]
+            assert x["total_sampling_ppm"] == y["total_sampling_ppm"] and x["total_carrier_ppm"] == y["total_carrier_ppm"]
+    assert sum(1 for x in got[0] if len(x["fcch_pos"]) > 200) >= 3            # the streams do lock: the comparison is not about sentinels
+
+
 def test_full_size_structural_properties(gpu, captures_10s, coef47, tpl):
     specs, raw = captures_10s
     got = gpu.calibrate_batch(None, CARRIER, tpl, coef47, device_ptr=raw.data_ptr(), n_iq=N_10S, n_streams=raw.shape[0])
