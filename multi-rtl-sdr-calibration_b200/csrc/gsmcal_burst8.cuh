@@ -365,16 +365,21 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
 #define T8_K 5                               // consecutive samples per thread in the fused passes
 // interp1 'linear' of consecutive outputs (load_window's arithmetic): the upper neighbour of one output is the lower neighbour of the next
 // except where the resampling ratio makes the source index skip or repeat, so it is kept in registers
+// sample r of the level-0 range as the TMA bulk copy left it in shared memory: the cached layout (one pad slot per 32 samples of the
+// window) starting at window sample o
+__device__ __forceinline__ int t8_pad(int r, int o) { return r + ((o + r) >> 5) - (o >> 5); }
 struct T8Lerp {
     i64 prev_i1 = -1;
     double2 prev_hi = {0.0, 0.0};
-    __device__ __forceinline__ double2 next(const double2 *S, i64 a_src, i64 last, i64 j, double s) {
+    template <bool PAD>
+    __device__ __forceinline__ double2 next(const double2 *S, i64 a_src, i64 last, i64 j, double s, int o = 0) {
         const double xq = (double)j * s;
         i64 i0 = (i64)floor(xq);
         if (i0 > last) i0 = last;
         const i64 i1 = (i0 + 1 > last) ? last : i0 + 1;
-        const double2 lo = (i0 == prev_i1) ? prev_hi : S[i0 - a_src];
-        const double2 hi = (i1 == i0) ? lo : S[i1 - a_src];
+        const int r0 = (int)(i0 - a_src), r1 = (int)(i1 - a_src);
+        const double2 lo = (i0 == prev_i1) ? prev_hi : S[PAD ? t8_pad(r0, o) : r0];
+        const double2 hi = (i1 == i0) ? lo : S[PAD ? t8_pad(r1, o) : r1];
         prev_i1 = i1; prev_hi = hi;
         return lerp_ref(lo, hi, xq - (double)i0);
     }
@@ -382,8 +387,9 @@ struct T8Lerp {
 #define T8_THREADS 256
 #define T8_SEG     10
 #define T8_NSEG    119                       // ceil(1184 / 10); the last segment is padded with zeros
-#define T8_BUF     1216
+#define T8_BUF     1256                      // 1208 samples of a level + the pad slots of the cached layout they span (one per 32)
 #define T8_SMEM    (2 * T8_BUF * 16)
+#define T8_LVL     1208                      // samples a resampling level may hold
 template <bool PROF>
 __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__restrict__ ctl, int which, const double *__restrict__ pos, int cap,
                                                              const double2 *__restrict__ tw, double *__restrict__ fo_out, double *__restrict__ gate_out,
@@ -397,6 +403,7 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
     __shared__ double sh_pb[8], sh_E, sh_pr;
     __shared__ double2 sh_x[8];
     __shared__ int sh_k0, sh_jbest, sh_flag;
+    __shared__ __align__(8) unsigned long long t8_bar;
     const int burst = blockIdx.x, stream = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const i64 idx_o = (i64)stream * cap + burst;
     // fetched side by side with the control block (one global-memory latency instead of three); garbage beyond the burst count is not used
@@ -432,20 +439,33 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
     if (b0 > n0 - 1) b0 = n0 - 1;
     const int n_l0 = (int)(b0 - a0 + 1), n_l1 = (int)(b1 - a1 + 1);
     const i64 wbase = ((i64)wpos_d - 65) * 8;
-    const bool covered = src.wcache && a0 >= wbase && b0 < wbase + B8_NSMP && n_l0 <= T8_BUF - 8 && n_l1 <= T8_BUF - 8 && start >= 0
+    const bool covered = src.wcache && a0 >= wbase && b0 < wbase + B8_NSMP && n_l0 <= T8_LVL && n_l1 <= T8_LVL && start >= 0
                          && (!derot || use1);                     // (derotation without resampling does not occur in the reference flow)
     if (!covered) {                                              // block-uniform
         if (tid == 0) need_old[idx_o] = 1;
         return;
     }
-    // ---- level 0 from the cache -> P ----
-    {
-        const double2 *wc = src.wcache + idx_o * B8_WLEN;
-        const int o = (int)(a0 - wbase);
-        for (int i = tid; i < n_l0; i += T8_THREADS) P[i] = wc[B8_WPAD(o + i)];
-        if (derot && tid == 0) { double sn, cs; sincos((double)a1 * c.dphi1, &sn, &cs); sh_base = make_double2(cs, sn); }
+    // ---- level 0 from the cache -> P: ONE TMA bulk copy of the contiguous part of the cached (padded) window that holds the range; it
+    //      stays in the padded layout (t8_pad) - no LDG + STS pass, no index arithmetic per sample ----
+    const int o = (int)(a0 - wbase);
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&t8_bar);
+    if (tid == 0) {
+        const double2 *wc = src.wcache + idx_o * B8_WLEN + B8_WPAD(o);
+        const unsigned bytes = (unsigned)((B8_WPAD(o + n_l0 - 1) - B8_WPAD(o) + 1) * sizeof(double2));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes));
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((unsigned)__cvta_generic_to_shared(P)), "l"(wc), "r"(bytes), "r"(bar) : "memory");
+        if (derot) { double sn, cs; sincos((double)a1 * c.dphi1, &sn, &cs); sh_base = make_double2(cs, sn); }
     }
-    __syncthreads();
+    __syncthreads();                                             // the barrier is initialised (and sh_base written) for everyone
+    {
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+    }
     T8_MARK(0);                                                  // level 0 from the cache (global-memory latency)
     // The L1/shared-memory data pipe is the busiest unit of this kernel (ncu: 68 % against 34 % for the FP64 pipe), so the passes below
     // give every thread T8_K CONSECUTIVE samples: interp1 re-uses the upper neighbour of one output as the lower neighbour of the next
@@ -473,7 +493,7 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
         for (int k = 0; k <= T8_K; ++k) {                        // (the K+1-th sample only feeds the pair sum when this level is the final one)
             const int i = nf + k;
             if (i < n_l1 && (k < T8_K || !use2)) {
-                double2 v = lc.next(P, a0, n0 - 1, a1 + i, s1);
+                double2 v = lc.next<true>(P, a0, n0 - 1, a1 + i, s1, o);
                 if (derot) { v = cmul(v, ph); ph = cmul(ph, st); }
                 if (k < T8_K) Q[i] = v;
                 if (!use2 && i < N) energy_pair(k, i, v, prev);
@@ -487,7 +507,7 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
             for (int k = 0; k <= T8_K; ++k) {
                 const int i = nf + k;
                 if (i < N) {
-                    const double2 v = l2.next(Q, a1, len1 - 1, a2 + i, s2);
+                    const double2 v = l2.next<false>(Q, a1, len1 - 1, a2 + i, s2);
                     if (k < T8_K) P[i] = v;
                     energy_pair(k, i, v, prev);
                 }
@@ -501,19 +521,24 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
         for (int k = 0; k <= T8_K; ++k) {
             const int i = nf + k;
             if (i < N) {
-                const double2 v = l2.next(P, a1, len1 - 1, a2 + i, s2);
+                const double2 v = l2.next<true>(P, a1, len1 - 1, a2 + i, s2, o);
                 if (k < T8_K) Q[i] = v;
                 energy_pair(k, i, v, prev);
             }
         }
         u = Q; spare = P;
-    } else {                                                     // level 0 is the burst
+    } else {                                                     // level 0 is the burst: out of the padded layout -> Q
         double2 prev = make_double2(0.0, 0.0);
 #pragma unroll
         for (int k = 0; k <= T8_K; ++k) {
             const int i = nf + k;
-            if (i < N) energy_pair(k, i, P[i], prev);
+            if (i < N) {
+                const double2 v = P[t8_pad(i, o)];
+                if (k < T8_K) Q[i] = v;
+                energy_pair(k, i, v, prev);
+            }
         }
+        u = Q; spare = P;
     }
     if (tid < T8_SEG * T8_NSEG - N + 2) u[N + tid] = make_double2(0.0, 0.0);     // zero padding of the last Horner segment
     T8_MARK(1);                                                  // interp1 / derotation levels (+ energy and phase slope on the fly)
