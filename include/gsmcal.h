@@ -259,7 +259,8 @@ int gsmcal_fcch_scan(const uint8_t *raw, int raw_mem, int64_t n_iq, int64_t n_ch
  * submitted batch on stderr; 15 = threads of the persistent column-sum kernel; 16 = stagger submitted batches (default 1; 0 = two
  * batches in lockstep); 17 = 4 KB ring stages per block of the TMA column-sum kernel of _submit (default 2; 0 = plain launches);
  * 18 = its blocks per SM (default 3); 19, value 1 = SCH correlation kernel capped at 56 registers; 21, value 1 = the burst chains of a
- * batch's stream groups one after the other; 22, value 1 = burst chains on normal-priority streams */
+ * batch's stream groups one after the other; 22, value 1 = burst chains on normal-priority streams; 23 = KB of shared memory per block
+ * of an extra kernel of sleeping blocks behind the chain (experiment: what the chain's SM slots cost) */
 int gsmcal_debug_set(int key, int value);
 /* key 1: number of bursts of the last fine FCCH search whose band certificate failed (all-bin fallback ran); 2: bursts that needed the
  * 64-bin band kernel; 10 + p: bursts the osr-8 tier-1 kernel proved after p passes (p = 0: left open); 30: bytes moved through the

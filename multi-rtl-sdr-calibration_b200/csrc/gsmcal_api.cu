@@ -37,6 +37,7 @@ int g_debug_hi_prio = 1;          // burst chain of each stream group on a high-
 int g_debug_core8_passes = B8_NPASS; // passes of 8 tracked bins in fine_core8_kernel (1..8)
 unsigned *g_last_pass_hist = nullptr, *g_prev_pass_hist = nullptr;   // counters of the last / the one-before-last batch (debug_get 50.., 150..)
 int g_debug_persist_threads = 256;  // block size of the persistent column-sum kernel (debug key 15)
+int g_debug_occupy = 0;            // debug key 23: KB of shared memory per block of an extra occupy_kernel launch behind the chain (0 = none)
 int g_debug_chain_serial = 0;      // debug key 21: the burst chains of a batch's stream groups run one after the other
 int g_debug_chain_lo = 0;          // debug key 22: ... on normal-priority streams (they only take what the FP64 blocks leave free)
 int g_debug_sch56 = 0;             // debug key 19: sch_corr_kernel capped at 56 registers
@@ -182,6 +183,7 @@ int get_ctx(Ctx **out) {
         CU(cudaFuncSetAttribute(sch_corr_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CU(cudaFuncSetAttribute(sch_corr_kernel<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CU(cudaFuncSetAttribute(colsum_u8_trickle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * (TRK_STAGE + 8)));
+        CU(cudaFuncSetAttribute(occupy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         CU(cudaFuncSetAttribute(colsum_u8_trickle_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CU(cudaFuncSetAttribute(materialise_r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         CU(cudaFuncSetAttribute(fir_full_tma_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -579,6 +581,7 @@ int gsmcal_debug_set(int key, int value) {
     if (key == 13) { g_debug_prof = value ? 1 : 0; return GSMCAL_OK; }
     if (key == 14) { g_debug_timeline = value ? 1 : 0; return GSMCAL_OK; }
     if (key == 16) { g_debug_gate = value ? 1 : 0; return GSMCAL_OK; }
+    if (key == 23) { g_debug_occupy = value < 0 ? 0 : (value > 96 ? 96 : value); return GSMCAL_OK; }
     if (key == 21) { g_debug_chain_serial = value != 0; return GSMCAL_OK; }
     if (key == 22) { g_debug_chain_lo = value != 0; return GSMCAL_OK; }
     if (key == 19) { g_debug_sch56 = value != 0; return GSMCAL_OK; }
@@ -1242,6 +1245,7 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
         if (g_debug_chain_serial && e_chain_prev) CU(cudaStreamWaitEvent(sh, e_chain_prev, 0));
         LAUNCH(mean_kernel, (unsigned)((nd + 127) / 128), 128, 0, sh, ws.ctl, (int)nd, n_iq);
         TRY(run_coarse(lazy_src(graw, n_iq, n_taps, 0, dec), len_dec, p, nd, cap, ws, sh));      // latency-bound chain: high priority
+        if (g_debug_occupy > 0) LAUNCH(occupy_kernel, (unsigned)nd, 64, (size_t)g_debug_occupy * 1024, sh, (long long)4500000, w.fine_raw);   // ~2.3 ms at 1.965 GHz
         CU(cudaEventRecord(e1, sh)); CU(cudaStreamWaitEvent(sg, e1, 0));
         if (e_chain_prev) CU(cudaEventDestroy(e_chain_prev));
         e_chain_prev = e1;

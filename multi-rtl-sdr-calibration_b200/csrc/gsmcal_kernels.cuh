@@ -1255,6 +1255,17 @@ __global__ void __maxnreg__(112) coarse_chain_kernel(WinSrc src, StreamCtl *ctl,
     if (tid == 0) ctl[stream].n_coarse = count;
 }
 
+// Experiment hook (debug key 23): blocks that only OCCUPY - `cycles` of spinning with the footprint given at launch (64 threads, dynamic
+// shared memory) - launched behind the burst chain on its high-priority stream, to tell what the chain costs the burst kernels of the
+// previous batch: the SM slots it holds, or the instructions it executes.
+__global__ void __launch_bounds__(64) occupy_kernel(long long cycles, double *sink) {
+    extern __shared__ double occ_sm[];
+    const long long t0 = clock64();
+    double acc = 0.0;
+    while (clock64() - t0 < cycles) { acc += occ_sm[threadIdx.x]; __nanosleep(200); }
+    if (acc == 12345.678) *sink = acc;
+}
+
 // ===================================================================================================
 // K5  fine FCCH position  FCCH_fine_correction.m:32-64
 // ===================================================================================================
