@@ -1254,7 +1254,7 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
         // in arrival order, so their stages interleave and both finish together) and both fronts execute while nothing else does.  Gated,
         // the FP64 stages of batch k+1 start when batch k is done and the front of batch k+1 - on the high-priority stream, with the
         // column sums as the small-footprint TMA-ring kernel - runs UNDER the FP64 stages of batch k.  Device timelines and the cost of the
-        // overlap (the ring's shared-memory traffic, the burst chain's register footprint): profiles/r2n, r2p, r2q and DESIGN.md section 8.
+        // overlap (the ring's shared-memory traffic, the burst chain): profiles/r2n, r2p, r2q, r2z, r2ak and DESIGN.md section 4.
         if (g_debug_gate && c->last_slot >= 0 && c->last_slot != slot && c->slots[c->last_slot].busy)
             CU(cudaStreamWaitEvent(sg, c->slots[c->last_slot].done, 0));
         CU(cudaEventDestroy(e0));
