@@ -208,8 +208,8 @@ int get_twiddle(Ctx &c, int N, cudaStream_t st, const double2 **out) {
     auto it = c.tw.find(N);
     if (it == c.tw.end()) {
         double2 *p = nullptr;
-        CU(cudaMalloc(&p, sizeof(double2) * N));
-        LAUNCH(twiddle_init_kernel, (N + 127) / 128, 128, 0, st, p, N);
+        CU(cudaMalloc(&p, sizeof(double2) * (N + TW_EXTRA)));
+        LAUNCH(twiddle_init_kernel, (N + TW_EXTRA + 127) / 128, 128, 0, st, p, N);
         c.tw[N] = p;
         *out = p;
     } else *out = it->second;

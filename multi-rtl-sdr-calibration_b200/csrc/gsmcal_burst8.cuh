@@ -200,7 +200,7 @@ __global__ void __maxnreg__(56) fine_core8_kernel(const uint8_t *__restrict__ ra
             // W^(32 c k) of the thread's four (consecutive) bins from two table entries, W^(32 c (k+1)) = W^(32 c k) W^(32 c): a scattered
             // 16-byte table read costs one L1 wavefront per lane, and the L1/shared data pipe is the busiest unit of this kernel
             double2 rot = tw[(32 * cch * kk[0]) % B8_N];
-            const double2 rstep = tw[(32 * cch) % B8_N];
+            const double2 rstep = tw[B8_N + 2 * TW_SEG + cch];    // W^(32 c) = tw[(32 * cch) % B8_N] from the compact copy
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 CS[(4 * q + b) * B8_CSL + cch + 1] = cmul(acc[b], rot);
@@ -574,7 +574,7 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
         // W^(n0 k) of the four bins from two table entries: W^(n0 (k+1)) = W^(n0 k) W^n0 (scattered 16-byte table reads cost a
         // wavefront per lane on the L1 data pipe)
         double2 rot = tw[(n0s * kf) % N];
-        const double2 rstep = tw[n0s];
+        const double2 rstep = tw[N + seg];                       // W^(10 seg) from the compact copy (same value as tw[n0s])
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             spare[(4 * q + b) * 120 + 4 * q + seg] = cmul(acc[b], rot);
@@ -685,7 +685,7 @@ __global__ void __maxnreg__(56) tone8_kernel(WinSrc src, const StreamCtl *__rest
             accm = make_double2(fma(accm.x, zm.x, fma(-accm.y, zm.y, v.x)), fma(accm.x, zm.y, fma(accm.y, zm.x, v.y)));
             acc0.x += v.x; acc0.y += v.y;
         }
-        const double2 t = tw[(n0s * (q + 1)) % N];               // W^{+n0 (q+1)}; its conjugate for the negative bin
+        const double2 t = tw[N + TW_SEG * q + seg];              // W^{+n0 (q+1)} = tw[(n0s * (q + 1)) % N] from the compact copies; its conjugate for the negative bin
         u[(2 * q) * 120 + 4 * q + seg] = cmul(accp, t);
         u[(2 * q + 1) * 120 + 4 * q + seg] = cmul(accm, make_double2(t.x, -t.y));
         if (q == 0) u[4 * 120 + 4 + seg] = acc0;

@@ -2520,10 +2520,17 @@ __global__ void mean_kernel(StreamCtl *ctl, int n_streams, i64 n_iq) {
     if (d < n_streams) { ctl[d].mu_re = stream_mean(ctl[d].sum_i, n_iq); ctl[d].mu_im = stream_mean(ctl[d].sum_q, n_iq); }
 }
 
+// tw[0..N): exp(-2*pi*i*j/N).  Behind it, three compact copies for the Horner segment / chunk rotations of tone8_kernel and
+// fine_core8_kernel: tw[N + s] = W^(10 s), tw[N + TW_SEG + s] = W^(20 s), tw[N + 2 TW_SEG + s] = W^(32 s), s < TW_SEG - the same values as
+// tw[(10 s) % N] ..., but a warp reads 16 consecutive entries (2 cache lines) instead of 16 lines
+#define TW_SEG 128
+#define TW_EXTRA (3 * TW_SEG)
 __global__ void twiddle_init_kernel(double2 *tw, int N) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < N) {
-        double sn, cs; sincospi(-2.0 * (double)j / (double)N, &sn, &cs);
+    if (j < N + TW_EXTRA) {
+        const int t = (j - N) / TW_SEG, sidx = (j - N) % TW_SEG;
+        const int e = (j < N) ? j : (int)(((t == 0 ? 10ll : (t == 1 ? 20ll : 32ll)) * sidx) % N);
+        double sn, cs; sincospi(-2.0 * (double)e / (double)N, &sn, &cs);
         tw[j] = make_double2(cs, sn);
     }
 }
