@@ -115,3 +115,20 @@ def test_demod_family_sentinels_and_loud_failure(built_lib):
         with pytest.raises(gsmcal.GsmcalError) as e:
             call()
         assert e.value.code == -2
+
+
+def test_every_debug_set_key_is_documented_in_the_header():
+    """gsmcal_debug_set's keys are the tuning surface the profiles/ scripts use: each key the library accepts must be described in the
+    comment above its declaration (include/gsmcal.h)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "multi-rtl-sdr-calibration_b200", "csrc", "gsmcal_api.cu")).read()
+    body = src[src.index("int gsmcal_debug_set(int key, int value)"):]
+    body = body[:body.index("\n}\n")]
+    keys = sorted({int(k) for k in re.findall(r"key == (\d+)", body)})
+    assert len(keys) >= 20
+    hdr = open(os.path.join(root, "include", "gsmcal.h")).read()
+    doc = hdr[hdr.index("test / tuning hooks"):hdr.index("int gsmcal_debug_set")]
+    documented = {int(k) for k in re.findall(r"(?:key |; |, )(\d+)(?:,| =)", doc)}
+    missing = [k for k in keys if k not in documented]
+    assert not missing, f"debug keys without a line in include/gsmcal.h: {missing}"
