@@ -129,6 +129,6 @@ def test_every_debug_set_key_is_documented_in_the_header():
     assert len(keys) >= 20
     hdr = open(os.path.join(root, "include", "gsmcal.h")).read()
     doc = hdr[hdr.index("test / tuning hooks"):hdr.index("int gsmcal_debug_set")]
-    documented = {int(k) for k in re.findall(r"(?:key |; |, )(\d+)(?:,| =)", doc)}
+    documented = {int(k) for k in re.findall(r"(?:key |; |, |\* )(\d+)(?:,| =)", doc)}
     missing = [k for k in keys if k not in documented]
     assert not missing, f"debug keys without a line in include/gsmcal.h: {missing}"
