@@ -205,8 +205,9 @@ __device__ void load_window(const WinSrc &src, const StreamCtl &c, int stream, i
     if (b0 > n0 - 1) b0 = n0 - 1;
     // derotation base phasor exp(1i*a1*dphi1): the argument reaches 1e5..1e6 rad (Payne-Hanek path of sincos, ~150 instructions), so ONE
     // thread evaluates it while the others stage and filter; it is read after the barriers below
-    __shared__ double2 lw_base;
+    __shared__ double2 lw_base, lw_step;                         // exp(1i*a1*dphi1); exp(1i*nt*dphi1), the per-iteration step of every thread
     if (derot && use1 && tid == 0) { double sn, cs; sincos((double)a1 * c.dphi1, &sn, &cs); lw_base = make_double2(cs, sn); }
+    if (derot && use1 && tid == 32 % nt) { double sn, cs; sincos((double)nt * c.dphi1, &sn, &cs); lw_step = make_double2(cs, sn); }
     const int n_l0 = (int)(b0 - a0 + 1);
     // unrolled FIR variants (taps zero-padded on the old side), one group of LW_R outputs per thread; longer windows or filters take the rolled loop
     const int nt_sel = ((n_l0 + LW_R - 1) / LW_R > nt) ? 0 : ((src.n_taps == 47) ? 47 : ((src.n_taps <= 48) ? 48 : (src.n_taps <= 64 ? 64 : 0)));
@@ -293,7 +294,7 @@ __device__ void load_window(const WinSrc &src, const StreamCtl &c, int stream, i
         if (derot) {
             double sn, cs;
             sincos((double)tid * c.dphi1, &sn, &cs); ph = cmul(lw_base, make_double2(cs, sn));
-            sincos((double)nt * c.dphi1, &sn, &cs); st = make_double2(cs, sn);
+            st = lw_step;
         }
         for (int i = tid; i < n_l1; i += nt) {
             i64 j = a1 + i;
