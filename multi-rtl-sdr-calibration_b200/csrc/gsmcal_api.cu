@@ -1217,14 +1217,21 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
         if (!g_tl_base) { CU(cudaEventCreate(&g_tl_base)); CU(cudaEventRecord(g_tl_base, fr)); }
         CU(cudaEventRecord(sl.tl[0], fr));
     }
+    std::vector<cudaEvent_t> e_sum_g;                            // per stream group: its column sums are done
     if (g_debug_persist_colsum > 0 || g_debug_trickle > 0) {
-        // all column sums in ONE persistent launch of fixed footprint on the high-priority front stream (see colsum_u8_persist_kernel,
-        // colsum_u8_trickle_kernel)
+        // the column sums as persistent launches of fixed footprint on the high-priority front stream (see colsum_u8_persist_kernel,
+        // colsum_u8_trickle_kernel), one per stream group, back to back: the burst chain of group g starts under the sums of group g+1
         int n_sm = 148; CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, g_device));
         cudaEvent_t e_in; CU(cudaEventCreateWithFlags(&e_in, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&e_sum, cudaEventDisableTiming));
         CU(cudaEventRecord(e_in, fr)); CU(cudaStreamWaitEvent(sl.front_hi, e_in, 0)); CU(cudaEventDestroy(e_in));
-        if (g_debug_persist_colsum > 0) TRY(run_colsum_u8_persist(raw_dev, n_iq, D, w.ctl, n_sm * g_debug_persist_colsum, sl.front_hi));
-        else TRY(run_colsum_u8_trickle(raw_dev, n_iq, D, w.ctl, n_sm * g_debug_trickle_blocks, g_debug_trickle, sl.front_hi));
+        for (int g = 0; g < n_groups; ++g) {
+            const i64 d0 = D * g / n_groups, d1 = D * (g + 1) / n_groups;
+            if (g_debug_persist_colsum > 0) TRY(run_colsum_u8_persist(raw_dev + d0 * per, n_iq, d1 - d0, w.ctl + d0, n_sm * g_debug_persist_colsum, sl.front_hi));
+            else TRY(run_colsum_u8_trickle(raw_dev + d0 * per, n_iq, d1 - d0, w.ctl + d0, n_sm * g_debug_trickle_blocks, g_debug_trickle, sl.front_hi));
+            cudaEvent_t eg; CU(cudaEventCreateWithFlags(&eg, cudaEventDisableTiming));
+            CU(cudaEventRecord(eg, sl.front_hi));
+            e_sum_g.push_back(eg);
+        }
         CU(cudaEventRecord(e_sum, sl.front_hi));
         if (sl.tl_on) CU(cudaEventRecord(sl.tl[1], sl.front_hi));
     }
@@ -1236,7 +1243,7 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
         Work ws = sub_work(w, d0, cap, g);
         const uint8_t *graw = raw_dev + d0 * per;
         cudaEvent_t e0, e1; CU(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
-        if (e_sum) CU(cudaStreamWaitEvent(sh, e_sum, 0));
+        if (e_sum) CU(cudaStreamWaitEvent(sh, e_sum_g[g], 0));
         else {
             TRY(run_colsum_u8(graw, n_iq, nd, ws.ctl, fr));     // HBM-bound sums back to back on the front stream (group 0 first)
             CU(cudaEventRecord(e0, fr)); CU(cudaStreamWaitEvent(sh, e0, 0));
@@ -1273,6 +1280,7 @@ int gsmcal_calibrate_batch_submit(int slot, const uint8_t *raw_dev, int64_t n_iq
         ev_done.push_back(ev);
     }
     if (e_sum) CU(cudaEventDestroy(e_sum));
+    for (cudaEvent_t eg : e_sum_g) CU(cudaEventDestroy(eg));
     if (e_chain_prev) CU(cudaEventDestroy(e_chain_prev));
     for (cudaEvent_t ev : ev_done) { CU(cudaStreamWaitEvent(fr, ev, 0)); CU(cudaEventDestroy(ev)); }
     CU(cudaMemcpyAsync(h_res, w.res, sl.n_res, cudaMemcpyDeviceToHost, fr));
