@@ -898,7 +898,10 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": dict(workload_config(world, D, n_iq, scaling), batches_in_flight=depth, streams_per_submitted_batch=sub),
+                "data": "synthetic", "config": dict(workload_config(world, D, n_iq, scaling), batches_in_flight=depth, streams_per_submitted_batch=sub,
+                               pipeline=("staggered batches (library default): the burst kernels of batch k+1 start when batch k is done; its column sums "
+                                         "(one-warp TMA-ring kernel) and burst chain run on a high-priority stream under the burst kernels of batch k"
+                                         if not any(k.startswith("16=0") for k in args.debug) else "two batches in lockstep (debug key 16=0)")),
                 "clocks": clocks, "e2e": e2e, "with_r_correct": with_r, "gpu_launches": int(launches),
                 "roofline": roofline, "roofline_hbm": roofline_hbm, "whole_path": whole_path, "fp64_peak_tflops_measured": fp64.value,
                 "cpu_baseline": cpu_baseline, "stage_ms": stage_ms, "stage_ms_note": f"sequential pass over all {D} streams of rank 0 (one stream group)",
